@@ -1,0 +1,275 @@
+"""ctypes binding of include/icet_b200.h and the Python mirror of the reference's `class ICET`."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import build as _build
+
+_FP, _IP, _BP = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+
+
+class IcetError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """ctor arguments of the reference (include/icet.h:38-40)."""
+    _fields_ = [("runlen", C.c_int32), ("bins_phi", C.c_int32), ("bins_theta", C.c_int32), ("n", C.c_int32),
+                ("thresh", C.c_float), ("buff", C.c_float), ("flags", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Result(C.Structure):
+    _fields_ = [("X", C.c_float * 6), ("pred_stds", C.c_float * 6), ("Q", C.c_float * 36), ("status", C.c_int32),
+                ("n_gauss1", C.c_int32), ("n_used", C.c_int32), ("n_dropped", C.c_int32), ("cond", C.c_float),
+                ("reserved", C.c_int32 * 3)]
+
+
+RESULT_DTYPE = np.dtype([("X", np.float32, 6), ("pred_stds", np.float32, 6), ("Q", np.float32, (6, 6)),
+                         ("status", np.int32), ("n_gauss1", np.int32), ("n_used", np.int32),
+                         ("n_dropped", np.int32), ("cond", np.float32), ("reserved", np.int32, 3)])
+assert RESULT_DTYPE.itemsize == C.sizeof(Result) == 224
+
+FLAG_FULL_EIG = 1
+
+_DUMP_FIELDS = [("cnt1", _IP), ("bounds", _FP), ("nin1", _IP), ("has1", _BP), ("mu1", _FP), ("sigma1", _FP),
+                ("evec1", _FP), ("eval1", _FP), ("lmask", _BP), ("cnt2", _IP), ("nin2", _IP), ("used2", _BP),
+                ("mu2", _FP), ("sigma2", _FP), ("Xit", _FP), ("HTWH", _FP), ("HTWdz", _FP)]
+
+
+class _Dump(C.Structure):
+    _fields_ = _DUMP_FIELDS
+
+
+EXPORTS = ["icet_b200_version", "icet_b200_last_error", "icet_b200_create", "icet_b200_destroy",
+           "icet_b200_set_stream", "icet_b200_set_chunk", "icet_b200_register", "icet_b200_register_batch",
+           "icet_b200_register_batch_device", "icet_b200_register_sequence_device", "icet_b200_synchronize",
+           "icet_b200_set_dump", "icet_b200_get_dump", "icet_b200_spherical_bins",
+           "icet_b200_synth_scans_device", "icet_b200_kernel_launches"]
+
+_LIB = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load_library() -> C.CDLL:
+    """Load libicet_b200.so.  Fails loudly when it has not been built -- there is no fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise IcetError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(icet_b200 has no CPU / PyTorch fallback)" % path)
+    L = C.CDLL(path)
+    vp = C.c_void_p
+    L.icet_b200_version.restype = C.c_int
+    L.icet_b200_last_error.restype = C.c_char_p
+    L.icet_b200_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.icet_b200_destroy.argtypes = [vp]
+    L.icet_b200_set_stream.argtypes = [vp, vp]
+    L.icet_b200_set_chunk.argtypes = [vp, C.c_int32]
+    L.icet_b200_register.argtypes = [vp, C.POINTER(Params), vp, C.c_int32, C.c_int32, vp, C.c_int32, C.c_int32,
+                                     vp, C.POINTER(Result)]
+    L.icet_b200_register_batch.argtypes = [vp, C.POINTER(Params), C.c_int32, vp, vp, vp, vp, vp, vp]
+    L.icet_b200_register_batch_device.argtypes = [vp, C.POINTER(Params), C.c_int32, vp, vp, vp, vp, vp, vp]
+    L.icet_b200_register_sequence_device.argtypes = [vp, C.POINTER(Params), C.c_int32, vp, C.c_int32, vp]
+    L.icet_b200_synchronize.argtypes = [vp]
+    L.icet_b200_set_dump.argtypes = [vp, C.c_int32]
+    L.icet_b200_get_dump.argtypes = [vp, C.POINTER(_Dump)]
+    L.icet_b200_spherical_bins.argtypes = [vp, C.POINTER(Params), vp, C.c_int32, C.c_int32, vp, vp]
+    L.icet_b200_synth_scans_device.argtypes = [vp, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+    L.icet_b200_kernel_launches.argtypes = [vp]
+    L.icet_b200_kernel_launches.restype = C.c_int64
+    _LIB = L
+    return L
+
+
+def as_planes(cloud) -> np.ndarray:
+    """N x 3 (any dtype/order) or 3 x N -> C-contiguous float32 [3, N] planes = the memory of a
+    column-major Eigen::MatrixXf(N, 3)."""
+    a = np.asarray(cloud)
+    if a.ndim != 2:
+        raise ValueError("cloud must be 2-D")
+    if a.shape[1] == 3 and a.shape[0] != 3:
+        a = a.T
+    elif a.shape[0] != 3:
+        raise ValueError("cloud must be N x 3 or 3 x N")
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def make_params(runlen=7, bins_phi=24, bins_theta=75, n=25, thresh=0.1, buff=0.1, flags=0) -> Params:
+    return Params(runlen, bins_phi, bins_theta, n, thresh, buff, flags, 0)
+
+
+class Context:
+    """One device context (workspace + stream).  Not thread-safe; use one per host thread."""
+
+    def __init__(self, device: int = -1):
+        self._L = load_library()
+        h = C.c_void_p()
+        self._h = None
+        self._check(self._L.icet_b200_create(device, C.byref(h)))
+        self._h = h
+
+    def _check(self, rc: int):
+        if rc < 0:
+            raise IcetError("icet_b200 error %d: %s" % (rc, self._L.icet_b200_last_error().decode()))
+        return rc
+
+    def close(self):
+        if self._h is not None:
+            self._L.icet_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration -----------------------------------------------------------------------
+    def set_stream(self, cuda_stream: int):
+        self._check(self._L.icet_b200_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def set_chunk(self, pairs: int):
+        self._check(self._L.icet_b200_set_chunk(self._h, pairs))
+
+    def synchronize(self):
+        self._check(self._L.icet_b200_synchronize(self._h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._L.icet_b200_kernel_launches(self._h))
+
+    # -- host-buffer registration ------------------------------------------------------------
+    def register(self, scan1, scan2, X0=None, params: Params | None = None, dump: bool = False):
+        p = params or make_params()
+        s1, s2 = as_planes(scan1), as_planes(scan2)
+        x0 = np.zeros(6, np.float32) if X0 is None else np.ascontiguousarray(X0, np.float32)
+        res = Result()
+        self._check(self._L.icet_b200_set_dump(self._h, 1 if dump else 0))
+        self._check(self._L.icet_b200_register(self._h, C.byref(p), s1.ctypes.data, s1.shape[1], s1.shape[1],
+                                               s2.ctypes.data, s2.shape[1], s2.shape[1], x0.ctypes.data,
+                                               C.byref(res)))
+        out = np.frombuffer(bytes(res), dtype=RESULT_DTYPE)[0]
+        if dump:
+            return out, self.get_dump(p)
+        return out
+
+    def register_batch(self, scans1, scans2, X0=None, params: Params | None = None) -> np.ndarray:
+        """scans1[i], scans2[i]: float32 [3, N_i] planes in HOST memory (pinned or pageable).  Passing the
+        same array object as scans2[i] and scans1[i+1] uploads it once."""
+        p = params or make_params()
+        npairs = len(scans1)
+        assert len(scans2) == npairs
+        for a in list(scans1) + list(scans2):
+            assert a.dtype == np.float32 and a.ndim == 2 and a.shape[0] == 3 and a.flags["C_CONTIGUOUS"]
+        p1 = (C.c_void_p * npairs)(*[a.ctypes.data for a in scans1])
+        p2 = (C.c_void_p * npairs)(*[a.ctypes.data for a in scans2])
+        n1 = np.array([a.shape[1] for a in scans1], np.int32)
+        n2 = np.array([a.shape[1] for a in scans2], np.int32)
+        x0p = None
+        if X0 is not None:
+            x0 = np.ascontiguousarray(X0, np.float32).reshape(npairs, 6)
+            x0p = x0.ctypes.data
+        out = np.zeros(npairs, RESULT_DTYPE)
+        self._check(self._L.icet_b200_register_batch(self._h, C.byref(p), npairs, p1, n1.ctypes.data, p2,
+                                                     n2.ctypes.data, x0p, out.ctypes.data))
+        return out
+
+    def register_batch_ptrs(self, ptrs1, n1, ptrs2, n2, out_ptr: int, x0_ptr: int = 0, params=None, device=False):
+        """Raw-pointer form (host or device pointers; `out_ptr` likewise)."""
+        p = params or make_params()
+        npairs = len(ptrs1)
+        a1 = (C.c_void_p * npairs)(*ptrs1)
+        a2 = (C.c_void_p * npairs)(*ptrs2)
+        n1 = np.ascontiguousarray(n1, np.int32)
+        n2 = np.ascontiguousarray(n2, np.int32)
+        f = self._L.icet_b200_register_batch_device if device else self._L.icet_b200_register_batch
+        self._check(f(self._h, C.byref(p), npairs, a1, n1.ctypes.data, a2, n2.ctypes.data,
+                      C.c_void_p(x0_ptr) if x0_ptr else None, C.c_void_p(out_ptr)))
+
+    # -- device-resident registration ----------------------------------------------------------
+    def register_sequence_device(self, scans_ptr: int, nscans: int, n: int, out_ptr: int, params=None):
+        """scans_ptr: device float32 [nscans, 3, n]; out_ptr: device buffer of (nscans-1)*224 bytes.
+        Asynchronous on the context's stream."""
+        p = params or make_params()
+        self._check(self._L.icet_b200_register_sequence_device(self._h, C.byref(p), nscans, C.c_void_p(scans_ptr),
+                                                               n, C.c_void_p(out_ptr)))
+
+    def synth_scans_device(self, out_ptr: int, nscans: int, first_scan=0, seed=20240, rings=64, azim=2048):
+        self._check(self._L.icet_b200_synth_scans_device(self._h, seed, first_scan, nscans, rings, azim,
+                                                         C.c_void_p(out_ptr)))
+
+    # -- parity-test helpers ---------------------------------------------------------------------
+    def spherical_bins(self, scan, params=None):
+        p = params or make_params()
+        s = as_planes(scan)
+        n = s.shape[1]
+        sph = np.zeros((3, n), np.float32)
+        cell = np.zeros(n, np.int32)
+        self._check(self._L.icet_b200_spherical_bins(self._h, C.byref(p), s.ctypes.data, n, n, sph.ctypes.data,
+                                                     cell.ctypes.data))
+        return sph, cell
+
+    def get_dump(self, p: Params) -> dict:
+        ncell, rl = p.bins_phi * p.bins_theta, p.runlen
+        shapes = {"cnt1": ((ncell,), np.int32), "bounds": ((ncell, 6), np.float32), "nin1": ((ncell,), np.int32),
+                  "has1": ((ncell,), np.uint8), "mu1": ((ncell, 3), np.float32), "sigma1": ((ncell, 3, 3), np.float32),
+                  "evec1": ((ncell, 3, 3), np.float32), "eval1": ((ncell, 3), np.float32),
+                  "lmask": ((ncell, 3), np.uint8), "cnt2": ((rl, ncell), np.int32), "nin2": ((rl, ncell), np.int32),
+                  "used2": ((rl, ncell), np.uint8), "mu2": ((rl, ncell, 3), np.float32),
+                  "sigma2": ((rl, ncell, 3, 3), np.float32), "Xit": ((rl, 6), np.float32),
+                  "HTWH": ((rl, 6, 6), np.float32), "HTWdz": ((rl, 6), np.float32)}
+        arrs = {k: np.zeros(s, d) for k, (s, d) in shapes.items()}
+        d = _Dump()
+        for name, ct in _DUMP_FIELDS:
+            setattr(d, name, arrs[name].ctypes.data_as(ct))
+        self._check(self._L.icet_b200_get_dump(self._h, C.byref(d)))
+        return arrs
+
+
+_DEFAULT_CTX: Context | None = None
+
+
+def default_context() -> Context:
+    global _DEFAULT_CTX
+    if _DEFAULT_CTX is None:
+        _DEFAULT_CTX = Context()
+    return _DEFAULT_CTX
+
+
+class ICET:
+    """Python mirror of the reference's `class ICET` (include/icet.h:36-116): all the work happens in the
+    constructor (src/icet.cpp:29-63); results are public attributes.
+
+        it = ICET(scan1, scan2, runlen, X0, num_bins_phi, num_bins_theta, n=25, thresh=0.1, buff=0.1)
+        it.X, it.pred_stds            # what odometry.cpp:77-79 / simpleMapMaker.cpp:120-122 read
+        it.Q                          # 6x6 error-bound covariance (noise_mat, src/icet.cpp:411)
+
+    scan1/scan2: N x 3 arrays (as Eigen::MatrixXf rows) or [3, N] planes.
+    """
+
+    def __init__(self, scan1, scan2, runlen, X0, num_bins_phi, num_bins_theta, n=25, thresh=0.1, buff=0.1,
+                 ctx: Context | None = None, debug: bool = False):
+        self.rl, self.numBinsPhi, self.numBinsTheta = runlen, num_bins_phi, num_bins_theta
+        self.n, self.thresh, self.buff = n, thresh, buff
+        ctx = ctx or default_context()
+        p = make_params(runlen, num_bins_phi, num_bins_theta, n, thresh, buff)
+        r = ctx.register(scan1, scan2, X0, p, dump=debug)
+        if debug:
+            r, self.debug = r
+            self.clusterBounds = self.debug["bounds"]
+        if r["status"] < 0:
+            raise IcetError("registration failed with status %d" % r["status"])
+        self.X = r["X"].copy()
+        self.pred_stds = r["pred_stds"].copy()
+        self.Q = r["Q"].copy()
+        self.status = int(r["status"])
+        self.result = r

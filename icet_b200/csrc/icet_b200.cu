@@ -1,0 +1,1333 @@
+// icet_b200/csrc/icet_b200.cu -- sm_100a kernels and the C ABI (include/icet_b200.h) of the
+// B200-native ICET registration hot path.
+//
+// Replaces the work of the reference constructor ICET::ICET (src/icet.cpp:29-63):
+//   fitScan1  (:68-107)  -> k_scan1_bin, k_cell_scan, k_scatter, k_cluster, k_pass<false>, k_fit1
+//   prepScan2 (:254-277) -> k_prep2
+//   fitScan2  (:372-436) -> per iteration: k_pass<true>, k_solve
+// All pairs of a chunk advance together through these kernels (bulk-synchronous over the batch),
+// everything stays on the device between iterations; the host only enqueues.
+//
+// Determinism: per-voxel statistics are accumulated as 64-bit fixed-point integers
+// (warp-aggregated with REDUX, then RED.64 to L2), so results do not depend on thread / block /
+// GPU partitioning or on atomic ordering.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/icet_b200.h"
+#include "icet_math.cuh"
+#include "synth.h"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(ICET_B200_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+  } while (0)
+
+constexpr int FPB = 21;                 // fixed-point: |d * scale| <= 2^FPB
+constexpr int FP_LIM = (1 << FPB);
+constexpr unsigned FULL = 0xffffffffu;
+constexpr uint32_t F_STAT1 = 1u;        // scan-1 statistics wanted for this cell
+constexpr uint32_t F_ACTIVE2 = 2u;      // voxel takes part in the scan-2 loop
+constexpr int SORT_SMEM = 4096;         // cells up to this many points are sorted in shared memory
+constexpr int NQ = 12;                  // accumulator words per cell
+
+struct PairDesc {
+  const float* s1;
+  const float* s2;
+  int n1, ld1, n2, ld2;
+};
+
+struct __align__(16) CellRec {  // read by every point of the pass kernels (two 16-byte loads)
+  float inner, outer;           // clusterBounds columns 4,5 (src/icet.cpp:149)
+  float refx, refy;
+  float refz, scale;            // fixed-point reference point and power-of-two scale
+  uint32_t flags;
+  int32_t cnt1;                 // points of scan 1 in this angular bin
+};
+
+struct Vox1 {     // scan-1 Gaussian, constants of the iteration loop (sigma1/mu1/U/L, include/icet.h:89-94)
+  double mu[3];
+  double S1n[6];  // sigma1 / (cnt1 - 1), upper triangle xx xy xz yy yz zz
+  double LV[9];   // L * U^T = L * V  (rows of V, zeroed where L is 0)
+  int lmask;      // bit k: L(k,k) == 1
+  int pad;
+};
+
+struct Dump {  // optional per-voxel recording (device memory), single-pair debugging only
+  int32_t* nin1; uint8_t* has1; float* mu1; float* sigma1; float* evec1; float* eval1; uint8_t* lmask;
+  int32_t* cnt2; int32_t* nin2; uint8_t* used2; float* mu2; float* sigma2; float* Xit; float* HTWH; float* HTWdz;
+};
+
+struct Chunk {  // everything a kernel needs, passed by value
+  const PairDesc* desc;
+  int npairs, ncell, nT, nP, n, runlen, flags;
+  float thresh, buff;
+  int n1max, n2max;
+  // scan 1
+  int32_t* cellid1;  // [P][n1max]
+  float* r1;         // [P][n1max]
+  float* rbuf;       // [P][n1max]  non-zero ranges grouped by cell
+  int32_t* cnt1;     // [P][ncell]
+  int32_t* cntz;     // [P][ncell]  zero-range points
+  int32_t* off;      // [P][ncell]
+  int32_t* cursor;   // [P][ncell]
+  int32_t* work;     // [P][ncell]  cells with cnt1 >= n
+  int32_t* nwork;    // [P]
+  CellRec* rec;      // [P][ncell]
+  unsigned long long* acc;  // [P][ncell][NQ]
+  Vox1* vox;         // [P][ncell]
+  const float* azE;  // [nT+1] float azimuth bin edges  (src/icet.cpp:136-137)
+  const float* elE;  // [nP+1] float elevation bin edges (src/icet.cpp:138-139)
+  // scan 2
+  float* pog;        // [P][3][n2max]  points2_OG
+  float* X;          // [P][6]
+  const float* x0;   // [P][6] or null
+  icet_b200_result* res;  // [P] device
+  Dump dump;
+  int dump_on;
+};
+
+// ----------------------------------------------------------------------------------------------
+// warp-aggregated fixed-point accumulation into acc[cell][*]
+//   q[0] += #lanes in the cell, q[1] += #lanes inside the cluster box,
+//   q[2..4] += sum d, q[5..10] += sum d d^T (xx xy xz yy yz zz)
+// `cell` < 0: lane takes no part.  Exact integer arithmetic => order independent.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_accumulate(unsigned long long* accp /* pair base */, int cell, bool in,
+                                                int fx, int fy, int fz) {
+  const int lane = threadIdx.x & 31;
+  unsigned todo = __ballot_sync(FULL, cell >= 0);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int c = __shfl_sync(FULL, cell, leader);
+    const bool mine = (cell == c);
+    const unsigned grp = __ballot_sync(FULL, mine);
+    const unsigned grp_in = __ballot_sync(FULL, mine && in);
+    todo &= ~grp;
+    long long val = 0;
+    if (lane == 0) val = __popc(grp);
+    if (lane == 1) val = __popc(grp_in);
+    int nlanes = 2;
+    if (grp_in) {  // warp-uniform
+      const bool m = mine && in;
+      const int dx = m ? fx : 0, dy = m ? fy : 0, dz = m ? fz : 0;
+      const int sx = __reduce_add_sync(FULL, dx);
+      const int sy = __reduce_add_sync(FULL, dy);
+      const int sz = __reduce_add_sync(FULL, dz);
+      if (lane == 2) val = sx;
+      if (lane == 3) val = sy;
+      if (lane == 4) val = sz;
+      // products: |d| <= 2^21 -> |p| <= 2^42; split into hi (signed) and lo (22 bits) so that the
+      // 32-lane sums fit REDUX's 32-bit adder
+      auto red64 = [&](int a, int b) -> long long {
+        long long p = (long long)a * (long long)b;
+        int hi = (int)(p >> 22);
+        int lo = (int)(p & 0x3FFFFF);
+        int shi = __reduce_add_sync(FULL, hi);
+        int slo = __reduce_add_sync(FULL, lo);
+        return ((long long)shi << 22) + (long long)slo;
+      };
+      long long pxx = red64(dx, dx), pxy = red64(dx, dy), pxz = red64(dx, dz);
+      long long pyy = red64(dy, dy), pyz = red64(dy, dz), pzz = red64(dz, dz);
+      if (lane == 5) val = pxx;
+      if (lane == 6) val = pxy;
+      if (lane == 7) val = pxz;
+      if (lane == 8) val = pyy;
+      if (lane == 9) val = pyz;
+      if (lane == 10) val = pzz;
+      nlanes = 11;
+    }
+    if (lane < nlanes) atomicAdd(accp + (size_t)c * NQ + lane, (unsigned long long)val);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K1: scan 1 -> spherical, cell index, per-cell histogram.
+// utils::cartesianToSpherical (src/utils.cpp:93-119) + sortSphericalCoordinates (src/icet.cpp:534-554)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scan1_bin(const Chunk ck) {
+  const int pair = blockIdx.y;
+  const PairDesc d = ck.desc[pair];
+  if ((int)(blockIdx.x * blockDim.x) >= d.n1) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int cell = -1;
+  bool zero = false;
+  if (i < d.n1) {
+    float x = __ldg(d.s1 + i), y = __ldg(d.s1 + d.ld1 + i), z = __ldg(d.s1 + 2 * (size_t)d.ld1 + i);
+    float r, th, ph;
+    icet::c2s(x, y, z, r, th, ph);
+    int bt, bp;
+    icet::bin_of(th, ph, ck.nT, ck.nP, bt, bp);
+    cell = ck.nT * bp + bt;
+    zero = (r == 0.0f);
+    ck.cellid1[(size_t)pair * ck.n1max + i] = cell;
+    ck.r1[(size_t)pair * ck.n1max + i] = r;
+  }
+  // warp-aggregated histogram
+  const int lane = threadIdx.x & 31;
+  const unsigned act = __ballot_sync(FULL, cell >= 0);
+  if (cell >= 0) {
+    const unsigned m = __match_any_sync(act, cell);
+    const unsigned mz = __ballot_sync(m, zero);
+    if (lane == __ffs(m) - 1) {
+      atomicAdd(&ck.cnt1[(size_t)pair * ck.ncell + cell], __popc(m));
+      if (mz) atomicAdd(&ck.cntz[(size_t)pair * ck.ncell + cell], __popc(mz));
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K2a: per pair: exclusive scan of the non-zero counts (offsets into rbuf), work list of cells with
+// cnt1 >= n (src/icet.cpp:115), default cell records (the else-branch :243-251: inner = outer = 0).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cell_scan(const Chunk ck) {
+  const int pair = blockIdx.x;
+  __shared__ int s_part[256];
+  __shared__ int s_wpart[256];
+  const int per = (ck.ncell + 255) / 256;
+  const int c0 = threadIdx.x * per, c1 = min(ck.ncell, c0 + per);
+  const int32_t* cnt1 = ck.cnt1 + (size_t)pair * ck.ncell;
+  const int32_t* cntz = ck.cntz + (size_t)pair * ck.ncell;
+  int s = 0, w = 0;
+  for (int c = c0; c < c1; c++) {
+    s += cnt1[c] - cntz[c];
+    w += (cnt1[c] >= ck.n) ? 1 : 0;
+  }
+  s_part[threadIdx.x] = s;
+  s_wpart[threadIdx.x] = w;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int a = 0, b = 0;
+    for (int t = 0; t < 256; t++) {
+      int v = s_part[t]; s_part[t] = a; a += v;
+      int u = s_wpart[t]; s_wpart[t] = b; b += u;
+    }
+    ck.nwork[pair] = b;
+    if (ck.x0) for (int k = 0; k < 6; k++) ck.X[pair * 6 + k] = ck.x0[pair * 6 + k];
+    else for (int k = 0; k < 6; k++) ck.X[pair * 6 + k] = 0.f;
+    icet_b200_result* R = ck.res + pair;
+    R->status = 0; R->n_gauss1 = 0; R->n_used = 0; R->n_dropped = 0; R->cond = 0.f;
+    for (int k = 0; k < 6; k++) { R->X[k] = ck.X[pair * 6 + k]; R->pred_stds[k] = 0.f; }
+    for (int k = 0; k < 36; k++) R->Q[k] = 0.f;
+    R->reserved[0] = R->reserved[1] = R->reserved[2] = 0;
+  }
+  __syncthreads();
+  int a = s_part[threadIdx.x], b = s_wpart[threadIdx.x];
+  for (int c = c0; c < c1; c++) {
+    ck.off[(size_t)pair * ck.ncell + c] = a;
+    a += cnt1[c] - cntz[c];
+    if (cnt1[c] >= ck.n) ck.work[(size_t)pair * ck.ncell + (b++)] = c;
+    CellRec rc;
+    rc.inner = 0.f; rc.outer = 0.f; rc.refx = rc.refy = rc.refz = 0.f; rc.scale = 0.f;
+    rc.flags = 0; rc.cnt1 = cnt1[c];
+    ck.rec[(size_t)pair * ck.ncell + c] = rc;
+  }
+}
+
+// K2b: group the non-zero ranges by cell
+__global__ void __launch_bounds__(256) k_scatter(const Chunk ck) {
+  const int pair = blockIdx.y;
+  const PairDesc d = ck.desc[pair];
+  if ((int)(blockIdx.x * blockDim.x) >= d.n1) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int cell = -1;
+  float r = 0.f;
+  if (i < d.n1) {
+    r = ck.r1[(size_t)pair * ck.n1max + i];
+    if (r != 0.0f) cell = ck.cellid1[(size_t)pair * ck.n1max + i];
+  }
+  const int lane = threadIdx.x & 31;
+  const unsigned act = __ballot_sync(FULL, cell >= 0);
+  if (cell >= 0) {
+    const unsigned m = __match_any_sync(act, cell);
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&ck.cursor[(size_t)pair * ck.ncell + cell], __popc(m));
+    base = __shfl_sync(m, base, leader);
+    const int rank = __popc(m & ((1u << lane) - 1));
+    ck.rbuf[(size_t)pair * ck.n1max + ck.off[(size_t)pair * ck.ncell + cell] + base + rank] = r;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K2c: per cell with cnt1 >= n: sort the ranges ascending (what src/icet.cpp:71-83 intends) and run
+// ICET::findCluster (src/icet.cpp:557-607) on them; write the cell record.
+// ----------------------------------------------------------------------------------------------
+// Bitonic-style network with all comparators ascending ("mirror" first step): works for any m,
+// indices >= m behave as +inf and are never touched.
+template <class Ptr>
+__device__ inline void block_sort_asc(Ptr a, int m) {
+  int p2 = 1;
+  while (p2 < m) p2 <<= 1;
+  for (int k = 2; k <= p2; k <<= 1) {
+    // mirror step: i with partner i ^ (k-1)
+    for (int t = threadIdx.x; t < p2 / 2; t += blockDim.x) {
+      int blk = t / (k / 2), o = t % (k / 2);
+      int i = blk * k + o, j = blk * k + (k - 1 - o);
+      if (j < m) {
+        float x = a[i], y = a[j];
+        if (y < x) { a[i] = y; a[j] = x; }
+      }
+    }
+    __syncthreads();
+    for (int j2 = k / 4; j2 >= 1; j2 >>= 1) {
+      for (int t = threadIdx.x; t < p2 / 2; t += blockDim.x) {
+        int i = (t / j2) * (2 * j2) + (t % j2), j = i + j2;
+        if (j < m) {
+          float x = a[i], y = a[j];
+          if (y < x) { a[i] = y; a[j] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// findCluster over the virtual sequence seq = [0 x nz, a[0..m)] (ascending); executed by warp 0,
+// every lane computes the same result.  A "break" at position i means seq[i] does not extend the
+// current run (reference :572); the run before a break is returned if it has >= n points (:577-582,
+// no zero check), the run that reaches the end of the data goes through the zero check (:592-603).
+template <class Ptr>
+__device__ inline void find_cluster_warp(Ptr a, int m, int nz, int n, float thresh, float buff, float& inner,
+                                         float& outer) {
+  const int lane = threadIdx.x & 31;
+  const int total = nz + m;
+  auto seq = [&](int i) -> float { return i < nz ? 0.0f : a[i - nz]; };
+  int start = 0;  // first element of the current run; the nz leading zeros never break (thresh >= 0)
+  bool found = false;
+  float fi = 0.f, fo = 0.f;
+  for (int base = nz; base < total && !found; base += 32) {
+    const int i = base + lane;
+    bool brk = false;
+    if (i < total && i > 0) brk = !(fabsf(seq(i - 1) - seq(i)) <= thresh);
+    unsigned mask = __ballot_sync(FULL, brk);
+    while (mask && !found) {
+      const int pos = base + __ffs(mask) - 1;
+      mask &= mask - 1;
+      if (pos - start >= n) {
+        fi = seq(start) - buff;
+        fo = seq(pos - 1) + buff;
+        found = true;
+      } else {
+        start = pos;
+      }
+    }
+  }
+  if (!found && total > 0 && total - start >= n) {
+    if (seq(start) != 0.0f) {
+      fi = seq(start) - buff;
+      fo = seq(total - 1) + buff;
+    }
+  }
+  inner = fi;
+  outer = fo;
+}
+
+__global__ void __launch_bounds__(128) k_cluster(const Chunk ck) {
+  const int pair = blockIdx.y;
+  __shared__ float s_r[SORT_SMEM];
+  const int nw = ck.nwork[pair];
+  for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+    const int cell = ck.work[(size_t)pair * ck.ncell + w];
+    const int cnt = ck.cnt1[(size_t)pair * ck.ncell + cell];
+    const int nz = ck.cntz[(size_t)pair * ck.ncell + cell];
+    const int m = cnt - nz;
+    float* g = ck.rbuf + (size_t)pair * ck.n1max + ck.off[(size_t)pair * ck.ncell + cell];
+    float inner, outer;
+    if (m <= SORT_SMEM) {
+      for (int i = threadIdx.x; i < m; i += blockDim.x) s_r[i] = g[i];
+      __syncthreads();
+      block_sort_asc(s_r, m);
+      if (threadIdx.x < 32) find_cluster_warp(s_r, m, nz, ck.n, ck.thresh, ck.buff, inner, outer);
+    } else {
+      __syncthreads();
+      block_sort_asc(g, m);
+      if (threadIdx.x < 32) find_cluster_warp(g, m, nz, ck.n, ck.thresh, ck.buff, inner, outer);
+    }
+    if (threadIdx.x == 0) {
+      const int bt = cell % ck.nT, bp = cell / ck.nT;
+      CellRec rc;
+      rc.inner = inner;
+      rc.outer = outer;
+      rc.cnt1 = cnt;
+      rc.flags = ((double)outer > 0.1) ? F_STAT1 : 0u;  // `outerDistance > 0.1` src/icet.cpp:158
+      // fixed-point frame of the voxel: reference point = centre of the spherical box, scale from
+      // a bound on the box diameter
+      const float azl = ck.azE[bt], azh = ck.azE[bt + 1], ell = ck.elE[bp], elh = ck.elE[bp + 1];
+      const float rm = 0.5f * (inner + outer), tm = 0.5f * (azl + azh), pm = 0.5f * (ell + elh);
+      icet::s2c(rm, tm, pm, rc.refx, rc.refy, rc.refz);
+      float D = (outer - inner) + fabsf(outer) * ((azh - azl) + (elh - ell));
+      int e;
+      frexpf(fmaxf(D, 1e-20f), &e);          // D < 2^e
+      rc.scale = ldexpf(1.0f, FPB - e - 1);  // |d| <= D  =>  |d*scale| < 2^(FPB-1)
+      ck.rec[(size_t)pair * ck.ncell + cell] = rc;
+    }
+    __syncthreads();
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K3 / K5a: one pass over the points of a scan: [transform,] spherical, cell, cluster-box test,
+// sph->cart round trip, fixed-point accumulation of count / sum / sum of products per voxel.
+//   SCAN2 = false: scan 1 (filterPointsInsideCluster + mean/cov of fitCells1, src/icet.cpp:155-162)
+//   SCAN2 = true : scan 2, one Gauss-Newton iteration (src/icet.cpp:375-388 + fitCells2 :290-306)
+// ----------------------------------------------------------------------------------------------
+template <bool SCAN2>
+__global__ void __launch_bounds__(256) k_pass(const Chunk ck) {
+  const int pair = blockIdx.y;
+  const PairDesc d = ck.desc[pair];
+  const int n = SCAN2 ? d.n2 : d.n1;
+  if ((int)(blockIdx.x * blockDim.x) >= n) return;
+  __shared__ float s_tr[12];
+  if (SCAN2) {
+    if (threadIdx.x == 0) {
+      const float* X = ck.X + pair * 6;
+      s_tr[0] = X[0]; s_tr[1] = X[1]; s_tr[2] = X[2];
+      icet::rotR(X[3], X[4], X[5], s_tr + 3);
+    }
+    __syncthreads();
+  }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int cell = -1;
+  bool in = false;
+  int fx = 0, fy = 0, fz = 0;
+  if (i < n) {
+    float x, y, z;
+    if (SCAN2) {
+      const float* pg = ck.pog + (size_t)pair * 3 * ck.n2max;
+      float px = __ldg(pg + i), py = __ldg(pg + ck.n2max + i), pz = __ldg(pg + 2 * (size_t)ck.n2max + i);
+      icet::transform(px, py, pz, s_tr, s_tr + 3, x, y, z);
+    } else {
+      x = __ldg(d.s1 + i); y = __ldg(d.s1 + d.ld1 + i); z = __ldg(d.s1 + 2 * (size_t)d.ld1 + i);
+    }
+    float r, th, ph;
+    icet::c2s(x, y, z, r, th, ph);
+    int bt, bp;
+    icet::bin_of(th, ph, ck.nT, ck.nP, bt, bp);
+    const int c = ck.nT * bp + bt;
+    const float4* rp = reinterpret_cast<const float4*>(ck.rec + (size_t)pair * ck.ncell + c);
+    const float4 ra = __ldg(rp), rb = __ldg(rp + 1);
+    const uint32_t flags = __float_as_uint(rb.z);
+    if (flags & (SCAN2 ? F_ACTIVE2 : F_STAT1)) {
+      cell = c;
+      // ICET::filterPointsInsideCluster src/icet.cpp:632-634 (inclusive float compares)
+      in = th >= __ldg(ck.azE + bt) && th <= __ldg(ck.azE + bt + 1) && ph >= __ldg(ck.elE + bp) &&
+           ph <= __ldg(ck.elE + bp + 1) && r >= ra.x && r <= ra.y;
+      if (in) {
+        float cx, cy, cz;
+        icet::s2c(r, th, ph, cx, cy, cz);  // statistics use round-tripped points (:159 / :303)
+        const float sc = rb.y;
+        fx = __float2int_rn((cx - ra.z) * sc);
+        fy = __float2int_rn((cy - ra.w) * sc);
+        fz = __float2int_rn((cz - rb.x) * sc);
+        fx = max(-FP_LIM, min(FP_LIM, fx));
+        fy = max(-FP_LIM, min(FP_LIM, fy));
+        fz = max(-FP_LIM, min(FP_LIM, fz));
+      }
+    }
+  }
+  warp_accumulate(ck.acc + (size_t)pair * ck.ncell * NQ, cell, in, fx, fy, fz);
+}
+
+// exact-sum -> mean / covariance (double) of a voxel
+__device__ __forceinline__ void stats_from_acc(const unsigned long long* q, const CellRec& rc, double mean[3],
+                                               double cov[6]) {
+  const double nin = (double)(long long)q[1];
+  const double inv = 1.0 / (double)rc.scale;
+  const double sx = (double)(long long)q[2], sy = (double)(long long)q[3], sz = (double)(long long)q[4];
+  mean[0] = (double)rc.refx + (sx / nin) * inv;
+  mean[1] = (double)rc.refy + (sy / nin) * inv;
+  mean[2] = (double)rc.refz + (sz / nin) * inv;
+  const double f = inv * inv / (nin - 1.0);
+  cov[0] = ((double)(long long)q[5] - sx * sx / nin) * f;
+  cov[1] = ((double)(long long)q[6] - sx * sy / nin) * f;
+  cov[2] = ((double)(long long)q[7] - sx * sz / nin) * f;
+  cov[3] = ((double)(long long)q[8] - sy * sy / nin) * f;
+  cov[4] = ((double)(long long)q[9] - sy * sz / nin) * f;
+  cov[5] = ((double)(long long)q[10] - sz * sz / nin) * f;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K4: per voxel of scan 1: mean / covariance, 3x3 eigen-decomposition, sigma points, L mask
+// (fitCells1 src/icet.cpp:158-232, testSigmaPoints :654-696); constants for the iteration loop.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_fit1(const Chunk ck) {
+  const int pair = blockIdx.y;
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ck.ncell) return;
+  const size_t ci = (size_t)pair * ck.ncell + cell;
+  CellRec rc = ck.rec[ci];
+  unsigned long long* q = ck.acc + ci * NQ;
+  bool has = false;
+  if (rc.flags & F_STAT1) {
+    const long long nin = (long long)q[1];
+    if (ck.dump_on) ck.dump.nin1[cell] = (int)nin;
+    // `filteredPoints.size() >= n` with size() = 3 * rows  (src/icet.cpp:158)
+    if (3 * nin >= ck.n && nin >= 2) {
+      has = true;
+      double mean[3], cov[6];
+      stats_from_acc(q, rc, mean, cov);
+      Vox1 v;
+      for (int k = 0; k < 3; k++) v.mu[k] = mean[k];
+      const double d1 = (double)(rc.cnt1 - 1);  // `indices1.size() - 1` (:315)
+      for (int k = 0; k < 6; k++) v.S1n[k] = cov[k] / d1;
+      float A[9] = {(float)cov[0], (float)cov[1], (float)cov[2], (float)cov[1], (float)cov[3],
+                    (float)cov[4], (float)cov[2], (float)cov[4], (float)cov[5]};
+      float ev[3], V[9];
+      icet::eig3f(A, ev, V);
+      // sigma points mu +- 2 sqrt(ev_k) * V.row(k)   (:187-202), tested in order 0+,0-,1+,1-,2+,2-
+      const float mu[3] = {(float)mean[0], (float)mean[1], (float)mean[2]};
+      const int bt = cell % ck.nT, bp = cell / ck.nT;
+      const float azl = ck.azE[bt], azh = ck.azE[bt + 1], ell = ck.elE[bp], elh = ck.elE[bp + 1];
+      bool inside[6] = {false, false, false, false, false, false};
+      for (int j = 0; j < 6; j++) {
+        const int k = j >> 1;
+        const float al = 2.0f * sqrtf(ev[k]);
+        float p[3];
+        for (int c = 0; c < 3; c++) {
+          float rot = al * V[3 * k + c];
+          p[c] = (j & 1) ? mu[c] - rot : mu[c] + rot;
+        }
+        float r, th, ph;
+        icet::c2s(p[0], p[1], p[2], r, th, ph);
+        if (th >= azl && th <= azh && ph >= ell && ph <= elh && r >= rc.inner && r <= rc.outer) inside[j] = true;
+        if (r > rc.outer) break;  // the early break of testSigmaPoints (:683-685)
+      }
+      int lm = 0;
+      for (int k = 0; k < 3; k++)
+        if (inside[2 * k] || inside[2 * k + 1]) lm |= (1 << k);
+      v.lmask = lm;
+      v.pad = 0;
+      for (int k = 0; k < 3; k++)
+        for (int c = 0; c < 3; c++) v.LV[3 * k + c] = (lm >> k & 1) ? (double)V[3 * k + c] : 0.0;
+      ck.vox[ci] = v;
+      if (ck.dump_on) {
+        for (int k = 0; k < 3; k++) { ck.dump.mu1[3 * cell + k] = (float)mean[k]; ck.dump.eval1[3 * cell + k] = ev[k]; }
+        for (int k = 0; k < 9; k++) { ck.dump.sigma1[9 * cell + k] = A[k]; ck.dump.evec1[9 * cell + k] = V[k]; }
+        for (int k = 0; k < 3; k++) ck.dump.lmask[3 * cell + k] = (lm >> k) & 1;
+      }
+    }
+  }
+  if (ck.dump_on) ck.dump.has1[cell] = has ? 1 : 0;
+  // gates of fitCells2 that do not depend on scan 2: `indices1.size() > n && bounds[5] > 1`
+  // (src/icet.cpp:290); a voxel without a scan-1 Gaussian is skipped.
+  uint32_t fl = rc.flags & ~F_ACTIVE2;
+  if (has && rc.cnt1 > ck.n && rc.outer > 1.0f) fl |= F_ACTIVE2;
+  if (fl != rc.flags) ck.rec[ci].flags = fl;
+  if (rc.flags & F_STAT1)
+    for (int k = 0; k < NQ; k++) q[k] = 0ull;  // hand the accumulators to the scan-2 loop
+  if (has) atomicAdd(&ck.res[pair].n_gauss1, 1);
+}
+
+// ----------------------------------------------------------------------------------------------
+// prepScan2 (src/icet.cpp:254-277): points2_OG = sphericalToCartesian(cartesianToSpherical(scan2)).
+// (The radial re-ordering of scan 2 only changes the reference's summation order.)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_prep2(const Chunk ck) {
+  const int pair = blockIdx.y;
+  const PairDesc d = ck.desc[pair];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.n2) return;
+  float x = __ldg(d.s2 + i), y = __ldg(d.s2 + d.ld2 + i), z = __ldg(d.s2 + 2 * (size_t)d.ld2 + i);
+  float r, th, ph;
+  icet::c2s(x, y, z, r, th, ph);
+  icet::s2c(r, th, ph, x, y, z);
+  float* pg = ck.pog + (size_t)pair * 3 * ck.n2max;
+  pg[i] = x;
+  pg[ck.n2max + i] = y;
+  pg[2 * (size_t)ck.n2max + i] = z;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K5b + K6: one CTA per pair.  Per voxel: scan-2 mean / covariance, R_noise, W, H_z, contributions
+// H^T W H_j and H^T W dz_j (fitCells2 src/icet.cpp:302-338); fixed-order block reduction; then one
+// thread: Q = pinv(H^T W H), pred_stds, checkCondition, dx, X += dx (src/icet.cpp:410-433, :443-492).
+// ----------------------------------------------------------------------------------------------
+constexpr int SOLVE_THREADS = 256;
+constexpr int NRED = 28;  // 21 (upper triangle of H^T W H) + 6 (H^T W dz) + 1 (voxels used)
+
+__global__ void __launch_bounds__(SOLVE_THREADS) k_solve(const Chunk ck, int iter) {
+  const int pair = blockIdx.x;
+  __shared__ float s_J[27];
+  __shared__ double s_red[SOLVE_THREADS / 32][NRED];
+  float* X = ck.X + pair * 6;
+  if (threadIdx.x == 0) icet::getH_J(X[3], X[4], X[5], s_J);
+  __syncthreads();
+  double acc[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; k++) acc[k] = 0.0;
+  for (int cell = threadIdx.x; cell < ck.ncell; cell += SOLVE_THREADS) {
+    const size_t ci = (size_t)pair * ck.ncell + cell;
+    const CellRec rc = ck.rec[ci];
+    if (!(rc.flags & F_ACTIVE2)) {
+      if (ck.dump_on) {
+        ck.dump.cnt2[(size_t)iter * ck.ncell + cell] = -1;
+        ck.dump.nin2[(size_t)iter * ck.ncell + cell] = -1;
+        ck.dump.used2[(size_t)iter * ck.ncell + cell] = 0;
+      }
+      continue;
+    }
+    unsigned long long q[NQ];
+    unsigned long long* qp = ck.acc + ci * NQ;
+#pragma unroll
+    for (int k = 0; k < NQ; k++) { q[k] = qp[k]; qp[k] = 0ull; }
+    const long long nbin = (long long)q[0], nin = (long long)q[1];
+    const bool use = nbin > ck.n && nin > ck.n;  // `indices2.size() > n` (:290), `rows > n` (:302)
+    if (ck.dump_on) {
+      ck.dump.cnt2[(size_t)iter * ck.ncell + cell] = (int)nbin;
+      ck.dump.nin2[(size_t)iter * ck.ncell + cell] = (nbin > ck.n) ? (int)nin : -1;
+      ck.dump.used2[(size_t)iter * ck.ncell + cell] = use ? 1 : 0;
+    }
+    if (!use) continue;
+    double mean[3], cov[6];
+    stats_from_acc(q, rc, mean, cov);
+    const Vox1 v = ck.vox[ci];
+    if (ck.dump_on) {
+      float* m2 = ck.dump.mu2 + ((size_t)iter * ck.ncell + cell) * 3;
+      float* s2 = ck.dump.sigma2 + ((size_t)iter * ck.ncell + cell) * 9;
+      for (int k = 0; k < 3; k++) m2[k] = (float)mean[k];
+      s2[0] = (float)cov[0]; s2[1] = (float)cov[1]; s2[2] = (float)cov[2];
+      s2[3] = (float)cov[1]; s2[4] = (float)cov[3]; s2[5] = (float)cov[4];
+      s2[6] = (float)cov[2]; s2[7] = (float)cov[4]; s2[8] = (float)cov[5];
+    }
+    // R_noise = sigma1/(|idx1|-1) + sigma2/(|idx2|-1)   (:315)
+    const double d2 = (double)(nbin - 1);
+    double Rn[9];
+    {
+      double r6[6];
+      for (int k = 0; k < 6; k++) r6[k] = v.S1n[k] + cov[k] / d2;
+      Rn[0] = r6[0]; Rn[1] = r6[1]; Rn[2] = r6[2]; Rn[3] = r6[1]; Rn[4] = r6[3]; Rn[5] = r6[4];
+      Rn[6] = r6[2]; Rn[7] = r6[4]; Rn[8] = r6[5];
+    }
+    // M = (L U^T) R_noise (L U^T)^T   (:317)
+    double T[9], M[9];
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) T[3 * a + b] = v.LV[3 * a] * Rn[b] + v.LV[3 * a + 1] * Rn[3 + b] + v.LV[3 * a + 2] * Rn[6 + b];
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) M[3 * a + b] = T[3 * a] * v.LV[3 * b] + T[3 * a + 1] * v.LV[3 * b + 1] + T[3 * a + 2] * v.LV[3 * b + 2];
+    // W = pinv(M)  (:320-321)
+    double W[9];
+    if (!icet::masked_inv3(M, v.lmask, W)) icet::cod_pinv(M, 3, 3, W);
+    // H_z = L U^T [ -I | Jx mu | Jy mu | Jz mu ]  (:324-329)
+    double H[18];
+    for (int a = 0; a < 3; a++) {
+      H[6 * a + 0] = (a == 0) ? -1.0 : 0.0;
+      H[6 * a + 1] = (a == 1) ? -1.0 : 0.0;
+      H[6 * a + 2] = (a == 2) ? -1.0 : 0.0;
+      for (int j = 0; j < 3; j++)
+        H[6 * a + 3 + j] = (double)s_J[9 * j + 3 * a] * mean[0] + (double)s_J[9 * j + 3 * a + 1] * mean[1] +
+                           (double)s_J[9 * j + 3 * a + 2] * mean[2];
+    }
+    double Hz[18];
+    for (int a = 0; a < 3; a++)
+      for (int c = 0; c < 6; c++) Hz[6 * a + c] = v.LV[3 * a] * H[c] + v.LV[3 * a + 1] * H[6 + c] + v.LV[3 * a + 2] * H[12 + c];
+    // dz = L U^T (mean2 - mu1)   (:335-337)
+    double dm[3] = {mean[0] - v.mu[0], mean[1] - v.mu[1], mean[2] - v.mu[2]};
+    double dz[3];
+    for (int a = 0; a < 3; a++) dz[a] = v.LV[3 * a] * dm[0] + v.LV[3 * a + 1] * dm[1] + v.LV[3 * a + 2] * dm[2];
+    // WHz (3x6), Wdz (3)
+    double WH[18], Wdz[3];
+    for (int a = 0; a < 3; a++) {
+      for (int c = 0; c < 6; c++) WH[6 * a + c] = W[3 * a] * Hz[c] + W[3 * a + 1] * Hz[6 + c] + W[3 * a + 2] * Hz[12 + c];
+      Wdz[a] = W[3 * a] * dz[0] + W[3 * a + 1] * dz[1] + W[3 * a + 2] * dz[2];
+    }
+    int t = 0;
+    for (int a = 0; a < 6; a++)
+      for (int b = a; b < 6; b++) acc[t++] += Hz[a] * WH[b] + Hz[6 + a] * WH[6 + b] + Hz[12 + a] * WH[12 + b];
+    for (int a = 0; a < 6; a++) acc[21 + a] += Hz[a] * Wdz[0] + Hz[6 + a] * Wdz[1] + Hz[12 + a] * Wdz[2];
+    acc[27] += 1.0;
+  }
+  // fixed-order reduction: lanes (xor butterfly), then warps in index order
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NRED; k++) {
+    double vsum = acc[k];
+    for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(FULL, vsum, o);
+    if (lane == 0) s_red[wid][k] = vsum;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double tot[NRED];
+  for (int k = 0; k < NRED; k++) {
+    double s = 0.0;
+    for (int w = 0; w < SOLVE_THREADS / 32; w++) s += s_red[w][k];
+    tot[k] = s;
+  }
+  double A[36], b[6];
+  {
+    int t = 0;
+    for (int a = 0; a < 6; a++)
+      for (int c = a; c < 6; c++) {
+        A[a * 6 + c] = tot[t];
+        A[c * 6 + a] = tot[t];
+        t++;
+      }
+    for (int a = 0; a < 6; a++) b[a] = tot[21 + a];
+  }
+  icet_b200_result* R = ck.res + pair;
+  double Q[36], dx[6], stds[6];
+  int dropped = 0, status = 0;
+  double cond_out;
+  bool fast = false;
+  if (!(ck.flags & ICET_B200_FLAG_FULL_EIG) && icet::chol_inv6(A, Q)) {
+    double trA = 0.0, trQ = 0.0;
+    for (int k = 0; k < 6; k++) { trA += A[k * 6 + k]; trQ += Q[k * 6 + k]; }
+    // cond <= trace(A) * trace(A^-1); comfortably below the 1e6 cutoff => no axis is dropped and
+    // pinv == inverse, so dx = A^-1 b  (src/icet.cpp:410-433 with an empty while-loop at :469)
+    if (trA * trQ < 0.999e6) {
+      fast = true;
+      cond_out = -(trA * trQ);
+    }
+  }
+  if (fast) {
+    for (int k = 0; k < 6; k++) {
+      double s = 0.0;
+      for (int j = 0; j < 6; j++) s += Q[k * 6 + j] * b[j];
+      dx[k] = s;
+      stds[k] = sqrt(fabs(Q[k * 6 + k]));
+    }
+  } else {
+    icet::cod_pinv(A, 6, 6, Q);  // noise_mat (:410-411)
+    for (int k = 0; k < 6; k++) stds[k] = sqrt(fabs(Q[k * 6 + k]));
+    double ev[6], U[36];
+    icet::jacobi6(A, ev, U);
+    const double cutoff = 1e6;
+    double condition = ev[5] / ev[0];
+    cond_out = condition;
+    int eyecount = 1;
+    while (fabs(condition) > cutoff) {  // checkCondition :469-486
+      if (eyecount > 5) { status = ICET_B200_COND_OVERFLOW; break; }
+      for (int k = 0; k < 6; k++) stds[k] += U[k * 6 + (eyecount - 1)];  // :479
+      dropped++;
+      condition = ev[5] / ev[eyecount];
+      eyecount++;
+    }
+    // dx = pinv(L2 lam U2^T) L2 U2^T b = sum over kept k of u_k (u_k . b) / lam_k, with the rank
+    // rule of the COD applied to the kept spectrum (:427-430)
+    double lmax = 0.0;
+    for (int k = dropped; k < 6; k++) lmax = fmax(lmax, fabs(ev[k]));
+    const double tiny = (double)FLT_EPSILON * (double)(6 - dropped) * lmax;
+    for (int k = 0; k < 6; k++) dx[k] = 0.0;
+    for (int k = dropped; k < 6; k++) {
+      if (!(fabs(ev[k]) > tiny)) continue;
+      double ub = 0.0;
+      for (int j = 0; j < 6; j++) ub += U[j * 6 + k] * b[j];
+      for (int j = 0; j < 6; j++) dx[j] += U[j * 6 + k] * (ub / ev[k]);
+    }
+  }
+  for (int k = 0; k < 6; k++) X[k] = (float)((double)X[k] + dx[k]);  // X += dx (:433), X is fp32
+  if (ck.dump_on) {
+    for (int k = 0; k < 6; k++) { ck.dump.Xit[iter * 6 + k] = X[k]; ck.dump.HTWdz[iter * 6 + k] = (float)b[k]; }
+    for (int k = 0; k < 36; k++) ck.dump.HTWH[iter * 36 + k] = (float)A[k];
+  }
+  if (iter == ck.runlen - 1) {
+    for (int k = 0; k < 6; k++) { R->X[k] = X[k]; R->pred_stds[k] = (float)stds[k]; }
+    for (int k = 0; k < 36; k++) R->Q[k] = (float)Q[k];
+    R->n_used = (int)(tot[27] + 0.5);
+    R->n_dropped = dropped;
+    R->cond = (float)cond_out;
+  }
+  if (status) R->status = status;
+}
+
+// spherical coordinates + cell index of a cloud (parity-test entry point)
+__global__ void k_sph_bins(const float* s, int n, int ld, int nT, int nP, float* sph, int32_t* cell) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float r, th, ph;
+  icet::c2s(s[i], s[ld + i], s[2 * (size_t)ld + i], r, th, ph);
+  int bt, bp;
+  icet::bin_of(th, ph, nT, nP, bt, bp);
+  sph[i] = r; sph[n + i] = th; sph[2 * (size_t)n + i] = ph;
+  cell[i] = nT * bp + bt;
+}
+
+// synthetic scans
+__global__ void k_synth(uint64_t seed, int first_scan, int nscans, int rings, int azim, const synth::Pose* poses,
+                        float* out) {
+  const int npts = rings * azim;
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (size_t)nscans * npts) return;
+  const int s = (int)(gid / npts), i = (int)(gid % npts);
+  const int ring = i / azim, az = i % azim;
+  float x, y, z;
+  synth::ray(seed, first_scan + s, poses[s], ring, rings, az, azim, x, y, z);
+  float* o = out + (size_t)s * 3 * npts;
+  o[i] = x; o[npts + i] = y; o[2 * (size_t)npts + i] = z;
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+      if (e != cudaSuccess) return fail(ICET_B200_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct icet_b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};
+  int chunk_pairs = 256;
+  int64_t launches = 0;
+  int dump_on = 0;
+  int sm_count = 148;
+  // workspace
+  DevBuf ws;        // one slab, carved per chunk
+  DevBuf zero_ws;   // (part of ws) -- region that must be cleared per chunk is contiguous
+  DevBuf edges;     // azE | elE
+  int edges_nT = -1, edges_nP = -1;
+  DevBuf stage[2];  // host-input staging of scans (double buffered)
+  DevBuf descbuf[2];
+  DevBuf x0buf[2];
+  DevBuf resbuf;    // device results for host-facing calls
+  DevBuf dumpbuf;
+  DevBuf posebuf;
+  void* pinned = nullptr;  // pinned host bounce for results / descriptors
+  size_t pinned_cap = 0;
+  // dump bookkeeping
+  icet_b200_params dump_params{};
+  bool dump_valid = false;
+  Dump dump_ptrs{};
+};
+
+namespace {
+
+struct Carve {
+  char* base;
+  size_t off = 0;
+  explicit Carve(void* b) : base((char*)b) {}
+  template <class T>
+  T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? (T*)(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+// Layout of the chunk workspace.  The first region (cnt1, cntz, cursor, acc) must be zero at chunk start.
+size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, Chunk& ck, size_t* zero_bytes) {
+  Carve c(base);
+  ck.cnt1 = c.take<int32_t>((size_t)P * ncell);
+  ck.cntz = c.take<int32_t>((size_t)P * ncell);
+  ck.cursor = c.take<int32_t>((size_t)P * ncell);
+  ck.acc = c.take<unsigned long long>((size_t)P * ncell * NQ);
+  c.off = (c.off + 255) & ~(size_t)255;
+  if (zero_bytes) *zero_bytes = c.off;
+  ck.off = c.take<int32_t>((size_t)P * ncell);
+  ck.work = c.take<int32_t>((size_t)P * ncell);
+  ck.nwork = c.take<int32_t>((size_t)P);
+  ck.rec = c.take<CellRec>((size_t)P * ncell);
+  ck.vox = c.take<Vox1>((size_t)P * ncell);
+  ck.cellid1 = c.take<int32_t>((size_t)P * n1max);
+  ck.r1 = c.take<float>((size_t)P * n1max);
+  ck.rbuf = c.take<float>((size_t)P * n1max);
+  ck.pog = c.take<float>((size_t)P * 3 * n2max);
+  ck.X = c.take<float>((size_t)P * 6);
+  return (c.off + 255) & ~(size_t)255;
+}
+
+int validate(const icet_b200_params* p) {
+  if (!p) return fail(ICET_B200_E_INVALID, "params is NULL");
+  if (p->runlen < 0 || p->runlen > 10000) return fail(ICET_B200_E_INVALID, "runlen out of range");
+  if (p->bins_phi < 1 || p->bins_theta < 1 || (long long)p->bins_phi * p->bins_theta > (1 << 20))
+    return fail(ICET_B200_E_INVALID, "bins_phi/bins_theta out of range");
+  if (p->n < 1) return fail(ICET_B200_E_INVALID, "n must be >= 1");
+  if (!(p->thresh >= 0.f) || !(p->buff >= 0.f)) return fail(ICET_B200_E_INVALID, "thresh/buff must be >= 0");
+  return 0;
+}
+
+int ensure_edges(icet_b200_ctx* ctx, int nT, int nP) {
+  if (ctx->edges_nT == nT && ctx->edges_nP == nP) return 0;
+  std::vector<float> e((size_t)nT + 1 + nP + 1);
+  // src/icet.cpp:136-139: float divide, double multiply, float store
+  for (int t = 0; t <= nT; t++) e[t] = (static_cast<float>(t) / nT) * (2 * M_PI);
+  for (int q = 0; q <= nP; q++) e[nT + 1 + q] = (static_cast<float>(q) / nP) * (M_PI);
+  int rc = ctx->edges.ensure(e.size() * sizeof(float));
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->edges.p, e.data(), e.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->edges_nT = nT;
+  ctx->edges_nP = nP;
+  return 0;
+}
+
+// Enqueue the whole registration of one chunk (descriptors already on the device).
+int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDesc* d_desc, int n1max, int n2max,
+              const float* d_x0, icet_b200_result* d_res, bool dump) {
+  const int nT = p->bins_theta, nP = p->bins_phi, ncell = nT * nP;
+  int rc = ensure_edges(ctx, nT, nP);
+  if (rc) return rc;
+  Chunk ck;
+  memset(&ck, 0, sizeof(ck));
+  size_t zero_bytes = 0;
+  size_t need = carve_chunk(nullptr, P, ncell, n1max, n2max, ck, &zero_bytes);
+  rc = ctx->ws.ensure(need);
+  if (rc) return rc;
+  carve_chunk(ctx->ws.p, P, ncell, n1max, n2max, ck, &zero_bytes);
+  ck.desc = d_desc;
+  ck.npairs = P; ck.ncell = ncell; ck.nT = nT; ck.nP = nP; ck.n = p->n; ck.runlen = p->runlen;
+  ck.flags = p->flags; ck.thresh = p->thresh; ck.buff = p->buff;
+  ck.n1max = n1max; ck.n2max = n2max;
+  ck.azE = (const float*)ctx->edges.p;
+  ck.elE = ck.azE + nT + 1;
+  ck.x0 = d_x0;
+  ck.res = d_res;
+  ck.dump_on = dump ? 1 : 0;
+  if (dump) ck.dump = ctx->dump_ptrs;
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemsetAsync(ctx->ws.p, 0, zero_bytes, st));
+  const dim3 g1((n1max + 255) / 256, P), g2((n2max + 255) / 256, P);
+  if (n1max > 0) { k_scan1_bin<<<g1, 256, 0, st>>>(ck); ctx->launches++; }
+  k_cell_scan<<<P, 256, 0, st>>>(ck); ctx->launches++;
+  if (n1max > 0) {
+    k_scatter<<<g1, 256, 0, st>>>(ck); ctx->launches++;
+    // enough CTAs to cover a typical work list (~25 % of the cells) in one pass; the kernel loops
+    int gx = std::max(1, std::min(ncell, std::max(64, (ctx->sm_count * 16 + P - 1) / P)));
+    k_cluster<<<dim3(gx, P), 128, 0, st>>>(ck); ctx->launches++;
+    k_pass<false><<<g1, 256, 0, st>>>(ck); ctx->launches++;
+  }
+  k_fit1<<<dim3((ncell + 127) / 128, P), 128, 0, st>>>(ck); ctx->launches++;
+  if (n2max > 0) { k_prep2<<<g2, 256, 0, st>>>(ck); ctx->launches++; }
+  for (int it = 0; it < p->runlen; it++) {
+    if (n2max > 0) { k_pass<true><<<g2, 256, 0, st>>>(ck); ctx->launches++; }
+    k_solve<<<P, SOLVE_THREADS, 0, st>>>(ck, it); ctx->launches++;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int ensure_pinned(icet_b200_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->pinned_cap) return 0;
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  ctx->pinned = nullptr;
+  ctx->pinned_cap = 0;
+  CK(cudaMallocHost(&ctx->pinned, bytes));
+  ctx->pinned_cap = bytes;
+  return 0;
+}
+
+int ensure_dump(icet_b200_ctx* ctx, const icet_b200_params* p) {
+  const size_t ncell = (size_t)p->bins_phi * p->bins_theta, rl = (size_t)std::max(1, p->runlen);
+  Carve c(nullptr);
+  auto lay = [&](Carve& cv, Dump& d) {
+    d.nin1 = cv.take<int32_t>(ncell); d.has1 = cv.take<uint8_t>(ncell); d.mu1 = cv.take<float>(ncell * 3);
+    d.sigma1 = cv.take<float>(ncell * 9); d.evec1 = cv.take<float>(ncell * 9); d.eval1 = cv.take<float>(ncell * 3);
+    d.lmask = cv.take<uint8_t>(ncell * 3);
+    d.cnt2 = cv.take<int32_t>(rl * ncell); d.nin2 = cv.take<int32_t>(rl * ncell); d.used2 = cv.take<uint8_t>(rl * ncell);
+    d.mu2 = cv.take<float>(rl * ncell * 3); d.sigma2 = cv.take<float>(rl * ncell * 9);
+    d.Xit = cv.take<float>(rl * 6); d.HTWH = cv.take<float>(rl * 36); d.HTWdz = cv.take<float>(rl * 6);
+  };
+  Dump tmp;
+  lay(c, tmp);
+  size_t need = c.off + 256;
+  int rc = ctx->dumpbuf.ensure(need);
+  if (rc) return rc;
+  Carve c2(ctx->dumpbuf.p);
+  lay(c2, ctx->dump_ptrs);
+  CK(cudaMemsetAsync(ctx->dumpbuf.p, 0, need, ctx->stream));
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int icet_b200_version(void) { return ICET_B200_VERSION; }
+const char* icet_b200_last_error(void) { return g_err.c_str(); }
+
+int icet_b200_create(int device, icet_b200_ctx** out) {
+  if (!out) return fail(ICET_B200_E_INVALID, "ctx out-pointer is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return fail(ICET_B200_E_NODEVICE, std::string("no CUDA device available (") +
+                                          (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                                          "); icet_b200 has no CPU fallback");
+  }
+  if (device < 0) CK(cudaGetDevice(&device));
+  if (device >= ndev) return fail(ICET_B200_E_INVALID, "device index out of range");
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(ICET_B200_E_NODEVICE, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                          std::to_string(prop.minor) + "; this library is built for sm_100a only");
+  CK(cudaSetDevice(device));
+  icet_b200_ctx* c = new icet_b200_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    CK(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+  }
+  *out = c;
+  return 0;
+}
+
+int icet_b200_destroy(icet_b200_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->copy_stream);
+  c->ws.release(); c->edges.release(); c->resbuf.release(); c->dumpbuf.release(); c->posebuf.release();
+  for (int i = 0; i < 2; i++) {
+    c->stage[i].release(); c->descbuf[i].release(); c->x0buf[i].release();
+    if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
+    if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+  }
+  if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+  return 0;
+}
+
+int icet_b200_set_stream(icet_b200_ctx* c, void* stream) {
+  if (!c) return fail(ICET_B200_E_INVALID, "ctx is NULL");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  c->stream = (cudaStream_t)stream;
+  c->own_stream = false;
+  return 0;
+}
+
+int icet_b200_set_chunk(icet_b200_ctx* c, int32_t m) {
+  if (!c) return fail(ICET_B200_E_INVALID, "ctx is NULL");
+  if (m < 0) return fail(ICET_B200_E_INVALID, "chunk must be >= 0");
+  c->chunk_pairs = m == 0 ? 256 : std::min(m, 65535);
+  return 0;
+}
+
+int icet_b200_synchronize(icet_b200_ctx* c) {
+  if (!c) return fail(ICET_B200_E_INVALID, "ctx is NULL");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int64_t icet_b200_kernel_launches(icet_b200_ctx* c) { return c ? c->launches : 0; }
+
+int icet_b200_set_dump(icet_b200_ctx* c, int32_t enable) {
+  if (!c) return fail(ICET_B200_E_INVALID, "ctx is NULL");
+  c->dump_on = enable ? 1 : 0;
+  if (!enable) c->dump_valid = false;
+  return 0;
+}
+
+// -- device-resident batch --------------------------------------------------------------------
+static int batch_device_impl(icet_b200_ctx* c, const icet_b200_params* p, int32_t npairs, const PairDesc* h_desc,
+                             const float* d_x0, icet_b200_result* d_out, bool dump) {
+  // h_desc lives in host memory; descriptors are uploaded per chunk through the pinned bounce buffer
+  int rc = ensure_pinned(c, (size_t)std::min(npairs, c->chunk_pairs) * sizeof(PairDesc) * 2 + 4096);
+  if (rc) return rc;
+  int slot = 0;
+  for (int base = 0; base < npairs; base += c->chunk_pairs, slot ^= 1) {
+    const int P = std::min(c->chunk_pairs, npairs - base);
+    int n1max = 0, n2max = 0;
+    for (int i = 0; i < P; i++) {
+      n1max = std::max(n1max, h_desc[base + i].n1);
+      n2max = std::max(n2max, h_desc[base + i].n2);
+    }
+    rc = c->descbuf[slot].ensure((size_t)P * sizeof(PairDesc));
+    if (rc) return rc;
+    // the pinned half `slot` may still be in flight from two chunks ago
+    CK(cudaEventSynchronize(c->ev_done[slot]));
+    PairDesc* hp = (PairDesc*)c->pinned + (size_t)slot * std::min(npairs, c->chunk_pairs);
+    memcpy(hp, h_desc + base, (size_t)P * sizeof(PairDesc));
+    CK(cudaMemcpyAsync(c->descbuf[slot].p, hp, (size_t)P * sizeof(PairDesc), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->ev_done[slot], c->stream));
+    rc = run_chunk(c, p, P, (const PairDesc*)c->descbuf[slot].p, n1max, n2max, d_x0 ? d_x0 + (size_t)base * 6 : nullptr,
+                   d_out + base, dump);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int icet_b200_register_batch_device(icet_b200_ctx* c, const icet_b200_params* p, int32_t npairs,
+                                    const float* const* scan1, const int32_t* n1, const float* const* scan2,
+                                    const int32_t* n2, const float* x0, icet_b200_result* out) {
+  if (!c) return fail(ICET_B200_E_INVALID, "ctx is NULL");
+  int rc = validate(p);
+  if (rc) return rc;
+  if (npairs < 0 || (npairs > 0 && (!scan1 || !scan2 || !n1 || !n2 || !out)))
+    return fail(ICET_B200_E_INVALID, "NULL argument");
+  if (npairs == 0) return 0;
+  CK(cudaSetDevice(c->device));
+  std::vector<PairDesc> d(npairs);
+  for (int i = 0; i < npairs; i++) {
+    if (n1[i] < 0 || n2[i] < 0 || (n1[i] > 0 && !scan1[i]) || (n2[i] > 0 && !scan2[i]))
+      return fail(ICET_B200_E_INVALID, "bad scan pointer / size in pair " + std::to_string(i));
+    d[i] = PairDesc{scan1[i], scan2[i], n1[i], n1[i], n2[i], n2[i]};
+  }
+  return batch_device_impl(c, p, npairs, d.data(), x0, out, false);
+}
+
+int icet_b200_register_sequence_device(icet_b200_ctx* c, const icet_b200_params* p, int32_t nscans,
+                                       const float* scans, int32_t n, icet_b200_result* out) {
+  if (!c) return fail(ICET_B200_E_INVALID, "ctx is NULL");
+  int rc = validate(p);
+  if (rc) return rc;
+  if (nscans < 1 || n < 0 || !scans || (nscans > 1 && !out)) return fail(ICET_B200_E_INVALID, "bad argument");
+  if (nscans == 1) return 0;
+  CK(cudaSetDevice(c->device));
+  std::vector<PairDesc> d(nscans - 1);
+  for (int i = 0; i < nscans - 1; i++)
+    d[i] = PairDesc{scans + (size_t)i * 3 * n, scans + (size_t)(i + 1) * 3 * n, n, n, n, n};
+  return batch_device_impl(c, p, nscans - 1, d.data(), nullptr, out, false);
+}
+
+// -- host-buffer entry points ------------------------------------------------------------------
+int icet_b200_register_batch(icet_b200_ctx* c, const icet_b200_params* p, int32_t npairs,
+                             const float* const* scan1, const int32_t* n1, const float* const* scan2,
+                             const int32_t* n2, const float* x0, icet_b200_result* out) {
+  if (!c) return fail(ICET_B200_E_INVALID, "ctx is NULL");
+  int rc = validate(p);
+  if (rc) return rc;
+  if (npairs < 0 || (npairs > 0 && (!scan1 || !scan2 || !n1 || !n2 || !out)))
+    return fail(ICET_B200_E_INVALID, "NULL argument");
+  if (npairs == 0) return 0;
+  for (int i = 0; i < npairs; i++)
+    if (n1[i] < 0 || n2[i] < 0 || (n1[i] > 0 && !scan1[i]) || (n2[i] > 0 && !scan2[i]))
+      return fail(ICET_B200_E_INVALID, "bad scan pointer / size in pair " + std::to_string(i));
+  CK(cudaSetDevice(c->device));
+  rc = c->resbuf.ensure((size_t)npairs * sizeof(icet_b200_result));
+  if (rc) return rc;
+  icet_b200_result* d_res = (icet_b200_result*)c->resbuf.p;
+  const int CH = c->chunk_pairs;
+  rc = ensure_pinned(c, (size_t)std::min(npairs, CH) * (sizeof(PairDesc) + 6 * sizeof(float)) * 2 + 4096);
+  if (rc) return rc;
+  const size_t pin_half = (size_t)std::min(npairs, CH) * (sizeof(PairDesc) + 6 * sizeof(float)) + 2048;
+  int slot = 0;
+  for (int base = 0; base < npairs; base += CH, slot ^= 1) {
+    const int P = std::min(CH, npairs - base);
+    // plan the staging area: every distinct consecutive scan is uploaded once
+    std::vector<PairDesc> d(P);
+    size_t floats = 0;
+    int n1max = 0, n2max = 0;
+    auto pad = [](size_t f) { return (f + 63) & ~(size_t)63; };
+    std::vector<size_t> off1(P), off2(P);
+    for (int i = 0; i < P; i++) {
+      const int g = base + i;
+      if (i > 0 && scan1[g] == scan2[g - 1] && n1[g] == n2[g - 1]) {
+        off1[i] = off2[i - 1];
+      } else {
+        off1[i] = floats;
+        floats += pad((size_t)3 * n1[g]);
+      }
+      off2[i] = floats;
+      floats += pad((size_t)3 * n2[g]);
+      n1max = std::max(n1max, n1[g]);
+      n2max = std::max(n2max, n2[g]);
+    }
+    // the staging slot was last used by chunk (base - 2*CH): wait for its compute to finish
+    CK(cudaEventSynchronize(c->ev_done[slot]));
+    rc = c->stage[slot].ensure(floats * sizeof(float));
+    if (rc) return rc;
+    rc = c->descbuf[slot].ensure((size_t)P * sizeof(PairDesc));
+    if (rc) return rc;
+    rc = c->x0buf[slot].ensure((size_t)P * 6 * sizeof(float));
+    if (rc) return rc;
+    float* sbase = (float*)c->stage[slot].p;
+    for (int i = 0; i < P; i++) {
+      const int g = base + i;
+      const bool shared = (i > 0 && off1[i] == off2[i - 1] && scan1[g] == scan2[g - 1]);
+      if (!shared && n1[g] > 0)
+        CK(cudaMemcpyAsync(sbase + off1[i], scan1[g], (size_t)3 * n1[g] * sizeof(float), cudaMemcpyHostToDevice,
+                           c->copy_stream));
+      if (n2[g] > 0)
+        CK(cudaMemcpyAsync(sbase + off2[i], scan2[g], (size_t)3 * n2[g] * sizeof(float), cudaMemcpyHostToDevice,
+                           c->copy_stream));
+      d[i] = PairDesc{sbase + off1[i], sbase + off2[i], n1[g], n1[g], n2[g], n2[g]};
+    }
+    char* hp = (char*)c->pinned + (size_t)slot * pin_half;
+    memcpy(hp, d.data(), (size_t)P * sizeof(PairDesc));
+    CK(cudaMemcpyAsync(c->descbuf[slot].p, hp, (size_t)P * sizeof(PairDesc), cudaMemcpyHostToDevice, c->copy_stream));
+    const float* d_x0 = nullptr;
+    if (x0) {
+      float* hx = (float*)(hp + (size_t)P * sizeof(PairDesc));
+      memcpy(hx, x0 + (size_t)base * 6, (size_t)P * 6 * sizeof(float));
+      CK(cudaMemcpyAsync(c->x0buf[slot].p, hx, (size_t)P * 6 * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+      d_x0 = (const float*)c->x0buf[slot].p;
+    }
+    CK(cudaEventRecord(c->ev_copy[slot], c->copy_stream));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_copy[slot], 0));
+    const bool dump = c->dump_on && npairs == 1;
+    if (dump) {
+      rc = ensure_dump(c, p);
+      if (rc) return rc;
+    }
+    rc = run_chunk(c, p, P, (const PairDesc*)c->descbuf[slot].p, n1max, n2max, d_x0, d_res + base, dump);
+    if (rc) return rc;
+    CK(cudaEventRecord(c->ev_done[slot], c->stream));
+    if (dump) {
+      c->dump_params = *p;
+      c->dump_valid = true;
+    }
+  }
+  CK(cudaMemcpyAsync(out, d_res, (size_t)npairs * sizeof(icet_b200_result), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int icet_b200_register(icet_b200_ctx* c, const icet_b200_params* p, const float* scan1, int32_t n1, int32_t ld1,
+                       const float* scan2, int32_t n2, int32_t ld2, const float x0[6], icet_b200_result* out) {
+  if (!c) return fail(ICET_B200_E_INVALID, "ctx is NULL");
+  if (!out) return fail(ICET_B200_E_INVALID, "out is NULL");
+  if (n1 < 0 || n2 < 0 || ld1 < n1 || ld2 < n2) return fail(ICET_B200_E_INVALID, "bad n / ld");
+  if (ld1 == n1 && ld2 == n2) return icet_b200_register_batch(c, p, 1, &scan1, &n1, &scan2, &n2, x0, out);
+  // general leading dimension: pack the three planes on the host side of the copy
+  std::vector<float> a((size_t)3 * n1), b((size_t)3 * n2);
+  for (int k = 0; k < 3; k++) {
+    if (n1) memcpy(a.data() + (size_t)k * n1, scan1 + (size_t)k * ld1, (size_t)n1 * sizeof(float));
+    if (n2) memcpy(b.data() + (size_t)k * n2, scan2 + (size_t)k * ld2, (size_t)n2 * sizeof(float));
+  }
+  const float* pa = a.data();
+  const float* pb = b.data();
+  return icet_b200_register_batch(c, p, 1, &pa, &n1, &pb, &n2, x0, out);
+}
+
+int icet_b200_get_dump(icet_b200_ctx* c, icet_b200_voxel_dump* o) {
+  if (!c || !o) return fail(ICET_B200_E_INVALID, "NULL argument");
+  if (!c->dump_valid) return fail(ICET_B200_E_INVALID, "no dump recorded: call icet_b200_set_dump(ctx,1) before icet_b200_register");
+  CK(cudaSetDevice(c->device));
+  const icet_b200_params& p = c->dump_params;
+  const size_t ncell = (size_t)p.bins_phi * p.bins_theta, rl = (size_t)p.runlen;
+  const Dump& d = c->dump_ptrs;
+  // workspace-resident pieces: cnt1 and the cell records of pair 0
+  Chunk ck;
+  memset(&ck, 0, sizeof(ck));
+  size_t zb;
+  // NOTE: the workspace layout of the last (single-pair) chunk
+  cudaStream_t st = c->stream;
+  CK(cudaStreamSynchronize(st));
+  // n1max/n2max only affect arrays behind rec/cnt1, which are carved first
+  carve_chunk(c->ws.p, 1, (int)ncell, 0, 0, ck, &zb);
+  if (o->cnt1) CK(cudaMemcpy(o->cnt1, ck.cnt1, ncell * 4, cudaMemcpyDeviceToHost));
+  if (o->bounds) {
+    std::vector<CellRec> rec(ncell);
+    CK(cudaMemcpy(rec.data(), ck.rec, ncell * sizeof(CellRec), cudaMemcpyDeviceToHost));
+    const int nT = p.bins_theta, nP = p.bins_phi;
+    for (size_t cidx = 0; cidx < ncell; cidx++) {
+      const int t = (int)(cidx % nT), q = (int)(cidx / nT);
+      float* b = o->bounds + cidx * 6;
+      b[0] = (static_cast<float>(t) / nT) * (2 * M_PI);
+      b[1] = (static_cast<float>(t + 1) / nT) * (2 * M_PI);
+      b[2] = (static_cast<float>(q) / nP) * (M_PI);
+      b[3] = (static_cast<float>(q + 1) / nP) * (M_PI);
+      b[4] = rec[cidx].inner;
+      b[5] = rec[cidx].outer;
+    }
+  }
+#define CP(dst, src, bytes) if (o->dst) CK(cudaMemcpy(o->dst, d.src, (bytes), cudaMemcpyDeviceToHost))
+  CP(nin1, nin1, ncell * 4); CP(has1, has1, ncell); CP(mu1, mu1, ncell * 12); CP(sigma1, sigma1, ncell * 36);
+  CP(evec1, evec1, ncell * 36); CP(eval1, eval1, ncell * 12); CP(lmask, lmask, ncell * 3);
+  CP(cnt2, cnt2, rl * ncell * 4); CP(nin2, nin2, rl * ncell * 4); CP(used2, used2, rl * ncell);
+  CP(mu2, mu2, rl * ncell * 12); CP(sigma2, sigma2, rl * ncell * 36); CP(Xit, Xit, rl * 24);
+  CP(HTWH, HTWH, rl * 144); CP(HTWdz, HTWdz, rl * 24);
+#undef CP
+  return 0;
+}
+
+int icet_b200_spherical_bins(icet_b200_ctx* c, const icet_b200_params* p, const float* scan, int32_t n, int32_t ld,
+                             float* sph, int32_t* cell) {
+  if (!c || !scan || !sph || !cell) return fail(ICET_B200_E_INVALID, "NULL argument");
+  int rc = validate(p);
+  if (rc) return rc;
+  if (n <= 0 || ld < n) return fail(ICET_B200_E_INVALID, "bad n / ld");
+  CK(cudaSetDevice(c->device));
+  rc = c->stage[0].ensure(((size_t)3 * ld + 3 * (size_t)n + n) * 4);
+  if (rc) return rc;
+  CK(cudaEventSynchronize(c->ev_done[0]));
+  float* d_s = (float*)c->stage[0].p;
+  float* d_sph = d_s + (size_t)3 * ld;
+  int32_t* d_cell = (int32_t*)(d_sph + (size_t)3 * n);
+  CK(cudaMemcpyAsync(d_s, scan, (size_t)3 * ld * 4, cudaMemcpyHostToDevice, c->stream));
+  k_sph_bins<<<(n + 255) / 256, 256, 0, c->stream>>>(d_s, n, ld, p->bins_theta, p->bins_phi, d_sph, d_cell);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(sph, d_sph, (size_t)3 * n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(cell, d_cell, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int icet_b200_synth_scans_device(icet_b200_ctx* c, uint64_t seed, int32_t first_scan, int32_t nscans, int32_t rings,
+                                 int32_t azim, float* out) {
+  if (!c || !out) return fail(ICET_B200_E_INVALID, "NULL argument");
+  if (first_scan < 0 || nscans < 1 || rings < 1 || azim < 1) return fail(ICET_B200_E_INVALID, "bad argument");
+  CK(cudaSetDevice(c->device));
+  // poses of scans first_scan .. first_scan+nscans-1 (composition of the per-step motions)
+  std::vector<synth::Pose> poses(nscans);
+  synth::Pose P;
+  synth::pose_identity(P);
+  for (int k = 0; k < first_scan + nscans; k++) {
+    if (k >= first_scan) poses[k - first_scan] = P;
+    double d[6];
+    synth::step_motion(seed, k, d);
+    synth::advance(P, d);
+  }
+  int rc = c->posebuf.ensure(poses.size() * sizeof(synth::Pose));
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpyAsync(c->posebuf.p, poses.data(), poses.size() * sizeof(synth::Pose), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const size_t total = (size_t)nscans * rings * azim;
+  k_synth<<<(unsigned)((total + 127) / 128), 128, 0, c->stream>>>(seed, first_scan, nscans, rings, azim,
+                                                                  (const synth::Pose*)c->posebuf.p, out);
+  c->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

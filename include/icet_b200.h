@@ -1,0 +1,169 @@
+/*
+ * include/icet_b200.h -- C ABI of the B200-native ICET registration hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  It replaces the
+ * work done inside the reference constructor
+ *     ICET::ICET(MatrixXf& scan1, MatrixXf& scan2, int runlen, VectorXf X0, int num_bins_phi,
+ *                int num_bins_theta, int n, float thresh, float buff)
+ *                                              reference include/icet.h:38-40, src/icet.cpp:29-63
+ * i.e. fitScan1 (src/icet.cpp:68-107), prepScan2 (:254-277) and runlen x fitScan2 (:372-436).
+ * The reference has no FFI/plugin layer of its own: its boundary is `class ICET`,
+ * which include/icet.h of this repo re-declares and forwards to the entry points below.
+ *
+ * Everything runs on the GPU (hand-written sm_100a kernels).  There is NO CPU fallback: every
+ * entry point fails with a non-zero status if no CUDA device is usable.
+ *
+ * Clouds are column-major N x 3 float32 (x-plane | y-plane | z-plane, leading dimension ld >= n),
+ * which is the memory of Eigen::MatrixXf::data() -- zero-copy from the reference's caller types.
+ */
+#ifndef ICET_B200_H
+#define ICET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICET_B200_VERSION 100
+
+/* status codes (return values; also icet_b200_result.status for per-pair conditions) */
+enum {
+  ICET_B200_OK = 0,
+  ICET_B200_COND_OVERFLOW = 1, /* checkCondition (src/icet.cpp:469-486) ran out of axes: the
+                                  reference would abort on an Eigen bounds assert here          */
+  ICET_B200_E_INVALID = -1,    /* bad argument                                                   */
+  ICET_B200_E_CUDA = -2,       /* CUDA runtime error (see icet_b200_last_error)                  */
+  ICET_B200_E_NODEVICE = -3,   /* no usable CUDA device / wrong architecture                     */
+  ICET_B200_E_NOMEM = -4
+};
+
+/* ctor arguments of the reference (include/icet.h:38-40) */
+typedef struct {
+  int32_t runlen;     /* Gauss-Newton iterations (7 in icet_cpp_demo / odometry, 12 in simpleMapMaker) */
+  int32_t bins_phi;   /* num_bins_phi   (elevation, pi / bins_phi each)   -- NB: phi comes first        */
+  int32_t bins_theta; /* num_bins_theta (azimuth, 2 pi / bins_theta each)                               */
+  int32_t n;          /* minimum cluster size (default 25)                                              */
+  float thresh;       /* radial jump threshold (default 0.1)                                            */
+  float buff;         /* radial buffer added to the cluster bounds (default 0.1)                        */
+  int32_t flags;      /* ICET_B200_FLAG_*                                                               */
+  int32_t reserved;
+} icet_b200_params;
+
+enum {
+  ICET_B200_FLAG_FULL_EIG = 1 /* always run the 6x6 eigen-decomposition of checkCondition (reports the
+                                 exact condition number); default: only when a cheap bound cannot
+                                 prove cond <= 1e6 (identical results either way)                      */
+};
+
+/* per-pair result: the members callers of `class ICET` read (X: all four callers; pred_stds:
+ * odometry.cpp:79, simpleMapMaker.cpp:122) plus the 6x6 error-bound covariance the reference
+ * computes but drops (noise_mat, src/icet.cpp:410-411). */
+typedef struct {
+  float X[6];          /* x, y, z, phi, theta, psi   (p' = (p + t) * R(phi,theta,psi), src/icet.cpp:375-378) */
+  float pred_stds[6];  /* sqrt|diag Q| (+ the checkCondition inflation of :479 when axes are dropped)         */
+  float Q[36];         /* pinv(H^T W H) of the last iteration, row-major                                      */
+  int32_t status;      /* ICET_B200_OK or ICET_B200_COND_OVERFLOW                                             */
+  int32_t n_gauss1;    /* voxels that got a scan-1 Gaussian                                                   */
+  int32_t n_used;      /* voxels that contributed to H^T W H in the last iteration                            */
+  int32_t n_dropped;   /* solution axes dropped by checkCondition in the last iteration                       */
+  float cond;          /* lambda_max/lambda_min of H^T W H if the eigen-decomposition ran, else the upper
+                          bound trace(A)*trace(A^-1) negated (always <= 1e6 in magnitude then)                */
+  int32_t reserved[3];
+} icet_b200_result;    /* 56 x 4 bytes */
+
+typedef struct icet_b200_ctx icet_b200_ctx; /* device workspace + stream; one per host thread */
+
+/* -- lifecycle ------------------------------------------------------------------------------ */
+int icet_b200_version(void);
+/* Thread-local description of the last failure on the calling thread. */
+const char* icet_b200_last_error(void);
+/* device < 0: use the current CUDA device.  Fails (no fallback) when none is present. */
+int icet_b200_create(int device, icet_b200_ctx** ctx);
+int icet_b200_destroy(icet_b200_ctx* ctx);
+/* All work of a context is issued on one stream (default: a private non-blocking stream).
+ * `stream` is a cudaStream_t; pass the caller's stream to order against its own work. */
+int icet_b200_set_stream(icet_b200_ctx* ctx, void* stream);
+/* Upper bound on the number of pairs processed per internal chunk (workspace ~3.7 MB/pair at
+ * 131 072-point scans). 0 restores the default (256). */
+int icet_b200_set_chunk(icet_b200_ctx* ctx, int32_t max_pairs_per_chunk);
+
+/* -- registration ---------------------------------------------------------------------------- */
+/* One pair, HOST buffers: replaces `ICET it(scan1, scan2, runlen, X0, nPhi, nTheta, n, thresh, buff)`
+ * (src/icet.cpp:29-63).  Blocking; copies the inputs to the device and the result back. */
+int icet_b200_register(icet_b200_ctx* ctx, const icet_b200_params* p, const float* scan1, int32_t n1,
+                       int32_t ld1, const float* scan2, int32_t n2, int32_t ld2, const float x0[6],
+                       icet_b200_result* out);
+
+/* A batch of independent pairs, HOST buffers.  scan1[i]/scan2[i] point to clouds of n1[i]/n2[i]
+ * points (leading dimension = point count).  x0: npairs*6 floats or NULL (zeros).  A scan that is
+ * scan2 of pair i and scan1 of pair i+1 (same pointer, odometry.cpp:73-76 usage) is uploaded once.
+ * Blocking. */
+int icet_b200_register_batch(icet_b200_ctx* ctx, const icet_b200_params* p, int32_t npairs,
+                             const float* const* scan1, const int32_t* n1, const float* const* scan2,
+                             const int32_t* n2, const float* x0, icet_b200_result* out);
+
+/* Same, DEVICE buffers: every scan pointer is device memory, x0 (or NULL) and `out` are device
+ * memory too.  Asynchronous on the context's stream; nothing is copied to the host. */
+int icet_b200_register_batch_device(icet_b200_ctx* ctx, const icet_b200_params* p, int32_t npairs,
+                                    const float* const* scan1, const int32_t* n1,
+                                    const float* const* scan2, const int32_t* n2, const float* x0,
+                                    icet_b200_result* out);
+
+/* Convenience for an odometry sequence stored back to back on the DEVICE: nscans clouds of n points
+ * each (scan k at scans + k*3*n); registers the nscans-1 consecutive pairs (k, k+1) with X0 = 0.
+ * `out` is device memory for nscans-1 results.  Asynchronous on the context's stream. */
+int icet_b200_register_sequence_device(icet_b200_ctx* ctx, const icet_b200_params* p, int32_t nscans,
+                                       const float* scans, int32_t n, icet_b200_result* out);
+
+int icet_b200_synchronize(icet_b200_ctx* ctx);
+
+/* -- per-voxel state of the most recent single-pair call (icet_b200_register) ------------------
+ * Mirrors the public members the reference exposes for visualisation / debugging:
+ *   clusterBounds (include/icet.h:83), sigma1/mu1/L/U (:89-94), pointIndices sizes (:95-96).
+ * Any pointer may be NULL.  ncell = bins_phi*bins_theta, cell = bins_theta*phi + theta. HOST memory. */
+typedef struct {
+  int32_t* cnt1;     /* [ncell] points of scan 1 per angular bin                                  */
+  float* bounds;     /* [ncell*6] azMin azMax elMin elMax inner outer (clusterBounds rows)        */
+  int32_t* nin1;     /* [ncell] scan-1 points inside the cluster box                              */
+  uint8_t* has1;     /* [ncell] Gaussian fitted                                                   */
+  float* mu1;        /* [ncell*3]                                                                 */
+  float* sigma1;     /* [ncell*9]                                                                 */
+  float* evec1;      /* [ncell*9] row-major V (columns = eigenvectors, ascending eigenvalues)     */
+  float* eval1;      /* [ncell*3]                                                                 */
+  uint8_t* lmask;    /* [ncell*3] diagonal of L                                                   */
+  /* scan 2 per iteration [runlen][ncell...] */
+  int32_t* cnt2;
+  int32_t* nin2;
+  uint8_t* used2;
+  float* mu2;        /* [runlen*ncell*3] */
+  float* sigma2;     /* [runlen*ncell*9] */
+  float* Xit;        /* [runlen*6]  X after each iteration     */
+  float* HTWH;       /* [runlen*36] */
+  float* HTWdz;      /* [runlen*6]  */
+} icet_b200_voxel_dump;
+
+/* Enable (1) / disable (0) recording of the per-voxel state for subsequent icet_b200_register calls. */
+int icet_b200_set_dump(icet_b200_ctx* ctx, int32_t enable);
+int icet_b200_get_dump(icet_b200_ctx* ctx, icet_b200_voxel_dump* out);
+
+/* Stage outputs used by the parity tests (HOST buffers, blocking):
+ * spherical coordinates [3*n] (r | theta | phi) and the cell index of each point,
+ * utils::cartesianToSpherical (src/utils.cpp:93-119) + ICET::sortSphericalCoordinates (src/icet.cpp:545-546). */
+int icet_b200_spherical_bins(icet_b200_ctx* ctx, const icet_b200_params* p, const float* scan, int32_t n,
+                             int32_t ld, float* sph, int32_t* cell);
+
+/* -- synthetic 64-channel scans (bench / test utility) --------------------------- */
+/* Writes nscans consecutive scans (index first_scan ...) of rings x azim points each to DEVICE memory
+ * `out` ([nscans][3][rings*azim] float32 planes).  Asynchronous on the context's stream. */
+int icet_b200_synth_scans_device(icet_b200_ctx* ctx, uint64_t seed, int32_t first_scan, int32_t nscans,
+                                 int32_t rings, int32_t azim, float* out);
+
+/* -- instrumentation ---------------------------------------------------------------------------- */
+/* Number of kernels this library has launched on the context since creation. */
+int64_t icet_b200_kernel_launches(icet_b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICET_B200_H */
