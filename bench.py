@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- registrations/s of the ICET hot path on synthetic 64-channel scans (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W             (N > 1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" registers --pairs-per-gpu consecutive scan pairs (64 rings x 2048 azimuth steps = 131 072
+points per scan, 75 x 24 spherical voxels, 7 iterations, X0 = 0) per GPU; scans are resident in HBM
+when the timed region starts (`value`), or start in pinned host memory (`e2e`).  Pairs are sharded by
+contiguous pair range across ranks (no data-path collective; one all_gather of 48 floats per pair
+closes each step), so scaling is weak: total pairs = N * pairs-per-gpu.
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RINGS, AZIM = 64, 2048
+NPTS = RINGS * AZIM
+RUNLEN, BINS_PHI, BINS_THETA, NMIN, THRESH, BUFF = 7, 24, 75, 25, 0.1, 0.1
+SEED = 20240
+METRIC = "registrations/s (64-ch, 75x24 vox, 7 it)"
+README_PAIRS_PER_S = 1000.0 / 35.0  # reference README.md:59: 35 ms / pair on a Ryzen 5800X (other hardware)
+B_ALG_PER_PAIR = 12 * (NPTS + NPTS) + 192
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc, self.thr = gpu_index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thr = threading.Thread(target=self._read, daemon=True)
+        self.thr.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_params():
+    return dict(runlen=RUNLEN, bins_phi=BINS_PHI, bins_theta=BINS_THETA, n=NMIN, thresh=THRESH, buff=BUFF)
+
+
+def cpu_time_sequence(scans_host: np.ndarray, threads: int):
+    """Time the CPU restatement of the reference path (oracle, -O3 -march=native like the reference's
+    CMakeLists.txt:38) on the given consecutive scans.  Returns (pairs/s, results)."""
+    from oracle import pyoracle as po
+    try:
+        res, dt = po.run_sequence(scans_host, nthreads=threads, native=True, **oracle_params())
+    except Exception:
+        res, dt = po.run_sequence(scans_host, nthreads=threads, native=False, **oracle_params())
+    return (scans_host.shape[0] - 1) / dt, res
+
+
+def run_reference(args, rank: int, world: int):
+    """Reference arm: the reference's own CPU implementation of the path.  The reference cannot be built here
+    (Eigen3 absent), so this times oracle/ (the CPU restatement, kind = "port") with all host threads."""
+    if rank != 0:
+        return
+    from tools import synth_host
+    cores = os.cpu_count() or 1
+    # one step = `sample` pairs: 2 per host thread (bounded so that the whole run ends within minutes)
+    sample = max(2, min(2 * cores, 256))
+    scans = synth_host.scans(sample + 1, first_scan=0, seed=SEED, rings=RINGS, azim=AZIM)
+    times = []
+    for s in range(args.warmup + args.steps):
+        pps, _ = cpu_time_sequence(scans, cores)
+        if s >= args.warmup:
+            times.append(sample / pps)
+    t = float(np.mean(times))
+    value = sample / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": value / README_PAIRS_PER_S, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.pairs_per_gpu, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": "%d consecutive synthetic 64-ch pairs per step, %d threads (one pair per thread "
+                                   "at a time); the reference C++ cannot be compiled here (no Eigen), this is the "
+                                   "oracle restatement built -O3 -march=native" % (sample, cores)},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(pairs_per_gpu: int, n_gpus: int) -> dict:
+    return {"workload": "BASELINE.json configs[2] shape: synthetic 64-channel odometry sequence, consecutive pairs "
+                        "(k,k+1), X0=0, pair-sharded by contiguous range",
+            "points_per_scan": NPTS, "rings": RINGS, "azimuth_steps": AZIM, "voxels": "75x24",
+            "iterations": RUNLEN, "pairs_per_gpu_per_step": pairs_per_gpu, "pairs_per_step": pairs_per_gpu * n_gpus,
+            "l2_policy": "inputs larger than L2 (%d scans x 1.5 MiB per GPU)" % (pairs_per_gpu + 1),
+            "seed": SEED}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs-per-gpu", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: W >= 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import icet_b200
+    from icet_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- icet_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print("bench.py: warning: --gpus %d but WORLD_SIZE=%d" % (args.gpus, world), file=sys.stderr)
+
+    P = args.pairs_per_gpu
+    ctx = icet_b200.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    params = api.make_params(RUNLEN, BINS_PHI, BINS_THETA, NMIN, THRESH, BUFF)
+
+    # synthetic sequence shard of this rank: scans [rank*P, rank*P + P], generated on the device
+    scans = torch.empty((P + 1, 3, NPTS), dtype=torch.float32, device=dev)
+    ctx.synth_scans_device(scans.data_ptr(), P + 1, first_scan=rank * P, seed=SEED, rings=RINGS, azim=AZIM)
+    results = torch.zeros((P, 56), dtype=torch.float32, device=dev)
+    gathered = torch.zeros((world * P, 48), dtype=torch.float32, device=dev) if world > 1 else None
+    torch.cuda.synchronize()
+
+    def step():
+        ctx.register_sequence_device(scans.data_ptr(), P + 1, NPTS, results.data_ptr(), params)
+        if world > 1:  # final gather of poses + covariances (X 6 | pred_stds 6 | Q 36)
+            dist.all_gather_into_tensor(gathered, results[:, :48].contiguous())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.kernel_launches - l0
+    t_ms = ev0.elapsed_time(ev1)
+    tt = torch.tensor([t_ms, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = tt.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = tt.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        t_ms, launches = float(tmax[0]), int(tsum[1])
+    value = world * P * args.steps / (t_ms * 1e-3)
+
+    # ---- per-kernel device time (separate pass, events around every launch) -------------------------
+    ctx.set_profile(True)
+    ctx.register_sequence_device(scans.data_ptr(), P + 1, NPTS, results.data_ptr(), params)
+    prof = ctx.get_profile()
+    ctx.set_profile(False)
+    tot_ms = sum(v[0] for v in prof.values())
+    dom = max(prof, key=lambda k: prof[k][0])
+    dom_ms, dom_n = prof[dom]
+    peak, peak_src = peaks()
+    # algorithmic bytes of one k_pass<scan2> launch: every scan-2 coordinate of the chunk read once
+    # (12 B / point) -- DESIGN.md "Kernels"; other kernels: see DESIGN.md
+    chunk_pairs = min(P, 256)
+    alg_bytes = {"k_pass<scan2>": 12.0 * NPTS * chunk_pairs, "k_pass<scan1>": 12.0 * NPTS * chunk_pairs,
+                 "k_prep2": 24.0 * NPTS * chunk_pairs, "k_scan1_bin": 20.0 * NPTS * chunk_pairs}.get(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "unit": "GB/s", "peak": peak, "peak_source": peak_src,
+                "traffic": None, "kernel_share_of_step": dom_ms / tot_ms if tot_ms else None,
+                "avg_launch_ms": dom_ms / dom_n if dom_n else None}
+    if alg_bytes and dom_n:
+        ach = alg_bytes / (dom_ms / dom_n * 1e-3) / 1e9
+        roofline.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_launch": alg_bytes})
+    path_gbs = B_ALG_PER_PAIR * (value / world) / 1e9
+    roofline_path = {"algorithmic_bytes_per_pair": B_ALG_PER_PAIR, "achieved_gbs_per_gpu": path_gbs,
+                     "frac": path_gbs / peak}
+
+    # ---- end to end through the C ABI with HOST buffers -----------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_scans = torch.empty((P + 1, 3, NPTS), dtype=torch.float32, pin_memory=True)
+        host_scans.copy_(scans)
+        torch.cuda.synchronize()
+        hs = host_scans.numpy()
+        host_out = torch.zeros((P, 56), dtype=torch.float32, pin_memory=True)
+        ptr0 = host_scans.data_ptr()
+        stride = 3 * NPTS * 4
+        p1 = [ptr0 + i * stride for i in range(P)]
+        p2 = [ptr0 + (i + 1) * stride for i in range(P)]
+        nn = np.full(P, NPTS, np.int32)
+
+        def e2e_step():
+            ctx.register_batch_ptrs(p1, nn, p2, nn, host_out.data_ptr(), params=params, device=False)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        nst = max(2, min(args.steps, 5))
+        for _ in range(nst):
+            e2e_step()
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        tw = torch.tensor([wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * P * nst / float(tw[0]), "unit": "pairs/s",
+               "h2d_bytes_per_step": int((P + 1) * stride + P * 24) * world, "d2h_bytes_per_step": int(P * 224) * world,
+               "note": "icet_b200_register_batch on pinned host scans (each scan uploaded once), results copied back; "
+                       "host wall clock around blocking calls, max over ranks"}
+        del hs
+
+    # ---- single-pair latency (BASELINE.json configs[1]) -----------------------------------------------------
+    latency = None
+    if rank == 0 and not args.no_latency:
+        res1 = torch.zeros((1, 56), dtype=torch.float32, device=dev)
+        lat = []
+        for i in range(230):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            ctx.register_sequence_device(scans.data_ptr(), 2, NPTS, res1.data_ptr(), params)
+            b.record(stream)
+            torch.cuda.synchronize()
+            if i >= 30:
+                lat.append(a.elapsed_time(b))
+        h1 = scans[0].cpu().numpy()
+        h2 = scans[1].cpu().numpy()
+        hl = []
+        for i in range(60):
+            t0 = time.perf_counter()
+            ctx.register(h1, h2, params=params)
+            if i >= 10:
+                hl.append((time.perf_counter() - t0) * 1e3)
+        latency = {"workload": "configs[1]: one synthetic 64-ch pair, 75x24, 7 it", "device_resident_p50_ms": float(np.median(lat)),
+                   "device_resident_p95_ms": float(np.percentile(lat, 95)), "host_api_p50_ms": float(np.median(hl)),
+                   "host_api_p95_ms": float(np.percentile(hl, 95)), "reps": len(lat)}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle on the box's host cores ------------------------
+    cpu_baseline = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = max(2, min(2 * cores, P, 256))
+        hs = scans[: sample + 1].cpu().numpy()
+        pps, ores = cpu_time_sequence(hs, cores)
+        cpu_baseline = {"value": pps, "unit": "pairs/s", "cores": cores, "kind": "port",
+                        "sample": "first %d pairs of the same synthetic sequence, %d host threads (one pair per thread "
+                                  "at a time); oracle restatement built -O3 -march=native (the reference cannot be "
+                                  "compiled here: no Eigen)" % (sample, cores)}
+        g = results[:sample].cpu().numpy()
+        parity = {"pairs_checked": sample, "max_abs_dX_m": float(np.abs(g[:, :3] - ores[:, :3]).max()),
+                  "max_abs_dX_rad": float(np.abs(g[:, 3:6] - ores[:, 3:6]).max())}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": value / README_PAIRS_PER_S,
+            "baseline_note": "reference README.md:59: 35 ms/pair (28.6 pairs/s) on a Ryzen 5800X CPU",
+            "dtype": "f32", "data": "synthetic", "config": workload_config(P, world), "clocks": clocks,
+            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_path": roofline_path,
+            "cpu_baseline": cpu_baseline, "latency": latency, "parity_vs_oracle": parity,
+            "kernel_ms_per_step": {k: round(v[0], 4) for k, v in prof.items()},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -48,7 +48,9 @@ EXPORTS = ["icet_b200_version", "icet_b200_last_error", "icet_b200_create", "ice
            "icet_b200_set_stream", "icet_b200_set_chunk", "icet_b200_register", "icet_b200_register_batch",
            "icet_b200_register_batch_device", "icet_b200_register_sequence_device", "icet_b200_synchronize",
            "icet_b200_set_dump", "icet_b200_get_dump", "icet_b200_spherical_bins",
-           "icet_b200_synth_scans_device", "icet_b200_kernel_launches"]
+           "icet_b200_synth_scans_device", "icet_b200_kernel_launches", "icet_b200_set_profile",
+           "icet_b200_get_profile", "icet_b200_kernel_name"]
+NKERNELS = 10
 
 _LIB = None
 
@@ -86,6 +88,10 @@ def load_library() -> C.CDLL:
     L.icet_b200_synth_scans_device.argtypes = [vp, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     L.icet_b200_kernel_launches.argtypes = [vp]
     L.icet_b200_kernel_launches.restype = C.c_int64
+    L.icet_b200_set_profile.argtypes = [vp, C.c_int32]
+    L.icet_b200_get_profile.argtypes = [vp, vp, vp]
+    L.icet_b200_kernel_name.argtypes = [C.c_int]
+    L.icet_b200_kernel_name.restype = C.c_char_p
     _LIB = L
     return L
 
@@ -146,6 +152,16 @@ class Context:
     @property
     def kernel_launches(self) -> int:
         return int(self._L.icet_b200_kernel_launches(self._h))
+
+    def set_profile(self, enable: bool):
+        self._check(self._L.icet_b200_set_profile(self._h, 1 if enable else 0))
+
+    def get_profile(self) -> dict:
+        """{kernel name: (summed device ms, launches)} since profiling was enabled."""
+        ms = np.zeros(NKERNELS, np.float64)
+        cnt = np.zeros(NKERNELS, np.int64)
+        self._check(self._L.icet_b200_get_profile(self._h, ms.ctypes.data, cnt.ctypes.data))
+        return {self._L.icet_b200_kernel_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(NKERNELS)}
 
     # -- host-buffer registration ------------------------------------------------------------
     def register(self, scan1, scan2, X0=None, params: Params | None = None, dump: bool = False):

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -93,6 +94,10 @@ struct Chunk {  // everything a kernel needs, passed by value
   Vox1* vox;         // [P][ncell]
   const float* azE;  // [nT+1] float azimuth bin edges  (src/icet.cpp:136-137)
   const float* elE;  // [nP+1] float elevation bin edges (src/icet.cpp:138-139)
+  icet::BinTable bth, bph;  // exact bin lookup tables (src/icet.cpp:545-546)
+  float* TR;         // [P][12] translation (3) and rotation R(X) (9) of the current iteration
+  float* J;          // [P][27] get_H derivative matrices Jx | Jy | Jz of the current iteration
+  double* part;      // [P][nblk][NRED] per-block partial sums of the voxel contributions
   // scan 2
   float* pog;        // [P][3][n2max]  points2_OG
   float* X;          // [P][6]
@@ -108,7 +113,11 @@ struct Chunk {  // everything a kernel needs, passed by value
 //   q[2..4] += sum d, q[5..10] += sum d d^T (xx xy xz yy yz zz)
 // `cell` < 0: lane takes no part.  Exact integer arithmetic => order independent.
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_accumulate(unsigned long long* accp /* pair base */, int cell, bool in,
+// Lanes 0..10 of the warp publish the 11 sums of one (warp, cell) group with a single RED.64
+// instruction (distinct addresses).  The sums are warp-uniform (REDUX results); they reach their lanes
+// through a 96-byte per-warp shared-memory slot: lane 0 stores, every lane reads its own word.
+__device__ __forceinline__ void warp_accumulate(unsigned long long* accp /* pair base */,
+                                                long long* wslot /* per-warp smem, 12 words */, int cell, bool in,
                                                 int fx, int fy, int fz) {
   const int lane = threadIdx.x & 31;
   unsigned todo = __ballot_sync(FULL, cell >= 0);
@@ -119,41 +128,51 @@ __device__ __forceinline__ void warp_accumulate(unsigned long long* accp /* pair
     const unsigned grp = __ballot_sync(FULL, mine);
     const unsigned grp_in = __ballot_sync(FULL, mine && in);
     todo &= ~grp;
-    long long val = 0;
-    if (lane == 0) val = __popc(grp);
-    if (lane == 1) val = __popc(grp_in);
-    int nlanes = 2;
-    if (grp_in) {  // warp-uniform
-      const bool m = mine && in;
-      const int dx = m ? fx : 0, dy = m ? fy : 0, dz = m ? fz : 0;
-      const int sx = __reduce_add_sync(FULL, dx);
-      const int sy = __reduce_add_sync(FULL, dy);
-      const int sz = __reduce_add_sync(FULL, dz);
-      if (lane == 2) val = sx;
-      if (lane == 3) val = sy;
-      if (lane == 4) val = sz;
-      // products: |d| <= 2^21 -> |p| <= 2^42; split into hi (signed) and lo (22 bits) so that the
-      // 32-lane sums fit REDUX's 32-bit adder
-      auto red64 = [&](int a, int b) -> long long {
-        long long p = (long long)a * (long long)b;
-        int hi = (int)(p >> 22);
-        int lo = (int)(p & 0x3FFFFF);
-        int shi = __reduce_add_sync(FULL, hi);
-        int slo = __reduce_add_sync(FULL, lo);
-        return ((long long)shi << 22) + (long long)slo;
-      };
-      long long pxx = red64(dx, dx), pxy = red64(dx, dy), pxz = red64(dx, dz);
-      long long pyy = red64(dy, dy), pyz = red64(dy, dz), pzz = red64(dz, dz);
-      if (lane == 5) val = pxx;
-      if (lane == 6) val = pxy;
-      if (lane == 7) val = pxz;
-      if (lane == 8) val = pyy;
-      if (lane == 9) val = pyz;
-      if (lane == 10) val = pzz;
-      nlanes = 11;
+    unsigned long long* q = accp + (size_t)c * NQ;
+    if (grp_in == 0) {  // warp-uniform: only the bin count changes
+      if (lane == 0) atomicAdd(q, (unsigned long long)__popc(grp));
+      continue;
     }
-    if (lane < nlanes) atomicAdd(accp + (size_t)c * NQ + lane, (unsigned long long)val);
+    const bool m = mine && in;
+    const int dx = m ? fx : 0, dy = m ? fy : 0, dz = m ? fz : 0;
+    const long long sx = __reduce_add_sync(FULL, dx);
+    const long long sy = __reduce_add_sync(FULL, dy);
+    const long long sz = __reduce_add_sync(FULL, dz);
+    // products: |d| <= 2^21 -> |p| <= 2^42; split into hi (signed) and lo (22 bits) so that the
+    // 32-lane sums fit REDUX's 32-bit adder
+    auto red64 = [&](int a, int b) -> long long {
+      const long long p = (long long)a * (long long)b;
+      const int shi = __reduce_add_sync(FULL, (int)(p >> 22));
+      const int slo = __reduce_add_sync(FULL, (int)(p & 0x3FFFFF));
+      return ((long long)shi << 22) + (long long)slo;
+    };
+    const long long pxx = red64(dx, dx), pxy = red64(dx, dy), pxz = red64(dx, dz);
+    const long long pyy = red64(dy, dy), pyz = red64(dy, dz), pzz = red64(dz, dz);
+    if (lane == 0) {
+      longlong2* w2 = reinterpret_cast<longlong2*>(wslot);
+      w2[0] = make_longlong2((long long)__popc(grp), (long long)__popc(grp_in));
+      w2[1] = make_longlong2(sx, sy);
+      w2[2] = make_longlong2(sz, pxx);
+      w2[3] = make_longlong2(pxy, pxz);
+      w2[4] = make_longlong2(pyy, pyz);
+      w2[5] = make_longlong2(pzz, 0);
+    }
+    __syncwarp();
+    if (lane < 11) atomicAdd(q + lane, (unsigned long long)wslot[lane]);
+    __syncwarp();
   }
+}
+
+__device__ __forceinline__ void cell_of(const Chunk& ck, float th, float ph, int& bt, int& bp) {
+  bt = icet::bin_lookup(th, ck.bth, 2 * M_PI);
+  bp = icet::bin_lookup(ph, ck.bph, M_PI);
+}
+// same, tables staged in shared memory: tab = azE[nT+1] | elE[nP+1] | Tth[nT+2] | Tph[nP+2]
+__device__ __forceinline__ void cell_of_smem(const Chunk& ck, const float* tab, float th, float ph, int& bt, int& bp) {
+  const float* Tth = tab + ck.nT + 1 + ck.nP + 1;
+  const float* Tph = Tth + ck.nT + 2;
+  bt = icet::bin_lookup(th, Tth, ck.bth.scale, ck.bth.amax, ck.nT, 2 * M_PI);
+  bp = icet::bin_lookup(ph, Tph, ck.bph.scale, ck.bph.amax, ck.nP, M_PI);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -172,7 +191,7 @@ __global__ void __launch_bounds__(256) k_scan1_bin(const Chunk ck) {
     float r, th, ph;
     icet::c2s(x, y, z, r, th, ph);
     int bt, bp;
-    icet::bin_of(th, ph, ck.nT, ck.nP, bt, bp);
+    cell_of(ck, th, ph, bt, bp);
     cell = ck.nT * bp + bt;
     zero = (r == 0.0f);
     ck.cellid1[(size_t)pair * ck.n1max + i] = cell;
@@ -220,6 +239,13 @@ __global__ void __launch_bounds__(256) k_cell_scan(const Chunk ck) {
     ck.nwork[pair] = b;
     if (ck.x0) for (int k = 0; k < 6; k++) ck.X[pair * 6 + k] = ck.x0[pair * 6 + k];
     else for (int k = 0; k < 6; k++) ck.X[pair * 6 + k] = 0.f;
+    {
+      float* TR = ck.TR + (size_t)pair * 12;
+      const float* X = ck.X + pair * 6;
+      TR[0] = X[0]; TR[1] = X[1]; TR[2] = X[2];
+      icet::rotR(X[3], X[4], X[5], TR + 3);
+      icet::getH_J(X[3], X[4], X[5], ck.J + (size_t)pair * 27);
+    }
     icet_b200_result* R = ck.res + pair;
     R->status = 0; R->n_gauss1 = 0; R->n_used = 0; R->n_dropped = 0; R->cond = 0.f;
     for (int k = 0; k < 6; k++) { R->X[k] = ck.X[pair * 6 + k]; R->pred_stds[k] = 0.f; }
@@ -387,79 +413,100 @@ __global__ void __launch_bounds__(128) k_cluster(const Chunk ck) {
 //   SCAN2 = false: scan 1 (filterPointsInsideCluster + mean/cov of fitCells1, src/icet.cpp:155-162)
 //   SCAN2 = true : scan 2, one Gauss-Newton iteration (src/icet.cpp:375-388 + fitCells2 :290-306)
 // ----------------------------------------------------------------------------------------------
+constexpr int PASS_THREADS = 256;
+constexpr int PASS_PPT = 4;  // points per thread (block tile = 1024 consecutive points)
+
+__host__ __device__ inline int pass_smem_bytes(int nT, int nP) {
+  return (PASS_THREADS / 32) * 12 * 8 + (2 * (nT + nP) + 6) * 4;
+}
+
 template <bool SCAN2>
-__global__ void __launch_bounds__(256) k_pass(const Chunk ck) {
+__global__ void __launch_bounds__(PASS_THREADS) k_pass(const Chunk ck) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  long long* wslots = reinterpret_cast<long long*>(smem_raw);
+  float* tab = reinterpret_cast<float*>(smem_raw + (PASS_THREADS / 32) * 12 * 8);
   const int pair = blockIdx.y;
   const PairDesc d = ck.desc[pair];
   const int n = SCAN2 ? d.n2 : d.n1;
-  if ((int)(blockIdx.x * blockDim.x) >= n) return;
-  __shared__ float s_tr[12];
-  if (SCAN2) {
-    if (threadIdx.x == 0) {
-      const float* X = ck.X + pair * 6;
-      s_tr[0] = X[0]; s_tr[1] = X[1]; s_tr[2] = X[2];
-      icet::rotR(X[3], X[4], X[5], s_tr + 3);
-    }
-    __syncthreads();
+  const int tile0 = blockIdx.x * (PASS_THREADS * PASS_PPT);
+  if (tile0 >= n) return;
+  {
+    const int ntab = 2 * (ck.nT + ck.nP) + 6;
+    for (int k = threadIdx.x; k < ntab; k += PASS_THREADS) tab[k] = __ldg(ck.azE + k);
   }
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int cell = -1;
-  bool in = false;
-  int fx = 0, fy = 0, fz = 0;
-  if (i < n) {
-    float x, y, z;
-    if (SCAN2) {
-      const float* pg = ck.pog + (size_t)pair * 3 * ck.n2max;
-      float px = __ldg(pg + i), py = __ldg(pg + ck.n2max + i), pz = __ldg(pg + 2 * (size_t)ck.n2max + i);
-      icet::transform(px, py, pz, s_tr, s_tr + 3, x, y, z);
-    } else {
-      x = __ldg(d.s1 + i); y = __ldg(d.s1 + d.ld1 + i); z = __ldg(d.s1 + 2 * (size_t)d.ld1 + i);
-    }
-    float r, th, ph;
-    icet::c2s(x, y, z, r, th, ph);
-    int bt, bp;
-    icet::bin_of(th, ph, ck.nT, ck.nP, bt, bp);
-    const int c = ck.nT * bp + bt;
-    const float4* rp = reinterpret_cast<const float4*>(ck.rec + (size_t)pair * ck.ncell + c);
-    const float4 ra = __ldg(rp), rb = __ldg(rp + 1);
-    const uint32_t flags = __float_as_uint(rb.z);
-    if (flags & (SCAN2 ? F_ACTIVE2 : F_STAT1)) {
-      cell = c;
-      // ICET::filterPointsInsideCluster src/icet.cpp:632-634 (inclusive float compares)
-      in = th >= __ldg(ck.azE + bt) && th <= __ldg(ck.azE + bt + 1) && ph >= __ldg(ck.elE + bp) &&
-           ph <= __ldg(ck.elE + bp + 1) && r >= ra.x && r <= ra.y;
-      if (in) {
-        float cx, cy, cz;
-        icet::s2c(r, th, ph, cx, cy, cz);  // statistics use round-tripped points (:159 / :303)
-        const float sc = rb.y;
-        fx = __float2int_rn((cx - ra.z) * sc);
-        fy = __float2int_rn((cy - ra.w) * sc);
-        fz = __float2int_rn((cz - rb.x) * sc);
-        fx = max(-FP_LIM, min(FP_LIM, fx));
-        fy = max(-FP_LIM, min(FP_LIM, fy));
-        fz = max(-FP_LIM, min(FP_LIM, fz));
+  float tr[12];
+  if (SCAN2) {
+    const float4* tp = reinterpret_cast<const float4*>(ck.TR + (size_t)pair * 12);
+    const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+    tr[0] = a.x; tr[1] = a.y; tr[2] = a.z; tr[3] = a.w; tr[4] = b.x; tr[5] = b.y; tr[6] = b.z; tr[7] = b.w;
+    tr[8] = c.x; tr[9] = c.y; tr[10] = c.z; tr[11] = c.w;
+  }
+  const float* px_ = SCAN2 ? ck.pog + (size_t)pair * 3 * ck.n2max : d.s1;
+  const size_t ld = SCAN2 ? (size_t)ck.n2max : (size_t)d.ld1;
+  const CellRec* recs = ck.rec + (size_t)pair * ck.ncell;
+  unsigned long long* accp = ck.acc + (size_t)pair * ck.ncell * NQ;
+  long long* wslot = wslots + (threadIdx.x >> 5) * 12;
+  const float* azE = tab;
+  const float* elE = tab + ck.nT + 1;
+  __syncthreads();
+#pragma unroll 1
+  for (int j = 0; j < PASS_PPT; j++) {
+    const int i = tile0 + j * PASS_THREADS + threadIdx.x;
+    if (tile0 + j * PASS_THREADS >= n) break;  // block-uniform
+    int cell = -1;
+    bool in = false;
+    int fx = 0, fy = 0, fz = 0;
+    if (i < n) {
+      float x = __ldg(px_ + i), y = __ldg(px_ + ld + i), z = __ldg(px_ + 2 * ld + i);
+      if (SCAN2) icet::transform(x, y, z, tr, tr + 3, x, y, z);
+      float r, th, ph;
+      icet::c2s(x, y, z, r, th, ph);
+      int bt, bp;
+      cell_of_smem(ck, tab, th, ph, bt, bp);
+      const int c = ck.nT * bp + bt;
+      const float4* rp = reinterpret_cast<const float4*>(recs + c);
+      const float4 rb = __ldg(rp + 1);
+      const uint32_t flags = __float_as_uint(rb.z);
+      if (flags & (SCAN2 ? F_ACTIVE2 : F_STAT1)) {
+        cell = c;
+        const float4 ra = __ldg(rp);
+        // ICET::filterPointsInsideCluster src/icet.cpp:632-634 (inclusive float compares)
+        in = th >= azE[bt] && th <= azE[bt + 1] && ph >= elE[bp] && ph <= elE[bp + 1] && r >= ra.x && r <= ra.y;
+        if (in) {
+          float cx, cy, cz;
+          icet::s2c(r, th, ph, cx, cy, cz);  // statistics use round-tripped points (:159 / :303)
+          const float sc = rb.y;
+          fx = __float2int_rn((cx - ra.z) * sc);
+          fy = __float2int_rn((cy - ra.w) * sc);
+          fz = __float2int_rn((cz - rb.x) * sc);
+          fx = max(-FP_LIM, min(FP_LIM, fx));
+          fy = max(-FP_LIM, min(FP_LIM, fy));
+          fz = max(-FP_LIM, min(FP_LIM, fz));
+        }
       }
     }
+    warp_accumulate(accp, wslot, cell, in, fx, fy, fz);
   }
-  warp_accumulate(ck.acc + (size_t)pair * ck.ncell * NQ, cell, in, fx, fy, fz);
 }
 
 // exact-sum -> mean / covariance (double) of a voxel
 __device__ __forceinline__ void stats_from_acc(const unsigned long long* q, const CellRec& rc, double mean[3],
                                                double cov[6]) {
   const double nin = (double)(long long)q[1];
-  const double inv = 1.0 / (double)rc.scale;
+  const double inv = 1.0 / (double)rc.scale;  // exact: the scale is a power of two
+  const double in_ = 1.0 / nin;
   const double sx = (double)(long long)q[2], sy = (double)(long long)q[3], sz = (double)(long long)q[4];
-  mean[0] = (double)rc.refx + (sx / nin) * inv;
-  mean[1] = (double)rc.refy + (sy / nin) * inv;
-  mean[2] = (double)rc.refz + (sz / nin) * inv;
+  const double mx = sx * in_, my = sy * in_, mz = sz * in_;
+  mean[0] = (double)rc.refx + mx * inv;
+  mean[1] = (double)rc.refy + my * inv;
+  mean[2] = (double)rc.refz + mz * inv;
   const double f = inv * inv / (nin - 1.0);
-  cov[0] = ((double)(long long)q[5] - sx * sx / nin) * f;
-  cov[1] = ((double)(long long)q[6] - sx * sy / nin) * f;
-  cov[2] = ((double)(long long)q[7] - sx * sz / nin) * f;
-  cov[3] = ((double)(long long)q[8] - sy * sy / nin) * f;
-  cov[4] = ((double)(long long)q[9] - sy * sz / nin) * f;
-  cov[5] = ((double)(long long)q[10] - sz * sz / nin) * f;
+  cov[0] = ((double)(long long)q[5] - sx * mx) * f;
+  cov[1] = ((double)(long long)q[6] - sx * my) * f;
+  cov[2] = ((double)(long long)q[7] - sx * mz) * f;
+  cov[3] = ((double)(long long)q[8] - sy * my) * f;
+  cov[4] = ((double)(long long)q[9] - sy * mz) * f;
+  cov[5] = ((double)(long long)q[10] - sz * mz) * f;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -554,34 +601,33 @@ __global__ void __launch_bounds__(256) k_prep2(const Chunk ck) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// K5b + K6: one CTA per pair.  Per voxel: scan-2 mean / covariance, R_noise, W, H_z, contributions
-// H^T W H_j and H^T W dz_j (fitCells2 src/icet.cpp:302-338); fixed-order block reduction; then one
-// thread: Q = pinv(H^T W H), pred_stds, checkCondition, dx, X += dx (src/icet.cpp:410-433, :443-492).
+// K5b: one thread per voxel.  Scan-2 mean / covariance, R_noise, W, H_z and the voxel's contributions
+// H^T W H_j (upper triangle, 21) and H^T W dz_j (6)  (fitCells2 src/icet.cpp:302-338); fixed-order
+// reduction over the block's 64 voxels -> one partial sum per block.
 // ----------------------------------------------------------------------------------------------
-constexpr int SOLVE_THREADS = 256;
+constexpr int VOX_THREADS = 64;
 constexpr int NRED = 28;  // 21 (upper triangle of H^T W H) + 6 (H^T W dz) + 1 (voxels used)
 
-__global__ void __launch_bounds__(SOLVE_THREADS) k_solve(const Chunk ck, int iter) {
-  const int pair = blockIdx.x;
-  __shared__ float s_J[27];
-  __shared__ double s_red[SOLVE_THREADS / 32][NRED];
-  float* X = ck.X + pair * 6;
-  if (threadIdx.x == 0) icet::getH_J(X[3], X[4], X[5], s_J);
-  __syncthreads();
+__global__ void __launch_bounds__(VOX_THREADS) k_vox2(const Chunk ck, int iter) {
+  const int pair = blockIdx.y;
+  const int cell = blockIdx.x * VOX_THREADS + threadIdx.x;
+  __shared__ double s_red[NRED];
+  const size_t ci = (size_t)pair * ck.ncell + cell;
+  bool active = false;
+  CellRec rc;
+  if (cell < ck.ncell) {
+    rc = ck.rec[ci];
+    active = (rc.flags & F_ACTIVE2) != 0;
+  }
   double acc[NRED];
 #pragma unroll
   for (int k = 0; k < NRED; k++) acc[k] = 0.0;
-  for (int cell = threadIdx.x; cell < ck.ncell; cell += SOLVE_THREADS) {
-    const size_t ci = (size_t)pair * ck.ncell + cell;
-    const CellRec rc = ck.rec[ci];
-    if (!(rc.flags & F_ACTIVE2)) {
-      if (ck.dump_on) {
-        ck.dump.cnt2[(size_t)iter * ck.ncell + cell] = -1;
-        ck.dump.nin2[(size_t)iter * ck.ncell + cell] = -1;
-        ck.dump.used2[(size_t)iter * ck.ncell + cell] = 0;
-      }
-      continue;
-    }
+  if (ck.dump_on && cell < ck.ncell && !active) {
+    ck.dump.cnt2[(size_t)iter * ck.ncell + cell] = -1;
+    ck.dump.nin2[(size_t)iter * ck.ncell + cell] = -1;
+    ck.dump.used2[(size_t)iter * ck.ncell + cell] = 0;
+  }
+  if (active) {
     unsigned long long q[NQ];
     unsigned long long* qp = ck.acc + ci * NQ;
 #pragma unroll
@@ -593,99 +639,151 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(const Chunk ck, int ite
       ck.dump.nin2[(size_t)iter * ck.ncell + cell] = (nbin > ck.n) ? (int)nin : -1;
       ck.dump.used2[(size_t)iter * ck.ncell + cell] = use ? 1 : 0;
     }
-    if (!use) continue;
-    double mean[3], cov[6];
-    stats_from_acc(q, rc, mean, cov);
-    const Vox1 v = ck.vox[ci];
-    if (ck.dump_on) {
-      float* m2 = ck.dump.mu2 + ((size_t)iter * ck.ncell + cell) * 3;
-      float* s2 = ck.dump.sigma2 + ((size_t)iter * ck.ncell + cell) * 9;
-      for (int k = 0; k < 3; k++) m2[k] = (float)mean[k];
-      s2[0] = (float)cov[0]; s2[1] = (float)cov[1]; s2[2] = (float)cov[2];
-      s2[3] = (float)cov[1]; s2[4] = (float)cov[3]; s2[5] = (float)cov[4];
-      s2[6] = (float)cov[2]; s2[7] = (float)cov[4]; s2[8] = (float)cov[5];
+    if (use) {
+      const float* J = ck.J + (size_t)pair * 27;
+      double mean[3], cov[6];
+      stats_from_acc(q, rc, mean, cov);
+      const Vox1 v = ck.vox[ci];
+      if (ck.dump_on) {
+        float* m2 = ck.dump.mu2 + ((size_t)iter * ck.ncell + cell) * 3;
+        float* s2 = ck.dump.sigma2 + ((size_t)iter * ck.ncell + cell) * 9;
+        for (int k = 0; k < 3; k++) m2[k] = (float)mean[k];
+        s2[0] = (float)cov[0]; s2[1] = (float)cov[1]; s2[2] = (float)cov[2];
+        s2[3] = (float)cov[1]; s2[4] = (float)cov[3]; s2[5] = (float)cov[4];
+        s2[6] = (float)cov[2]; s2[7] = (float)cov[4]; s2[8] = (float)cov[5];
+      }
+      // R_noise = sigma1/(|idx1|-1) + sigma2/(|idx2|-1)   (:315)
+      const double id2 = 1.0 / (double)(nbin - 1);
+      double Rn[9];
+      {
+        double r6[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) r6[k] = v.S1n[k] + cov[k] * id2;
+        Rn[0] = r6[0]; Rn[1] = r6[1]; Rn[2] = r6[2]; Rn[3] = r6[1]; Rn[4] = r6[3]; Rn[5] = r6[4];
+        Rn[6] = r6[2]; Rn[7] = r6[4]; Rn[8] = r6[5];
+      }
+      // M = (L U^T) R_noise (L U^T)^T   (:317)
+      double T[9], M[9];
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+          T[3 * a + b] = v.LV[3 * a] * Rn[b] + v.LV[3 * a + 1] * Rn[3 + b] + v.LV[3 * a + 2] * Rn[6 + b];
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+          M[3 * a + b] = T[3 * a] * v.LV[3 * b] + T[3 * a + 1] * v.LV[3 * b + 1] + T[3 * a + 2] * v.LV[3 * b + 2];
+      // W = pinv(M)  (:320-321)
+      double W[9];
+      if (!icet::masked_inv3(M, v.lmask, W)) icet::cod_pinv(M, 3, 3, W);
+      // H_z = L U^T [ -I | Jx mu | Jy mu | Jz mu ]  (:324-329)
+      double H[18];
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        H[6 * a + 0] = (a == 0) ? -1.0 : 0.0;
+        H[6 * a + 1] = (a == 1) ? -1.0 : 0.0;
+        H[6 * a + 2] = (a == 2) ? -1.0 : 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+          H[6 * a + 3 + j] = (double)__ldg(J + 9 * j + 3 * a) * mean[0] + (double)__ldg(J + 9 * j + 3 * a + 1) * mean[1] +
+                             (double)__ldg(J + 9 * j + 3 * a + 2) * mean[2];
+      }
+      double Hz[18];
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int c = 0; c < 6; c++)
+          Hz[6 * a + c] = v.LV[3 * a] * H[c] + v.LV[3 * a + 1] * H[6 + c] + v.LV[3 * a + 2] * H[12 + c];
+      // dz = L U^T (mean2 - mu1)   (:335-337)
+      const double dm[3] = {mean[0] - v.mu[0], mean[1] - v.mu[1], mean[2] - v.mu[2]};
+      double dz[3];
+#pragma unroll
+      for (int a = 0; a < 3; a++) dz[a] = v.LV[3 * a] * dm[0] + v.LV[3 * a + 1] * dm[1] + v.LV[3 * a + 2] * dm[2];
+      double WH[18], Wdz[3];
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int c = 0; c < 6; c++)
+          WH[6 * a + c] = W[3 * a] * Hz[c] + W[3 * a + 1] * Hz[6 + c] + W[3 * a + 2] * Hz[12 + c];
+        Wdz[a] = W[3 * a] * dz[0] + W[3 * a + 1] * dz[1] + W[3 * a + 2] * dz[2];
+      }
+      int t = 0;
+#pragma unroll
+      for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int b = a; b < 6; b++) acc[t++] = Hz[a] * WH[b] + Hz[6 + a] * WH[6 + b] + Hz[12 + a] * WH[12 + b];
+#pragma unroll
+      for (int a = 0; a < 6; a++) acc[21 + a] = Hz[a] * Wdz[0] + Hz[6 + a] * Wdz[1] + Hz[12 + a] * Wdz[2];
+      acc[27] = 1.0;
     }
-    // R_noise = sigma1/(|idx1|-1) + sigma2/(|idx2|-1)   (:315)
-    const double d2 = (double)(nbin - 1);
-    double Rn[9];
-    {
-      double r6[6];
-      for (int k = 0; k < 6; k++) r6[k] = v.S1n[k] + cov[k] / d2;
-      Rn[0] = r6[0]; Rn[1] = r6[1]; Rn[2] = r6[2]; Rn[3] = r6[1]; Rn[4] = r6[3]; Rn[5] = r6[4];
-      Rn[6] = r6[2]; Rn[7] = r6[4]; Rn[8] = r6[5];
-    }
-    // M = (L U^T) R_noise (L U^T)^T   (:317)
-    double T[9], M[9];
-    for (int a = 0; a < 3; a++)
-      for (int b = 0; b < 3; b++) T[3 * a + b] = v.LV[3 * a] * Rn[b] + v.LV[3 * a + 1] * Rn[3 + b] + v.LV[3 * a + 2] * Rn[6 + b];
-    for (int a = 0; a < 3; a++)
-      for (int b = 0; b < 3; b++) M[3 * a + b] = T[3 * a] * v.LV[3 * b] + T[3 * a + 1] * v.LV[3 * b + 1] + T[3 * a + 2] * v.LV[3 * b + 2];
-    // W = pinv(M)  (:320-321)
-    double W[9];
-    if (!icet::masked_inv3(M, v.lmask, W)) icet::cod_pinv(M, 3, 3, W);
-    // H_z = L U^T [ -I | Jx mu | Jy mu | Jz mu ]  (:324-329)
-    double H[18];
-    for (int a = 0; a < 3; a++) {
-      H[6 * a + 0] = (a == 0) ? -1.0 : 0.0;
-      H[6 * a + 1] = (a == 1) ? -1.0 : 0.0;
-      H[6 * a + 2] = (a == 2) ? -1.0 : 0.0;
-      for (int j = 0; j < 3; j++)
-        H[6 * a + 3 + j] = (double)s_J[9 * j + 3 * a] * mean[0] + (double)s_J[9 * j + 3 * a + 1] * mean[1] +
-                           (double)s_J[9 * j + 3 * a + 2] * mean[2];
-    }
-    double Hz[18];
-    for (int a = 0; a < 3; a++)
-      for (int c = 0; c < 6; c++) Hz[6 * a + c] = v.LV[3 * a] * H[c] + v.LV[3 * a + 1] * H[6 + c] + v.LV[3 * a + 2] * H[12 + c];
-    // dz = L U^T (mean2 - mu1)   (:335-337)
-    double dm[3] = {mean[0] - v.mu[0], mean[1] - v.mu[1], mean[2] - v.mu[2]};
-    double dz[3];
-    for (int a = 0; a < 3; a++) dz[a] = v.LV[3 * a] * dm[0] + v.LV[3 * a + 1] * dm[1] + v.LV[3 * a + 2] * dm[2];
-    // WHz (3x6), Wdz (3)
-    double WH[18], Wdz[3];
-    for (int a = 0; a < 3; a++) {
-      for (int c = 0; c < 6; c++) WH[6 * a + c] = W[3 * a] * Hz[c] + W[3 * a + 1] * Hz[6 + c] + W[3 * a + 2] * Hz[12 + c];
-      Wdz[a] = W[3 * a] * dz[0] + W[3 * a + 1] * dz[1] + W[3 * a + 2] * dz[2];
-    }
-    int t = 0;
-    for (int a = 0; a < 6; a++)
-      for (int b = a; b < 6; b++) acc[t++] += Hz[a] * WH[b] + Hz[6 + a] * WH[6 + b] + Hz[12 + a] * WH[12 + b];
-    for (int a = 0; a < 6; a++) acc[21 + a] += Hz[a] * Wdz[0] + Hz[6 + a] * Wdz[1] + Hz[12 + a] * Wdz[2];
-    acc[27] += 1.0;
   }
-  // fixed-order reduction: lanes (xor butterfly), then warps in index order
+  // fixed-order reduction: xor butterfly inside each warp, then warp 1 + warp 0
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool any = __syncthreads_or(acc[27] != 0.0);
+  double* out = ck.part + ((size_t)pair * gridDim.x + blockIdx.x) * NRED;
+  if (!any) {  // block-uniform: nothing to add
+    if (threadIdx.x < NRED) out[threadIdx.x] = 0.0;
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < NRED; k++) {
     double vsum = acc[k];
+#pragma unroll
     for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(FULL, vsum, o);
-    if (lane == 0) s_red[wid][k] = vsum;
+    acc[k] = vsum;
+  }
+  if (wid == 1 && lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NRED; k++) s_red[k] = acc[k];
   }
   __syncthreads();
-  if (threadIdx.x != 0) return;
-  double tot[NRED];
-  for (int k = 0; k < NRED; k++) {
-    double s = 0.0;
-    for (int w = 0; w < SOLVE_THREADS / 32; w++) s += s_red[w][k];
-    tot[k] = s;
+  if (wid == 0 && lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NRED; k++) out[k] = acc[k] + s_red[k];
   }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K6: one warp per pair.  Sums the block partials in index order, then lane 0: Q = pinv(H^T W H),
+// pred_stds, checkCondition, dx, X += dx (src/icet.cpp:410-433, :443-492) and the transform / get_H
+// trigonometry of the next iteration.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_solve6(const Chunk ck, int iter, int nblk) {
+  const int pair = blockIdx.x;
+  const int lane = threadIdx.x;
+  double mine = 0.0;
+  if (lane < NRED) {
+    const double* pp = ck.part + (size_t)pair * nblk * NRED + lane;
+    for (int b = 0; b < nblk; b++) mine += pp[(size_t)b * NRED];
+  }
+  double tot[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; k++) tot[k] = __shfl_sync(FULL, mine, k);
+  if (lane != 0) return;
+  float* X = ck.X + pair * 6;
   double A[36], b[6];
   {
     int t = 0;
+#pragma unroll
     for (int a = 0; a < 6; a++)
+#pragma unroll
       for (int c = a; c < 6; c++) {
         A[a * 6 + c] = tot[t];
         A[c * 6 + a] = tot[t];
         t++;
       }
+#pragma unroll
     for (int a = 0; a < 6; a++) b[a] = tot[21 + a];
   }
   icet_b200_result* R = ck.res + pair;
   double Q[36], dx[6], stds[6];
   int dropped = 0, status = 0;
-  double cond_out;
+  double cond_out = 0.0;
   bool fast = false;
   if (!(ck.flags & ICET_B200_FLAG_FULL_EIG) && icet::chol_inv6(A, Q)) {
     double trA = 0.0, trQ = 0.0;
+#pragma unroll
     for (int k = 0; k < 6; k++) { trA += A[k * 6 + k]; trQ += Q[k * 6 + k]; }
     // cond <= trace(A) * trace(A^-1); comfortably below the 1e6 cutoff => no axis is dropped and
     // pinv == inverse, so dx = A^-1 b  (src/icet.cpp:410-433 with an empty while-loop at :469)
@@ -695,17 +793,32 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(const Chunk ck, int ite
     }
   }
   if (fast) {
+#pragma unroll
     for (int k = 0; k < 6; k++) {
       double s = 0.0;
+#pragma unroll
       for (int j = 0; j < 6; j++) s += Q[k * 6 + j] * b[j];
       dx[k] = s;
       stds[k] = sqrt(fabs(Q[k * 6 + k]));
     }
   } else {
-    icet::cod_pinv(A, 6, 6, Q);  // noise_mat (:410-411)
-    for (int k = 0; k < 6; k++) stds[k] = sqrt(fabs(Q[k * 6 + k]));
     double ev[6], U[36];
     icet::jacobi6(A, ev, U);
+    // noise_mat = pinv(H^T W H) (:410-411) from the eigen-decomposition, with the rank rule of the COD
+    // (pivot > FLT_EPSILON * 6 * largest pivot) applied to the spectrum
+    {
+      double lm = 0.0;
+      for (int k = 0; k < 6; k++) lm = fmax(lm, fabs(ev[k]));
+      const double thr = (double)FLT_EPSILON * 6.0 * lm;
+      for (int i = 0; i < 36; i++) Q[i] = 0.0;
+      for (int k = 0; k < 6; k++) {
+        if (!(fabs(ev[k]) > thr)) continue;
+        const double il = 1.0 / ev[k];
+        for (int i = 0; i < 6; i++)
+          for (int j = 0; j < 6; j++) Q[i * 6 + j] += U[i * 6 + k] * U[j * 6 + k] * il;
+      }
+    }
+    for (int k = 0; k < 6; k++) stds[k] = sqrt(fabs(Q[k * 6 + k]));
     const double cutoff = 1e6;
     double condition = ev[5] / ev[0];
     cond_out = condition;
@@ -731,6 +844,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(const Chunk ck, int ite
     }
   }
   for (int k = 0; k < 6; k++) X[k] = (float)((double)X[k] + dx[k]);  // X += dx (:433), X is fp32
+  {  // trigonometry of the next iteration: utils::R (src/icet.cpp:375-376) and get_H (:507-527)
+    float* TR = ck.TR + (size_t)pair * 12;
+    TR[0] = X[0]; TR[1] = X[1]; TR[2] = X[2];
+    icet::rotR(X[3], X[4], X[5], TR + 3);
+    icet::getH_J(X[3], X[4], X[5], ck.J + (size_t)pair * 27);
+  }
   if (ck.dump_on) {
     for (int k = 0; k < 6; k++) { ck.dump.Xit[iter * 6 + k] = X[k]; ck.dump.HTWdz[iter * 6 + k] = (float)b[k]; }
     for (int k = 0; k < 36; k++) ck.dump.HTWH[iter * 36 + k] = (float)A[k];
@@ -746,13 +865,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(const Chunk ck, int ite
 }
 
 // spherical coordinates + cell index of a cloud (parity-test entry point)
-__global__ void k_sph_bins(const float* s, int n, int ld, int nT, int nP, float* sph, int32_t* cell) {
+__global__ void k_sph_bins(const float* s, int n, int ld, int nT, int nP, icet::BinTable bth, icet::BinTable bph,
+                           float* sph, int32_t* cell) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float r, th, ph;
   icet::c2s(s[i], s[ld + i], s[2 * (size_t)ld + i], r, th, ph);
   int bt, bp;
-  icet::bin_of(th, ph, nT, nP, bt, bp);
+  bt = icet::bin_lookup(th, bth, 2 * M_PI);
+  bp = icet::bin_lookup(ph, bph, M_PI);
   sph[i] = r; sph[n + i] = th; sph[2 * (size_t)n + i] = ph;
   cell[i] = nT * bp + bt;
 }
@@ -813,6 +934,13 @@ struct icet_b200_ctx {
   int64_t launches = 0;
   int dump_on = 0;
   int sm_count = 148;
+  // per-kernel timing (icet_b200_set_profile): events around every launch, summed on request
+  int profile_on = 0;
+  std::vector<cudaEvent_t> prof_ev;   // pairs (begin, end)
+  std::vector<int> prof_id;
+  size_t prof_used = 0;
+  double prof_ms[ICET_B200_NKERNELS] = {0};
+  int64_t prof_n[ICET_B200_NKERNELS] = {0};
   // workspace
   DevBuf ws;        // one slab, carved per chunk
   DevBuf zero_ws;   // (part of ws) -- region that must be cleared per chunk is contiguous
@@ -866,31 +994,91 @@ size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, Chunk& ck
   ck.rbuf = c.take<float>((size_t)P * n1max);
   ck.pog = c.take<float>((size_t)P * 3 * n2max);
   ck.X = c.take<float>((size_t)P * 6);
+  ck.TR = c.take<float>((size_t)P * 12);
+  ck.J = c.take<float>((size_t)P * 27);
+  ck.part = c.take<double>((size_t)P * ((ncell + 63) / 64) * 28);
   return (c.off + 255) & ~(size_t)255;
 }
 
 int validate(const icet_b200_params* p) {
   if (!p) return fail(ICET_B200_E_INVALID, "params is NULL");
   if (p->runlen < 0 || p->runlen > 10000) return fail(ICET_B200_E_INVALID, "runlen out of range");
-  if (p->bins_phi < 1 || p->bins_theta < 1 || (long long)p->bins_phi * p->bins_theta > (1 << 20))
+  if (p->bins_phi < 1 || p->bins_theta < 1 || p->bins_phi + p->bins_theta > 4096 ||
+      (long long)p->bins_phi * p->bins_theta > (1 << 20))
     return fail(ICET_B200_E_INVALID, "bins_phi/bins_theta out of range");
   if (p->n < 1) return fail(ICET_B200_E_INVALID, "n must be >= 1");
   if (!(p->thresh >= 0.f) || !(p->buff >= 0.f)) return fail(ICET_B200_E_INVALID, "thresh/buff must be >= 0");
   return 0;
 }
 
+// smallest fp32 a >= 0 with int((double(a)/period)*nb) >= k  (binary search over the fp32 bit patterns,
+// which are ordered like the values for a >= 0)
+float bin_threshold(int k, double period, int nb) {
+  auto f = [&](float a) { return static_cast<int>(((double)a / period) * nb); };
+  uint32_t lo = 0, hi = 0x41000000u;  // +0.0f .. 8.0f
+  while (lo < hi) {
+    uint32_t mid = lo + (hi - lo) / 2;
+    float a;
+    memcpy(&a, &mid, 4);
+    if (f(a) >= k) hi = mid; else lo = mid + 1;
+  }
+  float a;
+  memcpy(&a, &lo, 4);
+  return a;
+}
+
+// device tables that depend only on the bin counts: fp32 box edges (src/icet.cpp:136-139) and the
+// exact bin-lookup thresholds (src/icet.cpp:545-546)
 int ensure_edges(icet_b200_ctx* ctx, int nT, int nP) {
   if (ctx->edges_nT == nT && ctx->edges_nP == nP) return 0;
-  std::vector<float> e((size_t)nT + 1 + nP + 1);
+  std::vector<float> e((size_t)2 * (nT + nP) + 6);
+  float* azE = e.data();
+  float* elE = azE + nT + 1;
+  float* Tth = elE + nP + 1;
+  float* Tph = Tth + nT + 2;
   // src/icet.cpp:136-139: float divide, double multiply, float store
-  for (int t = 0; t <= nT; t++) e[t] = (static_cast<float>(t) / nT) * (2 * M_PI);
-  for (int q = 0; q <= nP; q++) e[nT + 1 + q] = (static_cast<float>(q) / nP) * (M_PI);
+  for (int t = 0; t <= nT; t++) azE[t] = (static_cast<float>(t) / nT) * (2 * M_PI);
+  for (int q = 0; q <= nP; q++) elE[q] = (static_cast<float>(q) / nP) * (M_PI);
+  for (int k = 0; k <= nT; k++) Tth[k] = bin_threshold(k, 2 * M_PI, nT);
+  for (int k = 0; k <= nP; k++) Tph[k] = bin_threshold(k, M_PI, nP);
+  Tth[nT + 1] = INFINITY;
+  Tph[nP + 1] = INFINITY;
   int rc = ctx->edges.ensure(e.size() * sizeof(float));
   if (rc) return rc;
   CK(cudaMemcpyAsync(ctx->edges.p, e.data(), e.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->edges_nT = nT;
   ctx->edges_nP = nP;
+  return 0;
+}
+
+void fill_tables(icet_b200_ctx* ctx, int nT, int nP, const float** azE, const float** elE, icet::BinTable* bth,
+                 icet::BinTable* bph) {
+  const float* base = (const float*)ctx->edges.p;
+  *azE = base;
+  *elE = base + nT + 1;
+  bth->T = base + nT + 1 + nP + 1;
+  bth->nb = nT;
+  bth->scale = (float)((double)nT / (2 * M_PI));
+  bth->amax = (float)(2 * M_PI);
+  bph->T = bth->T + nT + 2;
+  bph->nb = nP;
+  bph->scale = (float)((double)nP / M_PI);
+  bph->amax = (float)M_PI;
+}
+
+int prof_events(icet_b200_ctx* ctx, int id, cudaEvent_t* e0, cudaEvent_t* e1) {
+  if (ctx->prof_used + 2 > ctx->prof_ev.size()) {
+    for (int k = 0; k < 2; k++) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return fail(ICET_B200_E_CUDA, "cudaEventCreate failed");
+      ctx->prof_ev.push_back(e);
+    }
+  }
+  *e0 = ctx->prof_ev[ctx->prof_used];
+  *e1 = ctx->prof_ev[ctx->prof_used + 1];
+  ctx->prof_used += 2;
+  ctx->prof_id.push_back(id);
   return 0;
 }
 
@@ -911,8 +1099,7 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   ck.npairs = P; ck.ncell = ncell; ck.nT = nT; ck.nP = nP; ck.n = p->n; ck.runlen = p->runlen;
   ck.flags = p->flags; ck.thresh = p->thresh; ck.buff = p->buff;
   ck.n1max = n1max; ck.n2max = n2max;
-  ck.azE = (const float*)ctx->edges.p;
-  ck.elE = ck.azE + nT + 1;
+  fill_tables(ctx, nT, nP, &ck.azE, &ck.elE, &ck.bth, &ck.bph);
   ck.x0 = d_x0;
   ck.res = d_res;
   ck.dump_on = dump ? 1 : 0;
@@ -920,21 +1107,38 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   cudaStream_t st = ctx->stream;
   CK(cudaMemsetAsync(ctx->ws.p, 0, zero_bytes, st));
   const dim3 g1((n1max + 255) / 256, P), g2((n2max + 255) / 256, P);
-  if (n1max > 0) { k_scan1_bin<<<g1, 256, 0, st>>>(ck); ctx->launches++; }
-  k_cell_scan<<<P, 256, 0, st>>>(ck); ctx->launches++;
+  const int nblk = (ncell + VOX_THREADS - 1) / VOX_THREADS;
+  const int tile = PASS_THREADS * PASS_PPT;
+  const dim3 gp1((n1max + tile - 1) / tile, P), gp2((n2max + tile - 1) / tile, P);
+  // LAUNCH(id, kernel<<<...>>>(...)): counts the launch and, when profiling, brackets it with events
+#define LAUNCH(id, ...)                                                   \
+  do {                                                                    \
+    cudaEvent_t e0_ = nullptr, e1_ = nullptr;                             \
+    if (ctx->profile_on) {                                                \
+      if (prof_events(ctx, id, &e0_, &e1_)) return ICET_B200_E_CUDA;      \
+      cudaEventRecord(e0_, st);                                           \
+    }                                                                     \
+    __VA_ARGS__;                                                          \
+    if (e1_) cudaEventRecord(e1_, st);                                    \
+    ctx->launches++;                                                      \
+  } while (0)
+  if (n1max > 0) LAUNCH(0, k_scan1_bin<<<g1, 256, 0, st>>>(ck));
+  LAUNCH(1, k_cell_scan<<<P, 256, 0, st>>>(ck));
   if (n1max > 0) {
-    k_scatter<<<g1, 256, 0, st>>>(ck); ctx->launches++;
+    LAUNCH(2, k_scatter<<<g1, 256, 0, st>>>(ck));
     // enough CTAs to cover a typical work list (~25 % of the cells) in one pass; the kernel loops
     int gx = std::max(1, std::min(ncell, std::max(64, (ctx->sm_count * 16 + P - 1) / P)));
-    k_cluster<<<dim3(gx, P), 128, 0, st>>>(ck); ctx->launches++;
-    k_pass<false><<<g1, 256, 0, st>>>(ck); ctx->launches++;
+    LAUNCH(3, k_cluster<<<dim3(gx, P), 128, 0, st>>>(ck));
+    LAUNCH(4, k_pass<false><<<gp1, PASS_THREADS, pass_smem_bytes(nT, nP), st>>>(ck));
   }
-  k_fit1<<<dim3((ncell + 127) / 128, P), 128, 0, st>>>(ck); ctx->launches++;
-  if (n2max > 0) { k_prep2<<<g2, 256, 0, st>>>(ck); ctx->launches++; }
+  LAUNCH(5, k_fit1<<<dim3((ncell + 127) / 128, P), 128, 0, st>>>(ck));
+  if (n2max > 0) LAUNCH(6, k_prep2<<<g2, 256, 0, st>>>(ck));
   for (int it = 0; it < p->runlen; it++) {
-    if (n2max > 0) { k_pass<true><<<g2, 256, 0, st>>>(ck); ctx->launches++; }
-    k_solve<<<P, SOLVE_THREADS, 0, st>>>(ck, it); ctx->launches++;
+    if (n2max > 0) LAUNCH(7, k_pass<true><<<gp2, PASS_THREADS, pass_smem_bytes(nT, nP), st>>>(ck));
+    LAUNCH(8, k_vox2<<<dim3(nblk, P), VOX_THREADS, 0, st>>>(ck, it));
+    LAUNCH(9, k_solve6<<<P, 32, 0, st>>>(ck, it, nblk));
   }
+#undef LAUNCH
   CK(cudaGetLastError());
   return 0;
 }
@@ -1025,6 +1229,7 @@ int icet_b200_destroy(icet_b200_ctx* c) {
     if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
     if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
   }
+  for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -1057,6 +1262,44 @@ int icet_b200_synchronize(icet_b200_ctx* c) {
 }
 
 int64_t icet_b200_kernel_launches(icet_b200_ctx* c) { return c ? c->launches : 0; }
+
+static const char* const k_names[ICET_B200_NKERNELS] = {"k_scan1_bin", "k_cell_scan", "k_scatter", "k_cluster",
+                                                        "k_pass<scan1>", "k_fit1", "k_prep2", "k_pass<scan2>",
+                                                        "k_vox2", "k_solve6"};
+const char* icet_b200_kernel_name(int id) { return (id >= 0 && id < ICET_B200_NKERNELS) ? k_names[id] : ""; }
+
+static int prof_collect(icet_b200_ctx* c) {
+  CK(cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i < c->prof_id.size(); i++) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]));
+    c->prof_ms[c->prof_id[i]] += ms;
+    c->prof_n[c->prof_id[i]]++;
+  }
+  c->prof_id.clear();
+  c->prof_used = 0;
+  return 0;
+}
+
+int icet_b200_set_profile(icet_b200_ctx* c, int32_t enable) {
+  if (!c) return fail(ICET_B200_E_INVALID, "ctx is NULL");
+  CK(cudaSetDevice(c->device));
+  int rc = prof_collect(c);
+  if (rc) return rc;
+  if (enable && !c->profile_on)
+    for (int k = 0; k < ICET_B200_NKERNELS; k++) { c->prof_ms[k] = 0.0; c->prof_n[k] = 0; }
+  c->profile_on = enable ? 1 : 0;
+  return 0;
+}
+
+int icet_b200_get_profile(icet_b200_ctx* c, double* ms, int64_t* launches) {
+  if (!c || !ms || !launches) return fail(ICET_B200_E_INVALID, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  int rc = prof_collect(c);
+  if (rc) return rc;
+  for (int k = 0; k < ICET_B200_NKERNELS; k++) { ms[k] = c->prof_ms[k]; launches[k] = c->prof_n[k]; }
+  return 0;
+}
 
 int icet_b200_set_dump(icet_b200_ctx* c, int32_t enable) {
   if (!c) return fail(ICET_B200_E_INVALID, "ctx is NULL");
@@ -1293,7 +1536,12 @@ int icet_b200_spherical_bins(icet_b200_ctx* c, const icet_b200_params* p, const 
   float* d_sph = d_s + (size_t)3 * ld;
   int32_t* d_cell = (int32_t*)(d_sph + (size_t)3 * n);
   CK(cudaMemcpyAsync(d_s, scan, (size_t)3 * ld * 4, cudaMemcpyHostToDevice, c->stream));
-  k_sph_bins<<<(n + 255) / 256, 256, 0, c->stream>>>(d_s, n, ld, p->bins_theta, p->bins_phi, d_sph, d_cell);
+  rc = ensure_edges(c, p->bins_theta, p->bins_phi);
+  if (rc) return rc;
+  const float *azE, *elE;
+  icet::BinTable bth, bph;
+  fill_tables(c, p->bins_theta, p->bins_phi, &azE, &elE, &bth, &bph);
+  k_sph_bins<<<(n + 255) / 256, 256, 0, c->stream>>>(d_s, n, ld, p->bins_theta, p->bins_phi, bth, bph, d_sph, d_cell);
   c->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(sph, d_sph, (size_t)3 * n * 4, cudaMemcpyDeviceToHost, c->stream));

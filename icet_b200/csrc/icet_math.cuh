@@ -41,10 +41,33 @@ __device__ __forceinline__ void s2c(float r, float th, float ph, float& x, float
   z = __fmul_rn(r, cp);
 }
 
-// bin indices, ICET::sortSphericalCoordinates reference src/icet.cpp:545-546 (double math)
-__device__ __forceinline__ void bin_of(float th, float ph, int nT, int nP, int& bt, int& bp) {
-  bt = static_cast<int>(((double)th / (2 * M_PI)) * nT) % nT;
-  bp = static_cast<int>(((double)ph / M_PI) * nP) % nP;
+// bin indices, ICET::sortSphericalCoordinates reference src/icet.cpp:545-546:
+//     int((theta / (2*M_PI)) * numBinsTheta) % numBinsTheta     (double math on the fp32 angle)
+__device__ __forceinline__ int bin_formula(float a, double period, int nb) {
+  return static_cast<int>(((double)a / period) * nb) % nb;
+}
+// Exact table form of the same function.  f(a) = int((double(a)/period)*nb) is a non-decreasing step
+// function of the fp32 angle, so it is fully described by T[k] = the smallest fp32 a >= 0 with
+// f(a) >= k (k = 0..nb, computed on the host with the very same double expression; T[nb+1] = +inf).
+// An fp32 estimate of the bin is corrected by at most one step against T.  Angles beyond `amax`
+// (only the NaN sentinel 1000.0) take the formula.
+struct BinTable {
+  const float* T;  // nb + 2 entries
+  float scale;     // fp32(nb / period)
+  float amax;      // fp32(period): the largest angle the table covers
+  int nb;
+};
+// T may point to global or shared memory (the call is inlined, the address space is known statically)
+__device__ __forceinline__ int bin_lookup(float a, const float* T, float scale, float amax, int nb, double period) {
+  if (!(a <= amax) || a < 0.f) return bin_formula(a, period, nb);
+  int k = __float2int_rz(a * scale);
+  k = min(max(k, 0), nb);
+  if (a < T[k]) k--;
+  else if (a >= T[k + 1]) k++;
+  return k == nb ? 0 : k;
+}
+__device__ __forceinline__ int bin_lookup(float a, const BinTable& t, double period) {
+  return bin_lookup(a, t.T, t.scale, t.amax, t.nb, period);
 }
 
 // utils::R, reference src/utils.cpp:144-152 (row-major, fp32 trig on fp32 angles)
@@ -255,7 +278,7 @@ __device__ inline void make_householder(double* v, int len, int stride, double& 
   }
 }
 
-__device__ inline int cod_pinv(const double* A, int rows, int cols, double* P) {
+__device__ __noinline__ int cod_pinv(const double* A, int rows, int cols, double* P) {
   const int size = rows < cols ? rows : cols;
   const double eps_rank = (double)FLT_EPSILON;
   double qr[36], hC[6], cnU[6], cnD[6], zC[6];
@@ -420,7 +443,7 @@ __device__ inline bool masked_inv3(const double M[9], int mask, double W[9]) {
     double ia = d / det, ib = -b / det, id = a / det;
     tr = a + d;
     tri = ia + id;
-    if (!(tr * tri < 1e5)) return false;
+    if (!(tr * tri < 5e5)) return false;  // cond < 5e5: far from the COD rank threshold (pivot ratio 3.6e-7)
     W[idx[0] * 3 + idx[0]] = ia;
     W[idx[0] * 3 + idx[1]] = ib;
     W[idx[1] * 3 + idx[0]] = ib;
@@ -443,36 +466,49 @@ __device__ inline bool masked_inv3(const double M[9], int mask, double W[9]) {
 }
 
 // Cholesky-based inverse of a symmetric 6x6 (row-major).  Returns false if not positive definite.
-__device__ inline bool chol_inv6(const double* A, double* Ainv) {
+// Every loop has compile-time bounds and is fully unrolled so that G / Gi live in registers
+// (the routine runs on ONE thread per pair and sits on the critical path of every iteration).
+__device__ __forceinline__ bool chol_inv6(const double* __restrict__ A, double* __restrict__ Ainv) {
   double G[36];
-  for (int i = 0; i < 36; i++) G[i] = 0.0;
+  bool ok = true;
+#pragma unroll
   for (int j = 0; j < 6; j++) {
     double s = A[j * 6 + j];
+#pragma unroll
     for (int k = 0; k < j; k++) s -= G[j * 6 + k] * G[j * 6 + k];
-    if (!(s > 0.0)) return false;
-    double g = sqrt(s);
+    ok = ok && (s > 0.0);
+    const double g = sqrt(s);
+    const double ig = 1.0 / g;
     G[j * 6 + j] = g;
+#pragma unroll
     for (int i = j + 1; i < 6; i++) {
       double t = A[i * 6 + j];
+#pragma unroll
       for (int k = 0; k < j; k++) t -= G[i * 6 + k] * G[j * 6 + k];
-      G[i * 6 + j] = t / g;
+      G[i * 6 + j] = t * ig;
     }
   }
-  // invert the lower-triangular G in place -> Gi
+  if (!ok) return false;
+  // Gi = G^-1 (lower triangular)
   double Gi[36];
-  for (int i = 0; i < 36; i++) Gi[i] = 0.0;
+#pragma unroll
   for (int j = 0; j < 6; j++) {
     Gi[j * 6 + j] = 1.0 / G[j * 6 + j];
+#pragma unroll
     for (int i = j + 1; i < 6; i++) {
       double t = 0.0;
+#pragma unroll
       for (int k = j; k < i; k++) t -= G[i * 6 + k] * Gi[k * 6 + j];
       Gi[i * 6 + j] = t / G[i * 6 + i];
     }
   }
   // Ainv = Gi^T Gi
+#pragma unroll
   for (int i = 0; i < 6; i++)
+#pragma unroll
     for (int j = 0; j <= i; j++) {
       double t = 0.0;
+#pragma unroll
       for (int k = i; k < 6; k++) t += Gi[k * 6 + i] * Gi[k * 6 + j];
       Ainv[i * 6 + j] = t;
       Ainv[j * 6 + i] = t;
@@ -484,64 +520,95 @@ __device__ inline bool chol_inv6(const double* A, double* Ainv) {
 // U row-major with columns = eigenvectors.  Stands in for SelfAdjointEigenSolver<MatrixXf>
 // at reference src/icet.cpp:455-458 (only eigenvalues and sign-independent combinations of the
 // eigenvectors reach X; see DESIGN.md for the :479 inflation term).
-__device__ inline void jacobi6(const double* Ain, double* ev, double* U) {
-  double A[36];
+// All matrix indices are compile-time constants after unrolling, so A and U live in registers;
+// the routine is kept out of line because it runs only when the cheap condition bound fails.
+__device__ __noinline__ void jacobi6(const double* __restrict__ Ain, double* __restrict__ ev_out,
+                                     double* __restrict__ U_out) {
+  double A[36], U[36];
+#pragma unroll
   for (int i = 0; i < 36; i++) {
     A[i] = Ain[i];
     U[i] = 0.0;
   }
+#pragma unroll
   for (int i = 0; i < 6; i++) U[i * 6 + i] = 1.0;
-  for (int sweep = 0; sweep < 30; sweep++) {
+#pragma unroll 1
+  for (int sweep = 0; sweep < 24; sweep++) {
     double off = 0.0, dg = 0.0;
+#pragma unroll
     for (int i = 0; i < 6; i++) {
       dg += A[i * 6 + i] * A[i * 6 + i];
+#pragma unroll
       for (int j = i + 1; j < 6; j++) off += A[i * 6 + j] * A[i * 6 + j];
     }
-    if (off <= 1e-30 * dg || off == 0.0) break;
-    for (int p = 0; p < 5; p++)
+    if (!(off > 1e-34 * dg)) break;
+#pragma unroll
+    for (int p = 0; p < 5; p++) {
+#pragma unroll
       for (int q = p + 1; q < 6; q++) {
-        double apq = A[p * 6 + q];
-        if (apq == 0.0) continue;
-        double theta = (A[q * 6 + q] - A[p * 6 + p]) / (2.0 * apq);
-        double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-        for (int k = 0; k < 6; k++) {
-          double akp = A[k * 6 + p], akq = A[k * 6 + q];
-          A[k * 6 + p] = c * akp - s * akq;
-          A[k * 6 + q] = s * akp + c * akq;
-        }
-        for (int k = 0; k < 6; k++) {
-          double apk = A[p * 6 + k], aqk = A[q * 6 + k];
-          A[p * 6 + k] = c * apk - s * aqk;
-          A[q * 6 + k] = s * apk + c * aqk;
-        }
-        for (int k = 0; k < 6; k++) {
-          double ukp = U[k * 6 + p], ukq = U[k * 6 + q];
-          U[k * 6 + p] = c * ukp - s * ukq;
-          U[k * 6 + q] = s * ukp + c * ukq;
+        const double apq = A[p * 6 + q];
+        if (apq != 0.0) {
+          const double theta = (A[q * 6 + q] - A[p * 6 + p]) / (2.0 * apq);
+          const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+#pragma unroll
+          for (int k = 0; k < 6; k++) {
+            const double akp = A[k * 6 + p], akq = A[k * 6 + q];
+            A[k * 6 + p] = c * akp - sn * akq;
+            A[k * 6 + q] = sn * akp + c * akq;
+          }
+#pragma unroll
+          for (int k = 0; k < 6; k++) {
+            const double apk = A[p * 6 + k], aqk = A[q * 6 + k];
+            A[p * 6 + k] = c * apk - sn * aqk;
+            A[q * 6 + k] = sn * apk + c * aqk;
+          }
+#pragma unroll
+          for (int k = 0; k < 6; k++) {
+            const double ukp = U[k * 6 + p], ukq = U[k * 6 + q];
+            U[k * 6 + p] = c * ukp - sn * ukq;
+            U[k * 6 + q] = sn * ukp + c * ukq;
+          }
         }
       }
+    }
   }
+  double ev[6];
+#pragma unroll
   for (int i = 0; i < 6; i++) ev[i] = A[i * 6 + i];
+  // ascending selection sort (static indices: compare-exchange network over all pairs)
+#pragma unroll
   for (int i = 0; i < 5; i++) {
-    int k = i;
-    for (int j = i + 1; j < 6; j++)
-      if (ev[j] < ev[k]) k = j;
-    if (k != i) {
-      double t = ev[i]; ev[i] = ev[k]; ev[k] = t;
-      for (int r = 0; r < 6; r++) {
-        double u = U[r * 6 + i]; U[r * 6 + i] = U[r * 6 + k]; U[r * 6 + k] = u;
+#pragma unroll
+    for (int j = i + 1; j < 6; j++) {
+      if (ev[j] < ev[i]) {
+        const double t = ev[i]; ev[i] = ev[j]; ev[j] = t;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+          const double u = U[r * 6 + i]; U[r * 6 + i] = U[r * 6 + j]; U[r * 6 + j] = u;
+        }
       }
     }
   }
   // sign convention (the reference's is an artefact of Eigen's QR): largest component positive
+#pragma unroll
   for (int c = 0; c < 6; c++) {
-    int im = 0;
+    double best = U[c], mag = fabs(U[c]);
+#pragma unroll
     for (int r = 1; r < 6; r++)
-      if (fabs(U[r * 6 + c]) > fabs(U[im * 6 + c])) im = r;
-    if (U[im * 6 + c] < 0.0)
+      if (fabs(U[r * 6 + c]) > mag) {
+        mag = fabs(U[r * 6 + c]);
+        best = U[r * 6 + c];
+      }
+    if (best < 0.0) {
+#pragma unroll
       for (int r = 0; r < 6; r++) U[r * 6 + c] = -U[r * 6 + c];
+    }
   }
+#pragma unroll
+  for (int i = 0; i < 6; i++) ev_out[i] = ev[i];
+#pragma unroll
+  for (int i = 0; i < 36; i++) U_out[i] = U[i];
 }
 
 }  // namespace icet

@@ -1,7 +1,7 @@
 // icet_b200/csrc/synth.h -- deterministic synthetic 64-channel LiDAR scans (bench / test utility).
 //
 // Not part of the reference; it realises the synthetic workload SURVEY.md 8(d) / BASELINE.md 2
-// specify: a spinning LiDAR (rings linearly spaced in +-22.5 deg elevation, `azim` azimuth steps)
+// specify: a spinning LiDAR (ring centres linearly spaced inside +-22.5 deg elevation, `azim` azimuth steps)
 // driving along a street canyon (ground plane z = -1.8 m, side walls |y| = 8..15 m piecewise constant
 // in x, boxes and vertical cylinders hashed per 20 m tile), max range 120 m, 10 % dropped returns
 // stored as (0,0,0), range noise N(0, 0.01 m).  Every quantity is a pure function of
@@ -162,7 +162,9 @@ SYNTH_HD inline double cast(uint64_t seed, const double o[3], const double dir[3
 SYNTH_HD inline void ray(uint64_t seed, int k, const Pose& P, int ring, int rings, int az, int azim,
                          float& x, float& y, float& z) {
   const double deg = 0.017453292519943295;
-  double elev = (rings > 1) ? (-22.5 + 45.0 * (double)ring / (double)(rings - 1)) * deg : 0.0;
+  // ring centres of `rings` equal slices of [-22.5, +22.5] deg: no ring sits exactly on an elevation-bin
+  // edge of a (multiple of 24)-bin grid, which would turn a whole ring into "1-ulp edge points"
+  double elev = (-22.5 + 45.0 * ((double)ring + 0.5) / (double)rings) * deg;
   double azr = 6.283185307179586 * (double)az / (double)azim;
   double ds[3] = {cos(elev) * cos(azr), cos(elev) * sin(azr), sin(elev)};
   double dw[3];

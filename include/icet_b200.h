@@ -163,6 +163,14 @@ int icet_b200_synth_scans_device(icet_b200_ctx* ctx, uint64_t seed, int32_t firs
 /* Number of kernels this library has launched on the context since creation. */
 int64_t icet_b200_kernel_launches(icet_b200_ctx* ctx);
 
+/* Per-kernel device time: when enabled every kernel launch is bracketed by CUDA events on the context's
+ * stream (small overhead -- use a separate pass, not the throughput measurement).  Enabling resets the
+ * sums.  get_profile synchronises and returns, per kernel id, the summed milliseconds and launch count. */
+#define ICET_B200_NKERNELS 10
+int icet_b200_set_profile(icet_b200_ctx* ctx, int32_t enable);
+int icet_b200_get_profile(icet_b200_ctx* ctx, double ms[ICET_B200_NKERNELS], int64_t launches[ICET_B200_NKERNELS]);
+const char* icet_b200_kernel_name(int id);
+
 #ifdef __cplusplus
 }
 #endif
