@@ -176,7 +176,7 @@ def main():
     import torch.distributed as dist
 
     import icet_b200
-    from icet_b200 import api
+    from icet_b200 import api, sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- icet_b200 has no CPU fallback")
@@ -194,17 +194,19 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     params = api.make_params(RUNLEN, BINS_PHI, BINS_THETA, NMIN, THRESH, BUFF)
 
-    # synthetic sequence shard of this rank: scans [rank*P, rank*P + P], generated on the device
+    # synthetic sequence shard of this rank (contiguous pair range of the world*P-pair sequence), generated
+    # on the device
+    first_scan, nscans = sharding.shard_scans(world * P, rank, world)
+    assert nscans == P + 1
     scans = torch.empty((P + 1, 3, NPTS), dtype=torch.float32, device=dev)
-    ctx.synth_scans_device(scans.data_ptr(), P + 1, first_scan=rank * P, seed=SEED, rings=RINGS, azim=AZIM)
+    ctx.synth_scans_device(scans.data_ptr(), P + 1, first_scan=first_scan, seed=SEED, rings=RINGS, azim=AZIM)
     results = torch.zeros((P, 56), dtype=torch.float32, device=dev)
-    gathered = torch.zeros((world * P, 48), dtype=torch.float32, device=dev) if world > 1 else None
     torch.cuda.synchronize()
 
     def step():
         ctx.register_sequence_device(scans.data_ptr(), P + 1, NPTS, results.data_ptr(), params)
-        if world > 1:  # final gather of poses + covariances (X 6 | pred_stds 6 | Q 36)
-            dist.all_gather_into_tensor(gathered, results[:, :48].contiguous())
+        # final gather of poses + covariances (X 6 | pred_stds 6 | Q 36); no-op on one GPU
+        return sharding.gather_results(results[:, :48], world)
 
     def barrier():
         if world > 1:

@@ -789,6 +789,8 @@ struct Icet {
         float A[9], ev[3];
         for (int i = 0; i < 9; i++) A[i] = (float)cov[i];
         eig3<float>(A, P.eigen_flavor, ev, v.V);
+        if (out->evec1_in && out->evec1_in_mask && out->evec1_in_mask[cell])  // test-harness injection
+          for (int i = 0; i < 9; i++) v.V[i] = out->evec1_in[9 * cell + i];
         // sigma points :187-202: rotated = 2*sqrt(diag(ev)) * U^T = rows of (2 sqrt(ev_k)) V.row(k)
         float mu[3] = {(float)mean[0], (float)mean[1], (float)mean[2]};
         float sp[6][3];

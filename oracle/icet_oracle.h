@@ -89,6 +89,13 @@ typedef struct {
   float* points2_final;     /* [3*n2] public member points2 (src/icet.cpp:377-378 of the last
                                iteration), in the oracle's permuted row order, column-major           */
   int32_t* perm2;           /* [n2] original index of each permuted scan-2 row                         */
+
+  /* INPUT (optional, test harness only): eigenvector injection.  The signs Eigen's QR gives the 3x3
+   * eigenvectors flip under 1e-6-relative perturbations of the covariance for some voxels,
+   * so two correct implementations can disagree there.  For cells with evec1_in_mask[cell] != 0 the
+   * oracle uses evec1_in[cell*9..] (row-major V) instead of its own eigenvectors; eigenvalues stay.  */
+  const float* evec1_in;
+  const uint8_t* evec1_in_mask;
 } oracle_out;
 
 /* Clouds are column-major N x 3 (x-plane | y-plane | z-plane) with leading

@@ -61,7 +61,8 @@ _BIG = {"sph1", "cell1", "sph2", "cell2", "points2_final", "perm2"}
 
 class _Out(C.Structure):
     _fields_ = ([("X", C.c_float * 6), ("pred_stds", C.c_float * 6), ("Q", C.c_float * 36),
-                 ("status", C.c_int32)] + [(n, t) for n, t, _, _ in _DUMPS])
+                 ("status", C.c_int32)] + [(n, t) for n, t, _, _ in _DUMPS] +
+                [("evec1_in", _FP), ("evec1_in_mask", _BP)])
 
 
 def _build(native: bool) -> str:
@@ -138,7 +139,7 @@ class OracleResult:
 
 def run(scan1, scan2, runlen=7, X0=None, bins_phi=24, bins_theta=75, n=25, thresh=0.1, buff=0.1,
         order_mode=ORDER_SORTED, eigen_flavor=EIGEN_337, precise=False, dumps="small",
-        native=False) -> OracleResult:
+        native=False, evec_override=None) -> OracleResult:
     """Mirror of the reference constructor  ICET(scan1, scan2, runlen, X0, num_bins_phi,
     num_bins_theta, n, thresh, buff)  (include/icet.h:38-40).  dumps: None | "small" | "all"."""
     s1, s2 = as_planes(scan1), as_planes(scan2)
@@ -154,6 +155,12 @@ def run(scan1, scan2, runlen=7, X0=None, bins_phi=24, bins_theta=75, n=25, thres
             continue
         arrays[name] = np.zeros(shp(dims), dt)
         setattr(o, name, arrays[name].ctypes.data_as(ct))
+    if evec_override is not None:  # (evec [ncell,3,3] float32, mask [ncell] uint8): see icet_oracle.h
+        ev_in = np.ascontiguousarray(evec_override[0], np.float32)
+        ev_mask = np.ascontiguousarray(evec_override[1], np.uint8)
+        assert ev_in.size == 9 * dims["ncell"] and ev_mask.size == dims["ncell"]
+        o.evec1_in = ev_in.ctypes.data_as(_FP)
+        o.evec1_in_mask = ev_mask.ctypes.data_as(_BP)
     rc = lib(native).icet_oracle_run(C.byref(p), _fp(s1), n1, n1, _fp(s2), n2, n2, _fp(x0),
                                      C.byref(o))
     if rc != 0:

@@ -1,0 +1,148 @@
+"""CPU tests of the host side: the C ABI library builds, loads and exports every symbol include/icet_b200.h
+declares (no compute without a GPU), fails loudly without a device, the host-side layout helpers, the
+synthetic generator, pair sharding over world_size-2 gloo, and the reference arm of bench.py."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    import icet_b200
+    from icet_b200 import api
+    icet_b200.build()
+    hdr = open(os.path.join(ROOT, "include", "icet_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(icet_b200_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 18
+    L = icet_b200.load_library()
+    for name in declared:
+        assert hasattr(L, name), "missing export " + name
+    assert sorted(api.EXPORTS) == declared
+    assert L.icet_b200_version() == 100
+    assert C.sizeof(api.Result) == 224 and C.sizeof(api.Params) == 32
+    m = re.search(r"#define ICET_B200_NKERNELS (\d+)", hdr)
+    assert int(m.group(1)) == api.NKERNELS
+    assert L.icet_b200_kernel_name(7).decode() == "k_pass<scan2>"
+
+
+def test_library_links_no_cpu_fallback():
+    """The product library contains device code for sm_100a only and does not link the oracle."""
+    import icet_b200
+    lib = icet_b200.lib_path()
+    out = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+    ldd = subprocess.run(["ldd", lib], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd
+    src = open(os.path.join(ROOT, "icet_b200", "csrc", "icet_b200.cu")).read() + \
+        open(os.path.join(ROOT, "icet_b200", "api.py")).read()
+    assert "pyoracle" not in src and "icet_oracle" not in src  # the product never references the checker
+
+
+def test_no_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import icet_b200
+    with pytest.raises(icet_b200.IcetError) as e:
+        icet_b200.Context(0)
+    assert "no CPU fallback" in str(e.value)
+    L = icet_b200.load_library()
+    assert L.icet_b200_register(None, None, None, 0, 0, None, 0, 0, None, None) < 0
+    assert b"NULL" in L.icet_b200_last_error()
+
+
+def test_as_planes_layouts():
+    from icet_b200.api import as_planes
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((50, 3))
+    p = as_planes(a)
+    assert p.shape == (3, 50) and p.dtype == np.float32 and p.flags["C_CONTIGUOUS"]
+    np.testing.assert_array_equal(p, a.T.astype(np.float32))
+    np.testing.assert_array_equal(as_planes(np.asfortranarray(a)), p)     # Eigen's column-major N x 3
+    np.testing.assert_array_equal(as_planes(a.T.copy()), p)               # already planes
+    with pytest.raises(ValueError):
+        as_planes(np.zeros((4, 5)))
+
+
+def test_synth_host_generator_properties():
+    from tools import synth_host
+    S = synth_host.scans(2, rings=16, azim=256)
+    assert S.shape == (2, 3, 4096) and S.dtype == np.float32
+    S2 = synth_host.scans(2, rings=16, azim=256, nthreads=1)
+    np.testing.assert_array_equal(S, S2)                      # pure function of (seed, scan, ring, azimuth)
+    np.testing.assert_array_equal(synth_host.scans(1, first_scan=1, rings=16, azim=256)[0], S[1])
+    r = np.linalg.norm(S[0], axis=0)
+    zero = (r == 0)
+    assert 0.08 < zero.mean() < 0.35                          # dropped / no-hit returns are stored as (0,0,0)
+    assert r[~zero].min() > 0.25 and r.max() <= 120.5
+    el = np.degrees(np.arcsin(S[0, 2, ~zero] / r[~zero]))
+    assert el.min() > -22.6 and el.max() < 22.6
+    assert not np.array_equal(S[0], S[1])
+
+
+def test_shard_ranges_cover_all_pairs():
+    from icet_b200.sharding import shard_range, shard_scans
+    for total in (0, 1, 7, 4096):
+        for world in (1, 2, 3, 8):
+            got = []
+            for r in range(world):
+                lo, hi = shard_range(total, r, world)
+                got += list(range(lo, hi))
+                fs, ns = shard_scans(total, r, world)
+                assert (ns == 0) if hi == lo else (fs == lo and ns == hi - lo + 1)
+            assert got == list(range(total))
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, %r)
+import torch, torch.distributed as dist
+from icet_b200 import sharding
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+P = 6
+lo, hi = sharding.shard_range(world * P, rank, world)
+local = torch.zeros((P, 48))
+local[:, 0] = torch.arange(lo, hi, dtype=torch.float32)      # stand-in for X[0] of pair k: its global index
+local[:, 1] = float(rank)
+out = sharding.gather_results(local, world)
+assert out.shape == (world * P, 48)
+assert torch.equal(out[:, 0], torch.arange(world * P, dtype=torch.float32)), out[:, 0]
+assert torch.equal(out[:, 1], torch.arange(world).repeat_interleave(P).float())
+dist.barrier()
+if rank == 0:
+    print("GLOO_OK", world)
+dist.destroy_process_group()
+"""
+
+
+def test_pair_sharding_world2_gloo(tmp_path):
+    """N > 1 host path on CPU: contiguous pair ranges + the final all_gather keep the global pair order."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "GLOO_OK 2" in r.stdout
+
+
+def test_bench_reference_arm_runs():
+    """`bench.py --impl reference` times the CPU restatement on the host cores and prints one JSON line."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
