@@ -47,7 +47,7 @@ class _Dump(C.Structure):
 EXPORTS = ["icet_b200_version", "icet_b200_last_error", "icet_b200_create", "icet_b200_destroy",
            "icet_b200_set_stream", "icet_b200_set_chunk", "icet_b200_register", "icet_b200_register_batch",
            "icet_b200_register_batch_device", "icet_b200_register_sequence_device", "icet_b200_synchronize",
-           "icet_b200_set_dump", "icet_b200_get_dump", "icet_b200_spherical_bins",
+           "icet_b200_set_dump", "icet_b200_get_dump", "icet_b200_get_points2", "icet_b200_spherical_bins",
            "icet_b200_synth_scans_device", "icet_b200_kernel_launches", "icet_b200_set_profile",
            "icet_b200_get_profile", "icet_b200_kernel_name"]
 NKERNELS = 10
@@ -84,6 +84,7 @@ def load_library() -> C.CDLL:
     L.icet_b200_synchronize.argtypes = [vp]
     L.icet_b200_set_dump.argtypes = [vp, C.c_int32]
     L.icet_b200_get_dump.argtypes = [vp, C.POINTER(_Dump)]
+    L.icet_b200_get_points2.argtypes = [vp, vp, C.c_int32]
     L.icet_b200_spherical_bins.argtypes = [vp, C.POINTER(Params), vp, C.c_int32, C.c_int32, vp, vp]
     L.icet_b200_synth_scans_device.argtypes = [vp, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     L.icet_b200_kernel_launches.argtypes = [vp]
@@ -233,6 +234,12 @@ class Context:
         self._check(self._L.icet_b200_spherical_bins(self._h, C.byref(p), s.ctypes.data, n, n, sph.ctypes.data,
                                                      cell.ctypes.data))
         return sph, cell
+
+    def get_points2(self, n2: int) -> np.ndarray:
+        """[3, n2] planes: the reference's public `points2` member of the last `register` call."""
+        out = np.zeros((3, n2), np.float32)
+        self._check(self._L.icet_b200_get_points2(self._h, out.ctypes.data, n2))
+        return out
 
     def get_dump(self, p: Params) -> dict:
         ncell, rl = p.bins_phi * p.bins_theta, p.runlen

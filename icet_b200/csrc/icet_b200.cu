@@ -96,6 +96,7 @@ struct Chunk {  // everything a kernel needs, passed by value
   const float* elE;  // [nP+1] float elevation bin edges (src/icet.cpp:138-139)
   icet::BinTable bth, bph;  // exact bin lookup tables (src/icet.cpp:545-546)
   float* TR;         // [P][12] translation (3) and rotation R(X) (9) of the current iteration
+  float* TRprev;     // [P][12] transform the LAST iteration used (the reference's public `points2`)
   float* J;          // [P][27] get_H derivative matrices Jx | Jy | Jz of the current iteration
   double* part;      // [P][nblk][NRED] per-block partial sums of the voxel contributions
   // scan 2
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(256) k_cell_scan(const Chunk ck) {
       TR[0] = X[0]; TR[1] = X[1]; TR[2] = X[2];
       icet::rotR(X[3], X[4], X[5], TR + 3);
       icet::getH_J(X[3], X[4], X[5], ck.J + (size_t)pair * 27);
+      for (int k = 0; k < 12; k++) ck.TRprev[(size_t)pair * 12 + k] = TR[k];
     }
     icet_b200_result* R = ck.res + pair;
     R->status = 0; R->n_gauss1 = 0; R->n_used = 0; R->n_dropped = 0; R->cond = 0.f;
@@ -846,6 +848,8 @@ __global__ void __launch_bounds__(32) k_solve6(const Chunk ck, int iter, int nbl
   for (int k = 0; k < 6; k++) X[k] = (float)((double)X[k] + dx[k]);  // X += dx (:433), X is fp32
   {  // trigonometry of the next iteration: utils::R (src/icet.cpp:375-376) and get_H (:507-527)
     float* TR = ck.TR + (size_t)pair * 12;
+    if (iter == ck.runlen - 1)
+      for (int k = 0; k < 12; k++) ck.TRprev[(size_t)pair * 12 + k] = TR[k];
     TR[0] = X[0]; TR[1] = X[1]; TR[2] = X[2];
     icet::rotR(X[3], X[4], X[5], TR + 3);
     icet::getH_J(X[3], X[4], X[5], ck.J + (size_t)pair * 27);
@@ -862,6 +866,19 @@ __global__ void __launch_bounds__(32) k_solve6(const Chunk ck, int iter, int nbl
     R->cond = (float)cond_out;
   }
   if (status) R->status = status;
+}
+
+// public member `points2` of the reference: scan 2 as transformed by the last iteration
+// ((points2_OG + t) * R with the X that iteration STARTED from, src/icet.cpp:375-378), pair 0 of the chunk
+__global__ void k_points2(const Chunk ck, int n2, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n2) return;
+  const float* pg = ck.pog;
+  float x, y, z;
+  icet::transform(pg[i], pg[ck.n2max + i], pg[2 * (size_t)ck.n2max + i], ck.TRprev, ck.TRprev + 3, x, y, z);
+  out[i] = x;
+  out[n2 + i] = y;
+  out[2 * (size_t)n2 + i] = z;
 }
 
 // spherical coordinates + cell index of a cloud (parity-test entry point)
@@ -958,6 +975,10 @@ struct icet_b200_ctx {
   icet_b200_params dump_params{};
   bool dump_valid = false;
   Dump dump_ptrs{};
+  // the most recent single-pair chunk (for icet_b200_get_points2)
+  bool last_valid = false;
+  int last_n2 = 0, last_runlen = 0;
+  char last_ck[512];
 };
 
 namespace {
@@ -995,6 +1016,7 @@ size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, Chunk& ck
   ck.pog = c.take<float>((size_t)P * 3 * n2max);
   ck.X = c.take<float>((size_t)P * 6);
   ck.TR = c.take<float>((size_t)P * 12);
+  ck.TRprev = c.take<float>((size_t)P * 12);
   ck.J = c.take<float>((size_t)P * 27);
   ck.part = c.take<double>((size_t)P * ((ncell + 63) / 64) * 28);
   return (c.off + 255) & ~(size_t)255;
@@ -1140,6 +1162,9 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   }
 #undef LAUNCH
   CK(cudaGetLastError());
+  static_assert(sizeof(Chunk) <= 512, "Chunk too large for last_ck");
+  ctx->last_valid = (P == 1);
+  if (P == 1) memcpy(ctx->last_ck, &ck, sizeof(Chunk));
   return 0;
 }
 
@@ -1457,6 +1482,10 @@ int icet_b200_register_batch(icet_b200_ctx* c, const icet_b200_params* p, int32_
       c->dump_params = *p;
       c->dump_valid = true;
     }
+    if (npairs == 1) {
+      c->last_n2 = n2[0];
+      c->last_runlen = p->runlen;
+    }
   }
   CK(cudaMemcpyAsync(out, d_res, (size_t)npairs * sizeof(icet_b200_result), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -1519,6 +1548,27 @@ int icet_b200_get_dump(icet_b200_ctx* c, icet_b200_voxel_dump* o) {
   CP(mu2, mu2, rl * ncell * 12); CP(sigma2, sigma2, rl * ncell * 36); CP(Xit, Xit, rl * 24);
   CP(HTWH, HTWH, rl * 144); CP(HTWdz, HTWdz, rl * 24);
 #undef CP
+  return 0;
+}
+
+int icet_b200_get_points2(icet_b200_ctx* c, float* out, int32_t n2) {
+  if (!c || !out) return fail(ICET_B200_E_INVALID, "NULL argument");
+  if (!c->last_valid) return fail(ICET_B200_E_INVALID, "no single-pair registration to take points2 from");
+  if (n2 != c->last_n2) return fail(ICET_B200_E_INVALID, "n2 does not match the last registration");
+  if (n2 == 0) return 0;
+  CK(cudaSetDevice(c->device));
+  Chunk ck;
+  memcpy(&ck, c->last_ck, sizeof(Chunk));
+  // the staging buffers are idle here: use one for the device-side output
+  CK(cudaStreamSynchronize(c->stream));
+  int rc = c->resbuf.ensure((size_t)3 * n2 * sizeof(float) + 1024);
+  if (rc) return rc;
+  float* d_out = (float*)c->resbuf.p;
+  k_points2<<<(n2 + 255) / 256, 256, 0, c->stream>>>(ck, n2, d_out);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, d_out, (size_t)3 * n2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

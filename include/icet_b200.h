@@ -147,6 +147,12 @@ typedef struct {
 int icet_b200_set_dump(icet_b200_ctx* ctx, int32_t enable);
 int icet_b200_get_dump(icet_b200_ctx* ctx, icet_b200_voxel_dump* out);
 
+/* The reference's public member `points2` (include/icet.h:80) for the most recent icet_b200_register call: scan 2
+ * as transformed by the LAST iteration, i.e. with the X that iteration started from (src/icet.cpp:375-378 runs
+ * before :433), in the caller's point order (the reference leaves it in its internal permuted order).
+ * out: HOST buffer of 3*n2 floats (planes), n2 must equal the registered size. */
+int icet_b200_get_points2(icet_b200_ctx* ctx, float* out, int32_t n2);
+
 /* Stage outputs used by the parity tests (HOST buffers, blocking):
  * spherical coordinates [3*n] (r | theta | phi) and the cell index of each point,
  * utils::cartesianToSpherical (src/utils.cpp:93-119) + ICET::sortSphericalCoordinates (src/icet.cpp:545-546). */

@@ -361,3 +361,35 @@ def test_truncated_solution_axis(ctx, po):
     assert abs(r["X"][1] - o2.X[1]) < 2e-4 and abs(r["X"][2] - o2.X[2]) < 2e-4
     if r["n_dropped"] > 0:
         assert r["cond"] > 1e6
+
+
+def test_cpp_class_dropin_demo(ctx, po, frame_pair, tmp_path):
+    """The C++ `class ICET` of include/icet.h (host C++ over the C ABI, compiled against the test-only Eigen stub) run
+    through the headless icet_cpp_demo with the demo's X0 = [1,0,0,0,0,0] (reference src/icet_cpp_demo.cpp:31-38)."""
+    import json
+    import os
+    import subprocess
+    from conftest import ROOT
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "examples")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    s1, s2 = frame_pair
+    a, b = tmp_path / "a.f32", tmp_path / "b.f32"
+    s1.tofile(a)
+    s2.tofile(b)
+    out = subprocess.run([os.path.join(ROOT, "examples", "_build", "icet_cpp_demo_headless"), str(a), str(b), "f32"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    X = np.array(json.loads([l for l in out.stdout.splitlines() if l.startswith("X_JSON")][0][7:]), np.float32)
+    p7 = np.array(json.loads([l for l in out.stdout.splitlines() if l.startswith("P2_JSON")][0][8:]), np.float32)
+    x0 = [1, 0, 0, 0, 0, 0]
+    rpy = ctx.register(s1, s2, X0=x0)
+    np.testing.assert_array_equal(X, rpy["X"])                       # same library, same bits
+    o = po.run(s1, s2, X0=x0, dumps="all")
+    assert np.abs(X[:3] - o.X[:3]).max() < TOL_M and np.abs(X[3:] - o.X[3:]).max() < TOL_RAD
+    # public member points2: scan 2 transformed by the last iteration, here in the caller's row order
+    row = int(np.where(o.perm2 == 7)[0][0])
+    np.testing.assert_allclose(p7, o.points2_final[:, row], atol=2e-5)
+    p2 = ctx.get_points2(s2.shape[1])
+    inv = np.argsort(o.perm2)
+    np.testing.assert_allclose(p2, o.points2_final[:, inv], atol=5e-5)
+    assert "ellipsoids 336" in out.stdout and "clusterBounds 1800x6" in out.stdout

@@ -146,3 +146,65 @@ def test_bench_reference_arm_runs():
     assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+
+
+def _build_demo():
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "examples")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return os.path.join(ROOT, "examples", "_build", "icet_cpp_demo_headless")
+
+
+def test_cpp_dropin_class_compiles_and_fails_loudly_without_gpu(tmp_path, frame_pair):
+    """include/icet.h + icet_b200/host/*.cpp (the C++ host side over the C ABI) compile against the test-only Eigen
+    stub; without a GPU the constructor throws (std::runtime_error) instead of falling back to a CPU path."""
+    import icet_b200
+    icet_b200.build()
+    exe = _build_demo()
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present (the GPU test runs the demo)")
+    s1, s2 = frame_pair
+    a, b = tmp_path / "a.f32", tmp_path / "b.f32"
+    s1[:, :4096].tofile(a)
+    s2[:, :4096].tofile(b)
+    r = subprocess.run([exe, str(a), str(b), "f32"], capture_output=True, text=True)
+    assert r.returncode == 1
+    assert "no CPU fallback" in r.stderr
+
+
+def test_utils_loader_formats(tmp_path):
+    """Ouster CSV (two header rows, integer mm in columns 8-10) and tab-separated xyz (reference src/utils.cpp:19-88),
+    exercised through the C++ demo's loader path is GPU-only; here the parser is checked via a tiny C++ probe."""
+    probe = tmp_path / "probe.cpp"
+    probe.write_text('''
+#include <cstdio>
+#include "utils.h"
+int main(int argc, char** argv) {
+  Eigen::MatrixXf m = utils::loadPointCloudCSV(argv[1], argv[2]);
+  std::printf("%ld %ld", (long)m.rows(), (long)m.cols());
+  for (long i = 0; i < m.rows(); i++) std::printf(" %.4f %.4f %.4f", m(i,0), m(i,1), m(i,2));
+  Eigen::Matrix3f R = utils::R(0.1f, 0.2f, 0.3f);
+  std::printf(" R %.6f %.6f %.6f", R(0,0), R(0,1), R(2,2));
+  return 0;
+}''')
+    exe = tmp_path / "probe"
+    r = subprocess.run([os.environ.get("CXX", "g++"), "-std=c++17", "-I" + os.path.join(ROOT, "include"),
+                        "-I" + os.path.join(ROOT, "tests", "stubs"), "-o", str(exe), str(probe),
+                        os.path.join(ROOT, "icet_b200", "host", "utils.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    csv = tmp_path / "o.csv"
+    hdr = ",".join("c%d" % i for i in range(12))
+    csv.write_text(hdr + "\n" + hdr + "\n" + "\n".join(
+        ",".join(["0"] * 8 + [str(1000 * (i + 1)), str(-250 * i), str(3), "9"]) for i in range(3)) + "\n")
+    out = subprocess.run([str(exe), str(csv), "ouster"], capture_output=True, text=True).stdout.split()
+    assert out[:2] == ["3", "3"]
+    np.testing.assert_allclose([float(v) for v in out[2:11]], [1, 0, 0.003, 2, -0.25, 0.003, 3, -0.5, 0.003], atol=1e-6)
+    tsv = tmp_path / "t.txt"
+    tsv.write_text("1.5\t2.5\t-3\n4\t5\t6\n")
+    out = subprocess.run([str(exe), str(tsv), "txt"], capture_output=True, text=True).stdout.split()
+    assert out[:2] == ["2", "3"] and float(out[4]) == -3.0
+    # utils::R (reference src/utils.cpp:144-152): R(0,0) = cos(theta) cos(psi), R(2,2) = cos(phi) cos(theta)
+    i = out.index("R")
+    np.testing.assert_allclose([float(v) for v in out[i + 1:i + 4]],
+                               [np.cos(0.2) * np.cos(0.3), np.sin(0.3) * np.cos(0.1) + np.sin(0.1) * np.sin(0.2) * np.cos(0.3),
+                                np.cos(0.1) * np.cos(0.2)], rtol=1e-5)
