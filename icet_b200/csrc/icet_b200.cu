@@ -100,7 +100,9 @@ struct Chunk {  // everything a kernel needs, passed by value
   float* J;          // [P][27] get_H derivative matrices Jx | Jy | Jz of the current iteration
   double* part;      // [P][nblk][NRED] per-block partial sums of the voxel contributions
   // scan 2
-  float* pog;        // [P][3][n2max]  points2_OG
+  float* pog;        // [P][3][n2max]  points2_OG without the dropped returns (compacted, any order)
+  int32_t* n2c;      // [P] points stored in pog
+  int32_t* nz2;      // [P] dropped returns of scan 2 (points2_OG == 0)
   float* X;          // [P][6]
   const float* x0;   // [P][6] or null
   icet_b200_result* res;  // [P] device
@@ -109,59 +111,30 @@ struct Chunk {  // everything a kernel needs, passed by value
 };
 
 // ----------------------------------------------------------------------------------------------
-// warp-aggregated fixed-point accumulation into acc[cell][*]
-//   q[0] += #lanes in the cell, q[1] += #lanes inside the cluster box,
-//   q[2..4] += sum d, q[5..10] += sum d d^T (xx xy xz yy yz zz)
-// `cell` < 0: lane takes no part.  Exact integer arithmetic => order independent.
+// Fixed-point accumulators acc[cell][NQ] (64-bit integers, RED.64 to L2):
+//   q[0] += points in the angular bin, q[1] += points inside the cluster box,
+//   q[2..4] += sum d, q[5..10] += sum d d^T (xx xy xz yy yz zz),   d = round((p - ref) * scale)
+// Exact integer arithmetic => the sums do not depend on the order or grouping of the additions.
+// flush_run publishes the partial sums one lane collected over a run of consecutive points of the
+// same cell (<= PASS_K points, so the first-order sums fit 32 bits).
 // ----------------------------------------------------------------------------------------------
-// Lanes 0..10 of the warp publish the 11 sums of one (warp, cell) group with a single RED.64
-// instruction (distinct addresses).  The sums are warp-uniform (REDUX results); they reach their lanes
-// through a 96-byte per-warp shared-memory slot: lane 0 stores, every lane reads its own word.
-__device__ __forceinline__ void warp_accumulate(unsigned long long* accp /* pair base */,
-                                                long long* wslot /* per-warp smem, 12 words */, int cell, bool in,
-                                                int fx, int fy, int fz) {
-  const int lane = threadIdx.x & 31;
-  unsigned todo = __ballot_sync(FULL, cell >= 0);
-  while (todo) {
-    const int leader = __ffs(todo) - 1;
-    const int c = __shfl_sync(FULL, cell, leader);
-    const bool mine = (cell == c);
-    const unsigned grp = __ballot_sync(FULL, mine);
-    const unsigned grp_in = __ballot_sync(FULL, mine && in);
-    todo &= ~grp;
-    unsigned long long* q = accp + (size_t)c * NQ;
-    if (grp_in == 0) {  // warp-uniform: only the bin count changes
-      if (lane == 0) atomicAdd(q, (unsigned long long)__popc(grp));
-      continue;
-    }
-    const bool m = mine && in;
-    const int dx = m ? fx : 0, dy = m ? fy : 0, dz = m ? fz : 0;
-    const long long sx = __reduce_add_sync(FULL, dx);
-    const long long sy = __reduce_add_sync(FULL, dy);
-    const long long sz = __reduce_add_sync(FULL, dz);
-    // products: |d| <= 2^21 -> |p| <= 2^42; split into hi (signed) and lo (22 bits) so that the
-    // 32-lane sums fit REDUX's 32-bit adder
-    auto red64 = [&](int a, int b) -> long long {
-      const long long p = (long long)a * (long long)b;
-      const int shi = __reduce_add_sync(FULL, (int)(p >> 22));
-      const int slo = __reduce_add_sync(FULL, (int)(p & 0x3FFFFF));
-      return ((long long)shi << 22) + (long long)slo;
-    };
-    const long long pxx = red64(dx, dx), pxy = red64(dx, dy), pxz = red64(dx, dz);
-    const long long pyy = red64(dy, dy), pyz = red64(dy, dz), pzz = red64(dz, dz);
-    if (lane == 0) {
-      longlong2* w2 = reinterpret_cast<longlong2*>(wslot);
-      w2[0] = make_longlong2((long long)__popc(grp), (long long)__popc(grp_in));
-      w2[1] = make_longlong2(sx, sy);
-      w2[2] = make_longlong2(sz, pxx);
-      w2[3] = make_longlong2(pxy, pxz);
-      w2[4] = make_longlong2(pyy, pyz);
-      w2[5] = make_longlong2(pzz, 0);
-    }
-    __syncwarp();
-    if (lane < 11) atomicAdd(q + lane, (unsigned long long)wslot[lane]);
-    __syncwarp();
-  }
+__device__ __forceinline__ void flush_run(unsigned long long* accp /* pair base */, int cell, int nbin, int nin,
+                                          int sx, int sy, int sz, long long pxx, long long pxy, long long pxz,
+                                          long long pyy, long long pyz, long long pzz) {
+  if (cell < 0) return;
+  unsigned long long* q = accp + (size_t)cell * NQ;
+  atomicAdd(q, (unsigned long long)nbin);
+  if (nin == 0) return;  // only the bin count changes
+  atomicAdd(q + 1, (unsigned long long)nin);
+  atomicAdd(q + 2, (unsigned long long)(long long)sx);
+  atomicAdd(q + 3, (unsigned long long)(long long)sy);
+  atomicAdd(q + 4, (unsigned long long)(long long)sz);
+  atomicAdd(q + 5, (unsigned long long)pxx);
+  atomicAdd(q + 6, (unsigned long long)pxy);
+  atomicAdd(q + 7, (unsigned long long)pxz);
+  atomicAdd(q + 8, (unsigned long long)pyy);
+  atomicAdd(q + 9, (unsigned long long)pyz);
+  atomicAdd(q + 10, (unsigned long long)pzz);
 }
 
 __device__ __forceinline__ void cell_of(const Chunk& ck, float th, float ph, int& bt, int& bp) {
@@ -416,22 +389,68 @@ __global__ void __launch_bounds__(128) k_cluster(const Chunk ck) {
 //   SCAN2 = true : scan 2, one Gauss-Newton iteration (src/icet.cpp:375-388 + fitCells2 :290-306)
 // ----------------------------------------------------------------------------------------------
 constexpr int PASS_THREADS = 256;
-constexpr int PASS_PPT = 4;  // points per thread (block tile = 1024 consecutive points)
+constexpr int PASS_WARPS = PASS_THREADS / 32;
+constexpr int PASS_K = 16;                                  // consecutive points per lane in the accumulation phase
+constexpr int PASS_WTILE = 32 * PASS_K;                     // points per warp tile
+constexpr int PASS_WSLOTS = PASS_WTILE + PASS_WTILE / 16;   // 16-byte slots per warp tile (1 pad slot per 16)
+constexpr int PASS_TILE = PASS_WARPS * PASS_WTILE;          // points per block
 
 __host__ __device__ inline int pass_smem_bytes(int nT, int nP) {
-  return (PASS_THREADS / 32) * 12 * 8 + (2 * (nT + nP) + 6) * 4;
+  return PASS_WARPS * PASS_WSLOTS * 16 + (2 * (nT + nP) + 6) * 4;
 }
 
+// One point -> its accumulation entry {cell << 1 | inside, fx, fy, fz}; .x = -1 when the point's cell takes no
+// part (no cluster / voxel not active), fx = fy = fz = 0 when the point is outside the cluster box.
+template <bool SCAN2>
+__device__ __forceinline__ int4 pass_point(const Chunk& ck, const float* tab, const CellRec* recs, const float* tr,
+                                           float x, float y, float z) {
+  if (SCAN2) icet::transform(x, y, z, tr, tr + 3, x, y, z);
+  float r, th, ph;
+  icet::c2s(x, y, z, r, th, ph);
+  int bt, bp;
+  cell_of_smem(ck, tab, th, ph, bt, bp);
+  const int c = ck.nT * bp + bt;
+  const float4* rp = reinterpret_cast<const float4*>(recs + c);
+  const float4 rb = __ldg(rp + 1);
+  const uint32_t flags = __float_as_uint(rb.z);
+  int4 e = make_int4(-1, 0, 0, 0);
+  if (flags & (SCAN2 ? F_ACTIVE2 : F_STAT1)) {
+    const float* azE = tab;
+    const float* elE = tab + ck.nT + 1;
+    const float4 ra = __ldg(rp);
+    e.x = c << 1;
+    // ICET::filterPointsInsideCluster src/icet.cpp:632-634 (inclusive float compares)
+    const bool in = th >= azE[bt] && th <= azE[bt + 1] && ph >= elE[bp] && ph <= elE[bp + 1] && r >= ra.x && r <= ra.y;
+    if (in) {
+      float cx, cy, cz;
+      icet::s2c(r, th, ph, cx, cy, cz);  // statistics use round-tripped points (:159 / :303)
+      const float sc = rb.y;
+      int fx = __float2int_rn((cx - ra.z) * sc);
+      int fy = __float2int_rn((cy - ra.w) * sc);
+      int fz = __float2int_rn((cz - rb.x) * sc);
+      e.x |= 1;
+      e.y = max(-FP_LIM, min(FP_LIM, fx));
+      e.z = max(-FP_LIM, min(FP_LIM, fy));
+      e.w = max(-FP_LIM, min(FP_LIM, fz));
+    }
+  }
+  return e;
+}
+
+// Each warp works on tiles of PASS_WTILE consecutive points.  Phase A: lane-per-point (coalesced loads, all the
+// fp32 geometry), entries go to the warp's shared-memory tile.  Phase B: every lane walks PASS_K CONSECUTIVE
+// entries and sums runs of equal cell in registers (LiDAR scans list points ring by ring, so neighbours share
+// their voxel: ~27 points per run at 2048 azimuth steps / 75 bins); a run ends with one flush_run.
 template <bool SCAN2>
 __global__ void __launch_bounds__(PASS_THREADS) k_pass(const Chunk ck) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  long long* wslots = reinterpret_cast<long long*>(smem_raw);
-  float* tab = reinterpret_cast<float*>(smem_raw + (PASS_THREADS / 32) * 12 * 8);
+  int4* ent = reinterpret_cast<int4*>(smem_raw);
+  float* tab = reinterpret_cast<float*>(smem_raw + PASS_WARPS * PASS_WSLOTS * 16);
   const int pair = blockIdx.y;
   const PairDesc d = ck.desc[pair];
-  const int n = SCAN2 ? d.n2 : d.n1;
-  const int tile0 = blockIdx.x * (PASS_THREADS * PASS_PPT);
-  if (tile0 >= n) return;
+  const int n = SCAN2 ? ck.n2c[pair] : d.n1;
+  const int tile0 = blockIdx.x * PASS_TILE;
+  if (tile0 >= n && !(SCAN2 && blockIdx.x == 0)) return;
   {
     const int ntab = 2 * (ck.nT + ck.nP) + 6;
     for (int k = threadIdx.x; k < ntab; k += PASS_THREADS) tab[k] = __ldg(ck.azE + k);
@@ -447,47 +466,70 @@ __global__ void __launch_bounds__(PASS_THREADS) k_pass(const Chunk ck) {
   const size_t ld = SCAN2 ? (size_t)ck.n2max : (size_t)d.ld1;
   const CellRec* recs = ck.rec + (size_t)pair * ck.ncell;
   unsigned long long* accp = ck.acc + (size_t)pair * ck.ncell * NQ;
-  long long* wslot = wslots + (threadIdx.x >> 5) * 12;
-  const float* azE = tab;
-  const float* elE = tab + ck.nT + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int4* went = ent + warp * PASS_WSLOTS;
+  const int w0 = tile0 + warp * PASS_WTILE;
   __syncthreads();
-#pragma unroll 1
-  for (int j = 0; j < PASS_PPT; j++) {
-    const int i = tile0 + j * PASS_THREADS + threadIdx.x;
-    if (tile0 + j * PASS_THREADS >= n) break;  // block-uniform
-    int cell = -1;
-    bool in = false;
-    int fx = 0, fy = 0, fz = 0;
-    if (i < n) {
-      float x = __ldg(px_ + i), y = __ldg(px_ + ld + i), z = __ldg(px_ + 2 * ld + i);
-      if (SCAN2) icet::transform(x, y, z, tr, tr + 3, x, y, z);
-      float r, th, ph;
-      icet::c2s(x, y, z, r, th, ph);
-      int bt, bp;
-      cell_of_smem(ck, tab, th, ph, bt, bp);
-      const int c = ck.nT * bp + bt;
-      const float4* rp = reinterpret_cast<const float4*>(recs + c);
-      const float4 rb = __ldg(rp + 1);
-      const uint32_t flags = __float_as_uint(rb.z);
-      if (flags & (SCAN2 ? F_ACTIVE2 : F_STAT1)) {
-        cell = c;
-        const float4 ra = __ldg(rp);
-        // ICET::filterPointsInsideCluster src/icet.cpp:632-634 (inclusive float compares)
-        in = th >= azE[bt] && th <= azE[bt + 1] && ph >= elE[bp] && ph <= elE[bp + 1] && r >= ra.x && r <= ra.y;
-        if (in) {
-          float cx, cy, cz;
-          icet::s2c(r, th, ph, cx, cy, cz);  // statistics use round-tripped points (:159 / :303)
-          const float sc = rb.y;
-          fx = __float2int_rn((cx - ra.z) * sc);
-          fy = __float2int_rn((cy - ra.w) * sc);
-          fz = __float2int_rn((cz - rb.x) * sc);
-          fx = max(-FP_LIM, min(FP_LIM, fx));
-          fy = max(-FP_LIM, min(FP_LIM, fy));
-          fz = max(-FP_LIM, min(FP_LIM, fz));
+  if (w0 < n) {
+    // ---- phase A
+#pragma unroll 2
+    for (int j = 0; j < PASS_K; j++) {
+      const int i = w0 + j * 32 + lane;
+      int4 e = make_int4(-1, 0, 0, 0);
+      if (i < n) {
+        const float x = __ldg(px_ + i), y = __ldg(px_ + ld + i), z = __ldg(px_ + 2 * ld + i);
+        e = pass_point<SCAN2>(ck, tab, recs, tr, x, y, z);
+      }
+      const int slot = j * 32 + lane;
+      went[slot + (slot >> 4)] = e;
+    }
+    __syncwarp();
+    // ---- phase B
+    int cur = -1, nbin = 0, nin = 0, sx = 0, sy = 0, sz = 0;
+    long long pxx = 0, pxy = 0, pxz = 0, pyy = 0, pyz = 0, pzz = 0;
+    const int4* mine = went + lane * (PASS_K + 1);
+#pragma unroll 4
+    for (int j = 0; j < PASS_K; j++) {
+      const int4 e = mine[j];
+      const int key = e.x >> 1;  // -1 stays -1
+      if (key != cur) {
+        flush_run(accp, cur, nbin, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
+        cur = key;
+        nbin = nin = sx = sy = sz = 0;
+        pxx = pxy = pxz = pyy = pyz = pzz = 0;
+      }
+      nbin++;
+      nin += e.x & 1;
+      sx += e.y; sy += e.z; sz += e.w;
+      pxx += (long long)e.y * e.y; pxy += (long long)e.y * e.z; pxz += (long long)e.y * e.w;
+      pyy += (long long)e.z * e.z; pyz += (long long)e.z * e.w; pzz += (long long)e.w * e.w;
+    }
+    flush_run(accp, cur, nbin, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
+  }
+  if (SCAN2 && blockIdx.x == 0 && threadIdx.x == 0) {
+    // the dropped returns of scan 2: points2_OG == (0,0,0) for all of them, so they all land on t * R
+    // (src/icet.cpp:377-378) -- evaluated once, weighted with their number
+    const long long nz = ck.nz2[pair];
+    if (nz > 0) {
+      const int4 e = pass_point<true>(ck, tab, recs, tr, 0.0f, 0.0f, 0.0f);
+      if (e.x >= 0) {
+        unsigned long long* q = accp + (size_t)(e.x >> 1) * NQ;
+        atomicAdd(q, (unsigned long long)nz);
+        if (e.x & 1) {
+          const long long fx = e.y, fy = e.z, fz = e.w;
+          atomicAdd(q + 1, (unsigned long long)nz);
+          atomicAdd(q + 2, (unsigned long long)(nz * fx));
+          atomicAdd(q + 3, (unsigned long long)(nz * fy));
+          atomicAdd(q + 4, (unsigned long long)(nz * fz));
+          atomicAdd(q + 5, (unsigned long long)(nz * fx * fx));
+          atomicAdd(q + 6, (unsigned long long)(nz * fx * fy));
+          atomicAdd(q + 7, (unsigned long long)(nz * fx * fz));
+          atomicAdd(q + 8, (unsigned long long)(nz * fy * fy));
+          atomicAdd(q + 9, (unsigned long long)(nz * fy * fz));
+          atomicAdd(q + 10, (unsigned long long)(nz * fz * fz));
         }
       }
     }
-    warp_accumulate(accp, wslot, cell, in, fx, fy, fz);
   }
 }
 
@@ -590,16 +632,40 @@ __global__ void __launch_bounds__(128) k_fit1(const Chunk ck) {
 __global__ void __launch_bounds__(256) k_prep2(const Chunk ck) {
   const int pair = blockIdx.y;
   const PairDesc d = ck.desc[pair];
+  if ((int)(blockIdx.x * blockDim.x) >= d.n2) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.n2) return;
-  float x = __ldg(d.s2 + i), y = __ldg(d.s2 + d.ld2 + i), z = __ldg(d.s2 + 2 * (size_t)d.ld2 + i);
-  float r, th, ph;
-  icet::c2s(x, y, z, r, th, ph);
-  icet::s2c(r, th, ph, x, y, z);
-  float* pg = ck.pog + (size_t)pair * 3 * ck.n2max;
-  pg[i] = x;
-  pg[ck.n2max + i] = y;
-  pg[2 * (size_t)ck.n2max + i] = z;
+  float x = 0.f, y = 0.f, z = 0.f;
+  bool keep = false, zero = false;
+  if (i < d.n2) {
+    x = __ldg(d.s2 + i); y = __ldg(d.s2 + d.ld2 + i); z = __ldg(d.s2 + 2 * (size_t)d.ld2 + i);
+    float r, th, ph;
+    icet::c2s(x, y, z, r, th, ph);
+    icet::s2c(r, th, ph, x, y, z);
+    // Dropped returns: (0,0,0) stays (+0,+0,+0).  They are all the same point in every iteration, so they are
+    // counted here and evaluated once per iteration by k_pass<true> instead of being stored.
+    zero = (__float_as_uint(x) | __float_as_uint(y) | __float_as_uint(z)) == 0u;
+    keep = !zero;
+  }
+  // block-level compaction (the order of points2_OG is irrelevant: all sums over it are exact integers)
+  __shared__ int s_cnt[8], s_zero[8], s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned mk = __ballot_sync(FULL, keep), mz = __ballot_sync(FULL, zero);
+  if (lane == 0) { s_cnt[warp] = __popc(mk); s_zero[warp] = __popc(mz); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0, totz = 0;
+    for (int w = 0; w < 8; w++) { const int c = s_cnt[w]; s_cnt[w] = tot; tot += c; totz += s_zero[w]; }
+    s_base = tot ? atomicAdd(&ck.n2c[pair], tot) : 0;
+    if (totz) atomicAdd(&ck.nz2[pair], totz);
+  }
+  __syncthreads();
+  if (keep) {
+    const int o = s_base + s_cnt[warp] + __popc(mk & ((1u << lane) - 1));
+    float* pg = ck.pog + (size_t)pair * 3 * ck.n2max;
+    pg[o] = x;
+    pg[ck.n2max + o] = y;
+    pg[2 * (size_t)ck.n2max + o] = z;
+  }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -873,9 +939,12 @@ __global__ void __launch_bounds__(32) k_solve6(const Chunk ck, int iter, int nbl
 __global__ void k_points2(const Chunk ck, int n2, float* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n2) return;
-  const float* pg = ck.pog;
-  float x, y, z;
-  icet::transform(pg[i], pg[ck.n2max + i], pg[2 * (size_t)ck.n2max + i], ck.TRprev, ck.TRprev + 3, x, y, z);
+  const PairDesc d = ck.desc[0];
+  float x = d.s2[i], y = d.s2[d.ld2 + i], z = d.s2[2 * (size_t)d.ld2 + i];
+  float r, th, ph;
+  icet::c2s(x, y, z, r, th, ph);   // points2_OG (prepScan2, src/icet.cpp:263-275), recomputed: the workspace
+  icet::s2c(r, th, ph, x, y, z);   // copy is compacted
+  icet::transform(x, y, z, ck.TRprev, ck.TRprev + 3, x, y, z);
   out[i] = x;
   out[n2 + i] = y;
   out[2 * (size_t)n2 + i] = z;
@@ -951,6 +1020,7 @@ struct icet_b200_ctx {
   int64_t launches = 0;
   int dump_on = 0;
   int sm_count = 148;
+  int pass_smem_set = 0;  // dynamic shared memory the pass kernels are currently allowed
   // per-kernel timing (icet_b200_set_profile): events around every launch, summed on request
   int profile_on = 0;
   std::vector<cudaEvent_t> prof_ev;   // pairs (begin, end)
@@ -1003,6 +1073,8 @@ size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, Chunk& ck
   ck.cntz = c.take<int32_t>((size_t)P * ncell);
   ck.cursor = c.take<int32_t>((size_t)P * ncell);
   ck.acc = c.take<unsigned long long>((size_t)P * ncell * NQ);
+  ck.n2c = c.take<int32_t>((size_t)P);
+  ck.nz2 = c.take<int32_t>((size_t)P);
   c.off = (c.off + 255) & ~(size_t)255;
   if (zero_bytes) *zero_bytes = c.off;
   ck.off = c.take<int32_t>((size_t)P * ncell);
@@ -1130,8 +1202,14 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   CK(cudaMemsetAsync(ctx->ws.p, 0, zero_bytes, st));
   const dim3 g1((n1max + 255) / 256, P), g2((n2max + 255) / 256, P);
   const int nblk = (ncell + VOX_THREADS - 1) / VOX_THREADS;
-  const int tile = PASS_THREADS * PASS_PPT;
+  const int tile = PASS_TILE;
   const dim3 gp1((n1max + tile - 1) / tile, P), gp2((n2max + tile - 1) / tile, P);
+  const int psm = pass_smem_bytes(nT, nP);
+  if (psm > ctx->pass_smem_set) {
+    CK(cudaFuncSetAttribute(k_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
+    CK(cudaFuncSetAttribute(k_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
+    ctx->pass_smem_set = psm;
+  }
   // LAUNCH(id, kernel<<<...>>>(...)): counts the launch and, when profiling, brackets it with events
 #define LAUNCH(id, ...)                                                   \
   do {                                                                    \
@@ -1151,12 +1229,12 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
     // enough CTAs to cover a typical work list (~25 % of the cells) in one pass; the kernel loops
     int gx = std::max(1, std::min(ncell, std::max(64, (ctx->sm_count * 16 + P - 1) / P)));
     LAUNCH(3, k_cluster<<<dim3(gx, P), 128, 0, st>>>(ck));
-    LAUNCH(4, k_pass<false><<<gp1, PASS_THREADS, pass_smem_bytes(nT, nP), st>>>(ck));
+    LAUNCH(4, k_pass<false><<<gp1, PASS_THREADS, psm, st>>>(ck));
   }
   LAUNCH(5, k_fit1<<<dim3((ncell + 127) / 128, P), 128, 0, st>>>(ck));
   if (n2max > 0) LAUNCH(6, k_prep2<<<g2, 256, 0, st>>>(ck));
   for (int it = 0; it < p->runlen; it++) {
-    if (n2max > 0) LAUNCH(7, k_pass<true><<<gp2, PASS_THREADS, pass_smem_bytes(nT, nP), st>>>(ck));
+    if (n2max > 0) LAUNCH(7, k_pass<true><<<gp2, PASS_THREADS, psm, st>>>(ck));
     LAUNCH(8, k_vox2<<<dim3(nblk, P), VOX_THREADS, 0, st>>>(ck, it));
     LAUNCH(9, k_solve6<<<P, 32, 0, st>>>(ck, it, nblk));
   }

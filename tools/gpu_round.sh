@@ -1,0 +1,25 @@
+#!/bin/bash
+# One GPU visit: parity tests, smoke, bench (ours + reference arm), ncu launch list and one full capture
+# of the dominant kernel.  Run under gpurun from the repo root; everything lands in gpurun_out/.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh [tag]'
+TAG=${1:-r01}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.txt 2>&1
+nproc > $OUT/nproc.txt
+echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee $OUT/pytest_gpu.txt
+echo "== smoke" ; timeout 300 python __graft_entry__.py smoke 2>&1 | tail -5 | tee $OUT/smoke.txt
+echo "== bench" ; timeout 900 python bench.py --steps 5 --warmup 3 2> $OUT/bench.err | tee $OUT/bench.json
+tail -3 $OUT/bench.err
+if [ "${SKIP_REF:-0}" != "1" ]; then
+  echo "== bench reference arm" ; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2> $OUT/bench_ref.err | tee $OUT/bench_ref.json
+fi
+if [ "${SKIP_NCU:-0}" != "1" ]; then
+  echo "== ncu launch list"
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
+    python bench.py --steps 1 --warmup 3 --pairs-per-gpu 256 --no-cpu-baseline --no-latency --no-e2e > $OUT/ncu_bench.log 2>&1
+  echo "== ncu full capture of k_pass<scan2>, k_pass<scan1>"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pass -s 2 -c 3 -f -o $OUT/prof_kpass \
+    python bench.py --steps 1 --warmup 3 --pairs-per-gpu 256 --no-cpu-baseline --no-latency --no-e2e > $OUT/ncu_full.log 2>&1
+  ls -la $OUT
+fi
