@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""Turn one GPU visit (gpurun_out/<tag>/, written by tools/gpu_round.sh) into the tracked summary
+profiles/<tag>.md: bench lines, the ncu launch list aggregated per kernel, the key metrics of the
+`ncu --set full` capture of the dominant kernel and its hottest source lines.
+
+    python tools/profile_summary.py <tag> [kernel-regex-for-lines]
+"""
+import collections
+import csv
+import io
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+RAW_KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
+    "l1tex__t_bytes.sum", "lts__t_bytes.sum", "sm__cycles_elapsed.avg.per_second",
+]
+
+
+def launches_table(path):
+    rows = list(csv.reader(l for l in open(path) if l.startswith('"')))
+    h = rows[0]
+    ki, vi, gi, bi = h.index("Kernel Name"), h.index("Metric Value"), h.index("Grid Size"), h.index("Block Size")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        if len(r) <= vi:
+            continue
+        a = agg.setdefault(r[ki], [0, 0.0, r[gi], r[bi]])
+        a[0] += 1
+        a[1] += float(r[vi].replace(",", "")) / 1e3
+    ours = {k: a for k, a in agg.items() if "k_" in k and "k_synth" not in k}
+    tot = sum(a[1] for a in ours.values()) or 1.0
+    out = ["| kernel | launches | total us | avg us | share of path | grid | block |", "|---|---|---|---|---|---|---|"]
+    for k, a in agg.items():
+        share = "%.1f %%" % (100 * a[1] / tot) if k in ours else "(setup)"
+        out.append("| `%s` | %d | %.1f | %.1f | %s | %s | %s |" % (k.replace("<unnamed>::", "")[:60], a[0], a[1], a[1] / a[0],
+                                                                 share, a[2], a[3]))
+    return "\n".join(out)
+
+
+def raw_table(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    if len(rows) < 3:
+        return "(no raw page)"
+    h, u = rows[0], rows[1]
+    lines = []
+    for r in rows[2:]:
+        name = r[h.index("Kernel Name")].replace("<unnamed>::", "")
+        lines.append("**%s** (launch id %s)\n" % (name, r[0]))
+        lines.append("| metric | value | unit |\n|---|---|---|")
+        for k in RAW_KEYS:
+            if k in h:
+                i = h.index(k)
+                lines.append("| %s | %s | %s |" % (k, r[i], u[i]))
+        lines.append("")
+    return "\n".join(lines)
+
+
+def main():
+    tag = sys.argv[1]
+    d = os.path.join(ROOT, "gpurun_out", tag)
+    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+    md = ["# GPU visit `%s`" % tag, ""]
+    for f in ("gpu.txt", "nproc.txt", "pytest_gpu.txt", "smoke.txt"):
+        p = os.path.join(d, f)
+        if os.path.exists(p):
+            md += ["`%s`:" % f, "```", open(p).read().strip(), "```", ""]
+    for f in ("bench.json", "bench_ref.json"):
+        p = os.path.join(d, f)
+        if os.path.exists(p) and os.path.getsize(p):
+            md += ["## %s (CUDA-event timed, NOT under a profiler)" % f, "```json"]
+            for line in open(p):
+                line = line.strip()
+                if line.startswith("{"):
+                    md.append(json.dumps(json.loads(line), indent=1))
+            md += ["```", ""]
+    p = os.path.join(d, "launches.csv")
+    if os.path.exists(p):
+        md += ["## ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: "
+               "compare shares)", "", launches_table(p), ""]
+    reps = sorted(f for f in os.listdir(d) if f.endswith(".ncu-rep"))
+    for rep in reps:
+        md += ["## ncu --set full: %s" % rep, "", raw_table(os.path.join(d, rep)), ""]
+        if len(sys.argv) > 2:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), os.path.join(d, rep),
+                                sys.argv[2], "30"], capture_output=True, text=True)
+            md += ["Hottest source lines (executed instructions / stall samples):", "```", r.stdout.strip(), "```", ""]
+    out = os.path.join(ROOT, "profiles", tag + ".md")
+    open(out, "w").write("\n".join(md) + "\n")
+    print(out)
+
+
+if __name__ == "__main__":
+    main()
