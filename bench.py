@@ -160,6 +160,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-chunk", type=int, default=0, help="pairs per chunk of the host-buffer pipeline (0 = default)")
+    ap.add_argument("--unfused", action="store_true", help="diagnostic: 3 launches per iteration instead of k_loop")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
@@ -192,7 +194,10 @@ def main():
     ctx = icet_b200.Context(local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
-    params = api.make_params(RUNLEN, BINS_PHI, BINS_THETA, NMIN, THRESH, BUFF)
+    if args.host_chunk:
+        ctx.set_host_chunk(args.host_chunk)
+    params = api.make_params(RUNLEN, BINS_PHI, BINS_THETA, NMIN, THRESH, BUFF,
+                             flags=api.FLAG_UNFUSED_LOOP if args.unfused else 0)
 
     # synthetic sequence shard of this rank (contiguous pair range of the world*P-pair sequence), generated
     # on the device

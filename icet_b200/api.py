@@ -34,6 +34,8 @@ RESULT_DTYPE = np.dtype([("X", np.float32, 6), ("pred_stds", np.float32, 6), ("Q
 assert RESULT_DTYPE.itemsize == C.sizeof(Result) == 224
 
 FLAG_FULL_EIG = 1
+FLAG_UNFUSED_LOOP = 2
+FLAG_PERSISTENT_LOOP = 4
 
 _DUMP_FIELDS = [("cnt1", _IP), ("bounds", _FP), ("nin1", _IP), ("has1", _BP), ("mu1", _FP), ("sigma1", _FP),
                 ("evec1", _FP), ("eval1", _FP), ("lmask", _BP), ("cnt2", _IP), ("nin2", _IP), ("used2", _BP),
@@ -45,12 +47,12 @@ class _Dump(C.Structure):
 
 
 EXPORTS = ["icet_b200_version", "icet_b200_last_error", "icet_b200_create", "icet_b200_destroy",
-           "icet_b200_set_stream", "icet_b200_set_chunk", "icet_b200_register", "icet_b200_register_batch",
+           "icet_b200_set_stream", "icet_b200_set_chunk", "icet_b200_set_host_chunk", "icet_b200_set_lanes", "icet_b200_debug_timeline", "icet_b200_register", "icet_b200_register_batch",
            "icet_b200_register_batch_device", "icet_b200_register_sequence_device", "icet_b200_synchronize",
            "icet_b200_set_dump", "icet_b200_get_dump", "icet_b200_get_points2", "icet_b200_spherical_bins",
            "icet_b200_synth_scans_device", "icet_b200_kernel_launches", "icet_b200_set_profile",
            "icet_b200_get_profile", "icet_b200_kernel_name"]
-NKERNELS = 10
+NKERNELS = 11
 
 _LIB = None
 
@@ -76,6 +78,9 @@ def load_library() -> C.CDLL:
     L.icet_b200_destroy.argtypes = [vp]
     L.icet_b200_set_stream.argtypes = [vp, vp]
     L.icet_b200_set_chunk.argtypes = [vp, C.c_int32]
+    L.icet_b200_set_host_chunk.argtypes = [vp, C.c_int32]
+    L.icet_b200_set_lanes.argtypes = [vp, C.c_int32]
+    L.icet_b200_debug_timeline.argtypes = [vp, vp, C.c_int32]
     L.icet_b200_register.argtypes = [vp, C.POINTER(Params), vp, C.c_int32, C.c_int32, vp, C.c_int32, C.c_int32,
                                      vp, C.POINTER(Result)]
     L.icet_b200_register_batch.argtypes = [vp, C.POINTER(Params), C.c_int32, vp, vp, vp, vp, vp, vp]
@@ -146,6 +151,12 @@ class Context:
 
     def set_chunk(self, pairs: int):
         self._check(self._L.icet_b200_set_chunk(self._h, pairs))
+
+    def set_lanes(self, lanes: int):
+        self._check(self._L.icet_b200_set_lanes(self._h, lanes))
+
+    def set_host_chunk(self, pairs: int):
+        self._check(self._L.icet_b200_set_host_chunk(self._h, pairs))
 
     def synchronize(self):
         self._check(self._L.icet_b200_synchronize(self._h))
@@ -239,6 +250,12 @@ class Context:
         """[3, n2] planes: the reference's public `points2` member of the last `register` call."""
         out = np.zeros((3, n2), np.float32)
         self._check(self._L.icet_b200_get_points2(self._h, out.ctypes.data, n2))
+        return out
+
+    def debug_timeline(self, runlen: int) -> np.ndarray:
+        """%globaltimer stamps [runlen, 8] (ns) of the loop kernel for the last dumped single-pair call."""
+        out = np.zeros((runlen, 8), np.uint64)
+        self._check(self._L.icet_b200_debug_timeline(self._h, out.ctypes.data, runlen))
         return out
 
     def get_dump(self, p: Params) -> dict:

@@ -72,6 +72,7 @@ struct Vox1 {     // scan-1 Gaussian, constants of the iteration loop (sigma1/mu
 struct Dump {  // optional per-voxel recording (device memory), single-pair debugging only
   int32_t* nin1; uint8_t* has1; float* mu1; float* sigma1; float* evec1; float* eval1; uint8_t* lmask;
   int32_t* cnt2; int32_t* nin2; uint8_t* used2; float* mu2; float* sigma2; float* Xit; float* HTWH; float* HTWdz;
+  unsigned long long* tl;  // [runlen][8] globaltimer stamps of the loop kernel (debug)
 };
 
 struct Chunk {  // everything a kernel needs, passed by value
@@ -106,6 +107,12 @@ struct Chunk {  // everything a kernel needs, passed by value
   float* X;          // [P][6]
   const float* x0;   // [P][6] or null
   icet_b200_result* res;  // [P] device
+  // control words of the persistent Gauss-Newton kernel (k_loop)
+  unsigned* ticket;      // [1]  next task
+  unsigned* tiles_done;  // [P]  scan-2 tiles finished so far (all iterations)
+  int* iter_done;        // [P]  iterations whose solve has been published
+  unsigned* vox_done;    // [P][runlen] vox tasks finished per iteration
+  unsigned* vmask;       // [P][ceil(vt/32)] vox groups that wrote a partial sum (current iteration)
   Dump dump;
   int dump_on;
 };
@@ -390,13 +397,13 @@ __global__ void __launch_bounds__(128) k_cluster(const Chunk ck) {
 // ----------------------------------------------------------------------------------------------
 constexpr int PASS_THREADS = 256;
 constexpr int PASS_WARPS = PASS_THREADS / 32;
-constexpr int PASS_K = 16;                                  // consecutive points per lane in the accumulation phase
-constexpr int PASS_WTILE = 32 * PASS_K;                     // points per warp tile
-constexpr int PASS_WSLOTS = PASS_WTILE + PASS_WTILE / 16;   // 16-byte slots per warp tile (1 pad slot per 16)
-constexpr int PASS_TILE = PASS_WARPS * PASS_WTILE;          // points per block
+constexpr int PASS_K = 16;       // consecutive points per lane in the accumulation phase (throughput shape)
+constexpr int PASS_K_SMALL = 4;  // same for small batches (latency shape: more, smaller tiles)
 
-__host__ __device__ inline int pass_smem_bytes(int nT, int nP) {
-  return PASS_WARPS * PASS_WSLOTS * 16 + (2 * (nT + nP) + 6) * 4;
+__host__ __device__ constexpr int pass_wslots(int K) { return 32 * K + 32; }  // 16-byte slots per warp tile (1 pad per K)
+__host__ __device__ constexpr int pass_tile_points(int K) { return PASS_WARPS * 32 * K; }
+__host__ __device__ inline int pass_smem_bytes(int nT, int nP, int K) {
+  return PASS_WARPS * pass_wslots(K) * 16 + (2 * (nT + nP) + 6) * 4;
 }
 
 // One point -> its accumulation entry {cell << 1 | inside, fx, fy, fz}; .x = -1 when the point's cell takes no
@@ -437,19 +444,89 @@ __device__ __forceinline__ int4 pass_point(const Chunk& ck, const float* tab, co
   return e;
 }
 
-// Each warp works on tiles of PASS_WTILE consecutive points.  Phase A: lane-per-point (coalesced loads, all the
-// fp32 geometry), entries go to the warp's shared-memory tile.  Phase B: every lane walks PASS_K CONSECUTIVE
-// entries and sums runs of equal cell in registers (LiDAR scans list points ring by ring, so neighbours share
-// their voxel: ~27 points per run at 2048 azimuth steps / 75 bins); a run ends with one flush_run.
+// The dropped returns of scan 2: points2_OG == (0,0,0) for all of them, so they all land on t * R
+// (src/icet.cpp:377-378) -- evaluated once per iteration, weighted with their number.
+__device__ inline void pass_dropped_returns(const Chunk& ck, const float* tab, const CellRec* recs, const float* tr,
+                                            unsigned long long* accp, long long nz) {
+  if (nz <= 0) return;
+  const int4 e = pass_point<true>(ck, tab, recs, tr, 0.0f, 0.0f, 0.0f);
+  if (e.x < 0) return;
+  unsigned long long* q = accp + (size_t)(e.x >> 1) * NQ;
+  atomicAdd(q, (unsigned long long)nz);
+  if (e.x & 1) {
+    const long long fx = e.y, fy = e.z, fz = e.w;
+    atomicAdd(q + 1, (unsigned long long)nz);
+    atomicAdd(q + 2, (unsigned long long)(nz * fx));
+    atomicAdd(q + 3, (unsigned long long)(nz * fy));
+    atomicAdd(q + 4, (unsigned long long)(nz * fz));
+    atomicAdd(q + 5, (unsigned long long)(nz * fx * fx));
+    atomicAdd(q + 6, (unsigned long long)(nz * fx * fy));
+    atomicAdd(q + 7, (unsigned long long)(nz * fx * fz));
+    atomicAdd(q + 8, (unsigned long long)(nz * fy * fy));
+    atomicAdd(q + 9, (unsigned long long)(nz * fy * fz));
+    atomicAdd(q + 10, (unsigned long long)(nz * fz * fz));
+  }
+}
+
+// One warp tile of 32*K consecutive points.  Phase A:
+// lane-per-point (coalesced loads, all the fp32 geometry), entries go to the warp's shared-memory tile.  Phase B:
+// every lane walks K CONSECUTIVE entries and sums runs of equal cell in registers (LiDAR scans list points ring by
+// ring, so neighbours share their voxel: ~27 points per run at 2048 azimuth steps / 75 bins); a run ends with one
+// flush_run.  Only warp-level synchronisation inside.
+template <bool SCAN2, int K>
+__device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* the warp's pass_wslots(K) slots */,
+                                               const float* tab, const CellRec* recs, const float* tr,
+                                               const float* px_, size_t ld, int n, int w0,
+                                               unsigned long long* accp) {
+  const int lane = threadIdx.x & 31;
+  if (w0 >= n) return;
+  // ---- phase A
+#pragma unroll 2
+  for (int j = 0; j < K; j++) {
+    const int i = w0 + j * 32 + lane;
+    int4 e = make_int4(-1, 0, 0, 0);
+    if (i < n) {
+      const float x = __ldg(px_ + i), y = __ldg(px_ + ld + i), z = __ldg(px_ + 2 * ld + i);
+      e = pass_point<SCAN2>(ck, tab, recs, tr, x, y, z);
+    }
+    const int slot = j * 32 + lane;
+    went[slot + slot / K] = e;
+  }
+  __syncwarp();
+  // ---- phase B
+  int cur = -1, nbin = 0, nin = 0, sx = 0, sy = 0, sz = 0;
+  long long pxx = 0, pxy = 0, pxz = 0, pyy = 0, pyz = 0, pzz = 0;
+  const int4* mine = went + lane * (K + 1);
+#pragma unroll 4
+  for (int j = 0; j < K; j++) {
+    const int4 e = mine[j];
+    const int key = e.x >> 1;  // -1 stays -1
+    if (key != cur) {
+      flush_run(accp, cur, nbin, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
+      cur = key;
+      nbin = nin = sx = sy = sz = 0;
+      pxx = pxy = pxz = pyy = pyz = pzz = 0;
+    }
+    nbin++;
+    nin += e.x & 1;
+    sx += e.y; sy += e.z; sz += e.w;
+    pxx += (long long)e.y * e.y; pxy += (long long)e.y * e.z; pxz += (long long)e.y * e.w;
+    pyy += (long long)e.z * e.z; pyz += (long long)e.z * e.w; pzz += (long long)e.w * e.w;
+  }
+  flush_run(accp, cur, nbin, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
+  __syncwarp();
+}
+
 template <bool SCAN2>
 __global__ void __launch_bounds__(PASS_THREADS) k_pass(const Chunk ck) {
+  constexpr int K = PASS_K;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int4* ent = reinterpret_cast<int4*>(smem_raw);
-  float* tab = reinterpret_cast<float*>(smem_raw + PASS_WARPS * PASS_WSLOTS * 16);
+  float* tab = reinterpret_cast<float*>(smem_raw + PASS_WARPS * pass_wslots(K) * 16);
   const int pair = blockIdx.y;
   const PairDesc d = ck.desc[pair];
   const int n = SCAN2 ? ck.n2c[pair] : d.n1;
-  const int tile0 = blockIdx.x * PASS_TILE;
+  const int tile0 = blockIdx.x * pass_tile_points(K);
   if (tile0 >= n && !(SCAN2 && blockIdx.x == 0)) return;
   {
     const int ntab = 2 * (ck.nT + ck.nP) + 6;
@@ -466,71 +543,10 @@ __global__ void __launch_bounds__(PASS_THREADS) k_pass(const Chunk ck) {
   const size_t ld = SCAN2 ? (size_t)ck.n2max : (size_t)d.ld1;
   const CellRec* recs = ck.rec + (size_t)pair * ck.ncell;
   unsigned long long* accp = ck.acc + (size_t)pair * ck.ncell * NQ;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int4* went = ent + warp * PASS_WSLOTS;
-  const int w0 = tile0 + warp * PASS_WTILE;
   __syncthreads();
-  if (w0 < n) {
-    // ---- phase A
-#pragma unroll 2
-    for (int j = 0; j < PASS_K; j++) {
-      const int i = w0 + j * 32 + lane;
-      int4 e = make_int4(-1, 0, 0, 0);
-      if (i < n) {
-        const float x = __ldg(px_ + i), y = __ldg(px_ + ld + i), z = __ldg(px_ + 2 * ld + i);
-        e = pass_point<SCAN2>(ck, tab, recs, tr, x, y, z);
-      }
-      const int slot = j * 32 + lane;
-      went[slot + (slot >> 4)] = e;
-    }
-    __syncwarp();
-    // ---- phase B
-    int cur = -1, nbin = 0, nin = 0, sx = 0, sy = 0, sz = 0;
-    long long pxx = 0, pxy = 0, pxz = 0, pyy = 0, pyz = 0, pzz = 0;
-    const int4* mine = went + lane * (PASS_K + 1);
-#pragma unroll 4
-    for (int j = 0; j < PASS_K; j++) {
-      const int4 e = mine[j];
-      const int key = e.x >> 1;  // -1 stays -1
-      if (key != cur) {
-        flush_run(accp, cur, nbin, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
-        cur = key;
-        nbin = nin = sx = sy = sz = 0;
-        pxx = pxy = pxz = pyy = pyz = pzz = 0;
-      }
-      nbin++;
-      nin += e.x & 1;
-      sx += e.y; sy += e.z; sz += e.w;
-      pxx += (long long)e.y * e.y; pxy += (long long)e.y * e.z; pxz += (long long)e.y * e.w;
-      pyy += (long long)e.z * e.z; pyz += (long long)e.z * e.w; pzz += (long long)e.w * e.w;
-    }
-    flush_run(accp, cur, nbin, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
-  }
-  if (SCAN2 && blockIdx.x == 0 && threadIdx.x == 0) {
-    // the dropped returns of scan 2: points2_OG == (0,0,0) for all of them, so they all land on t * R
-    // (src/icet.cpp:377-378) -- evaluated once, weighted with their number
-    const long long nz = ck.nz2[pair];
-    if (nz > 0) {
-      const int4 e = pass_point<true>(ck, tab, recs, tr, 0.0f, 0.0f, 0.0f);
-      if (e.x >= 0) {
-        unsigned long long* q = accp + (size_t)(e.x >> 1) * NQ;
-        atomicAdd(q, (unsigned long long)nz);
-        if (e.x & 1) {
-          const long long fx = e.y, fy = e.z, fz = e.w;
-          atomicAdd(q + 1, (unsigned long long)nz);
-          atomicAdd(q + 2, (unsigned long long)(nz * fx));
-          atomicAdd(q + 3, (unsigned long long)(nz * fy));
-          atomicAdd(q + 4, (unsigned long long)(nz * fz));
-          atomicAdd(q + 5, (unsigned long long)(nz * fx * fx));
-          atomicAdd(q + 6, (unsigned long long)(nz * fx * fy));
-          atomicAdd(q + 7, (unsigned long long)(nz * fx * fz));
-          atomicAdd(q + 8, (unsigned long long)(nz * fy * fy));
-          atomicAdd(q + 9, (unsigned long long)(nz * fy * fz));
-          atomicAdd(q + 10, (unsigned long long)(nz * fz * fz));
-        }
-      }
-    }
-  }
+  pass_warp_tile<SCAN2, K>(ck, ent + (threadIdx.x >> 5) * pass_wslots(K), tab, recs, tr, px_, ld, n,
+                           tile0 + (threadIdx.x >> 5) * 32 * K, accp);
+  if (SCAN2 && blockIdx.x == 0 && threadIdx.x == 0) pass_dropped_returns(ck, tab, recs, tr, accp, ck.nz2[pair]);
 }
 
 // exact-sum -> mean / covariance (double) of a voxel
@@ -669,166 +685,146 @@ __global__ void __launch_bounds__(256) k_prep2(const Chunk ck) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// K5b: one thread per voxel.  Scan-2 mean / covariance, R_noise, W, H_z and the voxel's contributions
-// H^T W H_j (upper triangle, 21) and H^T W dz_j (6)  (fitCells2 src/icet.cpp:302-338); fixed-order
-// reduction over the block's 64 voxels -> one partial sum per block.
+// K5b: per voxel.  Scan-2 mean / covariance, R_noise, W, H_z and the voxel's contributions
+// H^T W H_j (upper triangle, 21) and H^T W dz_j (6)  (fitCells2 src/icet.cpp:302-338), ADDED to acc[].
+// Takes the voxel's integer accumulators (L2 reads: other SMs produced them) and clears them for the next
+// iteration.
 // ----------------------------------------------------------------------------------------------
 constexpr int VOX_THREADS = 64;
 constexpr int NRED = 28;  // 21 (upper triangle of H^T W H) + 6 (H^T W dz) + 1 (voxels used)
 
-__global__ void __launch_bounds__(VOX_THREADS) k_vox2(const Chunk ck, int iter) {
-  const int pair = blockIdx.y;
-  const int cell = blockIdx.x * VOX_THREADS + threadIdx.x;
-  __shared__ double s_red[NRED];
+// Gate of fitCells2 for one voxel (`indices2.size() > n` :290, `rows > n` :302).  Returns true if the voxel
+// contributes; its accumulators are then left in place for vox_algebra, otherwise they are cleared here.
+__device__ __forceinline__ bool vox_gate(const Chunk& ck, int pair, int cell, int iter) {
   const size_t ci = (size_t)pair * ck.ncell + cell;
-  bool active = false;
-  CellRec rc;
-  if (cell < ck.ncell) {
-    rc = ck.rec[ci];
-    active = (rc.flags & F_ACTIVE2) != 0;
-  }
-  double acc[NRED];
-#pragma unroll
-  for (int k = 0; k < NRED; k++) acc[k] = 0.0;
-  if (ck.dump_on && cell < ck.ncell && !active) {
-    ck.dump.cnt2[(size_t)iter * ck.ncell + cell] = -1;
-    ck.dump.nin2[(size_t)iter * ck.ncell + cell] = -1;
-    ck.dump.used2[(size_t)iter * ck.ncell + cell] = 0;
-  }
-  if (active) {
-    unsigned long long q[NQ];
-    unsigned long long* qp = ck.acc + ci * NQ;
-#pragma unroll
-    for (int k = 0; k < NQ; k++) { q[k] = qp[k]; qp[k] = 0ull; }
-    const long long nbin = (long long)q[0], nin = (long long)q[1];
-    const bool use = nbin > ck.n && nin > ck.n;  // `indices2.size() > n` (:290), `rows > n` (:302)
+  const uint32_t flags = ck.rec[ci].flags;
+  if (!(flags & F_ACTIVE2)) {
     if (ck.dump_on) {
-      ck.dump.cnt2[(size_t)iter * ck.ncell + cell] = (int)nbin;
-      ck.dump.nin2[(size_t)iter * ck.ncell + cell] = (nbin > ck.n) ? (int)nin : -1;
-      ck.dump.used2[(size_t)iter * ck.ncell + cell] = use ? 1 : 0;
+      ck.dump.cnt2[(size_t)iter * ck.ncell + cell] = -1;
+      ck.dump.nin2[(size_t)iter * ck.ncell + cell] = -1;
+      ck.dump.used2[(size_t)iter * ck.ncell + cell] = 0;
     }
-    if (use) {
-      const float* J = ck.J + (size_t)pair * 27;
-      double mean[3], cov[6];
-      stats_from_acc(q, rc, mean, cov);
-      const Vox1 v = ck.vox[ci];
-      if (ck.dump_on) {
-        float* m2 = ck.dump.mu2 + ((size_t)iter * ck.ncell + cell) * 3;
-        float* s2 = ck.dump.sigma2 + ((size_t)iter * ck.ncell + cell) * 9;
-        for (int k = 0; k < 3; k++) m2[k] = (float)mean[k];
-        s2[0] = (float)cov[0]; s2[1] = (float)cov[1]; s2[2] = (float)cov[2];
-        s2[3] = (float)cov[1]; s2[4] = (float)cov[3]; s2[5] = (float)cov[4];
-        s2[6] = (float)cov[2]; s2[7] = (float)cov[4]; s2[8] = (float)cov[5];
-      }
-      // R_noise = sigma1/(|idx1|-1) + sigma2/(|idx2|-1)   (:315)
-      const double id2 = 1.0 / (double)(nbin - 1);
-      double Rn[9];
-      {
-        double r6[6];
-#pragma unroll
-        for (int k = 0; k < 6; k++) r6[k] = v.S1n[k] + cov[k] * id2;
-        Rn[0] = r6[0]; Rn[1] = r6[1]; Rn[2] = r6[2]; Rn[3] = r6[1]; Rn[4] = r6[3]; Rn[5] = r6[4];
-        Rn[6] = r6[2]; Rn[7] = r6[4]; Rn[8] = r6[5];
-      }
-      // M = (L U^T) R_noise (L U^T)^T   (:317)
-      double T[9], M[9];
-#pragma unroll
-      for (int a = 0; a < 3; a++)
-#pragma unroll
-        for (int b = 0; b < 3; b++)
-          T[3 * a + b] = v.LV[3 * a] * Rn[b] + v.LV[3 * a + 1] * Rn[3 + b] + v.LV[3 * a + 2] * Rn[6 + b];
-#pragma unroll
-      for (int a = 0; a < 3; a++)
-#pragma unroll
-        for (int b = 0; b < 3; b++)
-          M[3 * a + b] = T[3 * a] * v.LV[3 * b] + T[3 * a + 1] * v.LV[3 * b + 1] + T[3 * a + 2] * v.LV[3 * b + 2];
-      // W = pinv(M)  (:320-321)
-      double W[9];
-      if (!icet::masked_inv3(M, v.lmask, W)) icet::cod_pinv(M, 3, 3, W);
-      // H_z = L U^T [ -I | Jx mu | Jy mu | Jz mu ]  (:324-329)
-      double H[18];
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        H[6 * a + 0] = (a == 0) ? -1.0 : 0.0;
-        H[6 * a + 1] = (a == 1) ? -1.0 : 0.0;
-        H[6 * a + 2] = (a == 2) ? -1.0 : 0.0;
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-          H[6 * a + 3 + j] = (double)__ldg(J + 9 * j + 3 * a) * mean[0] + (double)__ldg(J + 9 * j + 3 * a + 1) * mean[1] +
-                             (double)__ldg(J + 9 * j + 3 * a + 2) * mean[2];
-      }
-      double Hz[18];
-#pragma unroll
-      for (int a = 0; a < 3; a++)
-#pragma unroll
-        for (int c = 0; c < 6; c++)
-          Hz[6 * a + c] = v.LV[3 * a] * H[c] + v.LV[3 * a + 1] * H[6 + c] + v.LV[3 * a + 2] * H[12 + c];
-      // dz = L U^T (mean2 - mu1)   (:335-337)
-      const double dm[3] = {mean[0] - v.mu[0], mean[1] - v.mu[1], mean[2] - v.mu[2]};
-      double dz[3];
-#pragma unroll
-      for (int a = 0; a < 3; a++) dz[a] = v.LV[3 * a] * dm[0] + v.LV[3 * a + 1] * dm[1] + v.LV[3 * a + 2] * dm[2];
-      double WH[18], Wdz[3];
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-#pragma unroll
-        for (int c = 0; c < 6; c++)
-          WH[6 * a + c] = W[3 * a] * Hz[c] + W[3 * a + 1] * Hz[6 + c] + W[3 * a + 2] * Hz[12 + c];
-        Wdz[a] = W[3 * a] * dz[0] + W[3 * a + 1] * dz[1] + W[3 * a + 2] * dz[2];
-      }
-      int t = 0;
-#pragma unroll
-      for (int a = 0; a < 6; a++)
-#pragma unroll
-        for (int b = a; b < 6; b++) acc[t++] = Hz[a] * WH[b] + Hz[6 + a] * WH[6 + b] + Hz[12 + a] * WH[12 + b];
-#pragma unroll
-      for (int a = 0; a < 6; a++) acc[21 + a] = Hz[a] * Wdz[0] + Hz[6 + a] * Wdz[1] + Hz[12 + a] * Wdz[2];
-      acc[27] = 1.0;
-    }
+    return false;
   }
-  // fixed-order reduction: xor butterfly inside each warp, then warp 1 + warp 0
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const bool any = __syncthreads_or(acc[27] != 0.0);
-  double* out = ck.part + ((size_t)pair * gridDim.x + blockIdx.x) * NRED;
-  if (!any) {  // block-uniform: nothing to add
-    if (threadIdx.x < NRED) out[threadIdx.x] = 0.0;
-    return;
+  unsigned long long* qp = ck.acc + ci * NQ;
+  const ulonglong2 q01 = __ldcg(reinterpret_cast<const ulonglong2*>(qp));
+  const long long nbin = (long long)q01.x, nin = (long long)q01.y;
+  const bool use = nbin > ck.n && nin > ck.n;
+  if (ck.dump_on) {
+    ck.dump.cnt2[(size_t)iter * ck.ncell + cell] = (int)nbin;
+    ck.dump.nin2[(size_t)iter * ck.ncell + cell] = (nbin > ck.n) ? (int)nin : -1;
+    ck.dump.used2[(size_t)iter * ck.ncell + cell] = use ? 1 : 0;
+  }
+  if (!use && nbin != 0) {
+#pragma unroll
+    for (int k = 0; k < NQ; k++) qp[k] = 0ull;
+  }
+  return use;
+}
+
+// The algebra of one contributing voxel; takes (and clears) its accumulators.
+__device__ __forceinline__ void vox_algebra(const Chunk& ck, int pair, int cell, int iter, const float* Jm /* 27 */,
+                                            double acc[NRED]) {
+  const size_t ci = (size_t)pair * ck.ncell + cell;
+  const CellRec rc = ck.rec[ci];
+  unsigned long long q[NQ];
+  unsigned long long* qp = ck.acc + ci * NQ;
+#pragma unroll
+  for (int k = 0; k < NQ; k += 2) {
+    const ulonglong2 t = __ldcg(reinterpret_cast<const ulonglong2*>(qp + k));
+    q[k] = t.x;
+    q[k + 1] = t.y;
   }
 #pragma unroll
-  for (int k = 0; k < NRED; k++) {
-    double vsum = acc[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(FULL, vsum, o);
-    acc[k] = vsum;
+  for (int k = 0; k < NQ; k++) qp[k] = 0ull;
+  const long long nbin = (long long)q[0];
+  double mean[3], cov[6];
+  stats_from_acc(q, rc, mean, cov);
+  const Vox1 v = ck.vox[ci];
+  if (ck.dump_on) {
+    float* m2 = ck.dump.mu2 + ((size_t)iter * ck.ncell + cell) * 3;
+    float* s2 = ck.dump.sigma2 + ((size_t)iter * ck.ncell + cell) * 9;
+    for (int k = 0; k < 3; k++) m2[k] = (float)mean[k];
+    s2[0] = (float)cov[0]; s2[1] = (float)cov[1]; s2[2] = (float)cov[2];
+    s2[3] = (float)cov[1]; s2[4] = (float)cov[3]; s2[5] = (float)cov[4];
+    s2[6] = (float)cov[2]; s2[7] = (float)cov[4]; s2[8] = (float)cov[5];
   }
-  if (wid == 1 && lane == 0) {
+  // R_noise = sigma1/(|idx1|-1) + sigma2/(|idx2|-1)   (:315)
+  const double id2 = 1.0 / (double)(nbin - 1);
+  double Rn[9];
+  {
+    double r6[6];
 #pragma unroll
-    for (int k = 0; k < NRED; k++) s_red[k] = acc[k];
+    for (int k = 0; k < 6; k++) r6[k] = v.S1n[k] + cov[k] * id2;
+    Rn[0] = r6[0]; Rn[1] = r6[1]; Rn[2] = r6[2]; Rn[3] = r6[1]; Rn[4] = r6[3]; Rn[5] = r6[4];
+    Rn[6] = r6[2]; Rn[7] = r6[4]; Rn[8] = r6[5];
   }
-  __syncthreads();
-  if (wid == 0 && lane == 0) {
+  // M = (L U^T) R_noise (L U^T)^T   (:317)
+  double T[9], M[9];
 #pragma unroll
-    for (int k = 0; k < NRED; k++) out[k] = acc[k] + s_red[k];
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++)
+      T[3 * a + b] = v.LV[3 * a] * Rn[b] + v.LV[3 * a + 1] * Rn[3 + b] + v.LV[3 * a + 2] * Rn[6 + b];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++)
+      M[3 * a + b] = T[3 * a] * v.LV[3 * b] + T[3 * a + 1] * v.LV[3 * b + 1] + T[3 * a + 2] * v.LV[3 * b + 2];
+  // W = pinv(M)  (:320-321)
+  double W[9];
+  if (!icet::masked_inv3(M, v.lmask, W)) icet::cod_pinv(M, 3, 3, W);
+  // H_z = L U^T [ -I | Jx mu | Jy mu | Jz mu ]  (:324-329)
+  double H[18];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    H[6 * a + 0] = (a == 0) ? -1.0 : 0.0;
+    H[6 * a + 1] = (a == 1) ? -1.0 : 0.0;
+    H[6 * a + 2] = (a == 2) ? -1.0 : 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      H[6 * a + 3 + j] = (double)Jm[9 * j + 3 * a] * mean[0] + (double)Jm[9 * j + 3 * a + 1] * mean[1] +
+                         (double)Jm[9 * j + 3 * a + 2] * mean[2];
   }
+  double Hz[18];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int c = 0; c < 6; c++)
+      Hz[6 * a + c] = v.LV[3 * a] * H[c] + v.LV[3 * a + 1] * H[6 + c] + v.LV[3 * a + 2] * H[12 + c];
+  // dz = L U^T (mean2 - mu1)   (:335-337)
+  const double dm[3] = {mean[0] - v.mu[0], mean[1] - v.mu[1], mean[2] - v.mu[2]};
+  double dz[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) dz[a] = v.LV[3 * a] * dm[0] + v.LV[3 * a + 1] * dm[1] + v.LV[3 * a + 2] * dm[2];
+  double WH[18], Wdz[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+#pragma unroll
+    for (int c = 0; c < 6; c++)
+      WH[6 * a + c] = W[3 * a] * Hz[c] + W[3 * a + 1] * Hz[6 + c] + W[3 * a + 2] * Hz[12 + c];
+    Wdz[a] = W[3 * a] * dz[0] + W[3 * a + 1] * dz[1] + W[3 * a + 2] * dz[2];
+  }
+  int t = 0;
+#pragma unroll
+  for (int a = 0; a < 6; a++)
+#pragma unroll
+    for (int b = a; b < 6; b++) acc[t++] += Hz[a] * WH[b] + Hz[6 + a] * WH[6 + b] + Hz[12 + a] * WH[12 + b];
+#pragma unroll
+  for (int a = 0; a < 6; a++) acc[21 + a] += Hz[a] * Wdz[0] + Hz[6 + a] * Wdz[1] + Hz[12 + a] * Wdz[2];
+  acc[27] += 1.0;
+}
+
+__device__ __forceinline__ void vox_contrib(const Chunk& ck, int pair, int cell, int iter, const float* Jm,
+                                            double acc[NRED]) {
+  if (vox_gate(ck, pair, cell, iter)) vox_algebra(ck, pair, cell, iter, Jm, acc);
 }
 
 // ----------------------------------------------------------------------------------------------
-// K6: one warp per pair.  Sums the block partials in index order, then lane 0: Q = pinv(H^T W H),
-// pred_stds, checkCondition, dx, X += dx (src/icet.cpp:410-433, :443-492) and the transform / get_H
-// trigonometry of the next iteration.
+// K6: one thread per pair: Q = pinv(H^T W H), pred_stds, checkCondition, dx, X += dx (src/icet.cpp:410-433,
+// :443-492) and the transform / get_H trigonometry of the next iteration.  tot = the 28 sums over the voxels.
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_solve6(const Chunk ck, int iter, int nblk) {
-  const int pair = blockIdx.x;
-  const int lane = threadIdx.x;
-  double mine = 0.0;
-  if (lane < NRED) {
-    const double* pp = ck.part + (size_t)pair * nblk * NRED + lane;
-    for (int b = 0; b < nblk; b++) mine += pp[(size_t)b * NRED];
-  }
-  double tot[NRED];
-#pragma unroll
-  for (int k = 0; k < NRED; k++) tot[k] = __shfl_sync(FULL, mine, k);
-  if (lane != 0) return;
+__device__ __noinline__ void solve_pair(const Chunk& ck, int pair, int iter, const double* tot) {
   float* X = ck.X + pair * 6;
   double A[36], b[6];
   {
@@ -911,27 +907,355 @@ __global__ void __launch_bounds__(32) k_solve6(const Chunk ck, int iter, int nbl
       for (int j = 0; j < 6; j++) dx[j] += U[j * 6 + k] * (ub / ev[k]);
     }
   }
-  for (int k = 0; k < 6; k++) X[k] = (float)((double)X[k] + dx[k]);  // X += dx (:433), X is fp32
+  float Xn[6];
+  for (int k = 0; k < 6; k++) Xn[k] = (float)((double)__ldcg(X + k) + dx[k]);  // X += dx (:433), X is fp32
+  for (int k = 0; k < 6; k++) X[k] = Xn[k];
   {  // trigonometry of the next iteration: utils::R (src/icet.cpp:375-376) and get_H (:507-527)
     float* TR = ck.TR + (size_t)pair * 12;
     if (iter == ck.runlen - 1)
-      for (int k = 0; k < 12; k++) ck.TRprev[(size_t)pair * 12 + k] = TR[k];
-    TR[0] = X[0]; TR[1] = X[1]; TR[2] = X[2];
-    icet::rotR(X[3], X[4], X[5], TR + 3);
-    icet::getH_J(X[3], X[4], X[5], ck.J + (size_t)pair * 27);
+      for (int k = 0; k < 12; k++) ck.TRprev[(size_t)pair * 12 + k] = __ldcg(TR + k);
+    TR[0] = Xn[0]; TR[1] = Xn[1]; TR[2] = Xn[2];
+    icet::rotR(Xn[3], Xn[4], Xn[5], TR + 3);
+    icet::getH_J(Xn[3], Xn[4], Xn[5], ck.J + (size_t)pair * 27);
   }
   if (ck.dump_on) {
-    for (int k = 0; k < 6; k++) { ck.dump.Xit[iter * 6 + k] = X[k]; ck.dump.HTWdz[iter * 6 + k] = (float)b[k]; }
+    for (int k = 0; k < 6; k++) { ck.dump.Xit[iter * 6 + k] = Xn[k]; ck.dump.HTWdz[iter * 6 + k] = (float)b[k]; }
     for (int k = 0; k < 36; k++) ck.dump.HTWH[iter * 36 + k] = (float)A[k];
   }
   if (iter == ck.runlen - 1) {
-    for (int k = 0; k < 6; k++) { R->X[k] = X[k]; R->pred_stds[k] = (float)stds[k]; }
+    for (int k = 0; k < 6; k++) { R->X[k] = Xn[k]; R->pred_stds[k] = (float)stds[k]; }
     for (int k = 0; k < 36; k++) R->Q[k] = (float)Q[k];
     R->n_used = (int)(tot[27] + 0.5);
     R->n_dropped = dropped;
     R->cond = (float)cond_out;
   }
   if (status) R->status = status;
+}
+
+// Warp-parallel form of the common case of solve_pair: Gauss-Jordan elimination of [A | I | b] (13 columns, one
+// per lane, no pivoting: A = H^T W H is symmetric positive definite whenever this path is valid).  Returns (warp
+// uniform) false when a pivot is not positive or the bound trace(A) trace(A^-1) cannot prove cond <= 1e6; the caller
+// then runs solve_pair (eigen-decomposition + the reference's truncation loop) on one thread.
+__device__ __forceinline__ bool solve_pair_warp(const Chunk& ck, int pair, int iter, const double* tot) {
+  const int lane = threadIdx.x & 31;
+  double col[6];
+  {
+    // lane j < 6: column j of A; lane 6 + j: column j of I; lane 12: b
+    const int j = lane < 6 ? lane : 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const int lo = i < j ? i : j, hi = i < j ? j : i;
+      const double a = tot[lo * 6 - lo * (lo - 1) / 2 + (hi - lo)];  // packed upper triangle
+      col[i] = lane < 6 ? a : (lane < 12 ? (lane - 6 == i ? 1.0 : 0.0) : (lane == 12 ? tot[21 + i] : 0.0));
+    }
+  }
+  double trA = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) trA += tot[i * 6 - i * (i - 1) / 2];
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const double piv = __shfl_sync(FULL, col[k], k);
+    ok = ok && (piv > 0.0);
+    const double ip = 1.0 / piv;
+    col[k] *= ip;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      if (i == k) continue;
+      const double f = __shfl_sync(FULL, col[i], k);
+      col[i] -= f * col[k];
+    }
+  }
+  double trQ = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; k++) trQ += __shfl_sync(FULL, col[k], 6 + k);
+  // cond <= trace(A) * trace(A^-1); comfortably below the 1e6 cutoff => checkCondition drops nothing and
+  // pinv == inverse, so dx = A^-1 b  (src/icet.cpp:410-433 with an empty while-loop at :469)
+  if (!(ok && trA * trQ < 0.999e6)) return false;
+  float* X = ck.X + pair * 6;
+  icet_b200_result* R = ck.res + pair;
+  const bool last = iter == ck.runlen - 1;
+  if (lane == 12) {
+    float Xn[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) Xn[k] = (float)((double)__ldcg(X + k) + col[k]);  // X += dx (:433), X is fp32
+#pragma unroll
+    for (int k = 0; k < 6; k++) X[k] = Xn[k];
+    float* TR = ck.TR + (size_t)pair * 12;
+    if (last)
+      for (int k = 0; k < 12; k++) ck.TRprev[(size_t)pair * 12 + k] = __ldcg(TR + k);
+    TR[0] = Xn[0]; TR[1] = Xn[1]; TR[2] = Xn[2];
+    icet::rotR(Xn[3], Xn[4], Xn[5], TR + 3);
+    icet::getH_J(Xn[3], Xn[4], Xn[5], ck.J + (size_t)pair * 27);
+    if (ck.dump_on) {
+      for (int k = 0; k < 6; k++) { ck.dump.Xit[iter * 6 + k] = Xn[k]; ck.dump.HTWdz[iter * 6 + k] = (float)tot[21 + k]; }
+    }
+    if (last) {
+      for (int k = 0; k < 6; k++) R->X[k] = Xn[k];
+      R->n_used = (int)(tot[27] + 0.5);
+      R->n_dropped = 0;
+      R->cond = (float)(-(trA * trQ));
+    }
+  }
+  if (ck.dump_on && lane < 6) {
+    for (int i = 0; i < 6; i++) {
+      const int lo = i < lane ? i : lane, hi = i < lane ? lane : i;
+      ck.dump.HTWH[iter * 36 + i * 6 + lane] = (float)tot[lo * 6 - lo * (lo - 1) / 2 + (hi - lo)];
+    }
+  }
+  if (last && lane >= 6 && lane < 12) {
+    const int j = lane - 6;
+#pragma unroll
+    for (int i = 0; i < 6; i++) R->Q[i * 6 + j] = (float)col[i];
+    // pred_stds = sqrt|diag noise_mat| (:414-417)
+    double d = col[0];
+#pragma unroll
+    for (int i = 1; i < 6; i++) d = (j == i) ? col[i] : d;
+    R->pred_stds[j] = (float)sqrt(fabs(d));
+  }
+  return true;
+}
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TL(slot)                                                                         \
+  do {                                                                                   \
+    if (ck.dump_on && (threadIdx.x & 31) == 0) ck.dump.tl[(size_t)iter * 8 + (slot)] = gtime(); \
+  } while (0)
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// warp tiles of a pair that are counted in tiles_done per iteration: those that hold points, at least tile 0
+__device__ __forceinline__ int loop_tiles_of(int n2c, int tile_points) { return max(1, (n2c + tile_points - 1) / tile_points); }
+
+// One vox task of k_loop (see there): the fitCells2 algebra of 32 consecutive cells, and, for the task that
+// arrives last, the end of the iteration of the pair.
+__device__ __noinline__ void vox_task(const Chunk& ck, int iter, int pair, int grp, int tpt, int vt, double* w_tot,
+                                      float* w_J) {
+  const int lane = threadIdx.x & 31;
+  const int cell = grp * 32 + lane;
+  const bool active = cell < ck.ncell && (ck.rec[(size_t)pair * ck.ncell + cell].flags & F_ACTIVE2) != 0;
+  const bool any = __any_sync(FULL, active);
+  if (any) {
+    {
+      const int* cnt = reinterpret_cast<const int*>(ck.tiles_done + pair);
+      const int need = (iter + 1) * loop_tiles_of(__ldg(ck.n2c + pair), tpt);
+      while (ld_acquire(cnt) < need) __nanosleep(32);
+    }
+    if (lane < 27) w_J[lane] = __ldcg(ck.J + (size_t)pair * 27 + lane);
+    __syncwarp();
+    TL(1);
+    double acc[NRED];
+#pragma unroll
+    for (int k = 0; k < NRED; k++) acc[k] = 0.0;
+    if (cell < ck.ncell && vox_gate(ck, pair, cell, iter)) vox_algebra(ck, pair, cell, iter, w_J, acc);
+    if (__any_sync(FULL, acc[27] != 0.0)) {
+      double* out = ck.part + ((size_t)pair * vt + grp) * NRED;
+#pragma unroll
+      for (int k = 0; k < NRED; k++) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if (lane == k) out[k] = v;
+      }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        atomicOr(ck.vmask + (size_t)pair * ((vt + 31) / 32) + (grp >> 5), 1u << (grp & 31));
+      }
+    }
+    TL(2);
+  } else if (ck.dump_on && cell < ck.ncell) {
+    vox_gate(ck, pair, cell, iter);  // records the "inactive" markers
+  }
+  __threadfence();  // every lane: partial sums, cleared accumulators, the group's vmask bit
+  __syncwarp();
+  unsigned prev = 0;
+  if (lane == 0) {
+    prev = atomicAdd(ck.vox_done + (size_t)pair * ck.runlen + iter, 1u);
+  }
+  prev = __shfl_sync(FULL, prev, 0);
+  if (prev + 1u == (unsigned)vt) {
+    // -------------------------------------------------------------- end of the iteration of this pair
+    __threadfence();
+    TL(0);
+    double tot = 0.0;
+    const int nw = (vt + 31) / 32;
+    for (int w = 0; w < nw; w++) {
+      unsigned* mp = ck.vmask + (size_t)pair * nw + w;
+      unsigned m = __ldcg(mp);
+      if (lane == 0 && m) *mp = 0u;
+      const double* pp = ck.part + ((size_t)pair * vt + (size_t)w * 32) * NRED + (lane < NRED ? lane : 0);
+      while (m) {  // group order; four loads in flight
+        int g[4];
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          g[u] = m ? __ffs(m) - 1 : -1;
+          m = m ? (m & (m - 1)) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = (g[u] >= 0) ? __ldcg(pp + (size_t)g[u] * NRED) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (g[u] >= 0) tot += v[u];
+      }
+    }
+    __syncwarp();
+    if (lane < NRED) w_tot[lane] = tot;
+    __syncwarp();
+    TL(3);
+    bool done = false;
+    if (!(ck.flags & ICET_B200_FLAG_FULL_EIG)) done = solve_pair_warp(ck, pair, iter, w_tot);
+    if (!done && lane == 0) solve_pair(ck, pair, iter, w_tot);
+    __threadfence();  // every lane: X, TR, J, result fields
+    __syncwarp();
+    TL(4);
+    if (lane == 0) st_release(ck.iter_done + pair, iter + 1);
+    TL(5);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// The Gauss-Newton loop of every pair of the chunk in ONE persistent launch (fitScan2 x runlen,
+// src/icet.cpp:47, :372-436): nothing returns to the host between iterations.
+//
+// The worker is the WARP.  Work is a stream of tasks, ordered
+//     for it in 0..runlen:  [ (it, pair, tile) for every pair, tile ]  then  [ (it, pair, vox group) for every pair, group ]
+// and warps draw tickets from one counter.
+//   * tile task: one warp tile of scan 2 through pass_warp_tile (transform ... integer accumulation), then
+//     tiles_done[pair] += 1.  Needs X of iteration it: waits until iter_done[pair] >= it.
+//   * vox task: the fitCells2 algebra of 32 consecutive cells (one per lane), a fixed-order warp reduction of the
+//     28 sums into part[pair][group][28].  Needs all tiles of (pair, it): waits on tiles_done[pair].  The vox task
+//     that arrives last (vox_done[pair][it]) adds the partials in group order, solves the 6x6 system on the warp
+//     (solve_pair_warp), writes the next transform and publishes iter_done[pair] = it + 1.
+// Every task only ever waits for tasks with SMALLER tickets, which are held by warps that are already running, so
+// the scheme cannot deadlock whatever the number of resident warps.  With many pairs in flight nobody waits (the
+// solve of one pair overlaps the tiles of the others); with one pair the waits ARE the latency-critical path and
+// the vox groups / tiles of the pair spread over the whole GPU.
+// ----------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(PASS_THREADS, 3) k_loop(const Chunk ck, int tiles, int vt) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* tab = reinterpret_cast<float*>(smem_raw + PASS_WARPS * pass_wslots(K) * 16);
+  {
+    const int ntab = 2 * (ck.nT + ck.nP) + 6;
+    for (int k = threadIdx.x; k < ntab; k += PASS_THREADS) tab[k] = __ldg(ck.azE + k);
+  }
+  __syncthreads();  // the only block-wide barrier: from here on warps are independent workers
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int4* went = reinterpret_cast<int4*>(smem_raw) + warp * pass_wslots(K);
+  static_assert(pass_wslots(K) * 16 >= 512, "warp scratch too small");
+  double* w_tot = reinterpret_cast<double*>(went);                          // [28]   (vox tasks only)
+  float* w_J = reinterpret_cast<float*>(reinterpret_cast<char*>(went) + 256);  // [27]
+  const unsigned ntile = (unsigned)ck.npairs * (unsigned)tiles;
+  const unsigned per_iter = ntile + (unsigned)ck.npairs * (unsigned)vt;
+  const unsigned total = per_iter * (unsigned)ck.runlen;
+  unsigned t = 0;
+  if (lane == 0) t = atomicAdd(ck.ticket, 1u);
+  t = __shfl_sync(FULL, t, 0);
+  while (t < total) {
+    // the next ticket is drawn now; its round trip to L2 hides behind this task
+    unsigned t_next = 0;
+    if (lane == 0) t_next = atomicAdd(ck.ticket, 1u);
+    const int iter = (int)(t / per_iter);
+    unsigned rem = t - (unsigned)iter * per_iter;
+    if (rem < ntile) {
+      // ------------------------------------------------------------------ tile task
+      const int pair = (int)(rem / (unsigned)tiles);
+      const int tile = (int)(rem - (unsigned)pair * (unsigned)tiles);
+      const int n = __ldg(ck.n2c + pair);
+      const int w0 = tile * 32 * K;
+      if (w0 < n || tile == 0) {
+        if (iter > 0) {
+          const int* flag = ck.iter_done + pair;
+          while (ld_acquire(flag) < iter) __nanosleep(32);
+        }
+        float tr[12];
+        {
+          const float4* tp = reinterpret_cast<const float4*>(ck.TR + (size_t)pair * 12);
+          const float4 a = __ldcg(tp), b = __ldcg(tp + 1), c = __ldcg(tp + 2);
+          tr[0] = a.x; tr[1] = a.y; tr[2] = a.z; tr[3] = a.w; tr[4] = b.x; tr[5] = b.y; tr[6] = b.z; tr[7] = b.w;
+          tr[8] = c.x; tr[9] = c.y; tr[10] = c.z; tr[11] = c.w;
+        }
+        const CellRec* recs = ck.rec + (size_t)pair * ck.ncell;
+        unsigned long long* accp = ck.acc + (size_t)pair * ck.ncell * NQ;
+        if (tile == 0) TL(6);
+        pass_warp_tile<true, K>(ck, went, tab, recs, tr, ck.pog + (size_t)pair * 3 * ck.n2max, (size_t)ck.n2max, n, w0,
+                                accp);
+        if (tile == 0 && lane == 0) pass_dropped_returns(ck, tab, recs, tr, accp, __ldg(ck.nz2 + pair));
+        if (tile == 0) TL(7);
+        __threadfence();  // every lane: its accumulator updates are visible before the tile is counted
+        __syncwarp();
+        if (lane == 0) atomicAdd(ck.tiles_done + pair, 1u);
+      }  // tiles beyond the compacted point count of the pair are not counted (see loop_tiles_of)
+    } else {
+      // ------------------------------------------------------------------ vox task
+      rem -= ntile;
+      const int pair = (int)(rem / (unsigned)vt);
+      vox_task(ck, iter, pair, (int)(rem - (unsigned)pair * (unsigned)vt), 32 * K, vt, w_tot, w_J);
+    }
+    t = __shfl_sync(FULL, t_next, 0);
+  }
+}
+
+// Legacy split form of the loop (ICET_B200_FLAG_UNFUSED_LOOP): k_pass<true>, then these two, per iteration.
+__global__ void __launch_bounds__(VOX_THREADS) k_vox2(const Chunk ck, int iter) {
+  const int pair = blockIdx.y;
+  const int cell = blockIdx.x * VOX_THREADS + threadIdx.x;
+  __shared__ double s_red[NRED];
+  double acc[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; k++) acc[k] = 0.0;
+  if (cell < ck.ncell) vox_contrib(ck, pair, cell, iter, ck.J + (size_t)pair * 27, acc);
+  // fixed-order reduction: xor butterfly inside each warp, then warp 1 + warp 0
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool any = __syncthreads_or(acc[27] != 0.0);
+  double* out = ck.part + ((size_t)pair * gridDim.x + blockIdx.x) * NRED;
+  if (!any) {  // block-uniform: nothing to add
+    if (threadIdx.x < NRED) out[threadIdx.x] = 0.0;
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < NRED; k++) {
+    double vsum = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(FULL, vsum, o);
+    acc[k] = vsum;
+  }
+  if (wid == 1 && lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NRED; k++) s_red[k] = acc[k];
+  }
+  __syncthreads();
+  if (wid == 0 && lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NRED; k++) out[k] = acc[k] + s_red[k];
+  }
+}
+
+__global__ void __launch_bounds__(32) k_solve6(const Chunk ck, int iter, int nblk) {
+  const int pair = blockIdx.x;
+  const int lane = threadIdx.x;
+  __shared__ double s_tot[NRED];
+  if (lane < NRED) {
+    double mine = 0.0;
+    const double* pp = ck.part + (size_t)pair * nblk * NRED + lane;
+    for (int b = 0; b < nblk; b++) mine += pp[(size_t)b * NRED];
+    s_tot[lane] = mine;
+  }
+  __syncwarp();
+  if (lane == 0) solve_pair(ck, pair, iter, s_tot);
 }
 
 // public member `points2` of the reference: scan 2 as transformed by the last iteration
@@ -1009,18 +1333,28 @@ struct DevBuf {
 
 }  // namespace
 
+constexpr int ICET_LOOP_MAX_PAIRS = 1;  // chunks up to this size run the Gauss-Newton loop as one persistent kernel
+constexpr int ICET_NSLOT = 4;  // staging slots of the host-buffer pipeline
+constexpr int ICET_NLANE = 2;  // compute lanes: consecutive chunks alternate between two streams (each with its own
+                               // workspace) so that the latency-bound ends of one chunk's kernels overlap the other's
+
 struct icet_b200_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_copy[2] = {nullptr, nullptr};
-  cudaEvent_t ev_done[2] = {nullptr, nullptr};
+  cudaStream_t lane1 = nullptr;  // second compute lane (lane 0 is `stream`)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int nlanes = ICET_NLANE;
+  cudaEvent_t ev_copy[ICET_NSLOT] = {};
+  cudaEvent_t ev_done[ICET_NSLOT] = {};
   int chunk_pairs = 256;
+  int host_chunk = 64;  // pairs per chunk of the host-buffer pipeline (upload of chunk k+1 || registration of chunk k)
   int64_t launches = 0;
   int dump_on = 0;
   int sm_count = 148;
   int pass_smem_set = 0;  // dynamic shared memory the pass kernels are currently allowed
+  int loop_occ[2] = {0, 0};  // resident blocks per SM of k_loop<PASS_K>, k_loop<PASS_K_SMALL>
   // per-kernel timing (icet_b200_set_profile): events around every launch, summed on request
   int profile_on = 0;
   std::vector<cudaEvent_t> prof_ev;   // pairs (begin, end)
@@ -1029,13 +1363,13 @@ struct icet_b200_ctx {
   double prof_ms[ICET_B200_NKERNELS] = {0};
   int64_t prof_n[ICET_B200_NKERNELS] = {0};
   // workspace
-  DevBuf ws;        // one slab, carved per chunk
+  DevBuf ws[ICET_NLANE];  // one slab per compute lane, carved per chunk
   DevBuf zero_ws;   // (part of ws) -- region that must be cleared per chunk is contiguous
   DevBuf edges;     // azE | elE
   int edges_nT = -1, edges_nP = -1;
-  DevBuf stage[2];  // host-input staging of scans (double buffered)
-  DevBuf descbuf[2];
-  DevBuf x0buf[2];
+  DevBuf stage[ICET_NSLOT];  // host-input staging of scans (double buffered)
+  DevBuf descbuf[ICET_NSLOT];
+  DevBuf x0buf[ICET_NSLOT];
   DevBuf resbuf;    // device results for host-facing calls
   DevBuf dumpbuf;
   DevBuf posebuf;
@@ -1067,7 +1401,8 @@ struct Carve {
 };
 
 // Layout of the chunk workspace.  The first region (cnt1, cntz, cursor, acc) must be zero at chunk start.
-size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, Chunk& ck, size_t* zero_bytes) {
+size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runlen, Chunk& ck, size_t* zero_bytes) {
+  const int vt = (ncell + 31) / 32;
   Carve c(base);
   ck.cnt1 = c.take<int32_t>((size_t)P * ncell);
   ck.cntz = c.take<int32_t>((size_t)P * ncell);
@@ -1075,6 +1410,11 @@ size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, Chunk& ck
   ck.acc = c.take<unsigned long long>((size_t)P * ncell * NQ);
   ck.n2c = c.take<int32_t>((size_t)P);
   ck.nz2 = c.take<int32_t>((size_t)P);
+  ck.ticket = c.take<unsigned>(1);
+  ck.tiles_done = c.take<unsigned>((size_t)P);
+  ck.iter_done = c.take<int>((size_t)P);
+  ck.vox_done = c.take<unsigned>((size_t)P * std::max(1, runlen));
+  ck.vmask = c.take<unsigned>((size_t)P * ((vt + 31) / 32));
   c.off = (c.off + 255) & ~(size_t)255;
   if (zero_bytes) *zero_bytes = c.off;
   ck.off = c.take<int32_t>((size_t)P * ncell);
@@ -1090,7 +1430,7 @@ size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, Chunk& ck
   ck.TR = c.take<float>((size_t)P * 12);
   ck.TRprev = c.take<float>((size_t)P * 12);
   ck.J = c.take<float>((size_t)P * 27);
-  ck.part = c.take<double>((size_t)P * ((ncell + 63) / 64) * 28);
+  ck.part = c.take<double>((size_t)P * vt * 28);  // per vox group (k_loop) / per 64-voxel block (split loop)
   return (c.off + 255) & ~(size_t)255;
 }
 
@@ -1178,17 +1518,17 @@ int prof_events(icet_b200_ctx* ctx, int id, cudaEvent_t* e0, cudaEvent_t* e1) {
 
 // Enqueue the whole registration of one chunk (descriptors already on the device).
 int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDesc* d_desc, int n1max, int n2max,
-              const float* d_x0, icet_b200_result* d_res, bool dump) {
+              const float* d_x0, icet_b200_result* d_res, bool dump, int lane = 0) {
   const int nT = p->bins_theta, nP = p->bins_phi, ncell = nT * nP;
   int rc = ensure_edges(ctx, nT, nP);
   if (rc) return rc;
   Chunk ck;
   memset(&ck, 0, sizeof(ck));
   size_t zero_bytes = 0;
-  size_t need = carve_chunk(nullptr, P, ncell, n1max, n2max, ck, &zero_bytes);
-  rc = ctx->ws.ensure(need);
+  size_t need = carve_chunk(nullptr, P, ncell, n1max, n2max, p->runlen, ck, &zero_bytes);
+  rc = ctx->ws[lane].ensure(need);
   if (rc) return rc;
-  carve_chunk(ctx->ws.p, P, ncell, n1max, n2max, ck, &zero_bytes);
+  carve_chunk(ctx->ws[lane].p, P, ncell, n1max, n2max, p->runlen, ck, &zero_bytes);
   ck.desc = d_desc;
   ck.npairs = P; ck.ncell = ncell; ck.nT = nT; ck.nP = nP; ck.n = p->n; ck.runlen = p->runlen;
   ck.flags = p->flags; ck.thresh = p->thresh; ck.buff = p->buff;
@@ -1198,18 +1538,34 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   ck.res = d_res;
   ck.dump_on = dump ? 1 : 0;
   if (dump) ck.dump = ctx->dump_ptrs;
-  cudaStream_t st = ctx->stream;
-  CK(cudaMemsetAsync(ctx->ws.p, 0, zero_bytes, st));
+  cudaStream_t st = lane == 0 ? ctx->stream : ctx->lane1;
+  CK(cudaMemsetAsync(ctx->ws[lane].p, 0, zero_bytes, st));
   const dim3 g1((n1max + 255) / 256, P), g2((n2max + 255) / 256, P);
   const int nblk = (ncell + VOX_THREADS - 1) / VOX_THREADS;
-  const int tile = PASS_TILE;
-  const dim3 gp1((n1max + tile - 1) / tile, P), gp2((n2max + tile - 1) / tile, P);
-  const int psm = pass_smem_bytes(nT, nP);
+  // shape of the loop kernel: big tiles (16 points per lane) for throughput; small tiles (4 points per lane) when
+  // the chunk has too few big tiles to keep every resident block busy for several rounds
+  const int tile1 = pass_tile_points(PASS_K);
+  const dim3 gp1((n1max + tile1 - 1) / tile1, P), gp2((n2max + tile1 - 1) / tile1, P);
+  const int psm = pass_smem_bytes(nT, nP, PASS_K);
   if (psm > ctx->pass_smem_set) {
     CK(cudaFuncSetAttribute(k_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
     CK(cudaFuncSetAttribute(k_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
+    CK(cudaFuncSetAttribute(k_loop<PASS_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
+    CK(cudaFuncSetAttribute(k_loop<PASS_K_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->loop_occ[0], k_loop<PASS_K>, PASS_THREADS, psm));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->loop_occ[1], k_loop<PASS_K_SMALL>, PASS_THREADS,
+                                                     pass_smem_bytes(nT, nP, PASS_K_SMALL)));
     ctx->pass_smem_set = psm;
   }
+  // warp tiles: 32*K points.  Small K when the chunk has too few big tiles to keep every resident warp busy for
+  // several rounds per iteration (small batches, single-pair latency).
+  const int wt_big = 32 * PASS_K;
+  const long long big_tiles = (long long)P * ((n2max + wt_big - 1) / wt_big);
+  const bool small = big_tiles < 4LL * ctx->sm_count * std::max(1, ctx->loop_occ[0]) * PASS_WARPS;
+  const int K2 = small ? PASS_K_SMALL : PASS_K;
+  const int tiles2 = std::max(1, (n2max + 32 * K2 - 1) / (32 * K2));  // >= 1: tile 0 carries the dropped returns
+  const int vt = (ncell + 31) / 32;
+  const int psm2 = pass_smem_bytes(nT, nP, K2);
   // LAUNCH(id, kernel<<<...>>>(...)): counts the launch and, when profiling, brackets it with events
 #define LAUNCH(id, ...)                                                   \
   do {                                                                    \
@@ -1233,10 +1589,22 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   }
   LAUNCH(5, k_fit1<<<dim3((ncell + 127) / 128, P), 128, 0, st>>>(ck));
   if (n2max > 0) LAUNCH(6, k_prep2<<<g2, 256, 0, st>>>(ck));
-  for (int it = 0; it < p->runlen; it++) {
-    if (n2max > 0) LAUNCH(7, k_pass<true><<<gp2, PASS_THREADS, psm, st>>>(ck));
-    LAUNCH(8, k_vox2<<<dim3(nblk, P), VOX_THREADS, 0, st>>>(ck, it));
-    LAUNCH(9, k_solve6<<<P, 32, 0, st>>>(ck, it, nblk));
+  const bool use_loop = (p->flags & ICET_B200_FLAG_PERSISTENT_LOOP) ||
+                        (!(p->flags & ICET_B200_FLAG_UNFUSED_LOOP) && P <= ICET_LOOP_MAX_PAIRS);
+  if (!use_loop) {
+    for (int it = 0; it < p->runlen; it++) {
+      if (n2max > 0) LAUNCH(7, k_pass<true><<<gp2, PASS_THREADS, psm, st>>>(ck));
+      LAUNCH(8, k_vox2<<<dim3(nblk, P), VOX_THREADS, 0, st>>>(ck, it));
+      LAUNCH(9, k_solve6<<<P, 32, 0, st>>>(ck, it, nblk));
+    }
+  } else if (p->runlen > 0) {
+    // persistent: as many blocks as can be resident (more would only queue behind them)
+    const long long tasks = (long long)P * (tiles2 + vt) * p->runlen;
+    if (tasks >= (1LL << 32)) return fail(ICET_B200_E_INVALID, "chunk too large: reduce icet_b200_set_chunk");
+    const int occ = std::max(1, ctx->loop_occ[small ? 1 : 0]);
+    const int grid = (int)std::min<long long>((tasks + PASS_WARPS - 1) / PASS_WARPS, (long long)ctx->sm_count * occ);
+    if (small) LAUNCH(10, k_loop<PASS_K_SMALL><<<grid, PASS_THREADS, psm2, st>>>(ck, tiles2, vt));
+    else LAUNCH(10, k_loop<PASS_K><<<grid, PASS_THREADS, psm2, st>>>(ck, tiles2, vt));
   }
 #undef LAUNCH
   CK(cudaGetLastError());
@@ -1266,6 +1634,7 @@ int ensure_dump(icet_b200_ctx* ctx, const icet_b200_params* p) {
     d.cnt2 = cv.take<int32_t>(rl * ncell); d.nin2 = cv.take<int32_t>(rl * ncell); d.used2 = cv.take<uint8_t>(rl * ncell);
     d.mu2 = cv.take<float>(rl * ncell * 3); d.sigma2 = cv.take<float>(rl * ncell * 9);
     d.Xit = cv.take<float>(rl * 6); d.HTWH = cv.take<float>(rl * 36); d.HTWdz = cv.take<float>(rl * 6);
+    d.tl = cv.take<unsigned long long>(rl * 8);
   };
   Dump tmp;
   lay(c, tmp);
@@ -1313,7 +1682,10 @@ int icet_b200_create(int device, icet_b200_ctx** out) {
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->own_stream = true;
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; i++) {
+  CK(cudaStreamCreateWithFlags(&c->lane1, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  for (int i = 0; i < ICET_NSLOT; i++) {
     CK(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
   }
@@ -1326,8 +1698,10 @@ int icet_b200_destroy(icet_b200_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->copy_stream);
-  c->ws.release(); c->edges.release(); c->resbuf.release(); c->dumpbuf.release(); c->posebuf.release();
-  for (int i = 0; i < 2; i++) {
+  if (c->lane1) cudaStreamSynchronize(c->lane1);
+  for (int i = 0; i < ICET_NLANE; i++) c->ws[i].release();
+  c->edges.release(); c->resbuf.release(); c->dumpbuf.release(); c->posebuf.release();
+  for (int i = 0; i < ICET_NSLOT; i++) {
     c->stage[i].release(); c->descbuf[i].release(); c->x0buf[i].release();
     if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
     if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
@@ -1336,6 +1710,9 @@ int icet_b200_destroy(icet_b200_ctx* c) {
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->lane1) cudaStreamDestroy(c->lane1);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   delete c;
   return 0;
 }
@@ -1357,10 +1734,25 @@ int icet_b200_set_chunk(icet_b200_ctx* c, int32_t m) {
   return 0;
 }
 
+int icet_b200_set_host_chunk(icet_b200_ctx* c, int32_t m) {
+  if (!c) return fail(ICET_B200_E_INVALID, "ctx is NULL");
+  if (m < 0) return fail(ICET_B200_E_INVALID, "chunk must be >= 0");
+  c->host_chunk = m == 0 ? 64 : std::min(m, 65535);
+  return 0;
+}
+
 int icet_b200_synchronize(icet_b200_ctx* c) {
   if (!c) return fail(ICET_B200_E_INVALID, "ctx is NULL");
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
+  CK(cudaStreamSynchronize(c->lane1));
+  return 0;
+}
+
+int icet_b200_set_lanes(icet_b200_ctx* c, int32_t n) {
+  if (!c) return fail(ICET_B200_E_INVALID, "ctx is NULL");
+  if (n < 0 || n > ICET_NLANE) return fail(ICET_B200_E_INVALID, "lanes must be 0 (default), 1 or 2");
+  c->nlanes = n == 0 ? ICET_NLANE : n;
   return 0;
 }
 
@@ -1368,7 +1760,7 @@ int64_t icet_b200_kernel_launches(icet_b200_ctx* c) { return c ? c->launches : 0
 
 static const char* const k_names[ICET_B200_NKERNELS] = {"k_scan1_bin", "k_cell_scan", "k_scatter", "k_cluster",
                                                         "k_pass<scan1>", "k_fit1", "k_prep2", "k_pass<scan2>",
-                                                        "k_vox2", "k_solve6"};
+                                                        "k_vox2", "k_solve6", "k_loop"};
 const char* icet_b200_kernel_name(int id) { return (id >= 0 && id < ICET_B200_NKERNELS) ? k_names[id] : ""; }
 
 static int prof_collect(icet_b200_ctx* c) {
@@ -1417,9 +1809,19 @@ static int batch_device_impl(icet_b200_ctx* c, const icet_b200_params* p, int32_
   // h_desc lives in host memory; descriptors are uploaded per chunk through the pinned bounce buffer
   int rc = ensure_pinned(c, (size_t)std::min(npairs, c->chunk_pairs) * sizeof(PairDesc) * 2 + 4096);
   if (rc) return rc;
+  // consecutive chunks alternate between the two compute lanes (own stream + workspace each); lane 1 starts after
+  // everything already queued on the caller's stream and the caller's stream resumes after lane 1
+  const int nchunks = (npairs + c->chunk_pairs - 1) / c->chunk_pairs;
+  const bool two = c->nlanes > 1 && nchunks > 1 && !dump;
+  if (two) {
+    CK(cudaEventRecord(c->ev_fork, c->stream));
+    CK(cudaStreamWaitEvent(c->lane1, c->ev_fork, 0));
+  }
   int slot = 0;
   for (int base = 0; base < npairs; base += c->chunk_pairs, slot ^= 1) {
     const int P = std::min(c->chunk_pairs, npairs - base);
+    const int lane = two ? slot : 0;
+    cudaStream_t st = lane == 0 ? c->stream : c->lane1;
     int n1max = 0, n2max = 0;
     for (int i = 0; i < P; i++) {
       n1max = std::max(n1max, h_desc[base + i].n1);
@@ -1431,11 +1833,15 @@ static int batch_device_impl(icet_b200_ctx* c, const icet_b200_params* p, int32_
     CK(cudaEventSynchronize(c->ev_done[slot]));
     PairDesc* hp = (PairDesc*)c->pinned + (size_t)slot * std::min(npairs, c->chunk_pairs);
     memcpy(hp, h_desc + base, (size_t)P * sizeof(PairDesc));
-    CK(cudaMemcpyAsync(c->descbuf[slot].p, hp, (size_t)P * sizeof(PairDesc), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaEventRecord(c->ev_done[slot], c->stream));
+    CK(cudaMemcpyAsync(c->descbuf[slot].p, hp, (size_t)P * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(c->ev_done[slot], st));
     rc = run_chunk(c, p, P, (const PairDesc*)c->descbuf[slot].p, n1max, n2max, d_x0 ? d_x0 + (size_t)base * 6 : nullptr,
-                   d_out + base, dump);
+                   d_out + base, dump, lane);
     if (rc) return rc;
+  }
+  if (two) {
+    CK(cudaEventRecord(c->ev_join, c->lane1));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
   }
   return 0;
 }
@@ -1490,23 +1896,55 @@ int icet_b200_register_batch(icet_b200_ctx* c, const icet_b200_params* p, int32_
   rc = c->resbuf.ensure((size_t)npairs * sizeof(icet_b200_result));
   if (rc) return rc;
   icet_b200_result* d_res = (icet_b200_result*)c->resbuf.p;
-  const int CH = c->chunk_pairs;
-  rc = ensure_pinned(c, (size_t)std::min(npairs, CH) * (sizeof(PairDesc) + 6 * sizeof(float)) * 2 + 4096);
+  // Upload/compute pipeline: the batch is cut into chunks; chunk k+1 is uploaded (copy stream) while chunk k is
+  // registered (compute stream).  The link is the bottleneck at 64-channel size (1.5 MB per scan over PCIe against
+  // ~25 us of GPU time per pair), so the chunks are small (host_chunk pairs) and ramp up from / down to an eighth of
+  // that: the first upload and the last registration are the only parts that nothing overlaps.
+  const int CH = std::max(1, std::min(c->chunk_pairs, c->host_chunk));
+  std::vector<int> sizes;
+  {
+    int left = npairs;
+    std::vector<int> head, tail;
+    for (int s = std::max(1, CH / 8); s < CH && left > 2 * CH; s *= 2) {
+      head.push_back(s);
+      tail.push_back(s);
+      left -= 2 * s;
+    }
+    sizes = head;
+    while (left > 0) {
+      const int s = std::min(CH, left);
+      sizes.push_back(s);
+      left -= s;
+    }
+    for (size_t k = tail.size(); k-- > 0;) sizes.push_back(tail[k]);
+  }
+  const size_t pin_slot = (size_t)CH * (sizeof(PairDesc) + 6 * sizeof(float)) + 2048;
+  rc = ensure_pinned(c, pin_slot * ICET_NSLOT + 4096);
   if (rc) return rc;
-  const size_t pin_half = (size_t)std::min(npairs, CH) * (sizeof(PairDesc) + 6 * sizeof(float)) + 2048;
-  int slot = 0;
-  for (int base = 0; base < npairs; base += CH, slot ^= 1) {
-    const int P = std::min(CH, npairs - base);
-    // plan the staging area: every distinct consecutive scan is uploaded once
+  auto pad = [](size_t f) { return (f + 63) & ~(size_t)63; };
+  int base = 0;
+  const float* prev_scan2_dev = nullptr;  // device copy of the previous chunk's last scan 2
+  const bool two = c->nlanes > 1 && sizes.size() > 1 && !(c->dump_on && npairs == 1);
+  if (two) {
+    CK(cudaEventRecord(c->ev_fork, c->stream));
+    CK(cudaStreamWaitEvent(c->lane1, c->ev_fork, 0));
+  }
+  for (size_t k = 0; k < sizes.size(); base += sizes[k], k++) {
+    const int P = sizes[k];
+    const int slot = (int)(k % ICET_NSLOT);
+    // plan the staging area: a scan shared by consecutive pairs (scan2[g-1] == scan1[g]) is uploaded once, also
+    // across the chunk boundary (the previous chunk's staging slot is still intact, see the waits below)
     std::vector<PairDesc> d(P);
+    std::vector<size_t> off1(P), off2(P);
+    std::vector<char> up1(P);
     size_t floats = 0;
     int n1max = 0, n2max = 0;
-    auto pad = [](size_t f) { return (f + 63) & ~(size_t)63; };
-    std::vector<size_t> off1(P), off2(P);
     for (int i = 0; i < P; i++) {
       const int g = base + i;
-      if (i > 0 && scan1[g] == scan2[g - 1] && n1[g] == n2[g - 1]) {
-        off1[i] = off2[i - 1];
+      const bool shared = g > 0 && scan1[g] == scan2[g - 1] && n1[g] == n2[g - 1] && (i > 0 || prev_scan2_dev);
+      up1[i] = !shared;
+      if (shared) {
+        off1[i] = (i > 0) ? off2[i - 1] : (size_t)-1;
       } else {
         off1[i] = floats;
         floats += pad((size_t)3 * n1[g]);
@@ -1516,46 +1954,76 @@ int icet_b200_register_batch(icet_b200_ctx* c, const icet_b200_params* p, int32_
       n1max = std::max(n1max, n1[g]);
       n2max = std::max(n2max, n2[g]);
     }
-    // the staging slot was last used by chunk (base - 2*CH): wait for its compute to finish
+    // Slot reuse: this slot last held chunk k - NSLOT; chunk k - NSLOT + 1 may still read its last scan (shared
+    // across the boundary), so wait for THAT chunk's registration before overwriting.
     CK(cudaEventSynchronize(c->ev_done[slot]));
+    CK(cudaEventSynchronize(c->ev_done[(slot + 1) % ICET_NSLOT]));
     rc = c->stage[slot].ensure(floats * sizeof(float));
     if (rc) return rc;
-    rc = c->descbuf[slot].ensure((size_t)P * sizeof(PairDesc));
+    rc = c->descbuf[slot].ensure((size_t)CH * sizeof(PairDesc));
     if (rc) return rc;
-    rc = c->x0buf[slot].ensure((size_t)P * 6 * sizeof(float));
+    rc = c->x0buf[slot].ensure((size_t)CH * 6 * sizeof(float));
     if (rc) return rc;
     float* sbase = (float*)c->stage[slot].p;
+    // uploads; runs that are contiguous on both sides are merged into one copy
+    const float* run_src = nullptr;
+    float* run_dst = nullptr;
+    size_t run_floats = 0;
+    auto flush = [&]() -> int {
+      if (run_floats)
+        CK(cudaMemcpyAsync(run_dst, run_src, run_floats * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+      run_floats = 0;
+      return 0;
+    };
+    auto upload = [&](const float* src, float* dst, size_t nf) -> int {
+      if (nf == 0) return 0;
+      if (run_floats && src == run_src + run_floats && dst == run_dst + run_floats) {
+        run_floats += nf;
+        return 0;
+      }
+      int r = flush();
+      if (r) return r;
+      run_src = src;
+      run_dst = dst;
+      run_floats = nf;
+      return 0;
+    };
     for (int i = 0; i < P; i++) {
       const int g = base + i;
-      const bool shared = (i > 0 && off1[i] == off2[i - 1] && scan1[g] == scan2[g - 1]);
-      if (!shared && n1[g] > 0)
-        CK(cudaMemcpyAsync(sbase + off1[i], scan1[g], (size_t)3 * n1[g] * sizeof(float), cudaMemcpyHostToDevice,
-                           c->copy_stream));
-      if (n2[g] > 0)
-        CK(cudaMemcpyAsync(sbase + off2[i], scan2[g], (size_t)3 * n2[g] * sizeof(float), cudaMemcpyHostToDevice,
-                           c->copy_stream));
-      d[i] = PairDesc{sbase + off1[i], sbase + off2[i], n1[g], n1[g], n2[g], n2[g]};
+      if (up1[i]) {
+        rc = upload(scan1[g], sbase + off1[i], (size_t)3 * n1[g]);
+        if (rc) return rc;
+      }
+      rc = upload(scan2[g], sbase + off2[i], (size_t)3 * n2[g]);
+      if (rc) return rc;
+      const float* s1p = up1[i] ? sbase + off1[i] : (i > 0 ? sbase + off2[i - 1] : prev_scan2_dev);
+      d[i] = PairDesc{s1p, sbase + off2[i], n1[g], n1[g], n2[g], n2[g]};
     }
-    char* hp = (char*)c->pinned + (size_t)slot * pin_half;
+    rc = flush();
+    if (rc) return rc;
+    prev_scan2_dev = sbase + off2[P - 1];
+    char* hp = (char*)c->pinned + (size_t)slot * pin_slot;
     memcpy(hp, d.data(), (size_t)P * sizeof(PairDesc));
     CK(cudaMemcpyAsync(c->descbuf[slot].p, hp, (size_t)P * sizeof(PairDesc), cudaMemcpyHostToDevice, c->copy_stream));
     const float* d_x0 = nullptr;
     if (x0) {
-      float* hx = (float*)(hp + (size_t)P * sizeof(PairDesc));
+      float* hx = (float*)(hp + (size_t)CH * sizeof(PairDesc));
       memcpy(hx, x0 + (size_t)base * 6, (size_t)P * 6 * sizeof(float));
       CK(cudaMemcpyAsync(c->x0buf[slot].p, hx, (size_t)P * 6 * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
       d_x0 = (const float*)c->x0buf[slot].p;
     }
     CK(cudaEventRecord(c->ev_copy[slot], c->copy_stream));
-    CK(cudaStreamWaitEvent(c->stream, c->ev_copy[slot], 0));
+    const int lane = two ? (int)(k & 1) : 0;
+    cudaStream_t lst = lane == 0 ? c->stream : c->lane1;
+    CK(cudaStreamWaitEvent(lst, c->ev_copy[slot], 0));
     const bool dump = c->dump_on && npairs == 1;
     if (dump) {
       rc = ensure_dump(c, p);
       if (rc) return rc;
     }
-    rc = run_chunk(c, p, P, (const PairDesc*)c->descbuf[slot].p, n1max, n2max, d_x0, d_res + base, dump);
+    rc = run_chunk(c, p, P, (const PairDesc*)c->descbuf[slot].p, n1max, n2max, d_x0, d_res + base, dump, lane);
     if (rc) return rc;
-    CK(cudaEventRecord(c->ev_done[slot], c->stream));
+    CK(cudaEventRecord(c->ev_done[slot], lst));
     if (dump) {
       c->dump_params = *p;
       c->dump_valid = true;
@@ -1564,6 +2032,10 @@ int icet_b200_register_batch(icet_b200_ctx* c, const icet_b200_params* p, int32_
       c->last_n2 = n2[0];
       c->last_runlen = p->runlen;
     }
+  }
+  if (two) {
+    CK(cudaEventRecord(c->ev_join, c->lane1));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
   }
   CK(cudaMemcpyAsync(out, d_res, (size_t)npairs * sizeof(icet_b200_result), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -1602,7 +2074,7 @@ int icet_b200_get_dump(icet_b200_ctx* c, icet_b200_voxel_dump* o) {
   cudaStream_t st = c->stream;
   CK(cudaStreamSynchronize(st));
   // n1max/n2max only affect arrays behind rec/cnt1, which are carved first
-  carve_chunk(c->ws.p, 1, (int)ncell, 0, 0, ck, &zb);
+  carve_chunk(c->ws[0].p, 1, (int)ncell, 0, 0, p.runlen, ck, &zb);
   if (o->cnt1) CK(cudaMemcpy(o->cnt1, ck.cnt1, ncell * 4, cudaMemcpyDeviceToHost));
   if (o->bounds) {
     std::vector<CellRec> rec(ncell);
@@ -1626,6 +2098,15 @@ int icet_b200_get_dump(icet_b200_ctx* c, icet_b200_voxel_dump* o) {
   CP(mu2, mu2, rl * ncell * 12); CP(sigma2, sigma2, rl * ncell * 36); CP(Xit, Xit, rl * 24);
   CP(HTWH, HTWH, rl * 144); CP(HTWdz, HTWdz, rl * 24);
 #undef CP
+  return 0;
+}
+
+int icet_b200_debug_timeline(icet_b200_ctx* c, uint64_t* out, int32_t runlen) {
+  if (!c || !out) return fail(ICET_B200_E_INVALID, "NULL argument");
+  if (!c->dump_valid || runlen != c->dump_params.runlen) return fail(ICET_B200_E_INVALID, "no dump recorded");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(out, c->dump_ptrs.tl, (size_t)runlen * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -51,9 +51,14 @@ typedef struct {
 } icet_b200_params;
 
 enum {
-  ICET_B200_FLAG_FULL_EIG = 1 /* always run the 6x6 eigen-decomposition of checkCondition (reports the
+  ICET_B200_FLAG_FULL_EIG = 1, /* always run the 6x6 eigen-decomposition of checkCondition (reports the
                                  exact condition number); default: only when a cheap bound cannot
                                  prove cond <= 1e6 (identical results either way)                      */
+  /* The Gauss-Newton loop has two forms with the same per-voxel arithmetic: ONE persistent kernel for all
+   * iterations (warps draw dependency-ordered tasks; lowest latency for a single pair) and three launches per
+   * iteration (highest throughput for large chunks).  Default: persistent for single-pair chunks. */
+  ICET_B200_FLAG_UNFUSED_LOOP = 2,   /* always three launches per iteration */
+  ICET_B200_FLAG_PERSISTENT_LOOP = 4 /* always the persistent kernel        */
 };
 
 /* per-pair result: the members callers of `class ICET` read (X: all four callers; pred_stds:
@@ -87,6 +92,9 @@ int icet_b200_set_stream(icet_b200_ctx* ctx, void* stream);
 /* Upper bound on the number of pairs processed per internal chunk (workspace ~3.7 MB/pair at
  * 131 072-point scans). 0 restores the default (256). */
 int icet_b200_set_chunk(icet_b200_ctx* ctx, int32_t max_pairs_per_chunk);
+/* Chunk size of the HOST-buffer batch entry point (icet_b200_register_batch): the upload of one chunk overlaps the
+ * registration of the previous one, so smaller chunks hide more of the PCIe transfer. 0 restores the default (64). */
+int icet_b200_set_host_chunk(icet_b200_ctx* ctx, int32_t pairs_per_chunk);
 
 /* -- registration ---------------------------------------------------------------------------- */
 /* One pair, HOST buffers: replaces `ICET it(scan1, scan2, runlen, X0, nPhi, nTheta, n, thresh, buff)`
@@ -117,6 +125,9 @@ int icet_b200_register_sequence_device(icet_b200_ctx* ctx, const icet_b200_param
                                        const float* scans, int32_t n, icet_b200_result* out);
 
 int icet_b200_synchronize(icet_b200_ctx* ctx);
+/* Number of compute lanes (streams with their own workspace) consecutive chunks alternate between: 1 or 2
+ * (0 = default 2). */
+int icet_b200_set_lanes(icet_b200_ctx* ctx, int32_t lanes);
 
 /* -- per-voxel state of the most recent single-pair call (icet_b200_register) ------------------
  * Mirrors the public members the reference exposes for visualisation / debugging:
@@ -172,10 +183,14 @@ int64_t icet_b200_kernel_launches(icet_b200_ctx* ctx);
 /* Per-kernel device time: when enabled every kernel launch is bracketed by CUDA events on the context's
  * stream (small overhead -- use a separate pass, not the throughput measurement).  Enabling resets the
  * sums.  get_profile synchronises and returns, per kernel id, the summed milliseconds and launch count. */
-#define ICET_B200_NKERNELS 10
+#define ICET_B200_NKERNELS 11
 int icet_b200_set_profile(icet_b200_ctx* ctx, int32_t enable);
 int icet_b200_get_profile(icet_b200_ctx* ctx, double ms[ICET_B200_NKERNELS], int64_t launches[ICET_B200_NKERNELS]);
 const char* icet_b200_kernel_name(int id);
+/* Debug: %globaltimer stamps [runlen][8] of the persistent loop kernel for the most recent dumped single-pair call
+ * (0 last vox task arrived, 1 / 2 begin / end of the latest vox task, 3 partial sums added, 4 solve done,
+ * 5 iteration published, 6 / 7 begin / end of tile 0 of the iteration).  HOST buffer of runlen*8 values. */
+int icet_b200_debug_timeline(icet_b200_ctx* ctx, uint64_t* out, int32_t runlen);
 
 #ifdef __cplusplus
 }

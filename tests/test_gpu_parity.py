@@ -274,6 +274,33 @@ def test_batch_equals_single_and_is_deterministic(ctx):
     assert hb.tobytes() == a.tobytes()
 
 
+def test_persistent_loop_matches_split_loop(ctx):
+    """The persistent Gauss-Newton kernel (k_loop: tickets + per-pair iteration flags) against the diagnostic split
+    form (3 launches per iteration): same per-voxel arithmetic, only the order of the 28 double sums differs."""
+    from icet_b200 import api
+    dev = synth_device(ctx, 12, first=300)
+    a = register_sequence(ctx, dev, params(flags=api.FLAG_PERSISTENT_LOOP))
+    b = register_sequence(ctx, dev, params(flags=api.FLAG_UNFUSED_LOOP))
+    assert np.abs(a["X"] - b["X"]).max() < 2e-7
+    assert np.abs(a["Q"] - b["Q"]).max() <= 1e-6 * np.abs(b["Q"]).max()
+    np.testing.assert_array_equal(a["n_used"], b["n_used"])
+    # both shapes of the persistent kernel (latency tiles for few pairs, throughput tiles for many) agree bit for bit
+    host = dev.cpu().numpy()
+    one = ctx.register(host[3], host[4], params=params(flags=api.FLAG_PERSISTENT_LOOP))
+    assert one.tobytes() == a[3].tobytes()
+    big = synth_device(ctx, 65, first=300)
+    c = register_sequence(ctx, big, params(flags=api.FLAG_PERSISTENT_LOOP))
+    assert c[:11].tobytes() == a.tobytes()
+    # one and two compute lanes: same bits
+    ctx.set_chunk(16)
+    ctx.set_lanes(1)
+    d1 = register_sequence(ctx, big)
+    ctx.set_lanes(2)
+    d2 = register_sequence(ctx, big)
+    ctx.set_chunk(0)
+    assert d1.tobytes() == d2.tobytes()
+
+
 def test_point_order_invariance(ctx):
     """Shuffling the points of both clouds must not change a single bit of the result (order-independent
     integer statistics, value-based radial sort)."""
