@@ -245,10 +245,13 @@ def main():
     value = world * P * args.steps / (t_ms * 1e-3)
 
     # ---- per-kernel device time (separate pass, events around every launch) -------------------------
+    # (one compute lane here: with two, kernels of different chunks overlap and per-launch times are not additive)
+    ctx.set_lanes(1)
     ctx.set_profile(True)
     ctx.register_sequence_device(scans.data_ptr(), P + 1, NPTS, results.data_ptr(), params)
     prof = ctx.get_profile()
     ctx.set_profile(False)
+    ctx.set_lanes(0)
     tot_ms = sum(v[0] for v in prof.values())
     dom = max(prof, key=lambda k: prof[k][0])
     dom_ms, dom_n = prof[dom]

@@ -53,11 +53,11 @@ struct PairDesc {
   int n1, ld1, n2, ld2;
 };
 
-struct __align__(16) CellRec {  // read by every point of the pass kernels (two 16-byte loads)
+struct __align__(16) CellRec {  // read by the pass kernels: first half by every point, second half per run of inside points
   float inner, outer;           // clusterBounds columns 4,5 (src/icet.cpp:149)
-  float refx, refy;
-  float refz, scale;            // fixed-point reference point and power-of-two scale
   uint32_t flags;
+  float scale;                  // power-of-two scale of the voxel's fixed-point frame
+  float refx, refy, refz;       // reference point of the fixed-point frame
   int32_t cnt1;                 // points of scan 1 in this angular bin
 };
 
@@ -96,6 +96,7 @@ struct Chunk {  // everything a kernel needs, passed by value
   const float* azE;  // [nT+1] float azimuth bin edges  (src/icet.cpp:136-137)
   const float* elE;  // [nP+1] float elevation bin edges (src/icet.cpp:138-139)
   icet::BinTable bth, bph;  // exact bin lookup tables (src/icet.cpp:545-546)
+  const float* binrec;      // [(nT+1) + (nP+1)][4] bin + box records of the pass kernels (see bin_box)
   float* TR;         // [P][12] translation (3) and rotation R(X) (9) of the current iteration
   float* TRprev;     // [P][12] transform the LAST iteration used (the reference's public `points2`)
   float* J;          // [P][27] get_H derivative matrices Jx | Jy | Jz of the current iteration
@@ -113,6 +114,7 @@ struct Chunk {  // everything a kernel needs, passed by value
   int* iter_done;        // [P]  iterations whose solve has been published
   unsigned* vox_done;    // [P][runlen] vox tasks finished per iteration
   unsigned* vmask;       // [P][ceil(vt/32)] vox groups that wrote a partial sum (current iteration)
+  int* dbg;              // [8] watchdog record of k_loop: {tripped, kind, pair, iter, seen, need, ticket, -}
   Dump dump;
   int dump_on;
 };
@@ -122,40 +124,11 @@ struct Chunk {  // everything a kernel needs, passed by value
 //   q[0] += points in the angular bin, q[1] += points inside the cluster box,
 //   q[2..4] += sum d, q[5..10] += sum d d^T (xx xy xz yy yz zz),   d = round((p - ref) * scale)
 // Exact integer arithmetic => the sums do not depend on the order or grouping of the additions.
-// flush_run publishes the partial sums one lane collected over a run of consecutive points of the
-// same cell (<= PASS_K points, so the first-order sums fit 32 bits).
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void flush_run(unsigned long long* accp /* pair base */, int cell, int nbin, int nin,
-                                          int sx, int sy, int sz, long long pxx, long long pxy, long long pxz,
-                                          long long pyy, long long pyz, long long pzz) {
-  if (cell < 0) return;
-  unsigned long long* q = accp + (size_t)cell * NQ;
-  atomicAdd(q, (unsigned long long)nbin);
-  if (nin == 0) return;  // only the bin count changes
-  atomicAdd(q + 1, (unsigned long long)nin);
-  atomicAdd(q + 2, (unsigned long long)(long long)sx);
-  atomicAdd(q + 3, (unsigned long long)(long long)sy);
-  atomicAdd(q + 4, (unsigned long long)(long long)sz);
-  atomicAdd(q + 5, (unsigned long long)pxx);
-  atomicAdd(q + 6, (unsigned long long)pxy);
-  atomicAdd(q + 7, (unsigned long long)pxz);
-  atomicAdd(q + 8, (unsigned long long)pyy);
-  atomicAdd(q + 9, (unsigned long long)pyz);
-  atomicAdd(q + 10, (unsigned long long)pzz);
-}
-
 __device__ __forceinline__ void cell_of(const Chunk& ck, float th, float ph, int& bt, int& bp) {
   bt = icet::bin_lookup(th, ck.bth, 2 * M_PI);
   bp = icet::bin_lookup(ph, ck.bph, M_PI);
 }
-// same, tables staged in shared memory: tab = azE[nT+1] | elE[nP+1] | Tth[nT+2] | Tph[nP+2]
-__device__ __forceinline__ void cell_of_smem(const Chunk& ck, const float* tab, float th, float ph, int& bt, int& bp) {
-  const float* Tth = tab + ck.nT + 1 + ck.nP + 1;
-  const float* Tph = Tth + ck.nT + 2;
-  bt = icet::bin_lookup(th, Tth, ck.bth.scale, ck.bth.amax, ck.nT, 2 * M_PI);
-  bp = icet::bin_lookup(ph, Tph, ck.bph.scale, ck.bph.amax, ck.nP, M_PI);
-}
-
 // ----------------------------------------------------------------------------------------------
 // K1: scan 1 -> spherical, cell index, per-cell histogram.
 // utils::cartesianToSpherical (src/utils.cpp:93-119) + sortSphericalCoordinates (src/icet.cpp:534-554)
@@ -397,64 +370,82 @@ __global__ void __launch_bounds__(128) k_cluster(const Chunk ck) {
 // ----------------------------------------------------------------------------------------------
 constexpr int PASS_THREADS = 256;
 constexpr int PASS_WARPS = PASS_THREADS / 32;
-constexpr int PASS_K = 16;       // consecutive points per lane in the accumulation phase (throughput shape)
+constexpr int PASS_K = 16;       // rows of 32 points per warp tile (throughput shape)
 constexpr int PASS_K_SMALL = 4;  // same for small batches (latency shape: more, smaller tiles)
 
-__host__ __device__ constexpr int pass_wslots(int K) { return 32 * K + 32; }  // 16-byte slots per warp tile (1 pad per K)
+__host__ __device__ constexpr int pass_wslots(int K) { return 32 * K; }  // 16-byte entry slots per warp tile
 __host__ __device__ constexpr int pass_tile_points(int K) { return PASS_WARPS * 32 * K; }
+// shared memory: entry tiles, then the angular tables: (nT + 1) + (nP + 1) records {T[k], T[k+1], lo[k], hi[k]}
+__host__ __device__ inline int pass_tab_floats(int nT, int nP) { return 4 * (nT + nP + 2); }
 __host__ __device__ inline int pass_smem_bytes(int nT, int nP, int K) {
-  return PASS_WARPS * pass_wslots(K) * 16 + (2 * (nT + nP) + 6) * 4;
+  return PASS_WARPS * pass_wslots(K) * 16 + pass_tab_floats(nT, nP) * 4;
 }
 
-// One point -> its accumulation entry {cell << 1 | inside, fx, fy, fz}; .x = -1 when the point's cell takes no
-// part (no cluster / voxel not active), fx = fy = fz = 0 when the point is outside the cluster box.
-template <bool SCAN2>
-__device__ __forceinline__ int4 pass_point(const Chunk& ck, const float* tab, const CellRec* recs, const float* tr,
-                                           float x, float y, float z) {
-  if (SCAN2) icet::transform(x, y, z, tr, tr + 3, x, y, z);
-  float r, th, ph;
-  icet::c2s(x, y, z, r, th, ph);
-  int bt, bp;
-  cell_of_smem(ck, tab, th, ph, bt, bp);
-  const int c = ck.nT * bp + bt;
-  const float4* rp = reinterpret_cast<const float4*>(recs + c);
-  const float4 rb = __ldg(rp + 1);
-  const uint32_t flags = __float_as_uint(rb.z);
-  int4 e = make_int4(-1, 0, 0, 0);
-  if (flags & (SCAN2 ? F_ACTIVE2 : F_STAT1)) {
-    const float* azE = tab;
-    const float* elE = tab + ck.nT + 1;
-    const float4 ra = __ldg(rp);
-    e.x = c << 1;
-    // ICET::filterPointsInsideCluster src/icet.cpp:632-634 (inclusive float compares)
-    const bool in = th >= azE[bt] && th <= azE[bt + 1] && ph >= elE[bp] && ph <= elE[bp + 1] && r >= ra.x && r <= ra.y;
-    if (in) {
-      float cx, cy, cz;
-      icet::s2c(r, th, ph, cx, cy, cz);  // statistics use round-tripped points (:159 / :303)
-      const float sc = rb.y;
-      int fx = __float2int_rn((cx - ra.z) * sc);
-      int fy = __float2int_rn((cy - ra.w) * sc);
-      int fz = __float2int_rn((cz - rb.x) * sc);
-      e.x |= 1;
-      e.y = max(-FP_LIM, min(FP_LIM, fx));
-      e.z = max(-FP_LIM, min(FP_LIM, fy));
-      e.w = max(-FP_LIM, min(FP_LIM, fz));
-    }
+// Angular bin + box test in one table look-up.  rec[k] = {T[k], T[k+1], lo[k], hi[k]}:
+//   T    exact thresholds of int((double(a)/period)*nb) (src/icet.cpp:545-546): bin k  <=>  T[k] <= a < T[k+1]
+//   lo/hi the part of the bin that also passes the reference's inclusive fp32 box test against the bin edges
+//        (src/icet.cpp:136-139, :632-633): lo = max(T[k], E[k]), hi = min(pred(T[k+1]), E[k+1]).
+// Record nb (a == fp32(period), bin index nb % nb = 0) has an empty [lo, hi].  Angles beyond the table (only the
+// NaN sentinel 1000.0) take the double formula and never pass the box test.
+__device__ __forceinline__ int bin_box(float a, const float4* rec, float scale, float amax, int nb, double period,
+                                       bool& inbox) {
+  if (!(a <= amax)) {
+    inbox = false;
+    return icet::bin_formula(a, period, nb);
   }
-  return e;
+  int k = min(__float2int_rz(a * scale), nb);
+  float4 e = rec[k];
+  if (a < e.x) e = rec[--k];
+  else if (a >= e.y) e = rec[++k];
+  inbox = a >= e.z && a <= e.w;
+  return k == nb ? 0 : k;
+}
+
+// Stage 1 of a point: [transform,] spherical coordinates, cell, gates.  active = the cell takes part
+// (has a cluster / an active voxel); in = the point passes ICET::filterPointsInsideCluster (src/icet.cpp:632-634).
+template <bool SCAN2>
+__device__ __forceinline__ void point_stage1(const Chunk& ck, const float4* tth, const float4* tph, const CellRec* recs,
+                                             const float* tr, float x, float y, float z, int& c, bool& active,
+                                             bool& in, float& r, float& th, float& ph) {
+  if (SCAN2) icet::transform(x, y, z, tr, tr + 3, x, y, z);
+  icet::c2s(x, y, z, r, th, ph);
+  bool bt_in, bp_in;
+  const int bt = bin_box(th, tth, ck.bth.scale, ck.bth.amax, ck.nT, 2 * M_PI, bt_in);
+  const int bp = bin_box(ph, tph, ck.bph.scale, ck.bph.amax, ck.nP, M_PI, bp_in);
+  c = ck.nT * bp + bt;
+  const float4 ra = __ldg(reinterpret_cast<const float4*>(recs + c));  // inner, outer, flags, scale
+  active = (__float_as_uint(ra.z) & (SCAN2 ? F_ACTIVE2 : F_STAT1)) != 0;
+  in = active && bt_in && bp_in && r >= ra.x && r <= ra.y;
+}
+
+// Stage 2 of an inside point: sph->cart round trip (statistics use round-tripped points, src/icet.cpp:159 / :303)
+// and conversion to the voxel's fixed-point frame.
+__device__ __forceinline__ void point_stage2(float r, float th, float ph, float refx, float refy, float refz, float sc,
+                                             int& fx, int& fy, int& fz) {
+  float cx, cy, cz;
+  icet::s2c(r, th, ph, cx, cy, cz);
+  fx = max(-FP_LIM, min(FP_LIM, __float2int_rn((cx - refx) * sc)));
+  fy = max(-FP_LIM, min(FP_LIM, __float2int_rn((cy - refy) * sc)));
+  fz = max(-FP_LIM, min(FP_LIM, __float2int_rn((cz - refz) * sc)));
 }
 
 // The dropped returns of scan 2: points2_OG == (0,0,0) for all of them, so they all land on t * R
 // (src/icet.cpp:377-378) -- evaluated once per iteration, weighted with their number.
-__device__ inline void pass_dropped_returns(const Chunk& ck, const float* tab, const CellRec* recs, const float* tr,
-                                            unsigned long long* accp, long long nz) {
+__device__ inline void pass_dropped_returns(const Chunk& ck, const float4* tth, const float4* tph, const CellRec* recs,
+                                            const float* tr, unsigned long long* accp, long long nz) {
   if (nz <= 0) return;
-  const int4 e = pass_point<true>(ck, tab, recs, tr, 0.0f, 0.0f, 0.0f);
-  if (e.x < 0) return;
-  unsigned long long* q = accp + (size_t)(e.x >> 1) * NQ;
+  int c;
+  bool active, in;
+  float r, th, ph;
+  point_stage1<true>(ck, tth, tph, recs, tr, 0.0f, 0.0f, 0.0f, c, active, in, r, th, ph);
+  if (!active) return;
+  unsigned long long* q = accp + (size_t)c * NQ;
   atomicAdd(q, (unsigned long long)nz);
-  if (e.x & 1) {
-    const long long fx = e.y, fy = e.z, fz = e.w;
+  if (in) {
+    const CellRec rc = recs[c];
+    int ix, iy, iz;
+    point_stage2(r, th, ph, rc.refx, rc.refy, rc.refz, rc.scale, ix, iy, iz);
+    const long long fx = ix, fy = iy, fz = iz;
     atomicAdd(q + 1, (unsigned long long)nz);
     atomicAdd(q + 2, (unsigned long long)(nz * fx));
     atomicAdd(q + 3, (unsigned long long)(nz * fy));
@@ -468,11 +459,32 @@ __device__ inline void pass_dropped_returns(const Chunk& ck, const float* tab, c
   }
 }
 
-// One warp tile of 32*K consecutive points.  Phase A:
-// lane-per-point (coalesced loads, all the fp32 geometry), entries go to the warp's shared-memory tile.  Phase B:
-// every lane walks K CONSECUTIVE entries and sums runs of equal cell in registers (LiDAR scans list points ring by
-// ring, so neighbours share their voxel: ~27 points per run at 2048 azimuth steps / 75 bins); a run ends with one
-// flush_run.  Only warp-level synchronisation inside.
+// publishes the sums one lane collected over a run of consecutive inside points of one cell
+__device__ __forceinline__ void flush_in_run(unsigned long long* accp, int cell, int nin, int sx, int sy, int sz,
+                                             long long pxx, long long pxy, long long pxz, long long pyy, long long pyz,
+                                             long long pzz) {
+  if (cell < 0) return;
+  unsigned long long* q = accp + (size_t)cell * NQ;
+  atomicAdd(q + 1, (unsigned long long)nin);
+  atomicAdd(q + 2, (unsigned long long)(long long)sx);
+  atomicAdd(q + 3, (unsigned long long)(long long)sy);
+  atomicAdd(q + 4, (unsigned long long)(long long)sz);
+  atomicAdd(q + 5, (unsigned long long)pxx);
+  atomicAdd(q + 6, (unsigned long long)pxy);
+  atomicAdd(q + 7, (unsigned long long)pxz);
+  atomicAdd(q + 8, (unsigned long long)pyy);
+  atomicAdd(q + 9, (unsigned long long)pyz);
+  atomicAdd(q + 10, (unsigned long long)pzz);
+}
+
+// One warp tile of 32*K consecutive points.
+//  Phase A (lane per point, K rows, coalesced loads): stage 1 of every point.  Points of one cell that are
+//    neighbours in the row form runs (LiDAR scans list points ring by ring: ~27 per run at 2048 azimuth steps /
+//    75 bins); the head lane of a run adds the run length to the cell's bin count (one RED per run).  Inside points
+//    are COMPACTED into the warp's shared-memory tile as {cell, r, theta, phi} -- typically 40 % of the points.
+//  Phase B (lane per contiguous slice of the compacted list): stage 2 (the expensive round trip) only for inside
+//    points and with all lanes busy; sums of a run of equal cell stay in registers, one flush per run.
+// Only warp-level synchronisation inside.
 template <bool SCAN2, int K>
 __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* the warp's pass_wslots(K) slots */,
                                                const float* tab, const CellRec* recs, const float* tr,
@@ -480,40 +492,63 @@ __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* th
                                                unsigned long long* accp) {
   const int lane = threadIdx.x & 31;
   if (w0 >= n) return;
+  const float4* tth = reinterpret_cast<const float4*>(tab);
+  const float4* tph = tth + ck.nT + 1;
+  const unsigned lt = (1u << lane) - 1u;
+  int nin_tile = 0;
   // ---- phase A
 #pragma unroll 2
   for (int j = 0; j < K; j++) {
     const int i = w0 + j * 32 + lane;
-    int4 e = make_int4(-1, 0, 0, 0);
+    int c = -1;
+    bool active = false, in = false;
+    float r = 0.f, th = 0.f, ph = 0.f;
     if (i < n) {
       const float x = __ldg(px_ + i), y = __ldg(px_ + ld + i), z = __ldg(px_ + 2 * ld + i);
-      e = pass_point<SCAN2>(ck, tab, recs, tr, x, y, z);
+      point_stage1<SCAN2>(ck, tth, tph, recs, tr, x, y, z, c, active, in, r, th, ph);
     }
-    const int slot = j * 32 + lane;
-    went[slot + slot / K] = e;
+    // bin counts: one RED per run of equal (participating) cell in this row
+    const int key = active ? c : -1;
+    const int prev = __shfl_up_sync(FULL, key, 1);
+    const bool head = (lane == 0) || (key != prev);
+    const unsigned hm = __ballot_sync(FULL, head);
+    if (head && key >= 0) {
+      const unsigned nh = (lane == 31) ? 0u : (hm >> (lane + 1));
+      const int len = nh ? __ffs(nh) : 32 - lane;
+      atomicAdd(accp + (size_t)key * NQ, (unsigned long long)len);
+    }
+    // compaction of the inside points
+    const unsigned im = __ballot_sync(FULL, in);
+    if (in) went[nin_tile + __popc(im & lt)] = make_int4(c, __float_as_int(r), __float_as_int(th), __float_as_int(ph));
+    nin_tile += __popc(im);
   }
   __syncwarp();
-  // ---- phase B
-  int cur = -1, nbin = 0, nin = 0, sx = 0, sy = 0, sz = 0;
+  // ---- phase B: lane takes entries [lane*q, lane*q + q); q odd => conflict-free 16-byte shared loads
+  const int q = ((nin_tile + 31) >> 5) | 1;
+  const int e0 = lane * q, e1 = min(nin_tile, e0 + q);
+  int cur = -1, nin = 0, sx = 0, sy = 0, sz = 0;
   long long pxx = 0, pxy = 0, pxz = 0, pyy = 0, pyz = 0, pzz = 0;
-  const int4* mine = went + lane * (K + 1);
-#pragma unroll 4
-  for (int j = 0; j < K; j++) {
-    const int4 e = mine[j];
-    const int key = e.x >> 1;  // -1 stays -1
-    if (key != cur) {
-      flush_run(accp, cur, nbin, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
-      cur = key;
-      nbin = nin = sx = sy = sz = 0;
+  float refx = 0.f, refy = 0.f, refz = 0.f, sc = 0.f;
+#pragma unroll 2
+  for (int e = e0; e < e1; e++) {
+    const int4 v = went[e];
+    if (v.x != cur) {
+      flush_in_run(accp, cur, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
+      cur = v.x;
+      nin = sx = sy = sz = 0;
       pxx = pxy = pxz = pyy = pyz = pzz = 0;
+      const float4* rp = reinterpret_cast<const float4*>(recs + cur);
+      const float4 ra = __ldg(rp), rb = __ldg(rp + 1);
+      sc = ra.w; refx = rb.x; refy = rb.y; refz = rb.z;
     }
-    nbin++;
-    nin += e.x & 1;
-    sx += e.y; sy += e.z; sz += e.w;
-    pxx += (long long)e.y * e.y; pxy += (long long)e.y * e.z; pxz += (long long)e.y * e.w;
-    pyy += (long long)e.z * e.z; pyz += (long long)e.z * e.w; pzz += (long long)e.w * e.w;
+    int fx, fy, fz;
+    point_stage2(__int_as_float(v.y), __int_as_float(v.z), __int_as_float(v.w), refx, refy, refz, sc, fx, fy, fz);
+    nin++;
+    sx += fx; sy += fy; sz += fz;
+    pxx += (long long)fx * fx; pxy += (long long)fx * fy; pxz += (long long)fx * fz;
+    pyy += (long long)fy * fy; pyz += (long long)fy * fz; pzz += (long long)fz * fz;
   }
-  flush_run(accp, cur, nbin, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
+  flush_in_run(accp, cur, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
   __syncwarp();
 }
 
@@ -529,8 +564,8 @@ __global__ void __launch_bounds__(PASS_THREADS) k_pass(const Chunk ck) {
   const int tile0 = blockIdx.x * pass_tile_points(K);
   if (tile0 >= n && !(SCAN2 && blockIdx.x == 0)) return;
   {
-    const int ntab = 2 * (ck.nT + ck.nP) + 6;
-    for (int k = threadIdx.x; k < ntab; k += PASS_THREADS) tab[k] = __ldg(ck.azE + k);
+    const int ntab = pass_tab_floats(ck.nT, ck.nP);
+    for (int k = threadIdx.x; k < ntab; k += PASS_THREADS) tab[k] = __ldg(ck.binrec + k);
   }
   float tr[12];
   if (SCAN2) {
@@ -546,7 +581,9 @@ __global__ void __launch_bounds__(PASS_THREADS) k_pass(const Chunk ck) {
   __syncthreads();
   pass_warp_tile<SCAN2, K>(ck, ent + (threadIdx.x >> 5) * pass_wslots(K), tab, recs, tr, px_, ld, n,
                            tile0 + (threadIdx.x >> 5) * 32 * K, accp);
-  if (SCAN2 && blockIdx.x == 0 && threadIdx.x == 0) pass_dropped_returns(ck, tab, recs, tr, accp, ck.nz2[pair]);
+  if (SCAN2 && blockIdx.x == 0 && threadIdx.x == 0)
+    pass_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 1, recs, tr,
+                         accp, ck.nz2[pair]);
 }
 
 // exact-sum -> mean / covariance (double) of a voxel
@@ -1031,6 +1068,26 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Spin until *p >= need.  A protocol failure must not hang the GPU: after ~2 s the wait gives up, records what it
+// was waiting for in ck.dbg and marks the pair (results of the chunk are then invalid; the host reports an error).
+__device__ __noinline__ void loop_wait(const Chunk& ck, const int* p, int need, int kind, int pair, int iter, unsigned ticket) {
+  if (ld_acquire(p) >= need) return;
+  const unsigned long long t0 = gtime();
+  unsigned spins = 0;
+  for (;;) {
+    __nanosleep(40);
+    const int seen = ld_acquire(p);
+    if (seen >= need) return;
+    if ((++spins & 1023u) == 0 && gtime() - t0 > 2000000000ull) {
+      if ((threadIdx.x & 31) == 0 && atomicCAS(ck.dbg, 0, 1) == 0) {
+        ck.dbg[1] = kind; ck.dbg[2] = pair; ck.dbg[3] = iter; ck.dbg[4] = seen; ck.dbg[5] = need; ck.dbg[6] = (int)ticket;
+        ck.res[pair].status = ICET_B200_LOOP_TIMEOUT;
+      }
+      return;
+    }
+  }
+}
+
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -1047,11 +1104,8 @@ __device__ __noinline__ void vox_task(const Chunk& ck, int iter, int pair, int g
   const bool active = cell < ck.ncell && (ck.rec[(size_t)pair * ck.ncell + cell].flags & F_ACTIVE2) != 0;
   const bool any = __any_sync(FULL, active);
   if (any) {
-    {
-      const int* cnt = reinterpret_cast<const int*>(ck.tiles_done + pair);
-      const int need = (iter + 1) * loop_tiles_of(__ldg(ck.n2c + pair), tpt);
-      while (ld_acquire(cnt) < need) __nanosleep(32);
-    }
+    loop_wait(ck, reinterpret_cast<const int*>(ck.tiles_done + pair), (iter + 1) * loop_tiles_of(__ldg(ck.n2c + pair), tpt),
+              1, pair, iter, 0u);
     if (lane < 27) w_J[lane] = __ldcg(ck.J + (size_t)pair * 27 + lane);
     __syncwarp();
     TL(1);
@@ -1087,6 +1141,10 @@ __device__ __noinline__ void vox_task(const Chunk& ck, int iter, int pair, int g
   prev = __shfl_sync(FULL, prev, 0);
   if (prev + 1u == (unsigned)vt) {
     // -------------------------------------------------------------- end of the iteration of this pair
+    // Iterations of a pair are strictly ordered: groups without an active voxel do not wait for the tiles, so when
+    // NO group of the pair has one (degenerate inputs) nothing else would keep iteration k+1 from being closed
+    // before iteration k.
+    if (iter > 0) loop_wait(ck, ck.iter_done + pair, iter, 2, pair, iter, 0u);
     __threadfence();
     TL(0);
     double tot = 0.0;
@@ -1149,8 +1207,8 @@ __global__ void __launch_bounds__(PASS_THREADS, 3) k_loop(const Chunk ck, int ti
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* tab = reinterpret_cast<float*>(smem_raw + PASS_WARPS * pass_wslots(K) * 16);
   {
-    const int ntab = 2 * (ck.nT + ck.nP) + 6;
-    for (int k = threadIdx.x; k < ntab; k += PASS_THREADS) tab[k] = __ldg(ck.azE + k);
+    const int ntab = pass_tab_floats(ck.nT, ck.nP);
+    for (int k = threadIdx.x; k < ntab; k += PASS_THREADS) tab[k] = __ldg(ck.binrec + k);
   }
   __syncthreads();  // the only block-wide barrier: from here on warps are independent workers
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1177,10 +1235,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 3) k_loop(const Chunk ck, int ti
       const int n = __ldg(ck.n2c + pair);
       const int w0 = tile * 32 * K;
       if (w0 < n || tile == 0) {
-        if (iter > 0) {
-          const int* flag = ck.iter_done + pair;
-          while (ld_acquire(flag) < iter) __nanosleep(32);
-        }
+        if (iter > 0) loop_wait(ck, ck.iter_done + pair, iter, 0, pair, iter, t);
         float tr[12];
         {
           const float4* tp = reinterpret_cast<const float4*>(ck.TR + (size_t)pair * 12);
@@ -1193,7 +1248,9 @@ __global__ void __launch_bounds__(PASS_THREADS, 3) k_loop(const Chunk ck, int ti
         if (tile == 0) TL(6);
         pass_warp_tile<true, K>(ck, went, tab, recs, tr, ck.pog + (size_t)pair * 3 * ck.n2max, (size_t)ck.n2max, n, w0,
                                 accp);
-        if (tile == 0 && lane == 0) pass_dropped_returns(ck, tab, recs, tr, accp, __ldg(ck.nz2 + pair));
+        if (tile == 0 && lane == 0)
+          pass_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 1,
+                               recs, tr, accp, __ldg(ck.nz2 + pair));
         if (tile == 0) TL(7);
         __threadfence();  // every lane: its accumulator updates are visible before the tile is counted
         __syncwarp();
@@ -1354,6 +1411,7 @@ struct icet_b200_ctx {
   int dump_on = 0;
   int sm_count = 148;
   int pass_smem_set = 0;  // dynamic shared memory the pass kernels are currently allowed
+  int* loop_dbg[ICET_NLANE] = {nullptr, nullptr};  // watchdog record of the last k_loop launch per lane
   int loop_occ[2] = {0, 0};  // resident blocks per SM of k_loop<PASS_K>, k_loop<PASS_K_SMALL>
   // per-kernel timing (icet_b200_set_profile): events around every launch, summed on request
   int profile_on = 0;
@@ -1415,6 +1473,7 @@ size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runle
   ck.iter_done = c.take<int>((size_t)P);
   ck.vox_done = c.take<unsigned>((size_t)P * std::max(1, runlen));
   ck.vmask = c.take<unsigned>((size_t)P * ((vt + 31) / 32));
+  ck.dbg = c.take<int>(8);
   c.off = (c.off + 255) & ~(size_t)255;
   if (zero_bytes) *zero_bytes = c.off;
   ck.off = c.take<int32_t>((size_t)P * ncell);
@@ -1465,7 +1524,8 @@ float bin_threshold(int k, double period, int nb) {
 // exact bin-lookup thresholds (src/icet.cpp:545-546)
 int ensure_edges(icet_b200_ctx* ctx, int nT, int nP) {
   if (ctx->edges_nT == nT && ctx->edges_nP == nP) return 0;
-  std::vector<float> e((size_t)2 * (nT + nP) + 6);
+  const size_t nbase = (size_t)2 * (nT + nP) + 6;
+  std::vector<float> e(((nbase + 3) & ~(size_t)3) + (size_t)4 * (nT + nP + 2));
   float* azE = e.data();
   float* elE = azE + nT + 1;
   float* Tth = elE + nP + 1;
@@ -1477,6 +1537,22 @@ int ensure_edges(icet_b200_ctx* ctx, int nT, int nP) {
   for (int k = 0; k <= nP; k++) Tph[k] = bin_threshold(k, M_PI, nP);
   Tth[nT + 1] = INFINITY;
   Tph[nP + 1] = INFINITY;
+  // bin + box records (bin_box): {T[k], T[k+1], max(T[k], E[k]), min(pred(T[k+1]), E[k+1])}; record nb is empty
+  float* rec = e.data() + ((nbase + 3) & ~(size_t)3);
+  auto fill = [](float* out, const float* T, const float* E, int nb) {
+    for (int k = 0; k < nb; k++) {
+      out[4 * k + 0] = T[k];
+      out[4 * k + 1] = T[k + 1];
+      out[4 * k + 2] = std::max(T[k], E[k]);
+      out[4 * k + 3] = std::min(std::nextafterf(T[k + 1], -INFINITY), E[k + 1]);
+    }
+    out[4 * nb + 0] = T[nb];
+    out[4 * nb + 1] = INFINITY;
+    out[4 * nb + 2] = INFINITY;
+    out[4 * nb + 3] = -INFINITY;
+  };
+  fill(rec, Tth, azE, nT);
+  fill(rec + 4 * (nT + 1), Tph, elE, nP);
   int rc = ctx->edges.ensure(e.size() * sizeof(float));
   if (rc) return rc;
   CK(cudaMemcpyAsync(ctx->edges.p, e.data(), e.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -1487,8 +1563,9 @@ int ensure_edges(icet_b200_ctx* ctx, int nT, int nP) {
 }
 
 void fill_tables(icet_b200_ctx* ctx, int nT, int nP, const float** azE, const float** elE, icet::BinTable* bth,
-                 icet::BinTable* bph) {
+                 icet::BinTable* bph, const float** binrec = nullptr) {
   const float* base = (const float*)ctx->edges.p;
+  if (binrec) *binrec = base + ((((size_t)2 * (nT + nP) + 6) + 3) & ~(size_t)3);
   *azE = base;
   *elE = base + nT + 1;
   bth->T = base + nT + 1 + nP + 1;
@@ -1533,7 +1610,7 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   ck.npairs = P; ck.ncell = ncell; ck.nT = nT; ck.nP = nP; ck.n = p->n; ck.runlen = p->runlen;
   ck.flags = p->flags; ck.thresh = p->thresh; ck.buff = p->buff;
   ck.n1max = n1max; ck.n2max = n2max;
-  fill_tables(ctx, nT, nP, &ck.azE, &ck.elE, &ck.bth, &ck.bph);
+  fill_tables(ctx, nT, nP, &ck.azE, &ck.elE, &ck.bth, &ck.bph, &ck.binrec);
   ck.x0 = d_x0;
   ck.res = d_res;
   ck.dump_on = dump ? 1 : 0;
@@ -1603,6 +1680,7 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
     if (tasks >= (1LL << 32)) return fail(ICET_B200_E_INVALID, "chunk too large: reduce icet_b200_set_chunk");
     const int occ = std::max(1, ctx->loop_occ[small ? 1 : 0]);
     const int grid = (int)std::min<long long>((tasks + PASS_WARPS - 1) / PASS_WARPS, (long long)ctx->sm_count * occ);
+    ctx->loop_dbg[lane] = ck.dbg;
     if (small) LAUNCH(10, k_loop<PASS_K_SMALL><<<grid, PASS_THREADS, psm2, st>>>(ck, tiles2, vt));
     else LAUNCH(10, k_loop<PASS_K><<<grid, PASS_THREADS, psm2, st>>>(ck, tiles2, vt));
   }
@@ -1611,6 +1689,22 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   static_assert(sizeof(Chunk) <= 512, "Chunk too large for last_ck");
   ctx->last_valid = (P == 1);
   if (P == 1) memcpy(ctx->last_ck, &ck, sizeof(Chunk));
+  return 0;
+}
+
+// after a blocking call: did a wait inside k_loop give up?  (never expected; turns a would-be hang into an error)
+int check_loop_watchdog(icet_b200_ctx* ctx) {
+  for (int lane = 0; lane < ICET_NLANE; lane++) {
+    if (!ctx->loop_dbg[lane]) continue;
+    int d[8];
+    CK(cudaMemcpy(d, ctx->loop_dbg[lane], sizeof(d), cudaMemcpyDeviceToHost));
+    ctx->loop_dbg[lane] = nullptr;
+    if (d[0])
+      return fail(ICET_B200_E_CUDA, "persistent loop kernel: wait timed out (kind " + std::to_string(d[1]) + ", pair " +
+                                        std::to_string(d[2]) + ", iteration " + std::to_string(d[3]) + ", seen " +
+                                        std::to_string(d[4]) + ", need " + std::to_string(d[5]) + ", ticket " +
+                                        std::to_string(d[6]) + ")");
+  }
   return 0;
 }
 
@@ -2039,7 +2133,7 @@ int icet_b200_register_batch(icet_b200_ctx* c, const icet_b200_params* p, int32_
   }
   CK(cudaMemcpyAsync(out, d_res, (size_t)npairs * sizeof(icet_b200_result), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  return 0;
+  return check_loop_watchdog(c);
 }
 
 int icet_b200_register(icet_b200_ctx* c, const icet_b200_params* p, const float* scan1, int32_t n1, int32_t ld1,

@@ -32,6 +32,7 @@ enum {
   ICET_B200_OK = 0,
   ICET_B200_COND_OVERFLOW = 1, /* checkCondition (src/icet.cpp:469-486) ran out of axes: the
                                   reference would abort on an Eigen bounds assert here          */
+  ICET_B200_LOOP_TIMEOUT = 2,  /* internal: a wait inside the persistent loop kernel gave up (results invalid)   */
   ICET_B200_E_INVALID = -1,    /* bad argument                                                   */
   ICET_B200_E_CUDA = -2,       /* CUDA runtime error (see icet_b200_last_error)                  */
   ICET_B200_E_NODEVICE = -3,   /* no usable CUDA device / wrong architecture                     */

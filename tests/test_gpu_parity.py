@@ -359,6 +359,22 @@ def test_degenerate_inputs(ctx, po):
         assert np.all(r["pred_stds"] == 0) and np.all(r["Q"] == 0) and r["status"] == 0 and r["n_used"] == 0
 
 
+def test_persistent_loop_stress_degenerate(ctx):
+    """Many tiny registrations through the persistent loop kernel: with no active voxel nothing but the explicit
+    iteration order keeps the per-pair flags monotonic (regression test: this used to hang about once in 300 calls).
+    A protocol failure surfaces as IcetError (device-side watchdog), not as a hang."""
+    from icet_b200 import api
+    z = np.zeros((3, 4096), np.float32)
+    x0 = np.array([0.1, 0, 0, 0, 0, 0.01], np.float32)
+    cases = [(z, z), (np.zeros((3, 0), np.float32), z), (np.ones((3, 10), np.float32), np.ones((3, 17), np.float32))]
+    p = params(flags=api.FLAG_PERSISTENT_LOOP)
+    for rep in range(400):
+        for a, b in cases:
+            r = ctx.register(a, b, X0=x0, params=p)
+            assert r["status"] == 0
+            np.testing.assert_array_equal(r["X"], x0)
+
+
 def test_invalid_arguments_raise(ctx):
     import icet_b200
     z = np.zeros((3, 16), np.float32)
