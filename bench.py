@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--lanes", type=int, default=0, help="compute lanes (0 = default 2)")
     ap.add_argument("--host-chunk", type=int, default=0, help="pairs per chunk of the host-buffer pipeline (0 = default)")
     ap.add_argument("--unfused", action="store_true", help="diagnostic: 3 launches per iteration instead of k_loop")
     args = ap.parse_args()
@@ -196,6 +197,8 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     if args.host_chunk:
         ctx.set_host_chunk(args.host_chunk)
+    if args.lanes:
+        ctx.set_lanes(args.lanes)
     params = api.make_params(RUNLEN, BINS_PHI, BINS_THETA, NMIN, THRESH, BUFF,
                              flags=api.FLAG_UNFUSED_LOOP if args.unfused else 0)
 
@@ -251,7 +254,7 @@ def main():
     ctx.register_sequence_device(scans.data_ptr(), P + 1, NPTS, results.data_ptr(), params)
     prof = ctx.get_profile()
     ctx.set_profile(False)
-    ctx.set_lanes(0)
+    ctx.set_lanes(args.lanes)
     tot_ms = sum(v[0] for v in prof.values())
     dom = max(prof, key=lambda k: prof[k][0])
     dom_ms, dom_n = prof[dom]

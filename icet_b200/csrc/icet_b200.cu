@@ -485,7 +485,7 @@ __device__ __forceinline__ void flush_in_run(unsigned long long* accp, int cell,
 //  Phase B (lane per contiguous slice of the compacted list): stage 2 (the expensive round trip) only for inside
 //    points and with all lanes busy; sums of a run of equal cell stay in registers, one flush per run.
 // Only warp-level synchronisation inside.
-template <bool SCAN2, int K>
+template <bool SCAN2, int K, int PF = 2>
 __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* the warp's pass_wslots(K) slots */,
                                                const float* tab, const CellRec* recs, const float* tr,
                                                const float* px_, size_t ld, int n, int w0,
@@ -496,17 +496,32 @@ __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* th
   const float4* tph = tth + ck.nT + 1;
   const unsigned lt = (1u << lane) - 1u;
   int nin_tile = 0;
-  // ---- phase A
-#pragma unroll 2
+  // ---- phase A (the coordinates of row j + PF are requested before row j is worked on)
+  float bx[PF > 0 ? PF : 1], by[PF > 0 ? PF : 1], bz[PF > 0 ? PF : 1];
+#pragma unroll
+  for (int p = 0; p < PF; p++) {
+    const int i = w0 + p * 32 + lane;
+    bx[p] = by[p] = bz[p] = 0.f;
+    if (p < K && i < n) { bx[p] = __ldg(px_ + i); by[p] = __ldg(px_ + ld + i); bz[p] = __ldg(px_ + 2 * ld + i); }
+  }
+#pragma unroll(PF > 0 ? (K % (2 * PF) == 0 ? 2 * PF : PF) : 2)
   for (int j = 0; j < K; j++) {
     const int i = w0 + j * 32 + lane;
     int c = -1;
     bool active = false, in = false;
     float r = 0.f, th = 0.f, ph = 0.f;
-    if (i < n) {
-      const float x = __ldg(px_ + i), y = __ldg(px_ + ld + i), z = __ldg(px_ + 2 * ld + i);
-      point_stage1<SCAN2>(ck, tth, tph, recs, tr, x, y, z, c, active, in, r, th, ph);
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (PF > 0) {
+      constexpr int PFm = PF > 0 ? PF : 1;
+      x = bx[j % PFm]; y = by[j % PFm]; z = bz[j % PFm];
+      const int ip = i + PF * 32;
+      if (j + PF < K && ip < n) {
+        bx[j % PFm] = __ldg(px_ + ip); by[j % PFm] = __ldg(px_ + ld + ip); bz[j % PFm] = __ldg(px_ + 2 * ld + ip);
+      }
+    } else if (i < n) {
+      x = __ldg(px_ + i); y = __ldg(px_ + ld + i); z = __ldg(px_ + 2 * ld + i);
     }
+    if (i < n) point_stage1<SCAN2>(ck, tth, tph, recs, tr, x, y, z, c, active, in, r, th, ph);
     // bin counts: one RED per run of equal (participating) cell in this row
     const int key = active ? c : -1;
     const int prev = __shfl_up_sync(FULL, key, 1);
@@ -552,9 +567,8 @@ __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* th
   __syncwarp();
 }
 
-template <bool SCAN2>
-__global__ void __launch_bounds__(PASS_THREADS) k_pass(const Chunk ck) {
-  constexpr int K = PASS_K;
+template <bool SCAN2, int K = PASS_K, int MINB = 3, int PF = 2>
+__global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass(const Chunk ck) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int4* ent = reinterpret_cast<int4*>(smem_raw);
   float* tab = reinterpret_cast<float*>(smem_raw + PASS_WARPS * pass_wslots(K) * 16);
@@ -579,7 +593,7 @@ __global__ void __launch_bounds__(PASS_THREADS) k_pass(const Chunk ck) {
   const CellRec* recs = ck.rec + (size_t)pair * ck.ncell;
   unsigned long long* accp = ck.acc + (size_t)pair * ck.ncell * NQ;
   __syncthreads();
-  pass_warp_tile<SCAN2, K>(ck, ent + (threadIdx.x >> 5) * pass_wslots(K), tab, recs, tr, px_, ld, n,
+  pass_warp_tile<SCAN2, K, PF>(ck, ent + (threadIdx.x >> 5) * pass_wslots(K), tab, recs, tr, px_, ld, n,
                            tile0 + (threadIdx.x >> 5) * 32 * K, accp);
   if (SCAN2 && blockIdx.x == 0 && threadIdx.x == 0)
     pass_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 1, recs, tr,
@@ -1412,6 +1426,7 @@ struct icet_b200_ctx {
   int sm_count = 148;
   int pass_smem_set = 0;  // dynamic shared memory the pass kernels are currently allowed
   int* loop_dbg[ICET_NLANE] = {nullptr, nullptr};  // watchdog record of the last k_loop launch per lane
+  int pass_variant = 1;
   int loop_occ[2] = {0, 0};  // resident blocks per SM of k_loop<PASS_K>, k_loop<PASS_K_SMALL>
   // per-kernel timing (icet_b200_set_profile): events around every launch, summed on request
   int profile_on = 0;
@@ -1621,18 +1636,26 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   const int nblk = (ncell + VOX_THREADS - 1) / VOX_THREADS;
   // shape of the loop kernel: big tiles (16 points per lane) for throughput; small tiles (4 points per lane) when
   // the chunk has too few big tiles to keep every resident block busy for several rounds
-  const int tile1 = pass_tile_points(PASS_K);
+  // EXPERIMENT: shape of the split-loop pass kernels, ICET_B200_PASS_VARIANT = 0..5
+  static const int VK[6] = {16, 16, 8, 8, 8, 12};
+  const int var = ctx->pass_variant;
+  const int tile1 = pass_tile_points(VK[var]);
   const dim3 gp1((n1max + tile1 - 1) / tile1, P), gp2((n2max + tile1 - 1) / tile1, P);
-  const int psm = pass_smem_bytes(nT, nP, PASS_K);
-  if (psm > ctx->pass_smem_set) {
-    CK(cudaFuncSetAttribute(k_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
-    CK(cudaFuncSetAttribute(k_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
-    CK(cudaFuncSetAttribute(k_loop<PASS_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
-    CK(cudaFuncSetAttribute(k_loop<PASS_K_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->loop_occ[0], k_loop<PASS_K>, PASS_THREADS, psm));
+  const int psm = pass_smem_bytes(nT, nP, VK[var]);
+  const int psm_loop = pass_smem_bytes(nT, nP, PASS_K);
+#define PASS_VARIANTS(X) X(0, 16, 3, 0) X(1, 16, 3, 2) X(2, 8, 4, 0) X(3, 8, 4, 2) X(4, 8, 5, 2) X(5, 12, 4, 2)
+  if (psm_loop > ctx->pass_smem_set) {
+#define SETATTR(id, K_, MINB_, PF_)                                                                                         \
+    CK(cudaFuncSetAttribute(k_pass<false, K_, MINB_, PF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm_loop));         \
+    CK(cudaFuncSetAttribute(k_pass<true, K_, MINB_, PF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm_loop));
+    PASS_VARIANTS(SETATTR)
+#undef SETATTR
+    CK(cudaFuncSetAttribute(k_loop<PASS_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm_loop));
+    CK(cudaFuncSetAttribute(k_loop<PASS_K_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm_loop));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->loop_occ[0], k_loop<PASS_K>, PASS_THREADS, psm_loop));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->loop_occ[1], k_loop<PASS_K_SMALL>, PASS_THREADS,
                                                      pass_smem_bytes(nT, nP, PASS_K_SMALL)));
-    ctx->pass_smem_set = psm;
+    ctx->pass_smem_set = psm_loop;
   }
   // warp tiles: 32*K points.  Small K when the chunk has too few big tiles to keep every resident warp busy for
   // several rounds per iteration (small batches, single-pair latency).
@@ -1662,7 +1685,9 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
     // enough CTAs to cover a typical work list (~25 % of the cells) in one pass; the kernel loops
     int gx = std::max(1, std::min(ncell, std::max(64, (ctx->sm_count * 16 + P - 1) / P)));
     LAUNCH(3, k_cluster<<<dim3(gx, P), 128, 0, st>>>(ck));
-    LAUNCH(4, k_pass<false><<<gp1, PASS_THREADS, psm, st>>>(ck));
+#define L1(id, K_, MINB_, PF_) if (var == id) LAUNCH(4, k_pass<false, K_, MINB_, PF_><<<gp1, PASS_THREADS, psm, st>>>(ck));
+    PASS_VARIANTS(L1)
+#undef L1
   }
   LAUNCH(5, k_fit1<<<dim3((ncell + 127) / 128, P), 128, 0, st>>>(ck));
   if (n2max > 0) LAUNCH(6, k_prep2<<<g2, 256, 0, st>>>(ck));
@@ -1670,7 +1695,9 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
                         (!(p->flags & ICET_B200_FLAG_UNFUSED_LOOP) && P <= ICET_LOOP_MAX_PAIRS);
   if (!use_loop) {
     for (int it = 0; it < p->runlen; it++) {
-      if (n2max > 0) LAUNCH(7, k_pass<true><<<gp2, PASS_THREADS, psm, st>>>(ck));
+#define L2(id, K_, MINB_, PF_) if (var == id && n2max > 0) LAUNCH(7, k_pass<true, K_, MINB_, PF_><<<gp2, PASS_THREADS, psm, st>>>(ck));
+      PASS_VARIANTS(L2)
+#undef L2
       LAUNCH(8, k_vox2<<<dim3(nblk, P), VOX_THREADS, 0, st>>>(ck, it));
       LAUNCH(9, k_solve6<<<P, 32, 0, st>>>(ck, it, nblk));
     }
@@ -1783,6 +1810,7 @@ int icet_b200_create(int device, icet_b200_ctx** out) {
     CK(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
   }
+  if (const char* e = getenv("ICET_B200_PASS_VARIANT")) c->pass_variant = std::max(0, std::min(5, atoi(e)));
   *out = c;
   return 0;
 }
