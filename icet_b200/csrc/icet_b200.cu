@@ -375,8 +375,8 @@ constexpr int PASS_K_SMALL = 4;  // same for small batches (latency shape: more,
 
 __host__ __device__ constexpr int pass_wslots(int K) { return 32 * K; }  // 16-byte entry slots per warp tile
 __host__ __device__ constexpr int pass_tile_points(int K) { return PASS_WARPS * 32 * K; }
-// shared memory: entry tiles, then the angular tables: (nT + 1) + (nP + 1) records {T[k], T[k+1], lo[k], hi[k]}
-__host__ __device__ inline int pass_tab_floats(int nT, int nP) { return 4 * (nT + nP + 2); }
+// shared memory: entry tiles, then the angular tables: (nT + 2) + (nP + 2) records {T[k], T[k+1], lo[k], hi[k]}
+__host__ __device__ inline int pass_tab_floats(int nT, int nP) { return 4 * (nT + nP + 4); }
 __host__ __device__ inline int pass_smem_bytes(int nT, int nP, int K) {
   return PASS_WARPS * pass_wslots(K) * 16 + pass_tab_floats(nT, nP) * 4;
 }
@@ -385,20 +385,18 @@ __host__ __device__ inline int pass_smem_bytes(int nT, int nP, int K) {
 //   T    exact thresholds of int((double(a)/period)*nb) (src/icet.cpp:545-546): bin k  <=>  T[k] <= a < T[k+1]
 //   lo/hi the part of the bin that also passes the reference's inclusive fp32 box test against the bin edges
 //        (src/icet.cpp:136-139, :632-633): lo = max(T[k], E[k]), hi = min(pred(T[k+1]), E[k+1]).
-// Record nb (a == fp32(period), bin index nb % nb = 0) has an empty [lo, hi].  Angles beyond the table (only the
-// NaN sentinel 1000.0) take the double formula and never pass the box test.
-__device__ __forceinline__ int bin_box(float a, const float4* rec, float scale, float amax, int nb, double period,
-                                       bool& inbox) {
-  if (!(a <= amax)) {
-    inbox = false;
-    return icet::bin_formula(a, period, nb);
-  }
-  int k = min(__float2int_rz(a * scale), nb);
+// Record nb (a == fp32(period), bin index nb % nb = 0) and record nb + 1 (everything beyond the period, i.e. the
+// NaN sentinel 1000.0, whose bin `sbin` comes from the double formula on the host) have an empty [lo, hi].
+// The fp32 estimate of k is off by at most one (checked against T).
+__device__ __forceinline__ int bin_box(float a, const float4* rec, const icet::BinTable& bt, bool& inbox) {
+  int k = __float2int_rz(fminf(a, bt.acap) * bt.scale);
   float4 e = rec[k];
-  if (a < e.x) e = rec[--k];
-  else if (a >= e.y) e = rec[++k];
+  if (a < e.x || a >= e.y) {
+    k += (a < e.x) ? -1 : 1;
+    e = rec[k];
+  }
   inbox = a >= e.z && a <= e.w;
-  return k == nb ? 0 : k;
+  return k < bt.nb ? k : (k == bt.nb ? 0 : bt.sbin);
 }
 
 // Stage 1 of a point: [transform,] spherical coordinates, cell, gates.  active = the cell takes part
@@ -410,8 +408,8 @@ __device__ __forceinline__ void point_stage1(const Chunk& ck, const float4* tth,
   if (SCAN2) icet::transform(x, y, z, tr, tr + 3, x, y, z);
   icet::c2s(x, y, z, r, th, ph);
   bool bt_in, bp_in;
-  const int bt = bin_box(th, tth, ck.bth.scale, ck.bth.amax, ck.nT, 2 * M_PI, bt_in);
-  const int bp = bin_box(ph, tph, ck.bph.scale, ck.bph.amax, ck.nP, M_PI, bp_in);
+  const int bt = bin_box(th, tth, ck.bth, bt_in);
+  const int bp = bin_box(ph, tph, ck.bph, bp_in);
   c = ck.nT * bp + bt;
   const float4 ra = __ldg(reinterpret_cast<const float4*>(recs + c));  // inner, outer, flags, scale
   active = (__float_as_uint(ra.z) & (SCAN2 ? F_ACTIVE2 : F_STAT1)) != 0;
@@ -493,7 +491,7 @@ __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* th
   const int lane = threadIdx.x & 31;
   if (w0 >= n) return;
   const float4* tth = reinterpret_cast<const float4*>(tab);
-  const float4* tph = tth + ck.nT + 1;
+  const float4* tph = tth + ck.nT + 2;
   const unsigned lt = (1u << lane) - 1u;
   int nin_tile = 0;
   // ---- phase A (the coordinates of row j + PF are requested before row j is worked on)
@@ -596,7 +594,7 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass(const Chunk ck) {
   pass_warp_tile<SCAN2, K, PF>(ck, ent + (threadIdx.x >> 5) * pass_wslots(K), tab, recs, tr, px_, ld, n,
                            tile0 + (threadIdx.x >> 5) * 32 * K, accp);
   if (SCAN2 && blockIdx.x == 0 && threadIdx.x == 0)
-    pass_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 1, recs, tr,
+    pass_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 2, recs, tr,
                          accp, ck.nz2[pair]);
 }
 
@@ -1263,7 +1261,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 3) k_loop(const Chunk ck, int ti
         pass_warp_tile<true, K>(ck, went, tab, recs, tr, ck.pog + (size_t)pair * 3 * ck.n2max, (size_t)ck.n2max, n, w0,
                                 accp);
         if (tile == 0 && lane == 0)
-          pass_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 1,
+          pass_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 2,
                                recs, tr, accp, __ldg(ck.nz2 + pair));
         if (tile == 0) TL(7);
         __threadfence();  // every lane: its accumulator updates are visible before the tile is counted
@@ -1540,7 +1538,7 @@ float bin_threshold(int k, double period, int nb) {
 int ensure_edges(icet_b200_ctx* ctx, int nT, int nP) {
   if (ctx->edges_nT == nT && ctx->edges_nP == nP) return 0;
   const size_t nbase = (size_t)2 * (nT + nP) + 6;
-  std::vector<float> e(((nbase + 3) & ~(size_t)3) + (size_t)4 * (nT + nP + 2));
+  std::vector<float> e(((nbase + 3) & ~(size_t)3) + (size_t)4 * (nT + nP + 4));
   float* azE = e.data();
   float* elE = azE + nT + 1;
   float* Tth = elE + nP + 1;
@@ -1554,7 +1552,8 @@ int ensure_edges(icet_b200_ctx* ctx, int nT, int nP) {
   Tph[nP + 1] = INFINITY;
   // bin + box records (bin_box): {T[k], T[k+1], max(T[k], E[k]), min(pred(T[k+1]), E[k+1])}; record nb is empty
   float* rec = e.data() + ((nbase + 3) & ~(size_t)3);
-  auto fill = [](float* out, const float* T, const float* E, int nb) {
+  auto fill = [](float* out, const float* T, const float* E, int nb, double period) {
+    const float beyond = std::nextafterf((float)period, INFINITY);
     for (int k = 0; k < nb; k++) {
       out[4 * k + 0] = T[k];
       out[4 * k + 1] = T[k + 1];
@@ -1562,12 +1561,16 @@ int ensure_edges(icet_b200_ctx* ctx, int nT, int nP) {
       out[4 * k + 3] = std::min(std::nextafterf(T[k + 1], -INFINITY), E[k + 1]);
     }
     out[4 * nb + 0] = T[nb];
-    out[4 * nb + 1] = INFINITY;
+    out[4 * nb + 1] = beyond;
     out[4 * nb + 2] = INFINITY;
     out[4 * nb + 3] = -INFINITY;
+    out[4 * nb + 4] = beyond;
+    out[4 * nb + 5] = INFINITY;
+    out[4 * nb + 6] = INFINITY;
+    out[4 * nb + 7] = -INFINITY;
   };
-  fill(rec, Tth, azE, nT);
-  fill(rec + 4 * (nT + 1), Tph, elE, nP);
+  fill(rec, Tth, azE, nT, 2 * M_PI);
+  fill(rec + 4 * (nT + 2), Tph, elE, nP, M_PI);
   int rc = ctx->edges.ensure(e.size() * sizeof(float));
   if (rc) return rc;
   CK(cudaMemcpyAsync(ctx->edges.p, e.data(), e.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -1587,10 +1590,14 @@ void fill_tables(icet_b200_ctx* ctx, int nT, int nP, const float** azE, const fl
   bth->nb = nT;
   bth->scale = (float)((double)nT / (2 * M_PI));
   bth->amax = (float)(2 * M_PI);
+  bth->acap = (float)((nT + 1.25) / ((double)nT / (2 * M_PI)));
+  bth->sbin = static_cast<int>(((double)1000.0f / (2 * M_PI)) * nT) % nT;
   bph->T = bth->T + nT + 2;
   bph->nb = nP;
   bph->scale = (float)((double)nP / M_PI);
   bph->amax = (float)M_PI;
+  bph->acap = (float)((nP + 1.25) / ((double)nP / M_PI));
+  bph->sbin = static_cast<int>(((double)1000.0f / M_PI) * nP) % nP;
 }
 
 int prof_events(icet_b200_ctx* ctx, int id, cudaEvent_t* e0, cudaEvent_t* e1) {

@@ -18,13 +18,67 @@
 
 namespace icet {
 
+// theta of utils::cartesianToSpherical (src/utils.cpp:104-107): atan2f(y, x), plus 2*pi (double add) when negative.
+// Own evaluation instead of CUDA's atan2f (about half the instructions): t = min/max by reciprocal + one Newton
+// step, atan(t) = t + t^3 P(t^2) on [0,1] (degree-8 minimax, < 1 ulp), the octant fix-up pi/2 - a, pi - a in double
+// and ONE rounding to fp32 -- within 1 ulp of the correctly rounded atan2 (glibc's and CUDA's are within 1-2 ulp).
+// Zero / non-finite inputs take the library routine.
+__device__ __forceinline__ float theta_of(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const bool steep = ay > ax;  // selects (not fmaxf / fminf) so that a NaN coordinate reaches t
+  const float mx = steep ? ay : ax, mn = steep ? ax : ay;
+  float rc;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(mx));
+  const float t0 = mn * rc;
+  const float t = fmaf(fmaf(-t0, mx, mn), rc, t0);
+  float th;
+  if (t <= 1.0f) {  // false for NaN (0/0, inf/inf, NaN input)
+    const float s = t * t;
+    float p = -0.0019267977913841605f;
+    p = fmaf(p, s, 0.01150327268987894f);
+    p = fmaf(p, s, -0.03226083889603615f);
+    p = fmaf(p, s, 0.059030335396528244f);
+    p = fmaf(p, s, -0.08465225994586945f);
+    p = fmaf(p, s, 0.10972991585731506f);
+    p = fmaf(p, s, -0.14268141984939575f);
+    p = fmaf(p, s, 0.19998906552791595f);
+    p = fmaf(p, s, -0.3333331048488617f);
+    const float a = fmaf(t * s, p, t);
+    double v = (double)a;
+    v = steep ? (M_PI / 2 - v) : v;
+    v = (x < 0.0f) ? (M_PI - v) : v;
+    th = copysignf((float)v, y);
+  } else {
+    th = atan2f(y, x);
+  }
+  if (th < 0.0f) th = (float)((double)th + 2.0 * M_PI);  // theta(i) += 2.0 * M_PI    :105-107
+  return th;
+}
+
+// phi of utils::cartesianToSpherical (src/utils.cpp:108): acosf(q), q = z / r.  For |q| <= 0.5 (elevations within
+// +-30 degrees of the horizon: every ring of a spinning LiDAR) acos(q) = pi/2 - asin(q) with asin(q) = q + q^3 P(q^2)
+// and the subtraction done in double with one rounding to fp32 (within 1 ulp of correctly rounded); NaN (0/0 of a
+// dropped return) propagates.  Steeper rays take the library routine.
+__device__ __forceinline__ float phi_of(float q) {
+  if (!(fabsf(q) > 0.5f)) {
+    const float s = q * q;
+    float p = 0.0435001514852047f;
+    p = fmaf(p, s, 0.023313719779253006f);
+    p = fmaf(p, s, 0.045668356120586395f);
+    p = fmaf(p, s, 0.07493448257446289f);
+    p = fmaf(p, s, 0.166668102145195f);
+    const float corr = (q * s) * p;
+    return (float)((M_PI / 2 - (double)q) - (double)corr);
+  }
+  return acosf(q);
+}
+
 // utils::cartesianToSpherical, reference src/utils.cpp:93-119
 __device__ __forceinline__ void c2s(float x, float y, float z, float& r, float& th, float& ph) {
   float s = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
   r = __fsqrt_rn(s);                                        // rowwise().norm()          :98
-  th = atan2f(y, x);                                        //                           :104
-  if (th < 0.0f) th = (float)((double)th + 2.0 * M_PI);     // theta(i) += 2.0 * M_PI    :105-107
-  ph = acosf(__fdiv_rn(z, r));                              //                           :108
+  th = theta_of(y, x);                                      //                           :104-107
+  ph = phi_of(__fdiv_rn(z, r));                             //                           :108
   if (isnan(r)) r = 1000.0f;                                // isNaN().select(1000.0, .) :116
   if (isnan(th)) th = 1000.0f;
   if (isnan(ph)) ph = 1000.0f;
@@ -56,6 +110,8 @@ struct BinTable {
   float scale;     // fp32(nb / period)
   float amax;      // fp32(period): the largest angle the table covers
   int nb;
+  float acap;      // fp32 angle whose estimate lands in record nb + 1 (pass kernels: everything beyond the period)
+  int sbin;        // bin of the NaN sentinel 1000.0 by the double formula
 };
 // T may point to global or shared memory (the call is inlined, the address space is known statically)
 __device__ __forceinline__ int bin_lookup(float a, const float* T, float scale, float amax, int nb, double period) {

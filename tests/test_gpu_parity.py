@@ -112,6 +112,31 @@ def test_spherical_and_bins(ctx, po, name):
         print("%s: %d points, %d edge points %s" % (name, scan.shape[1], len(edge), edge.tolist()))
 
 
+def test_angles_within_one_ulp_of_correct_rounding(ctx):
+    """theta_of / phi_of (own atan2 / acos evaluations) against float64: at most 1 ulp from the correctly rounded
+    fp32 value over random directions, the axes, the octant diagonals and steep rays (library acosf path)."""
+    rng = np.random.default_rng(5)
+    n = 400000
+    pts = rng.normal(0, 20, (3, n)).astype(np.float32)
+    pts[2, : n // 2] *= 0.2                                   # LiDAR-like elevations (fast acos path)
+    k = 2000
+    for j, (sx, sy) in enumerate(((1, 0), (0, 1), (-1, 0), (0, -1), (1, 1), (-1, 1), (-1, -1), (1, -1))):
+        blk = slice(j * k, (j + 1) * k)
+        pts[0, blk] = sx * 10 + rng.normal(0, 1e-4, k) * (sx == 0) + rng.normal(0, 1e-6, k)
+        pts[1, blk] = sy * 10 + rng.normal(0, 1e-4, k) * (sy == 0) + rng.normal(0, 1e-6, k)
+    sph, _ = ctx.spherical_bins(pts)
+    x, y, z = pts.astype(np.float64)
+    th = np.arctan2(y, x).astype(np.float32)
+    th = np.where(th < 0, (th.astype(np.float64) + 2 * np.pi).astype(np.float32), th)
+    r32 = sph[0].astype(np.float64)
+    q = (pts[2] / sph[0]).astype(np.float32)                  # z / r as the path computes it (IEEE division)
+    ph = np.arccos(q.astype(np.float64)).astype(np.float32)
+    assert ulp_diff(sph[1], th).max() <= 1
+    assert ulp_diff(sph[2], ph).max() <= 2 and np.mean(ulp_diff(sph[2], ph) > 1) < 1e-3
+    print("theta: %.1f %% bit-equal to correctly rounded; phi: %.1f %%" %
+          (100 * np.mean(ulp_diff(sph[1], th) == 0), 100 * np.mean(ulp_diff(sph[2], ph) == 0)))
+
+
 def test_bin_lookup_table_is_exact(ctx, po):
     """The table form of int((a/period)*nb) % nb must agree with the double formula for EVERY fp32 angle: probe all
     values adjacent to the bin edges, the wrap-around values and random angles, for several grids."""
