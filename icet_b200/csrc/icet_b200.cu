@@ -319,7 +319,117 @@ __device__ inline void find_cluster_warp(Ptr a, int m, int nz, int n, float thre
   outer = fo;
 }
 
-__global__ void __launch_bounds__(128) k_cluster(const Chunk ck) {
+// writes the cell record of a clustered cell (clusterBounds columns 4,5 + the voxel's fixed-point frame)
+__device__ inline void write_cluster_rec(const Chunk& ck, int pair, int cell, int cnt, float inner, float outer) {
+  const int bt = cell % ck.nT, bp = cell / ck.nT;
+  CellRec rc;
+  rc.inner = inner;
+  rc.outer = outer;
+  rc.cnt1 = cnt;
+  rc.flags = ((double)outer > 0.1) ? F_STAT1 : 0u;  // `outerDistance > 0.1` src/icet.cpp:158
+  // fixed-point frame of the voxel: reference point = centre of the spherical box, scale from
+  // a bound on the box diameter
+  const float azl = ck.azE[bt], azh = ck.azE[bt + 1], ell = ck.elE[bp], elh = ck.elE[bp + 1];
+  const float rm = 0.5f * (inner + outer), tm = 0.5f * (azl + azh), pm = 0.5f * (ell + elh);
+  icet::s2c(rm, tm, pm, rc.refx, rc.refy, rc.refz);
+  float D = (outer - inner) + fabsf(outer) * ((azh - azl) + (elh - ell));
+  int e;
+  frexpf(fmaxf(D, 1e-20f), &e);          // D < 2^e
+  rc.scale = ldexpf(1.0f, FPB - e - 1);  // |d| <= D  =>  |d*scale| < 2^(FPB-1)
+  ck.rec[(size_t)pair * ck.ncell + cell] = rc;
+}
+
+// Bitonic sort of 32*EPL floats held EPL per lane; element index = lane*EPL + j.  Compare-exchange distances
+// below EPL stay inside a lane (registers), larger ones are one shuffle per element.  Fully unrolled.
+template <int EPL>
+__device__ __forceinline__ void warp_sort_regs(float (&v)[EPL]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 2; k <= 32 * EPL; k <<= 1) {
+#pragma unroll
+    for (int d = k >> 1; d > 0; d >>= 1) {
+      if (d >= EPL) {
+        const int ld = d / EPL;                                             // partner lane distance
+        const bool asc = (k >= 32 * EPL) || ((lane & (k / EPL)) == 0);
+        const bool keep_min = (((lane & ld) == 0) == asc);
+#pragma unroll
+        for (int j = 0; j < EPL; j++) {
+          const float o = __shfl_xor_sync(FULL, v[j], ld);
+          v[j] = keep_min ? fminf(v[j], o) : fmaxf(v[j], o);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < EPL; j++) {
+          if ((j & d) == 0) {
+            // direction bit k of the element index: in the register index for k < EPL, in the lane above
+            const bool asc = (k >= 32 * EPL) || (k < EPL ? ((j & k) == 0) : ((lane & (k / EPL)) == 0));
+            const float lo = fminf(v[j], v[j ^ d]), hi = fmaxf(v[j], v[j ^ d]);
+            v[j] = asc ? lo : hi;
+            v[j ^ d] = asc ? hi : lo;
+          }
+        }
+      }
+    }
+  }
+}
+
+// loads the m ranges of a cell (any order), sorts them in registers and leaves them ascending in the warp's
+// shared-memory row (index i stored at i + i/32: conflict-free for the blocked write and for consecutive reads)
+template <int EPL>
+__device__ __forceinline__ void warp_sort_cell(const float* __restrict__ g, int m, float* srow) {
+  const int lane = threadIdx.x & 31;
+  float v[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; j++) {
+    const int i = j * 32 + lane;  // coalesced; which register an unsorted value lands in is irrelevant
+    v[j] = i < m ? __ldg(g + i) : INFINITY;
+  }
+  warp_sort_regs<EPL>(v);
+#pragma unroll
+  for (int j = 0; j < EPL; j++) {
+    const int i = lane * EPL + j;
+    srow[i + (i >> 5)] = v[j];
+  }
+  __syncwarp();
+}
+
+struct PaddedRow {  // view of a shared-memory row written by warp_sort_cell
+  const float* p;
+  __device__ __forceinline__ float operator[](int i) const { return p[i + (i >> 5)]; }
+};
+
+constexpr int CLUSTER_WARPS = 4;
+constexpr int WSORT_MAX = 1024;  // cells up to this many non-zero ranges are sorted by one warp in registers
+
+// K2c: ONE WARP per cell with cnt1 >= n (a cell of a 64-ring scan holds ~260 ranges): register bitonic sort, then
+// ICET::findCluster on the sorted row.  Cells with more than WSORT_MAX ranges are left to k_cluster_big.
+__global__ void __launch_bounds__(CLUSTER_WARPS * 32) k_cluster(const Chunk ck) {
+  const int pair = blockIdx.y;
+  __shared__ float s_rows[CLUSTER_WARPS][WSORT_MAX + WSORT_MAX / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* srow = s_rows[warp];
+  const int nw = ck.nwork[pair];
+  for (int w = blockIdx.x * CLUSTER_WARPS + warp; w < nw; w += gridDim.x * CLUSTER_WARPS) {
+    const int cell = ck.work[(size_t)pair * ck.ncell + w];
+    const int cnt = ck.cnt1[(size_t)pair * ck.ncell + cell];
+    const int nz = ck.cntz[(size_t)pair * ck.ncell + cell];
+    const int m = cnt - nz;
+    if (m > WSORT_MAX) continue;
+    const float* g = ck.rbuf + (size_t)pair * ck.n1max + ck.off[(size_t)pair * ck.ncell + cell];
+    if (m <= 128) warp_sort_cell<4>(g, m, srow);
+    else if (m <= 256) warp_sort_cell<8>(g, m, srow);
+    else if (m <= 512) warp_sort_cell<16>(g, m, srow);
+    else warp_sort_cell<32>(g, m, srow);
+    float inner, outer;
+    find_cluster_warp(PaddedRow{srow}, m, nz, ck.n, ck.thresh, ck.buff, inner, outer);
+    if (lane == 0) write_cluster_rec(ck, pair, cell, cnt, inner, outer);
+    __syncwarp();
+  }
+}
+
+// K2c for the rare big cells (more than WSORT_MAX ranges, e.g. an accumulated map as scan 1): one CTA per cell,
+// bitonic network in shared memory (<= SORT_SMEM ranges) or in L2.
+__global__ void __launch_bounds__(128) k_cluster_big(const Chunk ck) {
   const int pair = blockIdx.y;
   __shared__ float s_r[SORT_SMEM];
   const int nw = ck.nwork[pair];
@@ -328,6 +438,7 @@ __global__ void __launch_bounds__(128) k_cluster(const Chunk ck) {
     const int cnt = ck.cnt1[(size_t)pair * ck.ncell + cell];
     const int nz = ck.cntz[(size_t)pair * ck.ncell + cell];
     const int m = cnt - nz;
+    if (m <= WSORT_MAX) continue;  // block-uniform
     float* g = ck.rbuf + (size_t)pair * ck.n1max + ck.off[(size_t)pair * ck.ncell + cell];
     float inner, outer;
     if (m <= SORT_SMEM) {
@@ -340,24 +451,7 @@ __global__ void __launch_bounds__(128) k_cluster(const Chunk ck) {
       block_sort_asc(g, m);
       if (threadIdx.x < 32) find_cluster_warp(g, m, nz, ck.n, ck.thresh, ck.buff, inner, outer);
     }
-    if (threadIdx.x == 0) {
-      const int bt = cell % ck.nT, bp = cell / ck.nT;
-      CellRec rc;
-      rc.inner = inner;
-      rc.outer = outer;
-      rc.cnt1 = cnt;
-      rc.flags = ((double)outer > 0.1) ? F_STAT1 : 0u;  // `outerDistance > 0.1` src/icet.cpp:158
-      // fixed-point frame of the voxel: reference point = centre of the spherical box, scale from
-      // a bound on the box diameter
-      const float azl = ck.azE[bt], azh = ck.azE[bt + 1], ell = ck.elE[bp], elh = ck.elE[bp + 1];
-      const float rm = 0.5f * (inner + outer), tm = 0.5f * (azl + azh), pm = 0.5f * (ell + elh);
-      icet::s2c(rm, tm, pm, rc.refx, rc.refy, rc.refz);
-      float D = (outer - inner) + fabsf(outer) * ((azh - azl) + (elh - ell));
-      int e;
-      frexpf(fmaxf(D, 1e-20f), &e);          // D < 2^e
-      rc.scale = ldexpf(1.0f, FPB - e - 1);  // |d| <= D  =>  |d*scale| < 2^(FPB-1)
-      ck.rec[(size_t)pair * ck.ncell + cell] = rc;
-    }
+    if (threadIdx.x == 0) write_cluster_rec(ck, pair, cell, cnt, inner, outer);
     __syncthreads();
   }
 }
@@ -1324,6 +1418,8 @@ __global__ void __launch_bounds__(32) k_solve6(const Chunk ck, int iter, int nbl
     s_tot[lane] = mine;
   }
   __syncwarp();
+  // (one thread: this kernel is bound by instruction fetch of once-executed code, the warp-parallel solve of
+  // k_loop is not faster here)
   if (lane == 0) solve_pair(ck, pair, iter, s_tot);
 }
 
@@ -1424,7 +1520,6 @@ struct icet_b200_ctx {
   int sm_count = 148;
   int pass_smem_set = 0;  // dynamic shared memory the pass kernels are currently allowed
   int* loop_dbg[ICET_NLANE] = {nullptr, nullptr};  // watchdog record of the last k_loop launch per lane
-  int pass_variant = 1;
   int loop_occ[2] = {0, 0};  // resident blocks per SM of k_loop<PASS_K>, k_loop<PASS_K_SMALL>
   // per-kernel timing (icet_b200_set_profile): events around every launch, summed on request
   int profile_on = 0;
@@ -1643,26 +1738,20 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   const int nblk = (ncell + VOX_THREADS - 1) / VOX_THREADS;
   // shape of the loop kernel: big tiles (16 points per lane) for throughput; small tiles (4 points per lane) when
   // the chunk has too few big tiles to keep every resident block busy for several rounds
-  // EXPERIMENT: shape of the split-loop pass kernels, ICET_B200_PASS_VARIANT = 0..5
-  static const int VK[6] = {16, 16, 8, 8, 8, 12};
-  const int var = ctx->pass_variant;
-  const int tile1 = pass_tile_points(VK[var]);
+  // pass kernels of the split loop: 16 rows per warp tile, 3 blocks / SM, coordinates prefetched 2 rows ahead
+  // (measured against 8 / 12 rows with 4-5 blocks and against no prefetch: profiles/r01_pass_variants.txt)
+  const int tile1 = pass_tile_points(PASS_K);
   const dim3 gp1((n1max + tile1 - 1) / tile1, P), gp2((n2max + tile1 - 1) / tile1, P);
-  const int psm = pass_smem_bytes(nT, nP, VK[var]);
-  const int psm_loop = pass_smem_bytes(nT, nP, PASS_K);
-#define PASS_VARIANTS(X) X(0, 16, 3, 0) X(1, 16, 3, 2) X(2, 8, 4, 0) X(3, 8, 4, 2) X(4, 8, 5, 2) X(5, 12, 4, 2)
-  if (psm_loop > ctx->pass_smem_set) {
-#define SETATTR(id, K_, MINB_, PF_)                                                                                         \
-    CK(cudaFuncSetAttribute(k_pass<false, K_, MINB_, PF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm_loop));         \
-    CK(cudaFuncSetAttribute(k_pass<true, K_, MINB_, PF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm_loop));
-    PASS_VARIANTS(SETATTR)
-#undef SETATTR
-    CK(cudaFuncSetAttribute(k_loop<PASS_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm_loop));
-    CK(cudaFuncSetAttribute(k_loop<PASS_K_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm_loop));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->loop_occ[0], k_loop<PASS_K>, PASS_THREADS, psm_loop));
+  const int psm = pass_smem_bytes(nT, nP, PASS_K);
+  if (psm > ctx->pass_smem_set) {
+    CK(cudaFuncSetAttribute(k_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
+    CK(cudaFuncSetAttribute(k_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
+    CK(cudaFuncSetAttribute(k_loop<PASS_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
+    CK(cudaFuncSetAttribute(k_loop<PASS_K_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->loop_occ[0], k_loop<PASS_K>, PASS_THREADS, psm));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->loop_occ[1], k_loop<PASS_K_SMALL>, PASS_THREADS,
                                                      pass_smem_bytes(nT, nP, PASS_K_SMALL)));
-    ctx->pass_smem_set = psm_loop;
+    ctx->pass_smem_set = psm;
   }
   // warp tiles: 32*K points.  Small K when the chunk has too few big tiles to keep every resident warp busy for
   // several rounds per iteration (small batches, single-pair latency).
@@ -1689,12 +1778,16 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   LAUNCH(1, k_cell_scan<<<P, 256, 0, st>>>(ck));
   if (n1max > 0) {
     LAUNCH(2, k_scatter<<<g1, 256, 0, st>>>(ck));
-    // enough CTAs to cover a typical work list (~25 % of the cells) in one pass; the kernel loops
-    int gx = std::max(1, std::min(ncell, std::max(64, (ctx->sm_count * 16 + P - 1) / P)));
-    LAUNCH(3, k_cluster<<<dim3(gx, P), 128, 0, st>>>(ck));
-#define L1(id, K_, MINB_, PF_) if (var == id) LAUNCH(4, k_pass<false, K_, MINB_, PF_><<<gp1, PASS_THREADS, psm, st>>>(ck));
-    PASS_VARIANTS(L1)
-#undef L1
+    // one warp per listed cell; enough CTAs to cover a typical work list (~25 % of the cells) in one pass
+    int gx = std::max(1, std::min((ncell + CLUSTER_WARPS - 1) / CLUSTER_WARPS,
+                                  std::max(32, (ctx->sm_count * 16 + P - 1) / P)));
+    LAUNCH(3, k_cluster<<<dim3(gx, P), CLUSTER_WARPS * 32, 0, st>>>(ck));
+    // big cells (> WSORT_MAX ranges) can only exist if a cell can hold that many points
+    if (n1max > WSORT_MAX) {
+      const int gb = std::max(1, std::min(ncell, std::max(8, (ctx->sm_count * 4 + P - 1) / P)));
+      LAUNCH(3, k_cluster_big<<<dim3(gb, P), 128, 0, st>>>(ck));
+    }
+    LAUNCH(4, k_pass<false><<<gp1, PASS_THREADS, psm, st>>>(ck));
   }
   LAUNCH(5, k_fit1<<<dim3((ncell + 127) / 128, P), 128, 0, st>>>(ck));
   if (n2max > 0) LAUNCH(6, k_prep2<<<g2, 256, 0, st>>>(ck));
@@ -1702,9 +1795,7 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
                         (!(p->flags & ICET_B200_FLAG_UNFUSED_LOOP) && P <= ICET_LOOP_MAX_PAIRS);
   if (!use_loop) {
     for (int it = 0; it < p->runlen; it++) {
-#define L2(id, K_, MINB_, PF_) if (var == id && n2max > 0) LAUNCH(7, k_pass<true, K_, MINB_, PF_><<<gp2, PASS_THREADS, psm, st>>>(ck));
-      PASS_VARIANTS(L2)
-#undef L2
+      if (n2max > 0) LAUNCH(7, k_pass<true><<<gp2, PASS_THREADS, psm, st>>>(ck));
       LAUNCH(8, k_vox2<<<dim3(nblk, P), VOX_THREADS, 0, st>>>(ck, it));
       LAUNCH(9, k_solve6<<<P, 32, 0, st>>>(ck, it, nblk));
     }
@@ -1817,7 +1908,6 @@ int icet_b200_create(int device, icet_b200_ctx** out) {
     CK(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
   }
-  if (const char* e = getenv("ICET_B200_PASS_VARIANT")) c->pass_variant = std::max(0, std::min(5, atoi(e)));
   *out = c;
   return 0;
 }
