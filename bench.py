@@ -267,6 +267,17 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "unit": "GB/s", "peak": peak, "peak_source": peak_src,
                 "traffic": None, "kernel_share_of_step": dom_ms / tot_ms if tot_ms else None,
                 "avg_launch_ms": dom_ms / dom_n if dom_n else None}
+    # DRAM bytes per launch of that kernel from the latest committed `ncu --set full` capture
+    # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/traffic.json, written by tools/profile_summary.py),
+    # scaled to this run's pairs per launch
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f).get(dom)
+        if tj:
+            roofline["traffic"] = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * chunk_pairs / tj["pairs_per_launch"]
+            roofline["traffic_source"] = "ncu --set full, visit %s (profiles/%s.md)" % (tj["visit"], tj["visit"])
+    except Exception:
+        pass
     if alg_bytes and dom_n:
         ach = alg_bytes / (dom_ms / dom_n * 1e-3) / 1e9
         roofline.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_launch": alg_bytes})

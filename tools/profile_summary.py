@@ -65,6 +65,38 @@ def raw_table(rep):
     return "\n".join(lines)
 
 
+def traffic_of(rep, tag, pairs_per_launch=256):
+    """{bench kernel name: dram bytes per launch} from the raw page (first launch of each kernel)."""
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    if len(rows) < 3:
+        return {}
+    h, u = rows[0], rows[1]
+    res = {}
+    for r in rows[2:]:
+        name = r[h.index("Kernel Name")]
+        key = None
+        if "k_pass<(bool)1" in name or "k_pass<true" in name or "k_pass<1," in name:
+            key = "k_pass<scan2>"
+        elif "k_pass<(bool)0" in name or "k_pass<false" in name or "k_pass<0," in name:
+            key = "k_pass<scan1>"
+        elif "k_loop" in name:
+            key = "k_loop"
+        if not key or key in res:
+            continue
+        def val(k):
+            i = h.index(k)
+            v = float(r[i].replace(",", ""))
+            unit = u[i].lower()
+            return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1)
+        try:
+            res[key] = {"visit": tag, "pairs_per_launch": pairs_per_launch,
+                        "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum")}
+        except ValueError:
+            pass
+    return res
+
+
 def main():
     tag = sys.argv[1]
     d = os.path.join(ROOT, "gpurun_out", tag)
@@ -94,6 +126,18 @@ def main():
             r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), os.path.join(d, rep),
                                 sys.argv[2], "30"], capture_output=True, text=True)
             md += ["Hottest source lines (executed instructions / stall samples):", "```", r.stdout.strip(), "```", ""]
+    # raw launch list next to the summary; DRAM traffic of the dominant kernel for bench.py's roofline.traffic
+    p = os.path.join(d, "launches.csv")
+    if os.path.exists(p):
+        import shutil
+        shutil.copy(p, os.path.join(ROOT, "profiles", tag + "_launches.csv"))
+    for rep in reps:
+        t = traffic_of(os.path.join(d, rep), tag)
+        if t:
+            tp = os.path.join(ROOT, "profiles", "traffic.json")
+            cur = json.load(open(tp)) if os.path.exists(tp) else {}
+            cur.update(t)
+            json.dump(cur, open(tp, "w"))
     out = os.path.join(ROOT, "profiles", tag + ".md")
     open(out, "w").write("\n".join(md) + "\n")
     print(out)
