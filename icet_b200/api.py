@@ -36,10 +36,29 @@ assert RESULT_DTYPE.itemsize == C.sizeof(Result) == 224
 FLAG_FULL_EIG = 1
 FLAG_UNFUSED_LOOP = 2
 FLAG_PERSISTENT_LOOP = 4
+FLAG_CHAIN_X0 = 8  # odometry.cpp:82: pair k+1 starts from the solution of pair k; X0 = one seed (pair 0)
 
 _DUMP_FIELDS = [("cnt1", _IP), ("bounds", _FP), ("nin1", _IP), ("has1", _BP), ("mu1", _FP), ("sigma1", _FP),
                 ("evec1", _FP), ("eval1", _FP), ("lmask", _BP), ("cnt2", _IP), ("nin2", _IP), ("used2", _BP),
                 ("mu2", _FP), ("sigma2", _FP), ("Xit", _FP), ("HTWH", _FP), ("HTWdz", _FP)]
+
+
+class OdometryParams(C.Structure):
+    """icet_b200_odometry_params: the steps the reference's ROS nodes wrap around the constructor."""
+    _fields_ = [("min_range", C.c_float), ("chain_x0", C.c_int32), ("rate_hz", C.c_float), ("guard_trans", C.c_float),
+                ("guard_rot", C.c_float), ("reserved", C.c_int32 * 3)]
+
+
+class Pose(C.Structure):
+    _fields_ = [("X_homo", C.c_float * 16), ("position", C.c_float * 3), ("orientation", C.c_float * 4),
+                ("covariance_diag", C.c_float * 6), ("twist", C.c_float * 6), ("X", C.c_float * 6),
+                ("n_points", C.c_int32), ("guarded", C.c_int32), ("frame", C.c_int32), ("reserved", C.c_int32)]
+
+
+POSE_DTYPE = np.dtype([("X_homo", np.float32, (4, 4)), ("position", np.float32, 3), ("orientation", np.float32, 4),
+                       ("covariance_diag", np.float32, 6), ("twist", np.float32, 6), ("X", np.float32, 6),
+                       ("n_points", np.int32), ("guarded", np.int32), ("frame", np.int32), ("reserved", np.int32)])
+assert POSE_DTYPE.itemsize == C.sizeof(Pose) == 180
 
 
 class _Dump(C.Structure):
@@ -51,7 +70,10 @@ EXPORTS = ["icet_b200_version", "icet_b200_last_error", "icet_b200_create", "ice
            "icet_b200_register_batch_device", "icet_b200_register_sequence_device", "icet_b200_synchronize",
            "icet_b200_set_dump", "icet_b200_get_dump", "icet_b200_get_points2", "icet_b200_spherical_bins",
            "icet_b200_synth_scans_device", "icet_b200_kernel_launches", "icet_b200_set_profile",
-           "icet_b200_get_profile", "icet_b200_kernel_name"]
+           "icet_b200_get_profile", "icet_b200_kernel_name",
+           "icet_b200_node_create", "icet_b200_node_destroy", "icet_b200_node_push_device", "icet_b200_node_push",
+           "icet_b200_node_current_scan", "icet_b200_node_last_result", "icet_b200_map_create",
+           "icet_b200_map_destroy", "icet_b200_map_add_scan_device", "icet_b200_map_get", "icet_b200_map_get_device"]
 NKERNELS = 11
 
 _LIB = None
@@ -97,6 +119,19 @@ def load_library() -> C.CDLL:
     L.icet_b200_set_profile.argtypes = [vp, C.c_int32]
     L.icet_b200_get_profile.argtypes = [vp, vp, vp]
     L.icet_b200_kernel_name.argtypes = [C.c_int]
+    L.icet_b200_node_create.argtypes = [vp, C.POINTER(Params), C.POINTER(OdometryParams), C.c_int32, vp, vp,
+                                        C.POINTER(vp)]
+    L.icet_b200_node_destroy.argtypes = [vp]
+    L.icet_b200_node_push_device.argtypes = [vp, C.c_int32, vp, C.c_int32, vp, vp]
+    L.icet_b200_node_push.argtypes = [vp, vp, C.c_int32, C.c_int32, C.POINTER(Result), C.POINTER(Pose)]
+    L.icet_b200_node_current_scan.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32)]
+    L.icet_b200_node_last_result.argtypes = [vp, C.POINTER(vp)]
+    L.icet_b200_map_create.argtypes = [vp, C.c_int32, C.POINTER(vp)]
+    L.icet_b200_map_destroy.argtypes = [vp]
+    L.icet_b200_map_add_scan_device.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp, C.c_int32, vp, C.c_float,
+                                                C.c_float]
+    L.icet_b200_map_get.argtypes = [vp, vp, C.c_int32, C.POINTER(C.c_int32)]
+    L.icet_b200_map_get_device.argtypes = [vp, vp, C.c_int32, vp]
     L.icet_b200_kernel_name.restype = C.c_char_p
     _LIB = L
     return L
@@ -204,7 +239,7 @@ class Context:
         n2 = np.array([a.shape[1] for a in scans2], np.int32)
         x0p = None
         if X0 is not None:
-            x0 = np.ascontiguousarray(X0, np.float32).reshape(npairs, 6)
+            x0 = np.ascontiguousarray(X0, np.float32).reshape(1 if (p.flags & FLAG_CHAIN_X0) else npairs, 6)
             x0p = x0.ctypes.data
         out = np.zeros(npairs, RESULT_DTYPE)
         self._check(self._L.icet_b200_register_batch(self._h, C.byref(p), npairs, p1, n1.ctypes.data, p2,

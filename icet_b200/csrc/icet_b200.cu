@@ -191,7 +191,11 @@ __global__ void __launch_bounds__(256) k_cell_scan(const Chunk ck) {
       int u = s_wpart[t]; s_wpart[t] = b; b += u;
     }
     ck.nwork[pair] = b;
-    if (ck.x0) for (int k = 0; k < 6; k++) ck.X[pair * 6 + k] = ck.x0[pair * 6 + k];
+    // chained pairs (ICET_B200_FLAG_CHAIN_X0, odometry.cpp:82): x0 holds ONE seed, that of pair 0; the later pairs are
+    // seeded by the last solve of their predecessor (chain_seed_next).  Without iterations the seed is the answer.
+    const bool chain = (ck.flags & ICET_B200_FLAG_CHAIN_X0) != 0;
+    if (ck.x0 && (!chain || pair == 0 || ck.runlen == 0))
+      for (int k = 0; k < 6; k++) ck.X[pair * 6 + k] = ck.x0[(chain ? 0 : pair * 6) + k];
     else for (int k = 0; k < 6; k++) ck.X[pair * 6 + k] = 0.f;
     {
       float* TR = ck.TR + (size_t)pair * 12;
@@ -967,6 +971,21 @@ __device__ __forceinline__ void vox_contrib(const Chunk& ck, int pair, int cell,
 // K6: one thread per pair: Q = pinv(H^T W H), pred_stds, checkCondition, dx, X += dx (src/icet.cpp:410-433,
 // :443-492) and the transform / get_H trigonometry of the next iteration.  tot = the 28 sums over the voxels.
 // ----------------------------------------------------------------------------------------------
+// Odometry chaining (odometry.cpp:82 `X0 << X[0], ...`): the registration of pair k+1 starts from the solution of
+// pair k.  Called by the thread that has just written X / TR / J of `pair` in the LAST iteration, before that
+// iteration is published.
+__device__ __forceinline__ void chain_seed_next(const Chunk& ck, int pair, const float* Xn) {
+  if (!(ck.flags & ICET_B200_FLAG_CHAIN_X0) || pair + 1 >= ck.npairs) return;
+  const int q = pair + 1;
+  for (int k = 0; k < 6; k++) { ck.X[q * 6 + k] = Xn[k]; ck.res[q].X[k] = Xn[k]; }
+  for (int k = 0; k < 12; k++) {
+    const float v = ck.TR[(size_t)pair * 12 + k];
+    ck.TR[(size_t)q * 12 + k] = v;
+    ck.TRprev[(size_t)q * 12 + k] = v;
+  }
+  for (int k = 0; k < 27; k++) ck.J[(size_t)q * 27 + k] = ck.J[(size_t)pair * 27 + k];
+}
+
 __device__ __noinline__ void solve_pair(const Chunk& ck, int pair, int iter, const double* tot) {
   float* X = ck.X + pair * 6;
   double A[36], b[6];
@@ -1060,6 +1079,7 @@ __device__ __noinline__ void solve_pair(const Chunk& ck, int pair, int iter, con
     TR[0] = Xn[0]; TR[1] = Xn[1]; TR[2] = Xn[2];
     icet::rotR(Xn[3], Xn[4], Xn[5], TR + 3);
     icet::getH_J(Xn[3], Xn[4], Xn[5], ck.J + (size_t)pair * 27);
+    if (iter == ck.runlen - 1) chain_seed_next(ck, pair, Xn);
   }
   if (ck.dump_on) {
     for (int k = 0; k < 6; k++) { ck.dump.Xit[iter * 6 + k] = Xn[k]; ck.dump.HTWdz[iter * 6 + k] = (float)b[k]; }
@@ -1130,6 +1150,7 @@ __device__ __forceinline__ bool solve_pair_warp(const Chunk& ck, int pair, int i
     TR[0] = Xn[0]; TR[1] = Xn[1]; TR[2] = Xn[2];
     icet::rotR(Xn[3], Xn[4], Xn[5], TR + 3);
     icet::getH_J(Xn[3], Xn[4], Xn[5], ck.J + (size_t)pair * 27);
+    if (last) chain_seed_next(ck, pair, Xn);
     if (ck.dump_on) {
       for (int k = 0; k < 6; k++) { ck.dump.Xit[iter * 6 + k] = Xn[k]; ck.dump.HTWdz[iter * 6 + k] = (float)tot[21 + k]; }
     }
@@ -1251,6 +1272,8 @@ __device__ __noinline__ void vox_task(const Chunk& ck, int iter, int pair, int g
     // NO group of the pair has one (degenerate inputs) nothing else would keep iteration k+1 from being closed
     // before iteration k.
     if (iter > 0) loop_wait(ck, ck.iter_done + pair, iter, 2, pair, iter, 0u);
+    else if ((ck.flags & ICET_B200_FLAG_CHAIN_X0) && pair > 0)
+      loop_wait(ck, ck.iter_done + pair - 1, ck.runlen, 3, pair, iter, 0u);  // X of this pair comes from pair - 1
     __threadfence();
     TL(0);
     double tot = 0.0;
@@ -1325,6 +1348,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 3) k_loop(const Chunk ck, int ti
   const unsigned ntile = (unsigned)ck.npairs * (unsigned)tiles;
   const unsigned per_iter = ntile + (unsigned)ck.npairs * (unsigned)vt;
   const unsigned total = per_iter * (unsigned)ck.runlen;
+  const bool chain = (ck.flags & ICET_B200_FLAG_CHAIN_X0) != 0;
   unsigned t = 0;
   if (lane == 0) t = atomicAdd(ck.ticket, 1u);
   t = __shfl_sync(FULL, t, 0);
@@ -1332,16 +1356,41 @@ __global__ void __launch_bounds__(PASS_THREADS, 3) k_loop(const Chunk ck, int ti
     // the next ticket is drawn now; its round trip to L2 hides behind this task
     unsigned t_next = 0;
     if (lane == 0) t_next = atomicAdd(ck.ticket, 1u);
-    const int iter = (int)(t / per_iter);
-    unsigned rem = t - (unsigned)iter * per_iter;
-    if (rem < ntile) {
+    // ticket -> task.  Independent pairs: iteration-major (see above).  Chained pairs (ICET_B200_FLAG_CHAIN_X0): pair-
+    // major, i.e. all iterations of pair k before any task of pair k + 1, whose first tiles wait for the last solve
+    // of pair k (it seeds X / TR / J of pair k + 1) -- still only waits on smaller tickets.
+    int iter, pair_t, sub;
+    bool is_tile;
+    if (chain) {
+      const unsigned per_it1 = (unsigned)(tiles + vt);
+      const unsigned per_pair = per_it1 * (unsigned)ck.runlen;
+      pair_t = (int)(t / per_pair);
+      const unsigned r1 = t - (unsigned)pair_t * per_pair;
+      iter = (int)(r1 / per_it1);
+      const unsigned r2 = r1 - (unsigned)iter * per_it1;
+      is_tile = r2 < (unsigned)tiles;
+      sub = is_tile ? (int)r2 : (int)(r2 - (unsigned)tiles);
+    } else {
+      iter = (int)(t / per_iter);
+      const unsigned rem = t - (unsigned)iter * per_iter;
+      is_tile = rem < ntile;
+      if (is_tile) {
+        pair_t = (int)(rem / (unsigned)tiles);
+        sub = (int)(rem - (unsigned)pair_t * (unsigned)tiles);
+      } else {
+        pair_t = (int)((rem - ntile) / (unsigned)vt);
+        sub = (int)((rem - ntile) - (unsigned)pair_t * (unsigned)vt);
+      }
+    }
+    if (is_tile) {
       // ------------------------------------------------------------------ tile task
-      const int pair = (int)(rem / (unsigned)tiles);
-      const int tile = (int)(rem - (unsigned)pair * (unsigned)tiles);
+      const int pair = pair_t;
+      const int tile = sub;
       const int n = __ldg(ck.n2c + pair);
       const int w0 = tile * 32 * K;
       if (w0 < n || tile == 0) {
         if (iter > 0) loop_wait(ck, ck.iter_done + pair, iter, 0, pair, iter, t);
+        else if (chain && pair > 0) loop_wait(ck, ck.iter_done + pair - 1, ck.runlen, 4, pair, iter, t);
         float tr[12];
         {
           const float4* tp = reinterpret_cast<const float4*>(ck.TR + (size_t)pair * 12);
@@ -1364,9 +1413,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 3) k_loop(const Chunk ck, int ti
       }  // tiles beyond the compacted point count of the pair are not counted (see loop_tiles_of)
     } else {
       // ------------------------------------------------------------------ vox task
-      rem -= ntile;
-      const int pair = (int)(rem / (unsigned)vt);
-      vox_task(ck, iter, pair, (int)(rem - (unsigned)pair * (unsigned)vt), 32 * K, vt, w_tot, w_J);
+      vox_task(ck, iter, pair_t, sub, 32 * K, vt, w_tot, w_J);
     }
     t = __shfl_sync(FULL, t_next, 0);
   }
@@ -1757,7 +1804,8 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   // several rounds per iteration (small batches, single-pair latency).
   const int wt_big = 32 * PASS_K;
   const long long big_tiles = (long long)P * ((n2max + wt_big - 1) / wt_big);
-  const bool small = big_tiles < 4LL * ctx->sm_count * std::max(1, ctx->loop_occ[0]) * PASS_WARPS;
+  const bool chain = (p->flags & ICET_B200_FLAG_CHAIN_X0) != 0;  // one pair at a time is in flight: latency shape
+  const bool small = chain || big_tiles < 4LL * ctx->sm_count * std::max(1, ctx->loop_occ[0]) * PASS_WARPS;
   const int K2 = small ? PASS_K_SMALL : PASS_K;
   const int tiles2 = std::max(1, (n2max + 32 * K2 - 1) / (32 * K2));  // >= 1: tile 0 carries the dropped returns
   const int vt = (ncell + 31) / 32;
@@ -1791,7 +1839,7 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   }
   LAUNCH(5, k_fit1<<<dim3((ncell + 127) / 128, P), 128, 0, st>>>(ck));
   if (n2max > 0) LAUNCH(6, k_prep2<<<g2, 256, 0, st>>>(ck));
-  const bool use_loop = (p->flags & ICET_B200_FLAG_PERSISTENT_LOOP) ||
+  const bool use_loop = chain || (p->flags & ICET_B200_FLAG_PERSISTENT_LOOP) ||
                         (!(p->flags & ICET_B200_FLAG_UNFUSED_LOOP) && P <= ICET_LOOP_MAX_PAIRS);
   if (!use_loop) {
     for (int it = 0; it < p->runlen; it++) {
@@ -1865,6 +1913,8 @@ int ensure_dump(icet_b200_ctx* ctx, const icet_b200_params* p) {
   CK(cudaMemsetAsync(ctx->dumpbuf.p, 0, need, ctx->stream));
   return 0;
 }
+
+#include "callers.cuh"
 
 }  // namespace
 
@@ -2024,14 +2074,18 @@ int icet_b200_set_dump(icet_b200_ctx* c, int32_t enable) {
 
 // -- device-resident batch --------------------------------------------------------------------
 static int batch_device_impl(icet_b200_ctx* c, const icet_b200_params* p, int32_t npairs, const PairDesc* h_desc,
-                             const float* d_x0, icet_b200_result* d_out, bool dump) {
-  // h_desc lives in host memory; descriptors are uploaded per chunk through the pinned bounce buffer
+                             const float* d_x0, icet_b200_result* d_out, bool dump, const PairDesc* d_desc_all = nullptr,
+                             int nmax_dev = 0) {
+  // h_desc lives in host memory; descriptors are uploaded per chunk through the pinned bounce buffer.
+  // d_desc_all (callers layer): the descriptors are already on the device -- built there, with data-dependent
+  // sizes no larger than nmax_dev -- and h_desc is not read.
   int rc = ensure_pinned(c, (size_t)std::min(npairs, c->chunk_pairs) * sizeof(PairDesc) * 2 + 4096);
   if (rc) return rc;
   // consecutive chunks alternate between the two compute lanes (own stream + workspace each); lane 1 starts after
   // everything already queued on the caller's stream and the caller's stream resumes after lane 1
   const int nchunks = (npairs + c->chunk_pairs - 1) / c->chunk_pairs;
-  const bool two = c->nlanes > 1 && nchunks > 1 && !dump;
+  const bool chain = (p->flags & ICET_B200_FLAG_CHAIN_X0) != 0;  // chunks depend on each other: one lane, in order
+  const bool two = c->nlanes > 1 && nchunks > 1 && !dump && !chain;
   if (two) {
     CK(cudaEventRecord(c->ev_fork, c->stream));
     CK(cudaStreamWaitEvent(c->lane1, c->ev_fork, 0));
@@ -2041,21 +2095,26 @@ static int batch_device_impl(icet_b200_ctx* c, const icet_b200_params* p, int32_
     const int P = std::min(c->chunk_pairs, npairs - base);
     const int lane = two ? slot : 0;
     cudaStream_t st = lane == 0 ? c->stream : c->lane1;
-    int n1max = 0, n2max = 0;
-    for (int i = 0; i < P; i++) {
-      n1max = std::max(n1max, h_desc[base + i].n1);
-      n2max = std::max(n2max, h_desc[base + i].n2);
+    int n1max = nmax_dev, n2max = nmax_dev;
+    const PairDesc* d_desc = d_desc_all ? d_desc_all + base : nullptr;
+    if (!d_desc) {
+      for (int i = 0; i < P; i++) {
+        n1max = std::max(n1max, h_desc[base + i].n1);
+        n2max = std::max(n2max, h_desc[base + i].n2);
+      }
+      rc = c->descbuf[slot].ensure((size_t)P * sizeof(PairDesc));
+      if (rc) return rc;
+      // the pinned half `slot` may still be in flight from two chunks ago
+      CK(cudaEventSynchronize(c->ev_done[slot]));
+      PairDesc* hp = (PairDesc*)c->pinned + (size_t)slot * std::min(npairs, c->chunk_pairs);
+      memcpy(hp, h_desc + base, (size_t)P * sizeof(PairDesc));
+      CK(cudaMemcpyAsync(c->descbuf[slot].p, hp, (size_t)P * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+      CK(cudaEventRecord(c->ev_done[slot], st));
+      d_desc = (const PairDesc*)c->descbuf[slot].p;
     }
-    rc = c->descbuf[slot].ensure((size_t)P * sizeof(PairDesc));
-    if (rc) return rc;
-    // the pinned half `slot` may still be in flight from two chunks ago
-    CK(cudaEventSynchronize(c->ev_done[slot]));
-    PairDesc* hp = (PairDesc*)c->pinned + (size_t)slot * std::min(npairs, c->chunk_pairs);
-    memcpy(hp, h_desc + base, (size_t)P * sizeof(PairDesc));
-    CK(cudaMemcpyAsync(c->descbuf[slot].p, hp, (size_t)P * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
-    CK(cudaEventRecord(c->ev_done[slot], st));
-    rc = run_chunk(c, p, P, (const PairDesc*)c->descbuf[slot].p, n1max, n2max, d_x0 ? d_x0 + (size_t)base * 6 : nullptr,
-                   d_out + base, dump, lane);
+    const float* x0c = d_x0 ? d_x0 + (chain ? 0 : (size_t)base * 6) : nullptr;
+    if (chain && base > 0) x0c = d_out[base - 1].X;  // stream order: the previous chunk has finished by then
+    rc = run_chunk(c, p, P, d_desc, n1max, n2max, x0c, d_out + base, dump, lane);
     if (rc) return rc;
   }
   if (two) {
@@ -2143,7 +2202,8 @@ int icet_b200_register_batch(icet_b200_ctx* c, const icet_b200_params* p, int32_
   auto pad = [](size_t f) { return (f + 63) & ~(size_t)63; };
   int base = 0;
   const float* prev_scan2_dev = nullptr;  // device copy of the previous chunk's last scan 2
-  const bool two = c->nlanes > 1 && sizes.size() > 1 && !(c->dump_on && npairs == 1);
+  const bool chain = (p->flags & ICET_B200_FLAG_CHAIN_X0) != 0;  // chunks depend on each other: one lane, in order
+  const bool two = c->nlanes > 1 && sizes.size() > 1 && !(c->dump_on && npairs == 1) && !chain;
   if (two) {
     CK(cudaEventRecord(c->ev_fork, c->stream));
     CK(cudaStreamWaitEvent(c->lane1, c->ev_fork, 0));
@@ -2225,10 +2285,13 @@ int icet_b200_register_batch(icet_b200_ctx* c, const icet_b200_params* p, int32_
     memcpy(hp, d.data(), (size_t)P * sizeof(PairDesc));
     CK(cudaMemcpyAsync(c->descbuf[slot].p, hp, (size_t)P * sizeof(PairDesc), cudaMemcpyHostToDevice, c->copy_stream));
     const float* d_x0 = nullptr;
-    if (x0) {
+    if (chain && base > 0) {
+      d_x0 = d_res[base - 1].X;  // the previous chunk's last solution (same stream, already ordered)
+    } else if (x0) {
+      const size_t nx = chain ? 6 : (size_t)P * 6;  // chained: one seed, that of pair 0
       float* hx = (float*)(hp + (size_t)CH * sizeof(PairDesc));
-      memcpy(hx, x0 + (size_t)base * 6, (size_t)P * 6 * sizeof(float));
-      CK(cudaMemcpyAsync(c->x0buf[slot].p, hx, (size_t)P * 6 * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+      memcpy(hx, x0 + (size_t)base * 6, nx * sizeof(float));
+      CK(cudaMemcpyAsync(c->x0buf[slot].p, hx, nx * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
       d_x0 = (const float*)c->x0buf[slot].p;
     }
     CK(cudaEventRecord(c->ev_copy[slot], c->copy_stream));
@@ -2405,5 +2468,7 @@ int icet_b200_synth_scans_device(icet_b200_ctx* c, uint64_t seed, int32_t first_
   CK(cudaGetLastError());
   return 0;
 }
+
+#include "callers_abi.inl"
 
 }  // extern "C"

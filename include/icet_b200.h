@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ICET_B200_VERSION 100
+#define ICET_B200_VERSION 101
 
 /* status codes (return values; also icet_b200_result.status for per-pair conditions) */
 enum {
@@ -59,7 +59,11 @@ enum {
    * iterations (warps draw dependency-ordered tasks; lowest latency for a single pair) and three launches per
    * iteration (highest throughput for large chunks).  Default: persistent for single-pair chunks. */
   ICET_B200_FLAG_UNFUSED_LOOP = 2,   /* always three launches per iteration */
-  ICET_B200_FLAG_PERSISTENT_LOOP = 4 /* always the persistent kernel        */
+  ICET_B200_FLAG_PERSISTENT_LOOP = 4, /* always the persistent kernel        */
+  /* Odometry chaining (odometry.cpp:82 `X0 << X[0], X[1], ...`): the pairs of a batch / sequence call are
+   * registered in order and pair k+1 starts from the solution of pair k.  `x0` then holds ONE seed (6 floats, pair 0)
+   * or NULL.  Runs as the persistent kernel with pair-major task order; nothing returns to the host in between. */
+  ICET_B200_FLAG_CHAIN_X0 = 8
 };
 
 /* per-pair result: the members callers of `class ICET` read (X: all four callers; pred_stds:
@@ -170,6 +174,79 @@ int icet_b200_get_points2(icet_b200_ctx* ctx, float* out, int32_t n2);
  * utils::cartesianToSpherical (src/utils.cpp:93-119) + ICET::sortSphericalCoordinates (src/icet.cpp:545-546). */
 int icet_b200_spherical_bins(icet_b200_ctx* ctx, const icet_b200_params* p, const float* scan, int32_t n,
                              int32_t ld, float* sph, int32_t* cell);
+
+/* -- callers either side of the path --------------------------------------------------
+ * The two ROS nodes of the reference wrap the constructor in the same few steps; these entry points keep those steps
+ * on the device so that filtered clouds, their data-dependent sizes, the seed of the next registration and the
+ * accumulated pose never visit the host:
+ *   OdometryNode::pointcloudCallback   src/odometry.cpp:38-168        (min_range 2, runlen 7, chain_x0 1, no guard)
+ *   MapMakerNode::pointcloudCallback   src/simpleMapMaker.cpp:78-240  (min_range 0.2, runlen 12, chain_x0 0, guard 0.3)
+ */
+typedef struct {
+  float min_range;     /* keep rows with ||p|| > min_range (odometry.cpp:57-70: 2.0; simpleMapMaker.cpp:100-112: 0.2);
+                          < 0: keep every row                                                                      */
+  int32_t chain_x0;    /* 1: X0 of the next registration = X of this one (odometry.cpp:82);
+                          0: X0 = 0 every time (simpleMapMaker.cpp:124)                                            */
+  float rate_hz;       /* twist = rate_hz * X (odometry.cpp:134-139 assumes a 10 Hz sensor)                        */
+  float guard_trans;   /* divergence guard (simpleMapMaker.cpp:128-137, :241-242: 0.3 / 0.3): if any |X| exceeds    */
+  float guard_rot;     /* its threshold the pose update uses X = 0;  <= 0: no guard (odometry.cpp has none)         */
+  int32_t reserved[3];
+} icet_b200_odometry_params;
+
+/* what the nodes publish per registration (nav_msgs::Odometry of odometry.cpp:104-140, the tf of both nodes) */
+typedef struct {
+  float X_homo[16];         /* accumulated transform, row-major 4x4 (X_homo = X_homo * X_homo_i, odometry.cpp:87-98)  */
+  float position[3];        /* X_homo(0..2, 3)                                              odometry.cpp:110-112      */
+  float orientation[4];     /* Eigen::Quaternionf(X_homo.topLeftCorner(3,3)) as x, y, z, w  odometry.cpp:114-119      */
+  float covariance_diag[6]; /* pose.covariance[0,7,14,21,28,35] = pred_stds                 odometry.cpp:126-131      */
+  float twist[6];           /* rate_hz * X                                                  odometry.cpp:134-139      */
+  float X[6];               /* the registration result the pose update used (after the guard)                         */
+  int32_t n_points;         /* rows of the current scan that passed the min-range filter                              */
+  int32_t guarded;          /* 1: the divergence guard replaced X by 0                                                */
+  int32_t frame;            /* registrations so far (frameCount - 1)                                                  */
+  int32_t reserved;
+} icet_b200_pose;           /* 45 x 4 bytes */
+
+typedef struct icet_b200_node icet_b200_node; /* state of one node: prev_pcl_matrix, X0, X_homo (all device resident) */
+
+/* max_points: capacity per scan.  X_homo0 (16 floats, row-major) / x0 (6 floats): HOST, NULL = identity / zeros. */
+int icet_b200_node_create(icet_b200_ctx* ctx, const icet_b200_params* p, const icet_b200_odometry_params* op,
+                          int32_t max_points, const float* X_homo0, const float* x0, icet_b200_node** node);
+int icet_b200_node_destroy(icet_b200_node* node);
+/* The callback for `nscans` consecutive scans in DEVICE memory ([nscans][3][n] planes), asynchronous on the context's
+ * stream.  The very first scan a node sees only becomes prev_pcl_matrix, unfiltered (odometry.cpp:47-52); every other
+ * scan is filtered and registered against its predecessor.  res / poses: DEVICE arrays with room for nscans entries.
+ * Returns the number of registrations enqueued (nscans, or nscans - 1 on the first call) or a negative status.
+ * With chain_x0 the registrations run as ONE persistent kernel in chain order (ICET_B200_FLAG_CHAIN_X0). */
+int icet_b200_node_push_device(icet_b200_node* node, int32_t nscans, const float* scans, int32_t n,
+                               icet_b200_result* res, icet_b200_pose* poses);
+/* The callback for one scan in HOST memory (planes, leading dimension ld), blocking.  Returns 0 when the scan only
+ * initialised the node, 1 when *res / *pose were written. */
+int icet_b200_node_push(icet_b200_node* node, const float* scan, int32_t n, int32_t ld, icet_b200_result* res,
+                        icet_b200_pose* pose);
+/* The filtered current scan (= prev_pcl_matrix for the next callback): device planes, leading dimension *ld, row count
+ * in device memory at *n_dev.  Valid until the next push. */
+int icet_b200_node_current_scan(icet_b200_node* node, const float** scan, const int32_t** n_dev, int32_t* ld);
+/* The device-resident result of the most recent registration (NULL before the first one). */
+int icet_b200_node_last_result(icet_b200_node* node, const icet_b200_result** res_dev);
+
+/* EigenQueue (simpleMapMaker.cpp:18-58): FIFO of map points (600 000 in the reference, :62), re-expressed in the
+ * newest sensor frame at every insertion. */
+typedef struct icet_b200_map icet_b200_map;
+int icet_b200_map_create(icet_b200_ctx* ctx, int32_t capacity, icet_b200_map** map);
+int icet_b200_map_destroy(icet_b200_map* map);
+/* EigenQueue::add_new_scan(newScan, trans, rot_mat) (:34-42): append rows of the DEVICE cloud `scan` (n rows, leading
+ * dimension ld; n_dev: optional device-resident row count, e.g. from icet_b200_node_current_scan) and re-express every
+ * stored row, `(matrix.rowwise() - trans) * rot_mat.inverse()`, with trans / rot_mat from X (6 floats, DEVICE memory,
+ * e.g. &result->X) after the divergence guard (<= 0: none).  idx: HOST list of `count` row numbers to append in that
+ * order -- the shuffled prefix of simpleMapMaker.cpp:150-159 -- or NULL for rows 0 .. count-1.  Asynchronous. */
+int icet_b200_map_add_scan_device(icet_b200_map* map, const float* scan, int32_t n, int32_t ld, const int32_t* n_dev,
+                                  const int32_t* idx, int32_t count, const float* X, float guard_trans,
+                                  float guard_rot);
+/* EigenQueue::getQueue (:44-51): rows oldest first.  out: planes with leading dimension ld_out (>= capacity unless the
+ * caller knows better), HOST memory, blocking / DEVICE memory, asynchronous (n_out then device memory too). */
+int icet_b200_map_get(icet_b200_map* map, float* out, int32_t ld_out, int32_t* n_out);
+int icet_b200_map_get_device(icet_b200_map* map, float* out, int32_t ld_out, int32_t* n_out);
 
 /* -- synthetic 64-channel scans (bench / test utility) --------------------------- */
 /* Writes nscans consecutive scans (index first_scan ...) of rings x azim points each to DEVICE memory
