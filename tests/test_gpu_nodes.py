@@ -140,3 +140,53 @@ def test_divergence_guard(ctx, scans):
     m = node.map_points()
     cur = scans[1][np.linalg.norm(scans[1].astype(np.float32), axis=1) > 0.2]
     np.testing.assert_array_equal(m, cur[g["sample"]])   # X = 0: the re-expression is the identity
+
+
+def test_cpp_node_classes(ctx, scans, tmp_path):
+    """The C++ mirrors (include/icet_nodes.h, examples/nodes_headless.cpp) replay the same scans: same library, so
+    the same bits as the Python mirrors; the map holds min(capacity, k * downsample) rows."""
+    import json
+    import os
+    import subprocess
+    from conftest import ROOT
+    from icet_b200 import MapMakerNode, OdometryNode
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "examples"), "all"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    exe = os.path.join(ROOT, "examples", "_build", "nodes_headless")
+    f = tmp_path / "seq.f32"
+    use = scans[:4]
+    np.stack([np.ascontiguousarray(s.T) for s in use]).tofile(f)
+    n = use[0].shape[0]
+
+    def poses(out):
+        rows = []
+        for l in out.splitlines():
+            if l.startswith("POSE"):
+                x = json.loads(l[l.index("X [") + 2: l.index("] pos") + 1])
+                p = json.loads(l[l.index("pos [") + 4: l.index("] quat") + 1])
+                q = json.loads(l[l.index("quat [") + 5: l.index("] points") + 1])
+                rows.append((np.float32(x), np.float32(p), np.float32(q), int(l.split("points ")[1].split()[0])))
+        return rows
+
+    out = subprocess.run([exe, "odometry", str(n), str(f)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    node = OdometryNode(ctx)
+    py = [node.callback(s) for s in use][1:]
+    cpp = poses(out.stdout)
+    assert len(cpp) == len(py) == 3
+    for (x, p, q, npts), g in zip(cpp, py):
+        np.testing.assert_array_equal(x, g["X"])
+        np.testing.assert_array_equal(p, g["position"])
+        np.testing.assert_array_equal(q, g["orientation"])
+        assert npts == g["n_points"]
+
+    out = subprocess.run([exe, "map", str(n), str(f), "5000", "2000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    mm = MapMakerNode(ctx, capacity=5000, downsample=2000)
+    py = [mm.callback(s) for s in use][1:]
+    cpp = poses(out.stdout)
+    for (x, p, q, npts), g in zip(cpp, py):
+        np.testing.assert_array_equal(x, g["X"])
+        np.testing.assert_array_equal(p, g["X_homo"][:3, 3])
+    ml = [l for l in out.stdout.splitlines() if l.startswith("MAP")][0]
+    assert "rows 5000" in ml
