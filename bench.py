@@ -222,6 +222,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="compute lanes (0 = default 2)")
     ap.add_argument("--host-chunk", type=int, default=0, help="pairs per chunk of the host-buffer pipeline (0 = default)")
     ap.add_argument("--unfused", action="store_true", help="diagnostic: 3 launches per iteration instead of k_loop")
+    ap.add_argument("--persistent", action="store_true", help="diagnostic: the persistent loop kernel for every chunk")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
@@ -259,7 +260,8 @@ def main():
     if args.lanes:
         ctx.set_lanes(args.lanes)
     params = api.make_params(RUNLEN, BINS_PHI, BINS_THETA, NMIN, THRESH, BUFF,
-                             flags=api.FLAG_UNFUSED_LOOP if args.unfused else 0)
+                             flags=api.FLAG_UNFUSED_LOOP if args.unfused else
+                             (api.FLAG_PERSISTENT_LOOP if args.persistent else 0))
 
     # synthetic sequence shard of this rank (contiguous pair range of the world*P-pair sequence), generated
     # on the device

@@ -61,6 +61,40 @@ POSE_DTYPE = np.dtype([("X_homo", np.float32, (4, 4)), ("position", np.float32, 
 assert POSE_DTYPE.itemsize == C.sizeof(Pose) == 180
 
 
+F32, F64, I32 = 0, 1, 2
+
+
+class Cloud(C.Structure):
+    """icet_b200_cloud: a caller's point buffer in its native layout (ingest)."""
+    _fields_ = [("data", C.c_void_p), ("n", C.c_int32), ("point_step", C.c_int32), ("off", C.c_int32 * 3),
+                ("dtype", C.c_int32), ("divide", C.c_float), ("plane_stride", C.c_int32)]
+
+
+def cloud_desc(a, divide: float = 0.0, point_step: int | None = None, offsets=None, dtype=None, n=None):
+    """Describe a host buffer without touching its elements.  Returns (Cloud, keep-alive object).
+      * N x 3 C-order float32 / float64 / int32 (records), N x 3 Fortran-order or 3 x N C-order (planes);
+      * raw bytes of a sensor_msgs::PointCloud2 (`a` = data, point_step, offsets = field offsets of x, y, z)."""
+    if point_step is not None:
+        buf = np.frombuffer(a, dtype=np.uint8) if not isinstance(a, np.ndarray) else a.view(np.uint8).reshape(-1)
+        cnt = buf.size // point_step if n is None else n
+        c = Cloud(buf.ctypes.data, cnt, point_step, (C.c_int32 * 3)(*offsets), F32 if dtype is None else dtype,
+                  divide, 0)
+        return c, buf
+    a = np.asarray(a)
+    code = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32}.get(a.dtype)
+    if code is None or a.ndim != 2:
+        raise ValueError("cloud must be a 2-D float32 / float64 / int32 array")
+    es = a.dtype.itemsize
+    if a.shape[1] == 3 and a.shape[0] != 3 and a.flags["C_CONTIGUOUS"]:
+        return Cloud(a.ctypes.data, a.shape[0], 3 * es, (C.c_int32 * 3)(0, es, 2 * es), code, divide, 0), a
+    if a.shape[1] == 3 and a.shape[0] != 3 and a.flags["F_CONTIGUOUS"]:
+        return Cloud(a.ctypes.data, a.shape[0], 0, (C.c_int32 * 3)(0, 0, 0), code, divide, a.shape[0]), a
+    if a.shape[0] == 3 and a.flags["C_CONTIGUOUS"]:
+        return Cloud(a.ctypes.data, a.shape[1], 0, (C.c_int32 * 3)(0, 0, 0), code, divide, a.shape[1]), a
+    a = np.ascontiguousarray(a)
+    return cloud_desc(a, divide)
+
+
 class _Dump(C.Structure):
     _fields_ = _DUMP_FIELDS
 
@@ -73,7 +107,8 @@ EXPORTS = ["icet_b200_version", "icet_b200_last_error", "icet_b200_create", "ice
            "icet_b200_get_profile", "icet_b200_kernel_name",
            "icet_b200_node_create", "icet_b200_node_destroy", "icet_b200_node_push_device", "icet_b200_node_push",
            "icet_b200_node_current_scan", "icet_b200_node_last_result", "icet_b200_map_create",
-           "icet_b200_map_destroy", "icet_b200_map_add_scan_device", "icet_b200_map_get", "icet_b200_map_get_device"]
+           "icet_b200_map_destroy", "icet_b200_map_add_scan_device", "icet_b200_map_get", "icet_b200_map_get_device",
+           "icet_b200_ingest", "icet_b200_register_clouds", "icet_b200_node_push_cloud"]
 NKERNELS = 11
 
 _LIB = None
@@ -132,6 +167,10 @@ def load_library() -> C.CDLL:
                                                 C.c_float]
     L.icet_b200_map_get.argtypes = [vp, vp, C.c_int32, C.POINTER(C.c_int32)]
     L.icet_b200_map_get_device.argtypes = [vp, vp, C.c_int32, vp]
+    L.icet_b200_ingest.argtypes = [vp, C.POINTER(Cloud), vp, C.c_int32]
+    L.icet_b200_register_clouds.argtypes = [vp, C.POINTER(Params), C.POINTER(Cloud), C.POINTER(Cloud), vp,
+                                            C.POINTER(Result)]
+    L.icet_b200_node_push_cloud.argtypes = [vp, C.POINTER(Cloud), C.POINTER(Result), C.POINTER(Pose)]
     L.icet_b200_kernel_name.restype = C.c_char_p
     _LIB = L
     return L
@@ -224,6 +263,23 @@ class Context:
         if dump:
             return out, self.get_dump(p)
         return out
+
+    def register_clouds(self, cloud1, cloud2, X0=None, params: Params | None = None, divide: float = 0.0):
+        """`register` for clouds in their native layout (N x 3 float64 / float32 / int32 in either order, or Cloud
+        descriptors): the raw bytes are uploaded and converted on the device -- no host-side astype / transpose."""
+        p = params or make_params()
+        c1, k1 = cloud1 if isinstance(cloud1, tuple) else cloud_desc(cloud1, divide)
+        c2, k2 = cloud2 if isinstance(cloud2, tuple) else cloud_desc(cloud2, divide)
+        x0 = np.zeros(6, np.float32) if X0 is None else np.ascontiguousarray(X0, np.float32)
+        res = Result()
+        self._check(self._L.icet_b200_set_dump(self._h, 0))
+        self._check(self._L.icet_b200_register_clouds(self._h, C.byref(p), C.byref(c1), C.byref(c2), x0.ctypes.data,
+                                                      C.byref(res)))
+        return np.frombuffer(bytes(res), dtype=RESULT_DTYPE)[0]
+
+    def ingest(self, cloud, out_ptr: int, ld: int, divide: float = 0.0):
+        c, keep = cloud if isinstance(cloud, tuple) else cloud_desc(cloud, divide)
+        self._check(self._L.icet_b200_ingest(self._h, C.byref(c), C.c_void_p(out_ptr), ld))
 
     def register_batch(self, scans1, scans2, X0=None, params: Params | None = None) -> np.ndarray:
         """scans1[i], scans2[i]: float32 [3, N_i] planes in HOST memory (pinned or pageable).  Passing the

@@ -335,3 +335,34 @@ __global__ void __launch_bounds__(256) k_map_get(const MapState* ms, const float
   }
   if (n_out && blockIdx.x == 0 && threadIdx.x == 0) *n_out = rows;
 }
+
+// ----------------------------------------------------------------------------------------------
+// Ingest: caller's records -> x | y | z float planes.  Replaces the host loops of
+// convertPCLtoEigen (odometry.cpp:186-192) and of loadPointCloudCSV's `rows[i] / 1000` (src/utils.cpp:42-52).
+// ----------------------------------------------------------------------------------------------
+struct IngestDesc {
+  const unsigned char* raw;  // device copy of the caller's bytes
+  int n, step, off[3], dtype, plane_stride;
+  float divide;
+};
+
+__device__ __forceinline__ float ingest_elem(const unsigned char* p, int dtype, float divide) {
+  float v;
+  if (dtype == ICET_B200_F32) v = *reinterpret_cast<const float*>(p);
+  else if (dtype == ICET_B200_F64) v = (float)*reinterpret_cast<const double*>(p);  // round to nearest, like cast<float>()
+  else v = (float)*reinterpret_cast<const int32_t*>(p);                             // static_cast<float>(int)
+  if (divide != 0.f && divide != 1.f) v = __fdiv_rn(v, divide);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_ingest(const IngestDesc d, float* out, int ld) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.n) return;
+  const int es = d.dtype == ICET_B200_F64 ? 8 : 4;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const unsigned char* p = d.plane_stride > 0 ? d.raw + ((size_t)k * d.plane_stride + i) * es
+                                                : d.raw + (size_t)i * d.step + d.off[k];
+    out[(size_t)k * ld + i] = ingest_elem(p, d.dtype, d.divide);
+  }
+}

@@ -306,3 +306,116 @@ int icet_b200_map_get(icet_b200_map* m, float* out, int32_t ld_out, int32_t* n_o
   if (e != cudaSuccess) return fail(ICET_B200_E_CUDA, std::string("map_get: ") + cudaGetErrorString(e));
   return 0;
 }
+
+// -- ingest ------------------------------------------------------------------------------------------------------
+static int cloud_bytes(const icet_b200_cloud* c, size_t* bytes) {
+  if (!c) return fail(ICET_B200_E_INVALID, "cloud is NULL");
+  if (c->n < 0 || (c->n > 0 && !c->data)) return fail(ICET_B200_E_INVALID, "bad cloud");
+  if (c->dtype != ICET_B200_F32 && c->dtype != ICET_B200_F64 && c->dtype != ICET_B200_I32)
+    return fail(ICET_B200_E_INVALID, "unknown dtype");
+  const int es = c->dtype == ICET_B200_F64 ? 8 : 4;
+  if (c->plane_stride > 0) {
+    if (c->plane_stride < c->n) return fail(ICET_B200_E_INVALID, "plane_stride smaller than n");
+    *bytes = ((size_t)2 * c->plane_stride + c->n) * es;
+    return 0;
+  }
+  if (c->point_step < es || c->point_step % es) return fail(ICET_B200_E_INVALID, "point_step must be a multiple of the element size");
+  for (int k = 0; k < 3; k++)
+    if (c->off[k] < 0 || c->off[k] % es || c->off[k] + es > c->point_step)
+      return fail(ICET_B200_E_INVALID, "field offset outside the record or misaligned");
+  *bytes = (size_t)c->n * c->point_step;
+  return 0;
+}
+
+// stages the raw bytes in `raw` (device) and converts into `out`; all on the context's stream
+static int ingest_into(icet_b200_ctx* c, const icet_b200_cloud* cl, DevBuf& raw, float* out, int32_t ld) {
+  size_t bytes = 0;
+  int rc = cloud_bytes(cl, &bytes);
+  if (rc) return rc;
+  if (ld < cl->n) return fail(ICET_B200_E_INVALID, "ld smaller than n");
+  if (cl->n == 0) return 0;
+  if (!out) return fail(ICET_B200_E_INVALID, "out is NULL");
+  if ((rc = raw.ensure(bytes))) return rc;
+  CK(cudaMemcpyAsync(raw.p, cl->data, bytes, cudaMemcpyHostToDevice, c->stream));
+  IngestDesc d;
+  d.raw = (const unsigned char*)raw.p;
+  d.n = cl->n; d.step = cl->point_step; d.dtype = cl->dtype; d.plane_stride = cl->plane_stride; d.divide = cl->divide;
+  for (int k = 0; k < 3; k++) d.off[k] = cl->off[k];
+  k_ingest<<<(cl->n + 255) / 256, 256, 0, c->stream>>>(d, out, ld);
+  c->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int icet_b200_ingest(icet_b200_ctx* c, const icet_b200_cloud* cl, float* out, int32_t ld) {
+  if (!c) return fail(ICET_B200_E_INVALID, "ctx is NULL");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));  // the staging buffer of the previous call is no longer read
+  int rc = ingest_into(c, cl, c->rawbuf[0], out, ld);
+  if (rc) return rc;
+  // pageable source: the runtime has copied it out before returning; pinned source: wait for the DMA
+  cudaPointerAttributes at;
+  if (cl->n > 0 && cudaPointerGetAttributes(&at, cl->data) == cudaSuccess && at.type == cudaMemoryTypeHost)
+    CK(cudaStreamSynchronize(c->stream));
+  cudaGetLastError();
+  return 0;
+}
+
+int icet_b200_register_clouds(icet_b200_ctx* c, const icet_b200_params* p, const icet_b200_cloud* s1,
+                              const icet_b200_cloud* s2, const float x0[6], icet_b200_result* out) {
+  if (!c || !out) return fail(ICET_B200_E_INVALID, "NULL argument");
+  int rc = validate(p);
+  if (rc) return rc;
+  size_t b1, b2;
+  if ((rc = cloud_bytes(s1, &b1)) || (rc = cloud_bytes(s2, &b2))) return rc;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  const int n1 = s1->n, n2 = s2->n;
+  const size_t l1 = ((size_t)n1 + 3) & ~(size_t)3, l2 = ((size_t)n2 + 3) & ~(size_t)3;
+  if ((rc = c->planebuf.ensure((3 * l1 + 3 * l2 + 8) * sizeof(float) + sizeof(icet_b200_result)))) return rc;
+  float* d1 = (float*)c->planebuf.p;
+  float* d2 = d1 + 3 * l1;
+  float* dx = d2 + 3 * l2;
+  icet_b200_result* dres = (icet_b200_result*)(dx + 8);
+  if ((rc = ingest_into(c, s1, c->rawbuf[0], d1, (int32_t)l1))) return rc;
+  if ((rc = ingest_into(c, s2, c->rawbuf[1], d2, (int32_t)l2))) return rc;
+  if (x0) CK(cudaMemcpyAsync(dx, x0, 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  PairDesc d{d1, d2, n1, (int)l1, n2, (int)l2};
+  const bool dump = c->dump_on != 0;
+  if (dump && (rc = ensure_dump(c, p))) return rc;
+  rc = batch_device_impl(c, p, 1, &d, x0 ? dx : nullptr, dres, dump);
+  if (rc) return rc;
+  if (dump) { c->dump_params = *p; c->dump_valid = true; }
+  c->last_n2 = n2;
+  c->last_runlen = p->runlen;
+  CK(cudaMemcpyAsync(out, dres, sizeof(icet_b200_result), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return check_loop_watchdog(c);
+}
+
+int icet_b200_node_push_cloud(icet_b200_node* nd, const icet_b200_cloud* cl, icet_b200_result* res, icet_b200_pose* pose) {
+  if (!nd || !cl) return fail(ICET_B200_E_INVALID, "NULL argument");
+  size_t bytes;
+  int rc = cloud_bytes(cl, &bytes);
+  if (rc) return rc;
+  if (cl->n > nd->cap) return fail(ICET_B200_E_INVALID, "cloud larger than the node's max_points");
+  icet_b200_ctx* c = nd->ctx;
+  CK(cudaSetDevice(c->device));
+  const int n = cl->n;
+  if ((rc = nd->hscan.ensure((size_t)3 * std::max(1, n) * sizeof(float)))) return rc;
+  if ((rc = nd->hres.ensure(sizeof(icet_b200_result)))) return rc;
+  if ((rc = nd->hpose.ensure(sizeof(icet_b200_pose)))) return rc;
+  CK(cudaStreamSynchronize(c->stream));
+  if ((rc = ingest_into(c, cl, c->rawbuf[0], (float*)nd->hscan.p, n))) return rc;
+  const int np = icet_b200_node_push_device(nd, 1, (const float*)nd->hscan.p, n, (icet_b200_result*)nd->hres.p,
+                                            (icet_b200_pose*)nd->hpose.p);
+  if (np < 0) return np;
+  if (np > 0) {
+    if (res) CK(cudaMemcpyAsync(res, nd->hres.p, sizeof(icet_b200_result), cudaMemcpyDeviceToHost, c->stream));
+    if (pose) CK(cudaMemcpyAsync(pose, nd->hpose.p, sizeof(icet_b200_pose), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  rc = check_loop_watchdog(c);
+  if (rc) return rc;
+  return np;
+}

@@ -46,6 +46,8 @@ constexpr uint32_t F_STAT1 = 1u;        // scan-1 statistics wanted for this cel
 constexpr uint32_t F_ACTIVE2 = 2u;      // voxel takes part in the scan-2 loop
 constexpr int SORT_SMEM = 4096;         // cells up to this many points are sorted in shared memory
 constexpr int NQ = 12;                  // accumulator words per cell
+constexpr int CLUSTER_WARPS = 4;
+constexpr int WSORT_MAX = 1024;         // cells up to this many non-zero ranges are sorted by one warp in registers
 
 struct PairDesc {
   const float* s1;
@@ -90,6 +92,7 @@ struct Chunk {  // everything a kernel needs, passed by value
   int32_t* cursor;   // [P][ncell]
   int32_t* work;     // [P][ncell]  cells with cnt1 >= n
   int32_t* nwork;    // [P]
+  int32_t* nbig;     // [P]  cells of the work list with more than WSORT_MAX non-zero ranges
   CellRec* rec;      // [P][ncell]
   unsigned long long* acc;  // [P][ncell][NQ]
   Vox1* vox;         // [P][ncell]
@@ -170,49 +173,63 @@ __global__ void __launch_bounds__(256) k_scan1_bin(const Chunk ck) {
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_cell_scan(const Chunk ck) {
   const int pair = blockIdx.x;
-  __shared__ int s_part[256];
-  __shared__ int s_wpart[256];
+  __shared__ int s_ws[8], s_ww[8];
   const int per = (ck.ncell + 255) / 256;
   const int c0 = threadIdx.x * per, c1 = min(ck.ncell, c0 + per);
   const int32_t* cnt1 = ck.cnt1 + (size_t)pair * ck.ncell;
   const int32_t* cntz = ck.cntz + (size_t)pair * ck.ncell;
-  int s = 0, w = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int s = 0, w = 0, big = 0;
   for (int c = c0; c < c1; c++) {
-    s += cnt1[c] - cntz[c];
+    const int m = cnt1[c] - cntz[c];
+    s += m;
     w += (cnt1[c] >= ck.n) ? 1 : 0;
+    big += (cnt1[c] >= ck.n && m > WSORT_MAX) ? 1 : 0;
   }
-  s_part[threadIdx.x] = s;
-  s_wpart[threadIdx.x] = w;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int a = 0, b = 0;
-    for (int t = 0; t < 256; t++) {
-      int v = s_part[t]; s_part[t] = a; a += v;
-      int u = s_wpart[t]; s_wpart[t] = b; b += u;
-    }
-    ck.nwork[pair] = b;
+  {
+    const int anybig = __syncthreads_count(big > 0);  // (number of threads that own a big cell: only zero / non-zero matters)
+    if (threadIdx.x == 0) ck.nbig[pair] = anybig;
+  }
+  // exclusive block scan of (s, w): inclusive warp scans, then the warp totals
+  int is = s, iw = w;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int ts = __shfl_up_sync(FULL, is, o), tw = __shfl_up_sync(FULL, iw, o);
+    if (lane >= o) { is += ts; iw += tw; }
+  }
+  if (lane == 31) { s_ws[warp] = is; s_ww[warp] = iw; }
+  // meanwhile: the per-pair state.  Warp 1 owns the result record, thread 0 the transform.
+  if (warp == 1) {
+    icet_b200_result* R = ck.res + pair;
     // chained pairs (ICET_B200_FLAG_CHAIN_X0, odometry.cpp:82): x0 holds ONE seed, that of pair 0; the later pairs are
     // seeded by the last solve of their predecessor (chain_seed_next).  Without iterations the seed is the answer.
     const bool chain = (ck.flags & ICET_B200_FLAG_CHAIN_X0) != 0;
-    if (ck.x0 && (!chain || pair == 0 || ck.runlen == 0))
-      for (int k = 0; k < 6; k++) ck.X[pair * 6 + k] = ck.x0[(chain ? 0 : pair * 6) + k];
-    else for (int k = 0; k < 6; k++) ck.X[pair * 6 + k] = 0.f;
-    {
-      float* TR = ck.TR + (size_t)pair * 12;
-      const float* X = ck.X + pair * 6;
-      TR[0] = X[0]; TR[1] = X[1]; TR[2] = X[2];
-      icet::rotR(X[3], X[4], X[5], TR + 3);
-      icet::getH_J(X[3], X[4], X[5], ck.J + (size_t)pair * 27);
-      for (int k = 0; k < 12; k++) ck.TRprev[(size_t)pair * 12 + k] = TR[k];
+    const bool seeded = ck.x0 && (!chain || pair == 0 || ck.runlen == 0);
+    if (lane < 6) {
+      const float x = seeded ? ck.x0[(chain ? 0 : pair * 6) + lane] : 0.f;
+      ck.X[pair * 6 + lane] = x;
+      R->X[lane] = x;
+      R->pred_stds[lane] = 0.f;
     }
-    icet_b200_result* R = ck.res + pair;
-    R->status = 0; R->n_gauss1 = 0; R->n_used = 0; R->n_dropped = 0; R->cond = 0.f;
-    for (int k = 0; k < 6; k++) { R->X[k] = ck.X[pair * 6 + k]; R->pred_stds[k] = 0.f; }
-    for (int k = 0; k < 36; k++) R->Q[k] = 0.f;
-    R->reserved[0] = R->reserved[1] = R->reserved[2] = 0;
+    for (int k = lane; k < 36; k += 32) R->Q[k] = 0.f;
+    if (lane == 6) { R->status = 0; R->n_gauss1 = 0; R->n_used = 0; R->n_dropped = 0; R->cond = 0.f; }
+    if (lane >= 7 && lane < 10) R->reserved[lane - 7] = 0;
+  }
+  if (threadIdx.x == 0) {
+    const bool chain = (ck.flags & ICET_B200_FLAG_CHAIN_X0) != 0;
+    const bool seeded = ck.x0 && (!chain || pair == 0 || ck.runlen == 0);
+    float X[6];
+    for (int k = 0; k < 6; k++) X[k] = seeded ? ck.x0[(chain ? 0 : pair * 6) + k] : 0.f;
+    float* TR = ck.TR + (size_t)pair * 12;
+    TR[0] = X[0]; TR[1] = X[1]; TR[2] = X[2];
+    icet::rotR(X[3], X[4], X[5], TR + 3);
+    icet::getH_J(X[3], X[4], X[5], ck.J + (size_t)pair * 27);
+    for (int k = 0; k < 12; k++) ck.TRprev[(size_t)pair * 12 + k] = TR[k];
   }
   __syncthreads();
-  int a = s_part[threadIdx.x], b = s_wpart[threadIdx.x];
+  int a = is - s, b = iw - w;
+  for (int q = 0; q < warp; q++) { a += s_ws[q]; b += s_ww[q]; }
+  if (threadIdx.x == 255) ck.nwork[pair] = b + w;
   for (int c = c0; c < c1; c++) {
     ck.off[(size_t)pair * ck.ncell + c] = a;
     a += cnt1[c] - cntz[c];
@@ -402,16 +419,15 @@ struct PaddedRow {  // view of a shared-memory row written by warp_sort_cell
   __device__ __forceinline__ float operator[](int i) const { return p[i + (i >> 5)]; }
 };
 
-constexpr int CLUSTER_WARPS = 4;
-constexpr int WSORT_MAX = 1024;  // cells up to this many non-zero ranges are sorted by one warp in registers
-
 // K2c: ONE WARP per cell with cnt1 >= n (a cell of a 64-ring scan holds ~260 ranges): register bitonic sort, then
-// ICET::findCluster on the sorted row.  Cells with more than WSORT_MAX ranges are left to k_cluster_big.
+// ICET::findCluster on the sorted row.  Cells with more than WSORT_MAX ranges take the CTA path at the end of the kernel.
 __global__ void __launch_bounds__(CLUSTER_WARPS * 32) k_cluster(const Chunk ck) {
   const int pair = blockIdx.y;
-  __shared__ float s_rows[CLUSTER_WARPS][WSORT_MAX + WSORT_MAX / 32];
+  constexpr int ROW = WSORT_MAX + WSORT_MAX / 32;
+  constexpr int SM_FLOATS = CLUSTER_WARPS * ROW > SORT_SMEM ? CLUSTER_WARPS * ROW : SORT_SMEM;
+  __shared__ float s_all[SM_FLOATS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* srow = s_rows[warp];
+  float* srow = s_all + warp * ROW;
   const int nw = ck.nwork[pair];
   for (int w = blockIdx.x * CLUSTER_WARPS + warp; w < nw; w += gridDim.x * CLUSTER_WARPS) {
     const int cell = ck.work[(size_t)pair * ck.ncell + w];
@@ -429,14 +445,11 @@ __global__ void __launch_bounds__(CLUSTER_WARPS * 32) k_cluster(const Chunk ck) 
     if (lane == 0) write_cluster_rec(ck, pair, cell, cnt, inner, outer);
     __syncwarp();
   }
-}
-
-// K2c for the rare big cells (more than WSORT_MAX ranges, e.g. an accumulated map as scan 1): one CTA per cell,
-// bitonic network in shared memory (<= SORT_SMEM ranges) or in L2.
-__global__ void __launch_bounds__(128) k_cluster_big(const Chunk ck) {
-  const int pair = blockIdx.y;
-  __shared__ float s_r[SORT_SMEM];
-  const int nw = ck.nwork[pair];
+  // The rare big cells (more than WSORT_MAX ranges, e.g. an accumulated map as scan 1; k_cell_scan counted them):
+  // the whole CTA per cell, bitonic network in shared memory (<= SORT_SMEM ranges) or in L2.
+  if (ck.nbig[pair] == 0) return;  // block-uniform
+  __syncthreads();
+  float* s_r = s_all;
   for (int w = blockIdx.x; w < nw; w += gridDim.x) {
     const int cell = ck.work[(size_t)pair * ck.ncell + w];
     const int cnt = ck.cnt1[(size_t)pair * ck.ncell + cell];
@@ -469,7 +482,8 @@ __global__ void __launch_bounds__(128) k_cluster_big(const Chunk ck) {
 constexpr int PASS_THREADS = 256;
 constexpr int PASS_WARPS = PASS_THREADS / 32;
 constexpr int PASS_K = 16;       // rows of 32 points per warp tile (throughput shape)
-constexpr int PASS_K_SMALL = 4;  // same for small batches (latency shape: more, smaller tiles)
+constexpr int PASS_K_SMALL = 4;  // same for small batches (latency shape: more, smaller tiles; 2 rows measured slower:
+                                 // twice the same-address ticket / tiles_done atomics per iteration)
 
 __host__ __device__ constexpr int pass_wslots(int K) { return 32 * K; }  // 16-byte entry slots per warp tile
 __host__ __device__ constexpr int pass_tile_points(int K) { return PASS_WARPS * 32 * K; }
@@ -1586,6 +1600,8 @@ struct icet_b200_ctx {
   DevBuf resbuf;    // device results for host-facing calls
   DevBuf dumpbuf;
   DevBuf posebuf;
+  DevBuf rawbuf[2];  // ingest: device copies of the callers' raw records
+  DevBuf planebuf;   // ingest: planes of the two clouds of icet_b200_register_clouds
   void* pinned = nullptr;  // pinned host bounce for results / descriptors
   size_t pinned_cap = 0;
   // dump bookkeeping
@@ -1634,6 +1650,7 @@ size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runle
   ck.off = c.take<int32_t>((size_t)P * ncell);
   ck.work = c.take<int32_t>((size_t)P * ncell);
   ck.nwork = c.take<int32_t>((size_t)P);
+  ck.nbig = c.take<int32_t>((size_t)P);
   ck.rec = c.take<CellRec>((size_t)P * ncell);
   ck.vox = c.take<Vox1>((size_t)P * ncell);
   ck.cellid1 = c.take<int32_t>((size_t)P * n1max);
@@ -1805,7 +1822,8 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   const int wt_big = 32 * PASS_K;
   const long long big_tiles = (long long)P * ((n2max + wt_big - 1) / wt_big);
   const bool chain = (p->flags & ICET_B200_FLAG_CHAIN_X0) != 0;  // one pair at a time is in flight: latency shape
-  const bool small = chain || big_tiles < 4LL * ctx->sm_count * std::max(1, ctx->loop_occ[0]) * PASS_WARPS;
+  const bool small_batch = big_tiles < 4LL * ctx->sm_count * std::max(1, ctx->loop_occ[0]) * PASS_WARPS;
+  const bool small = chain || small_batch;
   const int K2 = small ? PASS_K_SMALL : PASS_K;
   const int tiles2 = std::max(1, (n2max + 32 * K2 - 1) / (32 * K2));  // >= 1: tile 0 carries the dropped returns
   const int vt = (ncell + 31) / 32;
@@ -1830,12 +1848,12 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
     int gx = std::max(1, std::min((ncell + CLUSTER_WARPS - 1) / CLUSTER_WARPS,
                                   std::max(32, (ctx->sm_count * 16 + P - 1) / P)));
     LAUNCH(3, k_cluster<<<dim3(gx, P), CLUSTER_WARPS * 32, 0, st>>>(ck));
-    // big cells (> WSORT_MAX ranges) can only exist if a cell can hold that many points
-    if (n1max > WSORT_MAX) {
-      const int gb = std::max(1, std::min(ncell, std::max(8, (ctx->sm_count * 4 + P - 1) / P)));
-      LAUNCH(3, k_cluster_big<<<dim3(gb, P), 128, 0, st>>>(ck));
+    if (small_batch) {  // latency shape: 128 points per warp
+      const int tile_s = pass_tile_points(PASS_K_SMALL);
+      LAUNCH(4, k_pass<false, PASS_K_SMALL, 3, 1><<<dim3((n1max + tile_s - 1) / tile_s, P), PASS_THREADS, psm2, st>>>(ck));
+    } else {
+      LAUNCH(4, k_pass<false><<<gp1, PASS_THREADS, psm, st>>>(ck));
     }
-    LAUNCH(4, k_pass<false><<<gp1, PASS_THREADS, psm, st>>>(ck));
   }
   LAUNCH(5, k_fit1<<<dim3((ncell + 127) / 128, P), 128, 0, st>>>(ck));
   if (n2max > 0) LAUNCH(6, k_prep2<<<g2, 256, 0, st>>>(ck));
@@ -1970,6 +1988,7 @@ int icet_b200_destroy(icet_b200_ctx* c) {
   if (c->lane1) cudaStreamSynchronize(c->lane1);
   for (int i = 0; i < ICET_NLANE; i++) c->ws[i].release();
   c->edges.release(); c->resbuf.release(); c->dumpbuf.release(); c->posebuf.release();
+  c->rawbuf[0].release(); c->rawbuf[1].release(); c->planebuf.release();
   for (int i = 0; i < ICET_NSLOT; i++) {
     c->stage[i].release(); c->descbuf[i].release(); c->x0buf[i].release();
     if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);

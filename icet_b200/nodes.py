@@ -54,6 +54,15 @@ class Node:
             return None
         return (np.frombuffer(bytes(res), dtype=RESULT_DTYPE)[0], np.frombuffer(bytes(pose), dtype=POSE_DTYPE)[0])
 
+    def push_cloud(self, cloud, divide: float = 0.0):
+        """`push` for a cloud in its native layout (see api.cloud_desc): e.g. the bytes of a PointCloud2 message."""
+        c, keep = cloud if isinstance(cloud, tuple) else api.cloud_desc(cloud, divide)
+        res, pose = Result(), Pose()
+        rc = self.ctx._check(self._L.icet_b200_node_push_cloud(self._h, C.byref(c), C.byref(res), C.byref(pose)))
+        if rc == 0:
+            return None
+        return (np.frombuffer(bytes(res), dtype=RESULT_DTYPE)[0], np.frombuffer(bytes(pose), dtype=POSE_DTYPE)[0])
+
     def push_device(self, scans_ptr: int, nscans: int, n: int, res_ptr: int, pose_ptr: int) -> int:
         """nscans consecutive scans in device memory [nscans, 3, n]; asynchronous.  Returns the number of
         registrations whose result / pose will be written to the device arrays."""

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ICET_B200_VERSION 101
+#define ICET_B200_VERSION 102
 
 /* status codes (return values; also icet_b200_result.status for per-pair conditions) */
 enum {
@@ -247,6 +247,33 @@ int icet_b200_map_add_scan_device(icet_b200_map* map, const float* scan, int32_t
  * caller knows better), HOST memory, blocking / DEVICE memory, asynchronous (n_out then device memory too). */
 int icet_b200_map_get(icet_b200_map* map, float* out, int32_t ld_out, int32_t* n_out);
 int icet_b200_map_get_device(icet_b200_map* map, float* out, int32_t ld_out, int32_t* n_out);
+
+/* -- ingest ----------------------------------------------------------------------------------
+ * The reference's callers all convert what they hold into an N x 3 Eigen::MatrixXf on the host, one element at a time:
+ * convertPCLtoEigen (odometry.cpp:186-192) from the PointCloud2 records, loadPointCloudCSV (src/utils.cpp:19-61) from
+ * integer millimetres, the notebooks from float64 .npy arrays.  These entry points take the caller's buffer as it is:
+ * the raw bytes cross PCIe once and one kernel writes the x | y | z planes the path reads. */
+enum { ICET_B200_F32 = 0, ICET_B200_F64 = 1, ICET_B200_I32 = 2 };
+typedef struct {
+  const void* data;    /* HOST: n records of point_step bytes                                                          */
+  int32_t n;
+  int32_t point_step;  /* bytes per record: 12 numpy float32 N x 3, 24 float64 N x 3, 16 pcl::PointXYZ, PointCloud2.point_step */
+  int32_t off[3];      /* byte offsets of x, y, z inside a record (PointCloud2.fields[k].offset); multiples of the
+                          element size, like point_step                                                                */
+  int32_t dtype;       /* ICET_B200_F32 | ICET_B200_F64 (rounded to float like Eigen's cast<float>()) | ICET_B200_I32  */
+  float divide;        /* value = float(raw) / divide when != 0 and != 1 (src/utils.cpp:51: integer mm `/ 1000`)        */
+  int32_t plane_stride; /* 0: records (array of structures).  > 0: the buffer holds three planes of n elements,
+                           plane k starting plane_stride elements after plane k-1 (numpy Fortran order: n)             */
+} icet_b200_cloud;
+/* Converts one HOST cloud into DEVICE planes (out: 3 planes, leading dimension ld >= n).  Asynchronous on the context's
+ * stream once the raw bytes are staged (the call returns after the host buffer has been read). */
+int icet_b200_ingest(icet_b200_ctx* ctx, const icet_b200_cloud* cloud, float* out, int32_t ld);
+/* icet_b200_register for two clouds in their native layout (blocking). */
+int icet_b200_register_clouds(icet_b200_ctx* ctx, const icet_b200_params* p, const icet_b200_cloud* scan1,
+                              const icet_b200_cloud* scan2, const float x0[6], icet_b200_result* out);
+/* icet_b200_node_push for a cloud in its native layout, e.g. straight from a sensor_msgs::PointCloud2 (blocking). */
+int icet_b200_node_push_cloud(icet_b200_node* node, const icet_b200_cloud* cloud, icet_b200_result* res,
+                              icet_b200_pose* pose);
 
 /* -- synthetic 64-channel scans (bench / test utility) --------------------------- */
 /* Writes nscans consecutive scans (index first_scan ...) of rings x azim points each to DEVICE memory

@@ -190,3 +190,47 @@ def test_cpp_node_classes(ctx, scans, tmp_path):
         np.testing.assert_array_equal(p, g["X_homo"][:3, 3])
     ml = [l for l in out.stdout.splitlines() if l.startswith("MAP")][0]
     assert "rows 5000" in ml
+
+
+def test_ingest_native_layouts(ctx, frame_pair):
+    """clouds in the layouts the reference's callers hold them in -- float64 .npy arrays in C and
+    Fortran order (src/sample_data, python/point_clouds), PointCloud2 records (pcl::PointXYZ: 16-byte step),
+    integer millimetres (Ouster CSV, src/utils.cpp:42-52) -- converted on the device: bit-identical to converting on
+    the host the way the reference does (cast<float>(), `/ 1000`) and registering the planes."""
+    import torch
+    from icet_b200 import Node, api
+    s1, s2 = frame_pair                      # float32 [3, N] planes
+    ref = ctx.register(s1, s2)
+    a64, b64 = np.ascontiguousarray(s1.T.astype(np.float64)), np.ascontiguousarray(s2.T.astype(np.float64))
+    for a, b in ((a64, b64), (np.asfortranarray(a64), np.asfortranarray(b64)),
+                 (np.ascontiguousarray(s1.T), np.ascontiguousarray(s2.T))):
+        r = ctx.register_clouds(a, b)
+        assert r["X"].tobytes() == ref["X"].tobytes() and r["Q"].tobytes() == ref["Q"].tobytes()
+    # PointCloud2-style records: x, y, z, padding (pcl::PointXYZ), plus an intensity-first variant with offsets 4, 8, 12
+    n = s1.shape[1]
+    rec = np.zeros((n, 4), np.float32); rec[:, :3] = s1.T; rec[:, 3] = 7.0
+    rec2 = np.zeros((n, 5), np.float32); rec2[:, 1:4] = s2.T; rec2[:, 0] = 3.0
+    r = ctx.register_clouds(api.cloud_desc(rec.tobytes(), point_step=16, offsets=(0, 4, 8)),
+                            api.cloud_desc(rec2.tobytes(), point_step=20, offsets=(4, 8, 12)))
+    assert r["X"].tobytes() == ref["X"].tobytes()
+    # integer millimetres / 1000 (Ouster CSV path): the host reference conversion is float(int) / 1000.0f
+    mm1, mm2 = np.round(s1.T * 1000).astype(np.int32), np.round(s2.T * 1000).astype(np.int32)
+    h1 = (mm1.astype(np.float32) / np.float32(1000)).T.copy()
+    h2 = (mm2.astype(np.float32) / np.float32(1000)).T.copy()
+    rh = ctx.register(h1, h2)
+    r = ctx.register_clouds(mm1, mm2, divide=1000.0)
+    assert r["X"].tobytes() == rh["X"].tobytes() and r["pred_stds"].tobytes() == rh["pred_stds"].tobytes()
+    # plain conversion check, including double -> float rounding and a leading dimension
+    out = torch.zeros((3, n + 8), dtype=torch.float32, device="cuda")
+    v = (a64 * (1 + 1e-9)).copy()
+    ctx.ingest(v, out.data_ptr(), n + 8)
+    ctx.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy()[:, :n], v.astype(np.float32).T)
+    # the node callback straight from records
+    op = api.OdometryParams(2.0, 1, 10.0, 0.0, 0.0)
+    na, nb = Node(ctx, api.make_params(), op, n), Node(ctx, api.make_params(), op, n)
+    assert na.push(s1) is None and nb.push_cloud(api.cloud_desc(rec.tobytes(), point_step=16, offsets=(0, 4, 8))) is None
+    ra, rb = na.push(s2), nb.push_cloud(api.cloud_desc(rec2.tobytes(), point_step=20, offsets=(4, 8, 12)))
+    assert ra[0]["X"].tobytes() == rb[0]["X"].tobytes() and ra[1]["X_homo"].tobytes() == rb[1]["X_homo"].tobytes()
+    with pytest.raises(Exception):
+        ctx.register_clouds(api.cloud_desc(rec.tobytes(), point_step=16, offsets=(0, 4, 14)), a64)
