@@ -344,10 +344,12 @@ class Context:
         return out
 
     def debug_timeline(self, runlen: int) -> np.ndarray:
-        """%globaltimer stamps [runlen, 8] (ns) of the loop kernel for the last dumped single-pair call."""
-        out = np.zeros((runlen, 8), np.uint64)
+        """%globaltimer stamps [runlen, 16] (ns) of the loop kernel for the last dumped single-pair call."""
+        out = np.zeros(runlen * 16 + 6144, np.uint64)
         self._check(self._L.icet_b200_debug_timeline(self._h, out.ctypes.data, runlen))
-        return out
+        self.tile_stamps = out[runlen * 16: runlen * 16 + 4096].reshape(2048, 2)
+        self.tile_mid = out[runlen * 16 + 4096:]  # end of phase A of those tiles  # begin / end of the tiles of iteration 3 (debug)
+        return out[: runlen * 16].reshape(runlen, 16)
 
     def get_dump(self, p: Params) -> dict:
         ncell, rl = p.bins_phi * p.bins_theta, p.runlen

@@ -74,7 +74,7 @@ struct Vox1 {     // scan-1 Gaussian, constants of the iteration loop (sigma1/mu
 struct Dump {  // optional per-voxel recording (device memory), single-pair debugging only
   int32_t* nin1; uint8_t* has1; float* mu1; float* sigma1; float* evec1; float* eval1; uint8_t* lmask;
   int32_t* cnt2; int32_t* nin2; uint8_t* used2; float* mu2; float* sigma2; float* Xit; float* HTWH; float* HTWdz;
-  unsigned long long* tl;  // [runlen][8] globaltimer stamps of the loop kernel (debug)
+  unsigned long long* tl;  // [runlen][16] globaltimer stamps of the loop kernel (debug) + per-tile stamps of iteration 3
 };
 
 struct Chunk {  // everything a kernel needs, passed by value
@@ -599,7 +599,7 @@ template <bool SCAN2, int K, int PF = 2>
 __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* the warp's pass_wslots(K) slots */,
                                                const float* tab, const CellRec* recs, const float* tr,
                                                const float* px_, size_t ld, int n, int w0,
-                                               unsigned long long* accp) {
+                                               unsigned long long* accp, unsigned long long* dbg_stamp = nullptr) {
   const int lane = threadIdx.x & 31;
   if (w0 >= n) return;
   const float4* tth = reinterpret_cast<const float4*>(tab);
@@ -648,6 +648,11 @@ __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* th
     nin_tile += __popc(im);
   }
   __syncwarp();
+  if (dbg_stamp && lane == 0) {  // debug timeline: end of phase A
+    unsigned long long t_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    *dbg_stamp = t_;
+  }
   // ---- phase B: lane takes entries [lane*q, lane*q + q); q odd => conflict-free 16-byte shared loads
   const int q = ((nin_tile + 31) >> 5) | 1;
   const int e0 = lane * q, e1 = min(nin_tile, e0 + q);
@@ -853,6 +858,35 @@ __global__ void __launch_bounds__(256) k_prep2(const Chunk ck) {
 // ----------------------------------------------------------------------------------------------
 constexpr int VOX_THREADS = 64;
 constexpr int NRED = 28;  // 21 (upper triangle of H^T W H) + 6 (H^T W dz) + 1 (voxels used)
+
+// Sum over the 32 lanes of each of the NRED (28) per-lane values; lane k < NRED returns the total of value k.
+// Transposing butterfly: at distance o the lanes with bit o set keep the upper half of the remaining values and the
+// others the lower half, so 16 + 8 + 4 + 2 + 1 shuffles replace 28 x 5.  The pairing of the additions is that of the
+// plain xor butterfly (lanes L and L ^ o at every level), so the sums are bit-identical to it.
+__device__ __forceinline__ double warp_sum_transposed(const double (&acc)[NRED], int lane) {
+  double v[16];
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const double hi = (i + 16 < NRED) ? acc[i + 16] : 0.0;
+      const double send = up ? acc[i] : hi;
+      const double keep = up ? hi : acc[i];
+      v[i] = keep + __shfl_xor_sync(FULL, send, 16);
+    }
+  }
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; i++) {
+      const double send = up ? v[i] : v[i + o];
+      const double keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(FULL, send, o);
+    }
+  }
+  return v[0];
+}
 
 // Gate of fitCells2 for one voxel (`indices2.size() > n` :290, `rows > n` :302).  Returns true if the voxel
 // contributes; its accumulators are then left in place for vox_algebra, otherwise they are cleared here.
@@ -1201,7 +1235,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define TL(slot)                                                                         \
   do {                                                                                   \
-    if (ck.dump_on && (threadIdx.x & 31) == 0) ck.dump.tl[(size_t)iter * 8 + (slot)] = gtime(); \
+    if (ck.dump_on && (threadIdx.x & 31) == 0) ck.dump.tl[(size_t)iter * 16 + (slot)] = gtime(); \
   } while (0)
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -1254,17 +1288,13 @@ __device__ __noinline__ void vox_task(const Chunk& ck, int iter, int pair, int g
 #pragma unroll
     for (int k = 0; k < NRED; k++) acc[k] = 0.0;
     if (cell < ck.ncell && vox_gate(ck, pair, cell, iter)) vox_algebra(ck, pair, cell, iter, w_J, acc);
+    TL(8);
     if (__any_sync(FULL, acc[27] != 0.0)) {
       double* out = ck.part + ((size_t)pair * vt + grp) * NRED;
-#pragma unroll
-      for (int k = 0; k < NRED; k++) {
-        double v = acc[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        if (lane == k) out[k] = v;
-      }
-      __threadfence();
-      __syncwarp();
+      const double tot = warp_sum_transposed(acc, lane);
+      if (lane < NRED) out[lane] = tot;
+      TL(9);
+      // (the fence below, executed by every lane before vox_done is bumped, also covers these stores and the mask bit)
       if (lane == 0) {
         atomicOr(ck.vmask + (size_t)pair * ((vt + 31) / 32) + (grp >> 5), 1u << (grp & 31));
       }
@@ -1415,12 +1445,14 @@ __global__ void __launch_bounds__(PASS_THREADS, 3) k_loop(const Chunk ck, int ti
         const CellRec* recs = ck.rec + (size_t)pair * ck.ncell;
         unsigned long long* accp = ck.acc + (size_t)pair * ck.ncell * NQ;
         if (tile == 0) TL(6);
+        if (ck.dump_on && iter == 3 && tile < 2048 && lane == 0) ck.dump.tl[(size_t)ck.runlen * 16 + 2 * tile] = gtime();
         pass_warp_tile<true, K>(ck, went, tab, recs, tr, ck.pog + (size_t)pair * 3 * ck.n2max, (size_t)ck.n2max, n, w0,
-                                accp);
+                                accp, (ck.dump_on && iter == 3 && tile < 2048) ? ck.dump.tl + (size_t)ck.runlen * 16 + 4096 + tile : nullptr);
         if (tile == 0 && lane == 0)
           pass_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 2,
                                recs, tr, accp, __ldg(ck.nz2 + pair));
         if (tile == 0) TL(7);
+        if (ck.dump_on && iter == 3 && tile < 2048 && lane == 0) ck.dump.tl[(size_t)ck.runlen * 16 + 2 * tile + 1] = gtime();
         __threadfence();  // every lane: its accumulator updates are visible before the tile is counted
         __syncwarp();
         if (lane == 0) atomicAdd(ck.tiles_done + pair, 1u);
@@ -1450,22 +1482,10 @@ __global__ void __launch_bounds__(VOX_THREADS) k_vox2(const Chunk ck, int iter) 
     if (threadIdx.x < NRED) out[threadIdx.x] = 0.0;
     return;
   }
-#pragma unroll
-  for (int k = 0; k < NRED; k++) {
-    double vsum = acc[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(FULL, vsum, o);
-    acc[k] = vsum;
-  }
-  if (wid == 1 && lane == 0) {
-#pragma unroll
-    for (int k = 0; k < NRED; k++) s_red[k] = acc[k];
-  }
+  const double tot = warp_sum_transposed(acc, lane);
+  if (wid == 1 && lane < NRED) s_red[lane] = tot;
   __syncthreads();
-  if (wid == 0 && lane == 0) {
-#pragma unroll
-    for (int k = 0; k < NRED; k++) out[k] = acc[k] + s_red[k];
-  }
+  if (wid == 0 && lane < NRED) out[lane] = tot + s_red[lane];
 }
 
 __global__ void __launch_bounds__(32) k_solve6(const Chunk ck, int iter, int nblk) {
@@ -1919,7 +1939,7 @@ int ensure_dump(icet_b200_ctx* ctx, const icet_b200_params* p) {
     d.cnt2 = cv.take<int32_t>(rl * ncell); d.nin2 = cv.take<int32_t>(rl * ncell); d.used2 = cv.take<uint8_t>(rl * ncell);
     d.mu2 = cv.take<float>(rl * ncell * 3); d.sigma2 = cv.take<float>(rl * ncell * 9);
     d.Xit = cv.take<float>(rl * 6); d.HTWH = cv.take<float>(rl * 36); d.HTWdz = cv.take<float>(rl * 6);
-    d.tl = cv.take<unsigned long long>(rl * 8);
+    d.tl = cv.take<unsigned long long>(rl * 16 + 6144);  // + begin / end / mid of up to 2048 tiles of iteration 3
   };
   Dump tmp;
   lay(c, tmp);
@@ -2407,7 +2427,7 @@ int icet_b200_debug_timeline(icet_b200_ctx* c, uint64_t* out, int32_t runlen) {
   if (!c->dump_valid || runlen != c->dump_params.runlen) return fail(ICET_B200_E_INVALID, "no dump recorded");
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
-  CK(cudaMemcpy(out, c->dump_ptrs.tl, (size_t)runlen * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out, c->dump_ptrs.tl, ((size_t)runlen * 16 + 6144) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -292,9 +292,11 @@ int64_t icet_b200_kernel_launches(icet_b200_ctx* ctx);
 int icet_b200_set_profile(icet_b200_ctx* ctx, int32_t enable);
 int icet_b200_get_profile(icet_b200_ctx* ctx, double ms[ICET_B200_NKERNELS], int64_t launches[ICET_B200_NKERNELS]);
 const char* icet_b200_kernel_name(int id);
-/* Debug: %globaltimer stamps [runlen][8] of the persistent loop kernel for the most recent dumped single-pair call
+/* Debug: %globaltimer stamps [runlen][16] of the persistent loop kernel for the most recent dumped single-pair call
  * (0 last vox task arrived, 1 / 2 begin / end of the latest vox task, 3 partial sums added, 4 solve done,
- * 5 iteration published, 6 / 7 begin / end of tile 0 of the iteration).  HOST buffer of runlen*8 values. */
+ * 5 iteration published, 6 / 7 begin / end of tile 0 of the iteration, 8 / 9 algebra / partial sums of the latest
+ * vox task done), followed by begin / end stamps of up to 2048 tiles of iteration 3.
+ * HOST buffer of runlen*16 + 4096 values. */
 int icet_b200_debug_timeline(icet_b200_ctx* ctx, uint64_t* out, int32_t runlen);
 
 #ifdef __cplusplus
