@@ -122,6 +122,25 @@ struct Chunk {  // everything a kernel needs, passed by value
   int dump_on;
 };
 
+// Atomics on Chunk memory, with the address space spelled out.  Kernels that hand the Chunk to non-inlined device
+// functions by reference (k_loop) keep it in local memory, and the compiler then no longer knows which address space
+// the pointers it loads from there refer to: atomicAdd() becomes a GENERIC atomic that waits for a predicate from the
+// memory system (one L2 round trip each instead of a fire-and-forget RED) plus a shared-memory CAS fallback.
+__device__ __forceinline__ void red_add(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_add(unsigned* p, unsigned v) {
+  asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_or(unsigned* p, unsigned v) {
+  asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned atom_add(unsigned* p, unsigned v) {
+  unsigned r;
+  asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v) : "memory");
+  return r;
+}
+
 // ----------------------------------------------------------------------------------------------
 // Fixed-point accumulators acc[cell][NQ] (64-bit integers, RED.64 to L2):
 //   q[0] += points in the angular bin, q[1] += points inside the cluster box,
@@ -550,22 +569,22 @@ __device__ inline void pass_dropped_returns(const Chunk& ck, const float4* tth, 
   point_stage1<true>(ck, tth, tph, recs, tr, 0.0f, 0.0f, 0.0f, c, active, in, r, th, ph);
   if (!active) return;
   unsigned long long* q = accp + (size_t)c * NQ;
-  atomicAdd(q, (unsigned long long)nz);
+  red_add(q, (unsigned long long)nz);
   if (in) {
     const CellRec rc = recs[c];
     int ix, iy, iz;
     point_stage2(r, th, ph, rc.refx, rc.refy, rc.refz, rc.scale, ix, iy, iz);
     const long long fx = ix, fy = iy, fz = iz;
-    atomicAdd(q + 1, (unsigned long long)nz);
-    atomicAdd(q + 2, (unsigned long long)(nz * fx));
-    atomicAdd(q + 3, (unsigned long long)(nz * fy));
-    atomicAdd(q + 4, (unsigned long long)(nz * fz));
-    atomicAdd(q + 5, (unsigned long long)(nz * fx * fx));
-    atomicAdd(q + 6, (unsigned long long)(nz * fx * fy));
-    atomicAdd(q + 7, (unsigned long long)(nz * fx * fz));
-    atomicAdd(q + 8, (unsigned long long)(nz * fy * fy));
-    atomicAdd(q + 9, (unsigned long long)(nz * fy * fz));
-    atomicAdd(q + 10, (unsigned long long)(nz * fz * fz));
+    red_add(q + 1, (unsigned long long)nz);
+    red_add(q + 2, (unsigned long long)(nz * fx));
+    red_add(q + 3, (unsigned long long)(nz * fy));
+    red_add(q + 4, (unsigned long long)(nz * fz));
+    red_add(q + 5, (unsigned long long)(nz * fx * fx));
+    red_add(q + 6, (unsigned long long)(nz * fx * fy));
+    red_add(q + 7, (unsigned long long)(nz * fx * fz));
+    red_add(q + 8, (unsigned long long)(nz * fy * fy));
+    red_add(q + 9, (unsigned long long)(nz * fy * fz));
+    red_add(q + 10, (unsigned long long)(nz * fz * fz));
   }
 }
 
@@ -575,16 +594,16 @@ __device__ __forceinline__ void flush_in_run(unsigned long long* accp, int cell,
                                              long long pzz) {
   if (cell < 0) return;
   unsigned long long* q = accp + (size_t)cell * NQ;
-  atomicAdd(q + 1, (unsigned long long)nin);
-  atomicAdd(q + 2, (unsigned long long)(long long)sx);
-  atomicAdd(q + 3, (unsigned long long)(long long)sy);
-  atomicAdd(q + 4, (unsigned long long)(long long)sz);
-  atomicAdd(q + 5, (unsigned long long)pxx);
-  atomicAdd(q + 6, (unsigned long long)pxy);
-  atomicAdd(q + 7, (unsigned long long)pxz);
-  atomicAdd(q + 8, (unsigned long long)pyy);
-  atomicAdd(q + 9, (unsigned long long)pyz);
-  atomicAdd(q + 10, (unsigned long long)pzz);
+  red_add(q + 1, (unsigned long long)nin);
+  red_add(q + 2, (unsigned long long)(long long)sx);
+  red_add(q + 3, (unsigned long long)(long long)sy);
+  red_add(q + 4, (unsigned long long)(long long)sz);
+  red_add(q + 5, (unsigned long long)pxx);
+  red_add(q + 6, (unsigned long long)pxy);
+  red_add(q + 7, (unsigned long long)pxz);
+  red_add(q + 8, (unsigned long long)pyy);
+  red_add(q + 9, (unsigned long long)pyz);
+  red_add(q + 10, (unsigned long long)pzz);
 }
 
 // One warp tile of 32*K consecutive points.
@@ -640,7 +659,7 @@ __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* th
     if (head && key >= 0) {
       const unsigned nh = (lane == 31) ? 0u : (hm >> (lane + 1));
       const int len = nh ? __ffs(nh) : 32 - lane;
-      atomicAdd(accp + (size_t)key * NQ, (unsigned long long)len);
+      red_add(accp + (size_t)key * NQ, (unsigned long long)len);
     }
     // compaction of the inside points
     const unsigned im = __ballot_sync(FULL, in);
@@ -1296,7 +1315,7 @@ __device__ __noinline__ void vox_task(const Chunk& ck, int iter, int pair, int g
       TL(9);
       // (the fence below, executed by every lane before vox_done is bumped, also covers these stores and the mask bit)
       if (lane == 0) {
-        atomicOr(ck.vmask + (size_t)pair * ((vt + 31) / 32) + (grp >> 5), 1u << (grp & 31));
+        red_or(ck.vmask + (size_t)pair * ((vt + 31) / 32) + (grp >> 5), 1u << (grp & 31));
       }
     }
     TL(2);
@@ -1307,7 +1326,7 @@ __device__ __noinline__ void vox_task(const Chunk& ck, int iter, int pair, int g
   __syncwarp();
   unsigned prev = 0;
   if (lane == 0) {
-    prev = atomicAdd(ck.vox_done + (size_t)pair * ck.runlen + iter, 1u);
+    prev = atom_add(ck.vox_done + (size_t)pair * ck.runlen + iter, 1u);
   }
   prev = __shfl_sync(FULL, prev, 0);
   if (prev + 1u == (unsigned)vt) {
@@ -1394,12 +1413,12 @@ __global__ void __launch_bounds__(PASS_THREADS, 3) k_loop(const Chunk ck, int ti
   const unsigned total = per_iter * (unsigned)ck.runlen;
   const bool chain = (ck.flags & ICET_B200_FLAG_CHAIN_X0) != 0;
   unsigned t = 0;
-  if (lane == 0) t = atomicAdd(ck.ticket, 1u);
+  if (lane == 0) t = atom_add(ck.ticket, 1u);
   t = __shfl_sync(FULL, t, 0);
   while (t < total) {
     // the next ticket is drawn now; its round trip to L2 hides behind this task
     unsigned t_next = 0;
-    if (lane == 0) t_next = atomicAdd(ck.ticket, 1u);
+    if (lane == 0) t_next = atom_add(ck.ticket, 1u);
     // ticket -> task.  Independent pairs: iteration-major (see above).  Chained pairs (ICET_B200_FLAG_CHAIN_X0): pair-
     // major, i.e. all iterations of pair k before any task of pair k + 1, whose first tiles wait for the last solve
     // of pair k (it seeds X / TR / J of pair k + 1) -- still only waits on smaller tickets.
@@ -1455,7 +1474,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 3) k_loop(const Chunk ck, int ti
         if (ck.dump_on && iter == 3 && tile < 2048 && lane == 0) ck.dump.tl[(size_t)ck.runlen * 16 + 2 * tile + 1] = gtime();
         __threadfence();  // every lane: its accumulator updates are visible before the tile is counted
         __syncwarp();
-        if (lane == 0) atomicAdd(ck.tiles_done + pair, 1u);
+        if (lane == 0) red_add(ck.tiles_done + pair, 1u);
       }  // tiles beyond the compacted point count of the pair are not counted (see loop_tiles_of)
     } else {
       // ------------------------------------------------------------------ vox task
