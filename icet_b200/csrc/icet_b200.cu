@@ -614,7 +614,10 @@ __device__ __forceinline__ void flush_in_run(unsigned long long* accp, int cell,
 //  Phase B (lane per contiguous slice of the compacted list): stage 2 (the expensive round trip) only for inside
 //    points and with all lanes busy; sums of a run of equal cell stay in registers, one flush per run.
 // Only warp-level synchronisation inside.
-template <bool SCAN2, int K, int PF = 2>
+//  G > 1 (latency shape): stage 1 of G rows is evaluated back to back before the warp-synchronous bookkeeping of
+//    those rows, so that G independent dependency chains (each with a look-up of the cell record in the middle)
+//    overlap inside one warp; the tile's latency, not its instruction count, is what a single pair waits for.
+template <bool SCAN2, int K, int PF = 2, int G = 1>
 __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* the warp's pass_wslots(K) slots */,
                                                const float* tab, const CellRec* recs, const float* tr,
                                                const float* px_, size_t ld, int n, int w0,
@@ -625,6 +628,45 @@ __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* th
   const float4* tph = tth + ck.nT + 2;
   const unsigned lt = (1u << lane) - 1u;
   int nin_tile = 0;
+  if (G > 1) {
+    static_assert(G == 1 || K % G == 0, "rows per group must divide the tile");
+    // ---- phase A, grouped: all coordinates of the group in flight, then G stage-1 chains, then the bookkeeping
+#pragma unroll 1
+    for (int j0 = 0; j0 < K; j0 += G) {
+      float gx[G], gy[G], gz[G];
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        const int i = w0 + (j0 + g) * 32 + lane;
+        gx[g] = gy[g] = gz[g] = 0.f;
+        if (i < n) { gx[g] = __ldg(px_ + i); gy[g] = __ldg(px_ + ld + i); gz[g] = __ldg(px_ + 2 * ld + i); }
+      }
+      int gc[G];
+      bool gact[G], gin[G];
+      float gr[G], gth[G], gph[G];
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        const int i = w0 + (j0 + g) * 32 + lane;
+        gc[g] = -1; gact[g] = false; gin[g] = false; gr[g] = 0.f; gth[g] = 0.f; gph[g] = 0.f;
+        if (i < n) point_stage1<SCAN2>(ck, tth, tph, recs, tr, gx[g], gy[g], gz[g], gc[g], gact[g], gin[g], gr[g], gth[g], gph[g]);
+      }
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        const int key = gact[g] ? gc[g] : -1;
+        const int prev = __shfl_up_sync(FULL, key, 1);
+        const bool head = (lane == 0) || (key != prev);
+        const unsigned hm = __ballot_sync(FULL, head);
+        if (head && key >= 0) {
+          const unsigned nh = (lane == 31) ? 0u : (hm >> (lane + 1));
+          const int len = nh ? __ffs(nh) : 32 - lane;
+          red_add(accp + (size_t)key * NQ, (unsigned long long)len);
+        }
+        const unsigned im = __ballot_sync(FULL, gin[g]);
+        if (gin[g])
+          went[nin_tile + __popc(im & lt)] = make_int4(gc[g], __float_as_int(gr[g]), __float_as_int(gth[g]), __float_as_int(gph[g]));
+        nin_tile += __popc(im);
+      }
+    }
+  } else {
   // ---- phase A (the coordinates of row j + PF are requested before row j is worked on)
   float bx[PF > 0 ? PF : 1], by[PF > 0 ? PF : 1], bz[PF > 0 ? PF : 1];
 #pragma unroll
@@ -666,6 +708,7 @@ __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* th
     if (in) went[nin_tile + __popc(im & lt)] = make_int4(c, __float_as_int(r), __float_as_int(th), __float_as_int(ph));
     nin_tile += __popc(im);
   }
+  }  // G == 1
   __syncwarp();
   if (dbg_stamp && lane == 0) {  // debug timeline: end of phase A
     unsigned long long t_;
@@ -701,7 +744,7 @@ __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* th
   __syncwarp();
 }
 
-template <bool SCAN2, int K = PASS_K, int MINB = 3, int PF = 2>
+template <bool SCAN2, int K = PASS_K, int MINB = 3, int PF = 2, int G = 1>
 __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass(const Chunk ck) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int4* ent = reinterpret_cast<int4*>(smem_raw);
@@ -727,7 +770,7 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass(const Chunk ck) {
   const CellRec* recs = ck.rec + (size_t)pair * ck.ncell;
   unsigned long long* accp = ck.acc + (size_t)pair * ck.ncell * NQ;
   __syncthreads();
-  pass_warp_tile<SCAN2, K, PF>(ck, ent + (threadIdx.x >> 5) * pass_wslots(K), tab, recs, tr, px_, ld, n,
+  pass_warp_tile<SCAN2, K, PF, G>(ck, ent + (threadIdx.x >> 5) * pass_wslots(K), tab, recs, tr, px_, ld, n,
                            tile0 + (threadIdx.x >> 5) * 32 * K, accp);
   if (SCAN2 && blockIdx.x == 0 && threadIdx.x == 0)
     pass_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 2, recs, tr,
@@ -1168,6 +1211,9 @@ __device__ __noinline__ void solve_pair(const Chunk& ck, int pair, int iter, con
 // then runs solve_pair (eigen-decomposition + the reference's truncation loop) on one thread.
 __device__ __forceinline__ bool solve_pair_warp(const Chunk& ck, int pair, int iter, const double* tot) {
   const int lane = threadIdx.x & 31;
+  // requested now, used after the elimination: the current X and (last iteration) the transform it started from
+  const float x_old = lane < 6 ? __ldcg(ck.X + pair * 6 + lane) : 0.f;
+  const float tr_old = (lane < 12 && iter == ck.runlen - 1) ? __ldcg(ck.TR + (size_t)pair * 12 + lane) : 0.f;
   double col[6];
   {
     // lane j < 6: column j of A; lane 6 + j: column j of I; lane 12: b
@@ -1202,31 +1248,53 @@ __device__ __forceinline__ bool solve_pair_warp(const Chunk& ck, int pair, int i
   // cond <= trace(A) * trace(A^-1); comfortably below the 1e6 cutoff => checkCondition drops nothing and
   // pinv == inverse, so dx = A^-1 b  (src/icet.cpp:410-433 with an empty while-loop at :469)
   if (!(ok && trA * trQ < 0.999e6)) return false;
-  float* X = ck.X + pair * 6;
   icet_b200_result* R = ck.res + pair;
   const bool last = iter == ck.runlen - 1;
-  if (lane == 12) {
-    float Xn[6];
+  // ---- the update, warp-wide (one lane doing all of it serially was the longest stretch of the iteration)
+  // X += dx (:433), X is fp32: lane k < 6 owns component k (dx_k lives in lane 12's col[k])
+  double dxk = 0.0;
 #pragma unroll
-    for (int k = 0; k < 6; k++) Xn[k] = (float)((double)__ldcg(X + k) + col[k]);  // X += dx (:433), X is fp32
+  for (int k = 0; k < 6; k++) {
+    const double v = __shfl_sync(FULL, col[k], 12);
+    dxk = (lane == k) ? v : dxk;
+  }
+  const float xn = (float)((double)x_old + dxk);
+  // sines / cosines of the three angles on lanes 0..2, then every lane forms all of R(X) and the get_H matrices
+  // (~100 flops, same expressions as utils::R / get_H) and stores the entries it owns
+  float sv, cv;
+  sincosf(__shfl_sync(FULL, xn, 3 + (lane % 3)), &sv, &cv);
+  const float sph = __shfl_sync(FULL, sv, 0), cph = __shfl_sync(FULL, cv, 0);
+  const float sth = __shfl_sync(FULL, sv, 1), cth = __shfl_sync(FULL, cv, 1);
+  const float sps = __shfl_sync(FULL, sv, 2), cps = __shfl_sync(FULL, cv, 2);
+  float Rm[9], Jm[27];
+  icet::rotR_sc(sph, cph, sth, cth, sps, cps, Rm);
+  icet::getH_J_sc(sph, cph, sth, cth, sps, cps, Jm);
+  const float t_k = __shfl_sync(FULL, xn, lane < 3 ? lane : 0);
+  float trv = t_k, jv = 0.f;
 #pragma unroll
-    for (int k = 0; k < 6; k++) X[k] = Xn[k];
-    float* TR = ck.TR + (size_t)pair * 12;
-    if (last)
-      for (int k = 0; k < 12; k++) ck.TRprev[(size_t)pair * 12 + k] = __ldcg(TR + k);
-    TR[0] = Xn[0]; TR[1] = Xn[1]; TR[2] = Xn[2];
-    icet::rotR(Xn[3], Xn[4], Xn[5], TR + 3);
-    icet::getH_J(Xn[3], Xn[4], Xn[5], ck.J + (size_t)pair * 27);
-    if (last) chain_seed_next(ck, pair, Xn);
-    if (ck.dump_on) {
-      for (int k = 0; k < 6; k++) { ck.dump.Xit[iter * 6 + k] = Xn[k]; ck.dump.HTWdz[iter * 6 + k] = (float)tot[21 + k]; }
-    }
-    if (last) {
-      for (int k = 0; k < 6; k++) R->X[k] = Xn[k];
-      R->n_used = (int)(tot[27] + 0.5);
-      R->n_dropped = 0;
-      R->cond = (float)(-(trA * trQ));
-    }
+  for (int e = 0; e < 9; e++) trv = (lane == 3 + e) ? Rm[e] : trv;
+#pragma unroll
+  for (int e = 0; e < 27; e++) jv = (lane == e) ? Jm[e] : jv;
+  const bool seed = last && (ck.flags & ICET_B200_FLAG_CHAIN_X0) && pair + 1 < ck.npairs;  // odometry.cpp:82
+  if (lane < 6) {
+    ck.X[pair * 6 + lane] = xn;
+    if (last) R->X[lane] = xn;
+    if (seed) { ck.X[(pair + 1) * 6 + lane] = xn; ck.res[pair + 1].X[lane] = xn; }
+    if (ck.dump_on) { ck.dump.Xit[iter * 6 + lane] = xn; ck.dump.HTWdz[iter * 6 + lane] = (float)tot[21 + lane]; }
+  }
+  if (lane < 12) {
+    if (last) ck.TRprev[(size_t)pair * 12 + lane] = tr_old;  // the transform the LAST iteration used (`points2`)
+    ck.TR[(size_t)pair * 12 + lane] = trv;
+    if (seed) { ck.TR[(size_t)(pair + 1) * 12 + lane] = trv; ck.TRprev[(size_t)(pair + 1) * 12 + lane] = trv; }
+  }
+  if (lane < 27) {
+    ck.J[(size_t)pair * 27 + lane] = jv;
+    if (seed) ck.J[(size_t)(pair + 1) * 27 + lane] = jv;
+  }
+  if (last && lane == 12) {
+    R->n_used = (int)(tot[27] + 0.5);
+    R->n_dropped = 0;
+    R->cond = (float)(-(trA * trQ));
   }
   if (ck.dump_on && lane < 6) {
     for (int i = 0; i < 6; i++) {
@@ -1264,14 +1332,25 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 }
 // Spin until *p >= need.  A protocol failure must not hang the GPU: after ~2 s the wait gives up, records what it
 // was waiting for in ck.dbg and marks the pair (results of the chunk are then invalid; the host reports an error).
+// The polling itself uses RELAXED loads: an acquire load is followed by an invalidation of the SM's whole L1
+// (CCTL.IVALL), and thousands of spinning warps would keep every L1 of the GPU empty for the warps that do the work.
+// One acquire load after the condition has been seen orders the reads that follow.
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __noinline__ void loop_wait(const Chunk& ck, const int* p, int need, int kind, int pair, int iter, unsigned ticket) {
   if (ld_acquire(p) >= need) return;
   const unsigned long long t0 = gtime();
   unsigned spins = 0;
   for (;;) {
     __nanosleep(40);
-    const int seen = ld_acquire(p);
-    if (seen >= need) return;
+    const int seen = ld_relaxed(p);
+    if (seen >= need) {
+      ld_acquire(p);
+      return;
+    }
     if ((++spins & 1023u) == 0 && gtime() - t0 > 2000000000ull) {
       if ((threadIdx.x & 31) == 0 && atomicCAS(ck.dbg, 0, 1) == 0) {
         ck.dbg[1] = kind; ck.dbg[2] = pair; ck.dbg[3] = iter; ck.dbg[4] = seen; ck.dbg[5] = need; ck.dbg[6] = (int)ticket;
@@ -1465,7 +1544,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 3) k_loop(const Chunk ck, int ti
         unsigned long long* accp = ck.acc + (size_t)pair * ck.ncell * NQ;
         if (tile == 0) TL(6);
         if (ck.dump_on && iter == 3 && tile < 2048 && lane == 0) ck.dump.tl[(size_t)ck.runlen * 16 + 2 * tile] = gtime();
-        pass_warp_tile<true, K>(ck, went, tab, recs, tr, ck.pog + (size_t)pair * 3 * ck.n2max, (size_t)ck.n2max, n, w0,
+        pass_warp_tile<true, K, 2, (K <= 4 ? K : 1)>(ck, went, tab, recs, tr, ck.pog + (size_t)pair * 3 * ck.n2max, (size_t)ck.n2max, n, w0,
                                 accp, (ck.dump_on && iter == 3 && tile < 2048) ? ck.dump.tl + (size_t)ck.runlen * 16 + 4096 + tile : nullptr);
         if (tile == 0 && lane == 0)
           pass_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 2,
@@ -1889,7 +1968,7 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
     LAUNCH(3, k_cluster<<<dim3(gx, P), CLUSTER_WARPS * 32, 0, st>>>(ck));
     if (small_batch) {  // latency shape: 128 points per warp
       const int tile_s = pass_tile_points(PASS_K_SMALL);
-      LAUNCH(4, k_pass<false, PASS_K_SMALL, 3, 1><<<dim3((n1max + tile_s - 1) / tile_s, P), PASS_THREADS, psm2, st>>>(ck));
+      LAUNCH(4, k_pass<false, PASS_K_SMALL, 3, 1, PASS_K_SMALL><<<dim3((n1max + tile_s - 1) / tile_s, P), PASS_THREADS, psm2, st>>>(ck));
     } else {
       LAUNCH(4, k_pass<false><<<gp1, PASS_THREADS, psm, st>>>(ck));
     }

@@ -127,6 +127,18 @@ __device__ __forceinline__ int bin_lookup(float a, const BinTable& t, double per
 }
 
 // utils::R, reference src/utils.cpp:144-152 (row-major, fp32 trig on fp32 angles)
+// (the _sc forms take the six sines / cosines: the warp-parallel solve evaluates them once, on three lanes)
+__device__ __forceinline__ void rotR_sc(float sph, float cph, float sth, float cth, float sps, float cps, float* R) {
+  R[0] = cth * cps;
+  R[1] = sps * cph + sph * sth * cps;
+  R[2] = sph * sps - sth * cph * cps;
+  R[3] = -sps * cth;
+  R[4] = cph * cps - sph * sth * sps;
+  R[5] = sph * cps + sth * sps * cph;
+  R[6] = sth;
+  R[7] = -sph * cth;
+  R[8] = cph * cth;
+}
 __device__ inline void rotR(float phi, float theta, float psi, float* R) {
   float sph, cph, sth, cth, sps, cps;
   sincosf(phi, &sph, &cph);
@@ -154,6 +166,20 @@ __device__ __forceinline__ void transform(float px, float py, float pz, const fl
 
 // The three 3x3 derivative matrices of ICET::get_H, reference src/icet.cpp:507-527 (fp32 trig),
 // J = [Jx | Jy | Jz], each row-major.
+__device__ __forceinline__ void getH_J_sc(float sph, float cph, float sth, float cth, float sps, float cps, float* J) {
+  float* Jx = J;
+  float* Jy = J + 9;
+  float* Jz = J + 18;
+  Jx[0] = 0.f; Jx[1] = (-sps * sph + cph * sth * cps); Jx[2] = (cph * sps + sth * sph * cps);
+  Jx[3] = 0.f; Jx[4] = (-sph * cps - cph * sth * sps); Jx[5] = (cph * cps - sth * sps * sph);
+  Jx[6] = 0.f; Jx[7] = (-cph * cth);                   Jx[8] = (-sph * cth);
+  Jy[0] = (-sth * cps); Jy[1] = (cth * sph * cps);  Jy[2] = (-cth * cph * cps);
+  Jy[3] = (sps * sth);  Jy[4] = (-cth * sph * sps); Jy[5] = (cth * sps * cph);
+  Jy[6] = (cth);        Jy[7] = (sph * sth);        Jy[8] = (-sth * cph);
+  Jz[0] = (-cth * sps); Jz[1] = (cps * cph - sph * sth * sps);  Jz[2] = (cps * sph + sth * cph * sps);
+  Jz[3] = (-cps * cth); Jz[4] = (-sps * cph - sph * sth * cps); Jz[5] = (-sph * sps + sth * cps * cph);
+  Jz[6] = 0.f; Jz[7] = 0.f; Jz[8] = 0.f;
+}
 __device__ inline void getH_J(float phi, float theta, float psi, float* J) {
   float sph, cph, sth, cth, sps, cps;
   sincosf(phi, &sph, &cph);
