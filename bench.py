@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-callers", action="store_true", help="skip the odometry / map-maker node measurements")
     ap.add_argument("--lanes", type=int, default=0, help="compute lanes (0 = default 2)")
+    ap.add_argument("--chunk", type=int, default=0, help="pairs per chunk of the device-resident path (0 = default)")
     ap.add_argument("--host-chunk", type=int, default=0, help="pairs per chunk of the host-buffer pipeline (0 = default)")
     ap.add_argument("--unfused", action="store_true", help="diagnostic: 3 launches per iteration instead of k_loop")
     ap.add_argument("--persistent", action="store_true", help="diagnostic: the persistent loop kernel for every chunk")
@@ -257,6 +258,8 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     if args.host_chunk:
         ctx.set_host_chunk(args.host_chunk)
+    if args.chunk:
+        ctx.set_chunk(args.chunk)
     if args.lanes:
         ctx.set_lanes(args.lanes)
     params = api.make_params(RUNLEN, BINS_PHI, BINS_THETA, NMIN, THRESH, BUFF,

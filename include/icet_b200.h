@@ -130,8 +130,8 @@ int icet_b200_register_sequence_device(icet_b200_ctx* ctx, const icet_b200_param
                                        const float* scans, int32_t n, icet_b200_result* out);
 
 int icet_b200_synchronize(icet_b200_ctx* ctx);
-/* Number of compute lanes (streams with their own workspace) consecutive chunks alternate between: 1 or 2
- * (0 = default 2). */
+/* Number of compute lanes (streams with their own workspace) consecutive chunks rotate over: 1 .. 4
+ * (0 = default 4). */
 int icet_b200_set_lanes(icet_b200_ctx* ctx, int32_t lanes);
 
 /* -- per-voxel state of the most recent single-pair call (icet_b200_register) ------------------
