@@ -2605,7 +2605,7 @@ int icet_b200_synth_scans_device(icet_b200_ctx* c, uint64_t seed, int32_t first_
   for (int k = 0; k < first_scan + nscans; k++) {
     if (k >= first_scan) poses[k - first_scan] = P;
     double d[6];
-    synth::step_motion(seed, k, d);
+    synth::drive_step(seed, k, P, d);
     synth::advance(P, d);
   }
   int rc = c->posebuf.ensure(poses.size() * sizeof(synth::Pose));

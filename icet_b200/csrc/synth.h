@@ -68,6 +68,20 @@ SYNTH_HD inline void advance(Pose& P, const double d[6]) {
       Rn[3 * i + j] = P.R[3 * i] * Rs[j] + P.R[3 * i + 1] * Rs[3 + j] + P.R[3 * i + 2] * Rs[6 + j];
   for (int i = 0; i < 9; i++) P.R[i] = Rn[i];
 }
+// The driver: the random step of scan k plus a gentle correction towards the lane (y = 0, level, heading along +x),
+// so that the trajectory stays inside the street for sequences of any length (a pure random walk of the heading and
+// of the pitch leaves the canyon -- and the ground -- after a few hundred scans and the returns disappear).  The
+// corrections are a fraction of the random terms per step; the pose of scan k stays a pure function of (seed, k).
+SYNTH_HD inline void drive_step(uint64_t seed, int k, const Pose& P, double d[6]) {
+  step_motion(seed, k, d);
+  const double yaw = atan2(P.R[3], P.R[0]);
+  const double pitch = -asin(P.R[6] > 1.0 ? 1.0 : (P.R[6] < -1.0 ? -1.0 : P.R[6]));
+  const double roll = atan2(P.R[7], P.R[8]);
+  d[5] += 0.15 * (-0.03 * P.t[1] - yaw);   // steer back to the lane centre
+  d[4] += 0.15 * (-pitch);
+  d[3] += 0.15 * (-roll);
+  d[2] += 0.05 * (-P.t[2]);                // suspension: the sensor height stays near its nominal value
+}
 SYNTH_HD inline void pose_identity(Pose& P) {
   for (int i = 0; i < 9; i++) P.R[i] = (i % 4 == 0) ? 1.0 : 0.0;
   P.t[0] = P.t[1] = P.t[2] = 0.0;

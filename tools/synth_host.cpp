@@ -16,7 +16,7 @@ extern "C" int synth_host_scans(uint64_t seed, int first_scan, int nscans, int r
   for (int k = 0; k < first_scan + nscans; k++) {
     if (k >= first_scan) poses[k - first_scan] = P;
     double d[6];
-    synth::step_motion(seed, k, d);
+    synth::drive_step(seed, k, P, d);
     synth::advance(P, d);
   }
   const int npts = rings * azim;
@@ -39,4 +39,13 @@ extern "C" int synth_host_scans(uint64_t seed, int first_scan, int nscans, int r
 }
 
 // relative motion between consecutive scans k -> k+1 as the generator defines it (dx dy dz roll pitch yaw)
-extern "C" void synth_host_motion(uint64_t seed, int k, double d[6]) { synth::step_motion(seed, k, d); }
+extern "C" void synth_host_motion(uint64_t seed, int k, double d[6]) {
+  synth::Pose P;
+  synth::pose_identity(P);
+  double e[6];
+  for (int j = 0; j < k; j++) {
+    synth::drive_step(seed, j, P, e);
+    synth::advance(P, e);
+  }
+  synth::drive_step(seed, k, P, d);
+}
