@@ -85,6 +85,8 @@ struct Chunk {  // everything a kernel needs, passed by value
   // scan 1
   int32_t* cellid1;  // [P][n1max]
   float* r1;         // [P][n1max]
+  float* th1;        // [P][n1max]  theta, phi of scan 1 (K1 -> K3: the second pass over scan 1 does not redo the
+  float* ph1;        // [P][n1max]  spherical conversion)
   float* rbuf;       // [P][n1max]  non-zero ranges grouped by cell
   int32_t* cnt1;     // [P][ncell]
   int32_t* cntz;     // [P][ncell]  zero-range points
@@ -155,6 +157,9 @@ __device__ __forceinline__ void cell_of(const Chunk& ck, float th, float ph, int
 // K1: scan 1 -> spherical, cell index, per-cell histogram.
 // utils::cartesianToSpherical (src/utils.cpp:93-119) + sortSphericalCoordinates (src/icet.cpp:534-554)
 // ----------------------------------------------------------------------------------------------
+constexpr int32_t CELL_INBOX = 0x40000000;  // cellid1 flag: the point passes the fp32 az / el box test of its own bin
+__device__ __forceinline__ int bin_box(float a, const float4* rec, const icet::BinTable& bt, bool& inbox);
+
 __global__ void __launch_bounds__(256) k_scan1_bin(const Chunk ck) {
   const int pair = blockIdx.y;
   const PairDesc d = ck.desc[pair];
@@ -166,12 +171,19 @@ __global__ void __launch_bounds__(256) k_scan1_bin(const Chunk ck) {
     float x = __ldg(d.s1 + i), y = __ldg(d.s1 + d.ld1 + i), z = __ldg(d.s1 + 2 * (size_t)d.ld1 + i);
     float r, th, ph;
     icet::c2s(x, y, z, r, th, ph);
-    int bt, bp;
-    cell_of(ck, th, ph, bt, bp);
+    // bin and box test in one look-up (same records as the pass kernels, read through L1 here)
+    const float4* tth = reinterpret_cast<const float4*>(ck.binrec);
+    const float4* tph = tth + ck.nT + 2;
+    bool bt_in, bp_in;
+    const int bt = bin_box(th, tth, ck.bth, bt_in);
+    const int bp = bin_box(ph, tph, ck.bph, bp_in);
     cell = ck.nT * bp + bt;
     zero = (r == 0.0f);
-    ck.cellid1[(size_t)pair * ck.n1max + i] = cell;
-    ck.r1[(size_t)pair * ck.n1max + i] = r;
+    const size_t o = (size_t)pair * ck.n1max + i;
+    ck.cellid1[o] = cell | ((bt_in && bp_in) ? CELL_INBOX : 0);
+    ck.r1[o] = r;
+    ck.th1[o] = th;
+    ck.ph1[o] = ph;
   }
   // warp-aggregated histogram
   const int lane = threadIdx.x & 31;
@@ -270,7 +282,7 @@ __global__ void __launch_bounds__(256) k_scatter(const Chunk ck) {
   float r = 0.f;
   if (i < d.n1) {
     r = ck.r1[(size_t)pair * ck.n1max + i];
-    if (r != 0.0f) cell = ck.cellid1[(size_t)pair * ck.n1max + i];
+    if (r != 0.0f) cell = ck.cellid1[(size_t)pair * ck.n1max + i] & ~CELL_INBOX;
   }
   const int lane = threadIdx.x & 31;
   const unsigned act = __ballot_sync(FULL, cell >= 0);
@@ -621,14 +633,48 @@ template <bool SCAN2, int K, int PF = 2, int G = 1>
 __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* the warp's pass_wslots(K) slots */,
                                                const float* tab, const CellRec* recs, const float* tr,
                                                const float* px_, size_t ld, int n, int w0,
-                                               unsigned long long* accp, unsigned long long* dbg_stamp = nullptr) {
+                                               unsigned long long* accp, unsigned long long* dbg_stamp = nullptr,
+                                               const int32_t* s1_cell = nullptr, const float* s1_th = nullptr,
+                                               const float* s1_ph = nullptr) {
   const int lane = threadIdx.x & 31;
   if (w0 >= n) return;
   const float4* tth = reinterpret_cast<const float4*>(tab);
   const float4* tph = tth + ck.nT + 2;
   const unsigned lt = (1u << lane) - 1u;
   int nin_tile = 0;
-  if (G > 1) {
+  if (!SCAN2) {
+    // ---- phase A, scan 1: K1 already stored cell (+ box flag), r, theta, phi of every point; only the range test
+    // against the cluster bounds (known since K2c) is left.  px_ = r1 of the pair; th / ph are read for inside points.
+    // Rows in groups of R: every load of the group is requested before the first use, so that the only dependent
+    // look-up left (the cell record) overlaps across the rows of the group.
+    constexpr int R = (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1);
+#pragma unroll 1
+    for (int j0 = 0; j0 < K; j0 += R) {
+      int cid[R];
+      float rr[R], tt[R], pp[R];
+#pragma unroll
+      for (int g = 0; g < R; g++) {
+        const int i = w0 + (j0 + g) * 32 + lane;
+        cid[g] = -1; rr[g] = 0.f; tt[g] = 0.f; pp[g] = 0.f;
+        if (i < n) { cid[g] = __ldg(s1_cell + i); rr[g] = __ldg(px_ + i); tt[g] = __ldg(s1_th + i); pp[g] = __ldg(s1_ph + i); }
+      }
+      float4 ra[R];
+#pragma unroll
+      for (int g = 0; g < R; g++) {
+        ra[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cid[g] >= 0) ra[g] = __ldg(reinterpret_cast<const float4*>(recs + (cid[g] & ~CELL_INBOX)));  // inner, outer, flags, scale
+      }
+#pragma unroll
+      for (int g = 0; g < R; g++) {
+        const bool in = cid[g] >= 0 && (cid[g] & CELL_INBOX) && (__float_as_uint(ra[g].z) & F_STAT1) && rr[g] >= ra[g].x &&
+                        rr[g] <= ra[g].y;
+        const unsigned im = __ballot_sync(FULL, in);
+        if (in)
+          went[nin_tile + __popc(im & lt)] = make_int4(cid[g] & ~CELL_INBOX, __float_as_int(rr[g]), __float_as_int(tt[g]), __float_as_int(pp[g]));
+        nin_tile += __popc(im);
+      }
+    }
+  } else if (G > 1) {
     static_assert(G == 1 || K % G == 0, "rows per group must divide the tile");
     // ---- phase A, grouped: all coordinates of the group in flight, then G stage-1 chains, then the bookkeeping
 #pragma unroll 1
@@ -765,13 +811,15 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass(const Chunk ck) {
     tr[0] = a.x; tr[1] = a.y; tr[2] = a.z; tr[3] = a.w; tr[4] = b.x; tr[5] = b.y; tr[6] = b.z; tr[7] = b.w;
     tr[8] = c.x; tr[9] = c.y; tr[10] = c.z; tr[11] = c.w;
   }
-  const float* px_ = SCAN2 ? ck.pog + (size_t)pair * 3 * ck.n2max : d.s1;
+  const size_t o1 = (size_t)pair * ck.n1max;
+  const float* px_ = SCAN2 ? ck.pog + (size_t)pair * 3 * ck.n2max : ck.r1 + o1;
   const size_t ld = SCAN2 ? (size_t)ck.n2max : (size_t)d.ld1;
   const CellRec* recs = ck.rec + (size_t)pair * ck.ncell;
   unsigned long long* accp = ck.acc + (size_t)pair * ck.ncell * NQ;
   __syncthreads();
   pass_warp_tile<SCAN2, K, PF, G>(ck, ent + (threadIdx.x >> 5) * pass_wslots(K), tab, recs, tr, px_, ld, n,
-                           tile0 + (threadIdx.x >> 5) * 32 * K, accp);
+                           tile0 + (threadIdx.x >> 5) * 32 * K, accp, nullptr, SCAN2 ? nullptr : ck.cellid1 + o1,
+                           SCAN2 ? nullptr : ck.th1 + o1, SCAN2 ? nullptr : ck.ph1 + o1);
   if (SCAN2 && blockIdx.x == 0 && threadIdx.x == 0)
     pass_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 2, recs, tr,
                          accp, ck.nz2[pair]);
@@ -1730,7 +1778,7 @@ struct icet_b200_ctx {
   // the most recent single-pair chunk (for icet_b200_get_points2)
   bool last_valid = false;
   int last_n2 = 0, last_runlen = 0;
-  char last_ck[512];
+  char last_ck[640];
 };
 
 namespace {
@@ -1774,6 +1822,8 @@ size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runle
   ck.vox = c.take<Vox1>((size_t)P * ncell);
   ck.cellid1 = c.take<int32_t>((size_t)P * n1max);
   ck.r1 = c.take<float>((size_t)P * n1max);
+  ck.th1 = c.take<float>((size_t)P * n1max);
+  ck.ph1 = c.take<float>((size_t)P * n1max);
   ck.rbuf = c.take<float>((size_t)P * n1max);
   ck.pog = c.take<float>((size_t)P * 3 * n2max);
   ck.X = c.take<float>((size_t)P * 6);
@@ -1996,7 +2046,7 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   }
 #undef LAUNCH
   CK(cudaGetLastError());
-  static_assert(sizeof(Chunk) <= 512, "Chunk too large for last_ck");
+  static_assert(sizeof(Chunk) <= 640, "Chunk too large for last_ck");
   ctx->last_valid = (P == 1);
   if (P == 1) memcpy(ctx->last_ck, &ck, sizeof(Chunk));
   return 0;
