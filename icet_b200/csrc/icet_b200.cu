@@ -928,10 +928,22 @@ __global__ void __launch_bounds__(256) k_prep2(const Chunk ck) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   float x = 0.f, y = 0.f, z = 0.f;
   bool keep = false, zero = false;
+  // Consecutive pairs of a sequence share a scan: scan 2 of this pair is scan 1 of the next one, whose spherical
+  // coordinates K1 has already stored (same function, same inputs) -- read them instead of converting again.
+  bool shared = false;
+  if (pair + 1 < ck.npairs) {
+    const PairDesc nx = ck.desc[pair + 1];
+    shared = nx.s1 == d.s2 && nx.n1 == d.n2 && nx.ld1 == d.ld2;
+  }
   if (i < d.n2) {
-    x = __ldg(d.s2 + i); y = __ldg(d.s2 + d.ld2 + i); z = __ldg(d.s2 + 2 * (size_t)d.ld2 + i);
     float r, th, ph;
-    icet::c2s(x, y, z, r, th, ph);
+    if (shared) {
+      const size_t o = (size_t)(pair + 1) * ck.n1max + i;
+      r = __ldg(ck.r1 + o); th = __ldg(ck.th1 + o); ph = __ldg(ck.ph1 + o);
+    } else {
+      x = __ldg(d.s2 + i); y = __ldg(d.s2 + d.ld2 + i); z = __ldg(d.s2 + 2 * (size_t)d.ld2 + i);
+      icet::c2s(x, y, z, r, th, ph);
+    }
     icet::s2c(r, th, ph, x, y, z);
     // Dropped returns: (0,0,0) stays (+0,+0,+0).  They are all the same point in every iteration, so they are
     // counted here and evaluated once per iteration by k_pass<true> instead of being stored.
