@@ -1749,6 +1749,7 @@ struct icet_b200_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaStream_t lanes[ICET_NLANE] = {};  // compute lanes 1.. (lane 0 is `stream`)
   cudaEvent_t ev_fork = nullptr, ev_join[ICET_NLANE] = {};
+  cudaEvent_t ev_aux[2] = {};  // single-pair chunks: prepScan2 runs beside the scan-1 kernels on lane 1
   int nlanes_default = 4;
   int nlanes = 4;
   cudaEvent_t ev_copy[ICET_NSLOT] = {};
@@ -2021,6 +2022,15 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
     if (e1_) cudaEventRecord(e1_, st);                                    \
     ctx->launches++;                                                      \
   } while (0)
+  // Latency shape (one pair): prepScan2 does not depend on the scan-1 kernels, so it runs beside them on lane 1.
+  const bool prep_aside = P == 1 && n2max > 0 && lane == 0 && !ctx->profile_on && ctx->lanes[1] != nullptr;
+  if (prep_aside) {
+    CK(cudaEventRecord(ctx->ev_aux[0], st));  // after the workspace has been cleared and the descriptor uploaded
+    CK(cudaStreamWaitEvent(ctx->lanes[1], ctx->ev_aux[0], 0));
+    k_prep2<<<g2, 256, 0, ctx->lanes[1]>>>(ck);
+    ctx->launches++;
+    CK(cudaEventRecord(ctx->ev_aux[1], ctx->lanes[1]));
+  }
   if (n1max > 0) LAUNCH(0, k_scan1_bin<<<g1, 256, 0, st>>>(ck));
   LAUNCH(1, k_cell_scan<<<P, 256, 0, st>>>(ck));
   if (n1max > 0) {
@@ -2037,7 +2047,8 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
     }
   }
   LAUNCH(5, k_fit1<<<dim3((ncell + 127) / 128, P), 128, 0, st>>>(ck));
-  if (n2max > 0) LAUNCH(6, k_prep2<<<g2, 256, 0, st>>>(ck));
+  if (prep_aside) CK(cudaStreamWaitEvent(st, ctx->ev_aux[1], 0));
+  else if (n2max > 0) LAUNCH(6, k_prep2<<<g2, 256, 0, st>>>(ck));
   const bool use_loop = chain || (p->flags & ICET_B200_FLAG_PERSISTENT_LOOP) ||
                         (!(p->flags & ICET_B200_FLAG_UNFUSED_LOOP) && P <= ICET_LOOP_MAX_PAIRS);
   if (!use_loop) {
@@ -2155,6 +2166,7 @@ int icet_b200_create(int device, icet_b200_ctx** out) {
     CK(cudaEventCreateWithFlags(&c->ev_join[l], cudaEventDisableTiming));
   }
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  for (int k = 0; k < 2; k++) CK(cudaEventCreateWithFlags(&c->ev_aux[k], cudaEventDisableTiming));
   for (int i = 0; i < ICET_NSLOT; i++) {
     CK(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
@@ -2187,6 +2199,8 @@ int icet_b200_destroy(icet_b200_ctx* c) {
     if (c->ev_join[l]) cudaEventDestroy(c->ev_join[l]);
   }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  for (int k = 0; k < 2; k++)
+    if (c->ev_aux[k]) cudaEventDestroy(c->ev_aux[k]);
   delete c;
   return 0;
 }

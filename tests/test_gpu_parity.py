@@ -461,3 +461,42 @@ def test_cpp_class_dropin_demo(ctx, po, frame_pair, tmp_path):
     inv = np.argsort(o.perm2)
     np.testing.assert_allclose(p2, o.points2_final[:, inv], atol=5e-5)
     assert "ellipsoids 336" in out.stdout and "clusterBounds 1800x6" in out.stdout
+
+
+def test_chained_batch_equals_seeded_single_calls(ctx):
+    """ICET_B200_FLAG_CHAIN_X0 (odometry.cpp:82 done on the device): a batch whose pair k+1 starts from the solution of
+    pair k -- one persistent kernel per chunk, the seed crossing chunk boundaries in device memory -- is bit-identical
+    to blocking single-pair calls seeded by hand, for host and for device buffers."""
+    import torch
+    from icet_b200 import api
+    from tools import synth_host
+    ns = 8
+    scans = synth_host.scans(ns, first_scan=40, seed=20240, rings=64, azim=2048)
+    x = np.array([0.3, 0.0, 0.0, 0.0, 0.0, 0.01], np.float32)   # a seed for pair 0
+    x0 = x.copy()
+    seq = []
+    for k in range(ns - 1):
+        r = ctx.register(scans[k], scans[k + 1], x)
+        x = r["X"].copy()
+        seq.append(r.copy())
+    pc = api.make_params(flags=api.FLAG_CHAIN_X0)
+    s1, s2 = [scans[k] for k in range(ns - 1)], [scans[k + 1] for k in range(ns - 1)]
+    try:
+        ctx.set_chunk(3)
+        out = ctx.register_batch(s1, s2, x0, pc)
+    finally:
+        ctx.set_chunk(0)
+    for k in range(ns - 1):
+        assert out[k]["X"].tobytes() == seq[k]["X"].tobytes(), k
+        assert out[k]["Q"].tobytes() == seq[k]["Q"].tobytes(), k
+    dev = torch.from_numpy(scans).cuda()
+    res = torch.zeros((ns - 1, 56), dtype=torch.float32, device="cuda")
+    xs = torch.from_numpy(x0).cuda()
+    n = scans.shape[2]
+    ptr, stride = dev.data_ptr(), 3 * n * 4
+    nn = np.full(ns - 1, n, np.int32)
+    ctx.register_batch_ptrs([ptr + k * stride for k in range(ns - 1)], nn, [ptr + (k + 1) * stride for k in range(ns - 1)],
+                            nn, res.data_ptr(), x0_ptr=xs.data_ptr(), params=pc, device=True)
+    ctx.synchronize()
+    d = res.cpu().numpy().view(api.RESULT_DTYPE).reshape(-1)
+    assert d["X"].tobytes() == out["X"].tobytes()
