@@ -476,11 +476,19 @@ __global__ void __launch_bounds__(CLUSTER_WARPS * 32) k_cluster(const Chunk ck) 
     if (lane == 0) write_cluster_rec(ck, pair, cell, cnt, inner, outer);
     __syncwarp();
   }
-  // The rare big cells (more than WSORT_MAX ranges, e.g. an accumulated map as scan 1; k_cell_scan counted them):
-  // the whole CTA per cell, bitonic network in shared memory (<= SORT_SMEM ranges) or in L2.
+  // The big cells (more than WSORT_MAX ranges: an accumulated map as scan 1; k_cell_scan counted them), the whole CTA per
+  // cell.  findCluster only needs to know where consecutive SORTED ranges are more than `thresh` apart, so no sort:
+  // the ranges are dropped into buckets half a threshold wide (count, min, max per bucket; ranges inside one bucket
+  // are closer than the threshold by construction), windows of NBKT buckets are walked in ascending order, and the
+  // walk stops at the first run that qualifies.  O(m) per window instead of the O(m log^2 m) of a bitonic network
+  // (a 2 M-point map: 217 ms -> well under 1 ms).  Fallback for thresholds / ranges the buckets cannot cover: sort.
   if (ck.nbig[pair] == 0) return;  // block-uniform
   __syncthreads();
-  float* s_r = s_all;
+  constexpr int NBKT = (SM_FLOATS - 8) / 3;
+  int* b_cnt = reinterpret_cast<int*>(s_all);
+  int* b_min = b_cnt + NBKT;
+  int* b_max = b_min + NBKT;
+  int* s_ctl = b_max + NBKT;  // [0] points seen so far, [1] done, [2..3] result bits
   for (int w = blockIdx.x; w < nw; w += gridDim.x) {
     const int cell = ck.work[(size_t)pair * ck.ncell + w];
     const int cnt = ck.cnt1[(size_t)pair * ck.ncell + cell];
@@ -488,16 +496,97 @@ __global__ void __launch_bounds__(CLUSTER_WARPS * 32) k_cluster(const Chunk ck) 
     const int m = cnt - nz;
     if (m <= WSORT_MAX) continue;  // block-uniform
     float* g = ck.rbuf + (size_t)pair * ck.n1max + ck.off[(size_t)pair * ck.ncell + cell];
-    float inner, outer;
-    if (m <= SORT_SMEM) {
-      for (int i = threadIdx.x; i < m; i += blockDim.x) s_r[i] = g[i];
+    // largest range of the cell (the ranges are >= 0: their bit patterns order like the values)
+    __syncthreads();
+    if (threadIdx.x == 0) s_ctl[0] = 0;
+    __syncthreads();
+    {
+      int mx = 0;
+      for (int i = threadIdx.x; i < m; i += blockDim.x) mx = max(mx, __float_as_int(g[i]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+      if (lane == 0) atomicMax(&s_ctl[0], mx);
+    }
+    __syncthreads();
+    const float rmax = __int_as_float(s_ctl[0]);
+    const float wdt = 0.5f * ck.thresh, inv_w = 1.0f / wdt;
+    const bool buckets_ok = ck.thresh > 1e-6f && rmax * inv_w < 64.0f * NBKT;  // false for inf / NaN as well
+    float inner = 0.f, outer = 0.f;
+    if (buckets_ok) {
+      // state of the walk (warp 0, uniform across its lanes)
+      int idx = nz, start = 0;
+      float start_val = 0.f, prev_val = 0.f;
+      bool found = false;
       __syncthreads();
-      block_sort_asc(s_r, m);
-      if (threadIdx.x < 32) find_cluster_warp(s_r, m, nz, ck.n, ck.thresh, ck.buff, inner, outer);
+      if (threadIdx.x == 0) { s_ctl[0] = 0; s_ctl[1] = 0; }
+      for (int win = 0;; win++) {
+        for (int k = threadIdx.x; k < NBKT; k += blockDim.x) { b_cnt[k] = 0; b_min[k] = 0x7f800000; b_max[k] = 0; }
+        __syncthreads();
+        if (s_ctl[1]) break;  // found, or every range has been walked
+        const int lo = win * NBKT;
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+          const float r = g[i];
+          const int k = __float2int_rd(r * inv_w) - lo;
+          if (k >= 0 && k < NBKT) {
+            atomicAdd(&b_cnt[k], 1);
+            atomicMin(&b_min[k], __float_as_int(r));
+            atomicMax(&b_max[k], __float_as_int(r));
+          }
+        }
+        __syncthreads();
+        if (warp == 0) {
+          int seen = 0;
+          for (int base = 0; base < NBKT && !found; base += 32) {
+            const int k = base + lane;
+            const int c = k < NBKT ? b_cnt[k] : 0;
+            unsigned mask = __ballot_sync(FULL, c > 0);
+            while (mask && !found) {
+              const int kb = base + __ffs(mask) - 1;
+              mask &= mask - 1;
+              const int bc = b_cnt[kb];
+              const float mn = __int_as_float(b_min[kb]), mxv = __int_as_float(b_max[kb]);
+              if (idx > 0) {
+                if (!(fabsf(prev_val - mn) <= ck.thresh)) {  // a break in front of this bucket (reference :572)
+                  if (idx - start >= ck.n) {
+                    inner = start_val - ck.buff;             // :577-582, no zero check
+                    outer = prev_val + ck.buff;
+                    found = true;
+                    break;
+                  }
+                  start = idx;
+                  start_val = mn;
+                }
+              } else {
+                start_val = mn;
+              }
+              idx += bc;
+              seen += bc;
+              prev_val = mxv;
+            }
+          }
+          if (lane == 0) {
+            s_ctl[0] += seen;
+            if (found || s_ctl[0] >= m) s_ctl[1] = 1;
+          }
+        }
+        __syncthreads();
+      }
+      if (warp == 0 && !found && nz + m - start >= ck.n && start_val != 0.0f) {  // end of the data (:592-603)
+        inner = start_val - ck.buff;
+        outer = prev_val + ck.buff;
+      }
     } else {
-      __syncthreads();
-      block_sort_asc(g, m);
-      if (threadIdx.x < 32) find_cluster_warp(g, m, nz, ck.n, ck.thresh, ck.buff, inner, outer);
+      float* s_r = s_all;
+      if (m <= SORT_SMEM) {
+        for (int i = threadIdx.x; i < m; i += blockDim.x) s_r[i] = g[i];
+        __syncthreads();
+        block_sort_asc(s_r, m);
+        if (threadIdx.x < 32) find_cluster_warp(s_r, m, nz, ck.n, ck.thresh, ck.buff, inner, outer);
+      } else {
+        __syncthreads();
+        block_sort_asc(g, m);
+        if (threadIdx.x < 32) find_cluster_warp(g, m, nz, ck.n, ck.thresh, ck.buff, inner, outer);
+      }
     }
     if (threadIdx.x == 0) write_cluster_rec(ck, pair, cell, cnt, inner, outer);
     __syncthreads();

@@ -500,3 +500,25 @@ def test_chained_batch_equals_seeded_single_calls(ctx):
     ctx.synchronize()
     d = res.cpu().numpy().view(api.RESULT_DTYPE).reshape(-1)
     assert d["X"].tobytes() == out["X"].tobytes()
+
+
+def test_big_cells_bucket_clustering(ctx, po):
+    """Cells with thousands of ranges (an accumulated map as scan 1, coarse grids) take the bucket form of findCluster
+    (no sort: count / min / max per half-threshold bucket, walked in ascending order).  Cluster bounds must be
+    bit-identical to the oracle's sorted walk (src/icet.cpp:557-607), also for other thresholds, and the registration
+    within the usual tolerances."""
+    dev = synth_device(ctx, 3, first=60)
+    host = dev.cpu().numpy()
+    big = np.ascontiguousarray(np.concatenate([host[0], host[1]], axis=1))   # 262 144 points
+    for kw in (dict(bins_phi=8, bins_theta=20), dict(bins_phi=8, bins_theta=20, thresh=0.03, buff=0.2, n=40),
+               dict(bins_phi=12, bins_theta=30, thresh=0.5)):
+        p = params(**kw)
+        r, g = ctx.register(big, host[2], params=p, dump=True)
+        o = po.run(big, host[2], dumps="small", **kw)
+        m = g["cnt1"].max()
+        assert m > 4096, m                                 # beyond the shared-memory sort size of the fallback, too
+        np.testing.assert_array_equal(g["cnt1"], o.cnt1)
+        np.testing.assert_array_equal(g["bounds"], o.bounds)
+        np.testing.assert_array_equal(g["has1"], o.has1)
+        o2, o64, nbad = oracle_with_gpu_signs(po, big, host[2], g, o, **kw)
+        check_final(r, o2, o64)
