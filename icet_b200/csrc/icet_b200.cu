@@ -502,7 +502,16 @@ __global__ void __launch_bounds__(CLUSTER_WARPS * 32) k_cluster(const Chunk ck) 
     __syncthreads();
     {
       int mx = 0;
-      for (int i = threadIdx.x; i < m; i += blockDim.x) mx = max(mx, __float_as_int(g[i]));
+      for (int i0 = threadIdx.x; i0 < m; i0 += 8 * blockDim.x) {  // eight loads in flight per thread
+        int v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int i = i0 + u * blockDim.x;
+          v[u] = i < m ? __float_as_int(g[i]) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) mx = max(mx, v[u]);
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
       if (lane == 0) atomicMax(&s_ctl[0], mx);
@@ -524,13 +533,22 @@ __global__ void __launch_bounds__(CLUSTER_WARPS * 32) k_cluster(const Chunk ck) 
         __syncthreads();
         if (s_ctl[1]) break;  // found, or every range has been walked
         const int lo = win * NBKT;
-        for (int i = threadIdx.x; i < m; i += blockDim.x) {
-          const float r = g[i];
-          const int k = __float2int_rd(r * inv_w) - lo;
-          if (k >= 0 && k < NBKT) {
-            atomicAdd(&b_cnt[k], 1);
-            atomicMin(&b_min[k], __float_as_int(r));
-            atomicMax(&b_max[k], __float_as_int(r));
+        for (int i0 = threadIdx.x; i0 < m; i0 += 8 * blockDim.x) {  // eight loads in flight per thread
+          float rv[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int i = i0 + u * blockDim.x;
+            rv[u] = i < m ? g[i] : -1.0f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const float r = rv[u];
+            const int k = __float2int_rd(r * inv_w) - lo;
+            if (r >= 0.0f && k >= 0 && k < NBKT) {
+              atomicAdd(&b_cnt[k], 1);
+              atomicMin(&b_min[k], __float_as_int(r));
+              atomicMax(&b_max[k], __float_as_int(r));
+            }
           }
         }
         __syncthreads();
