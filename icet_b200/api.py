@@ -115,7 +115,8 @@ _LIB = None
 
 
 def lib_path() -> str:
-    return _build.LIB
+    """The in-tree library; ICET_B200_LIB overrides it (A/B runs of two builds on the same GPU box)."""
+    return os.environ.get("ICET_B200_LIB") or _build.LIB
 
 
 def load_library() -> C.CDLL:

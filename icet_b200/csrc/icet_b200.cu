@@ -620,8 +620,8 @@ __global__ void __launch_bounds__(CLUSTER_WARPS * 32) k_cluster(const Chunk ck) 
 constexpr int PASS_THREADS = 256;
 constexpr int PASS_WARPS = PASS_THREADS / 32;
 constexpr int PASS_K = 16;       // rows of 32 points per warp tile (throughput shape)
-constexpr int PASS_K_SMALL = 4;  // same for small batches (latency shape: more, smaller tiles; 2 rows measured slower:
-                                 // twice the same-address ticket / tiles_done atomics per iteration)
+constexpr int PASS_K_SMALL = 4;  // same for small batches (latency shape: more, smaller tiles; 2 rows: the same
+                                 // single-pair latency within 1 %, with twice the tasks)
 
 __host__ __device__ constexpr int pass_wslots(int K) { return 32 * K; }  // 16-byte entry slots per warp tile
 __host__ __device__ constexpr int pass_tile_points(int K) { return PASS_WARPS * 32 * K; }
@@ -1662,9 +1662,11 @@ __global__ void __launch_bounds__(PASS_THREADS, 3) k_loop(const Chunk ck, int ti
   if (lane == 0) t = atom_add(ck.ticket, 1u);
   t = __shfl_sync(FULL, t, 0);
   while (t < total) {
-    // the next ticket is drawn now; its round trip to L2 hides behind this task
+    // Throughput shape: the next ticket is drawn now, its round trip to L2 hides behind this task.  Latency shape
+    // (small tiles, more resident warps than tasks per iteration): one ticket per warp -- a warp that holds two
+    // tiles of the same iteration starts the second one a whole tile late, while idle warps could have taken it.
     unsigned t_next = 0;
-    if (lane == 0) t_next = atom_add(ck.ticket, 1u);
+    if (K > PASS_K_SMALL && lane == 0) t_next = atom_add(ck.ticket, 1u);
     // ticket -> task.  Independent pairs: iteration-major (see above).  Chained pairs (ICET_B200_FLAG_CHAIN_X0): pair-
     // major, i.e. all iterations of pair k before any task of pair k + 1, whose first tiles wait for the last solve
     // of pair k (it seeds X / TR / J of pair k + 1) -- still only waits on smaller tickets.
@@ -1726,6 +1728,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 3) k_loop(const Chunk ck, int ti
       // ------------------------------------------------------------------ vox task
       vox_task(ck, iter, pair_t, sub, 32 * K, vt, w_tot, w_J);
     }
+    if (K <= PASS_K_SMALL && lane == 0) t_next = atom_add(ck.ticket, 1u);
     t = __shfl_sync(FULL, t_next, 0);
   }
 }
