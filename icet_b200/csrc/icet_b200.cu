@@ -619,7 +619,8 @@ __global__ void __launch_bounds__(CLUSTER_WARPS * 32) k_cluster(const Chunk ck) 
 // ----------------------------------------------------------------------------------------------
 constexpr int PASS_THREADS = 256;
 constexpr int PASS_WARPS = PASS_THREADS / 32;
-constexpr int PASS_K = 16;       // rows of 32 points per warp tile (throughput shape)
+constexpr int PASS_K = 12;       // rows of 32 points per warp tile (throughput shape): 48 KB of entry tiles per CTA,
+constexpr int PASS_MINB = 4;     // so that four CTAs (32 warps, 64 registers per thread) fit an SM (r01g: +3 % over 16 / 3)
 constexpr int PASS_K_SMALL = 4;  // same for small batches (latency shape: more, smaller tiles; 2 rows: the same
                                  // single-pair latency within 1 %, with twice the tasks)
 
@@ -897,7 +898,7 @@ __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* th
   __syncwarp();
 }
 
-template <bool SCAN2, int K = PASS_K, int MINB = 3, int PF = 2, int G = 1>
+template <bool SCAN2, int K = PASS_K, int MINB = PASS_MINB, int PF = 2, int G = 1>
 __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass(const Chunk ck) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int4* ent = reinterpret_cast<int4*>(smem_raw);
@@ -2094,7 +2095,7 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   const int nblk = (ncell + VOX_THREADS - 1) / VOX_THREADS;
   // shape of the loop kernel: big tiles (16 points per lane) for throughput; small tiles (4 points per lane) when
   // the chunk has too few big tiles to keep every resident block busy for several rounds
-  // pass kernels of the split loop: 16 rows per warp tile, 3 blocks / SM, coordinates prefetched 2 rows ahead
+  // pass kernels of the split loop: 12 rows per warp tile, 4 blocks / SM, coordinates prefetched 2 rows ahead
   // (measured against 8 / 12 rows with 4-5 blocks and against no prefetch: profiles/r01_pass_variants.txt)
   const int tile1 = pass_tile_points(PASS_K);
   const dim3 gp1((n1max + tile1 - 1) / tile1, P), gp2((n2max + tile1 - 1) / tile1, P);
