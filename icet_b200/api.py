@@ -36,6 +36,7 @@ assert RESULT_DTYPE.itemsize == C.sizeof(Result) == 224
 FLAG_FULL_EIG = 1
 FLAG_UNFUSED_LOOP = 2
 FLAG_PERSISTENT_LOOP = 4
+FLAG_SHIPPED_ORDER = 16  # validation: cluster in the row order the reference's broken permutation loop leaves (single pair)
 FLAG_CHAIN_X0 = 8  # odometry.cpp:82: pair k+1 starts from the solution of pair k; X0 = one seed (pair 0)
 
 _DUMP_FIELDS = [("cnt1", _IP), ("bounds", _FP), ("nin1", _IP), ("has1", _BP), ("mu1", _FP), ("sigma1", _FP),
@@ -391,11 +392,14 @@ class ICET:
     """
 
     def __init__(self, scan1, scan2, runlen, X0, num_bins_phi, num_bins_theta, n=25, thresh=0.1, buff=0.1,
-                 ctx: Context | None = None, debug: bool = False):
+                 ctx: Context | None = None, debug: bool = False, shipped_row_order: bool = False):
         self.rl, self.numBinsPhi, self.numBinsTheta = runlen, num_bins_phi, num_bins_theta
         self.n, self.thresh, self.buff = n, thresh, buff
         ctx = ctx or default_context()
-        p = make_params(runlen, num_bins_phi, num_bins_theta, n, thresh, buff)
+        # shipped_row_order: cluster in the row order the reference's broken permutation loop leaves (validation
+        # against an unmodified reference build); default: the sorted order its comments intend
+        p = make_params(runlen, num_bins_phi, num_bins_theta, n, thresh, buff,
+                        flags=FLAG_SHIPPED_ORDER if shipped_row_order else 0)
         r = ctx.register(scan1, scan2, X0, p, dump=debug)
         if debug:
             r, self.debug = r

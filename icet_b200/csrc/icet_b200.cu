@@ -88,6 +88,8 @@ struct Chunk {  // everything a kernel needs, passed by value
   float* th1;        // [P][n1max]  theta, phi of scan 1 (K1 -> K3: the second pass over scan 1 does not redo the
   float* ph1;        // [P][n1max]  spherical conversion)
   float* rbuf;       // [P][n1max]  non-zero ranges grouped by cell
+  unsigned long long* kbuf;  // [n1max]  ICET_B200_FLAG_SHIPPED_ORDER: (row position << 32 | range bits) grouped by cell
+  int32_t* pos1;     // [n1max]  ... position of every row of scan 1 in the reference's shipped row order
   int32_t* cnt1;     // [P][ncell]
   int32_t* cntz;     // [P][ncell]  zero-range points
   int32_t* off;      // [P][ncell]
@@ -313,7 +315,8 @@ __device__ inline void block_sort_asc(Ptr a, int m) {
       int blk = t / (k / 2), o = t % (k / 2);
       int i = blk * k + o, j = blk * k + (k - 1 - o);
       if (j < m) {
-        float x = a[i], y = a[j];
+        auto x = a[i];
+        auto y = a[j];
         if (y < x) { a[i] = y; a[j] = x; }
       }
     }
@@ -322,7 +325,8 @@ __device__ inline void block_sort_asc(Ptr a, int m) {
       for (int t = threadIdx.x; t < p2 / 2; t += blockDim.x) {
         int i = (t / j2) * (2 * j2) + (t % j2), j = i + j2;
         if (j < m) {
-          float x = a[i], y = a[j];
+          auto x = a[i];
+          auto y = a[j];
           if (y < x) { a[i] = y; a[j] = x; }
         }
       }
@@ -607,6 +611,67 @@ __global__ void __launch_bounds__(CLUSTER_WARPS * 32) k_cluster(const Chunk ck) 
       }
     }
     if (threadIdx.x == 0) write_cluster_rec(ck, pair, cell, cnt, inner, outer);
+    __syncthreads();
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// ICET_B200_FLAG_SHIPPED_ORDER (single pair, validation): clustering in the row order the reference ends up with
+// after its broken permutation loop (src/icet.cpp:72-83); ck.pos1 holds that position for every row of scan 1.
+// Zero ranges are ordinary members of the sequence here.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_off_shipped(const Chunk ck) {  // offsets of ALL points per cell
+  const int pair = blockIdx.x;
+  __shared__ int s_part[256];
+  const int per = (ck.ncell + 255) / 256;
+  const int c0 = threadIdx.x * per, c1 = min(ck.ncell, c0 + per);
+  const int32_t* cnt1 = ck.cnt1 + (size_t)pair * ck.ncell;
+  int s = 0;
+  for (int c = c0; c < c1; c++) s += cnt1[c];
+  s_part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int a = 0;
+    for (int t = 0; t < 256; t++) { const int v = s_part[t]; s_part[t] = a; a += v; }
+  }
+  __syncthreads();
+  int a = s_part[threadIdx.x];
+  for (int c = c0; c < c1; c++) {
+    ck.off[(size_t)pair * ck.ncell + c] = a;
+    ck.cursor[(size_t)pair * ck.ncell + c] = 0;
+    a += cnt1[c];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_scatter_shipped(const Chunk ck) {
+  const int pair = blockIdx.y;
+  const PairDesc d = ck.desc[pair];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.n1) return;
+  const size_t o = (size_t)pair * ck.n1max + i;
+  const int cell = ck.cellid1[o] & ~CELL_INBOX;
+  const int slot = atomicAdd(&ck.cursor[(size_t)pair * ck.ncell + cell], 1);
+  const unsigned long long key = ((unsigned long long)(unsigned)ck.pos1[o] << 32) | (unsigned)__float_as_uint(ck.r1[o]);
+  ck.kbuf[(size_t)pair * ck.n1max + ck.off[(size_t)pair * ck.ncell + cell] + slot] = key;
+}
+
+struct KeyRanges {  // the ranges of a cell in row order: low words of the keys sorted by position
+  const unsigned long long* k;
+  __device__ __forceinline__ float operator[](int i) const { return __uint_as_float((unsigned)(k[i] & 0xffffffffull)); }
+};
+
+__global__ void __launch_bounds__(128) k_cluster_shipped(const Chunk ck) {
+  const int pair = blockIdx.y;
+  const int nw = ck.nwork[pair];
+  for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+    const int cell = ck.work[(size_t)pair * ck.ncell + w];
+    const int m = ck.cnt1[(size_t)pair * ck.ncell + cell];
+    unsigned long long* g = ck.kbuf + (size_t)pair * ck.n1max + ck.off[(size_t)pair * ck.ncell + cell];
+    __syncthreads();
+    block_sort_asc(g, m);  // by row position (the high word is unique)
+    float inner = 0.f, outer = 0.f;
+    if (threadIdx.x < 32) find_cluster_warp(KeyRanges{g}, m, 0, ck.n, ck.thresh, ck.buff, inner, outer);
+    if (threadIdx.x == 0) write_cluster_rec(ck, pair, cell, m, inner, outer);
     __syncthreads();
   }
 }
@@ -1921,7 +1986,8 @@ struct Carve {
 };
 
 // Layout of the chunk workspace.  The first region (cnt1, cntz, cursor, acc) must be zero at chunk start.
-size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runlen, Chunk& ck, size_t* zero_bytes) {
+size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runlen, Chunk& ck, size_t* zero_bytes,
+                   bool shipped = false) {
   const int vt = (ncell + 31) / 32;
   Carve c(base);
   ck.cnt1 = c.take<int32_t>((size_t)P * ncell);
@@ -1949,6 +2015,8 @@ size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runle
   ck.th1 = c.take<float>((size_t)P * n1max);
   ck.ph1 = c.take<float>((size_t)P * n1max);
   ck.rbuf = c.take<float>((size_t)P * n1max);
+  ck.kbuf = shipped ? c.take<unsigned long long>((size_t)P * n1max) : nullptr;
+  ck.pos1 = shipped ? c.take<int32_t>((size_t)P * n1max) : nullptr;
   ck.pog = c.take<float>((size_t)P * 3 * n2max);
   ck.X = c.take<float>((size_t)P * 6);
   ck.TR = c.take<float>((size_t)P * 12);
@@ -2076,10 +2144,13 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   Chunk ck;
   memset(&ck, 0, sizeof(ck));
   size_t zero_bytes = 0;
-  size_t need = carve_chunk(nullptr, P, ncell, n1max, n2max, p->runlen, ck, &zero_bytes);
+  const bool shipped = (p->flags & ICET_B200_FLAG_SHIPPED_ORDER) != 0;
+  if (shipped && P != 1)
+    return fail(ICET_B200_E_INVALID, "ICET_B200_FLAG_SHIPPED_ORDER is a single-pair validation mode");
+  size_t need = carve_chunk(nullptr, P, ncell, n1max, n2max, p->runlen, ck, &zero_bytes, shipped);
   rc = ctx->ws[lane].ensure(need);
   if (rc) return rc;
-  carve_chunk(ctx->ws[lane].p, P, ncell, n1max, n2max, p->runlen, ck, &zero_bytes);
+  carve_chunk(ctx->ws[lane].p, P, ncell, n1max, n2max, p->runlen, ck, &zero_bytes, shipped);
   ck.desc = d_desc;
   ck.npairs = P; ck.ncell = ncell; ck.nT = nT; ck.nP = nP; ck.n = p->n; ck.runlen = p->runlen;
   ck.flags = p->flags; ck.thresh = p->thresh; ck.buff = p->buff;
@@ -2145,11 +2216,36 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   if (n1max > 0) LAUNCH(0, k_scan1_bin<<<g1, 256, 0, st>>>(ck));
   LAUNCH(1, k_cell_scan<<<P, 256, 0, st>>>(ck));
   if (n1max > 0) {
+    if (shipped) {
+      // The row order the reference ends up with (src/icet.cpp:72-83), reproduced on the host from the ranges the
+      // device computed: the same index sort by range (std::sort; the reference's std::execution::par falls back
+      // to it without TBB) and the same swap loop, which is NOT a valid permutation application.
+      std::vector<float> hr((size_t)n1max);
+      CK(cudaMemcpyAsync(hr.data(), ck.r1, (size_t)n1max * sizeof(float), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      std::vector<int> index((size_t)n1max), orig((size_t)n1max), pos((size_t)n1max);
+      for (int i = 0; i < n1max; i++) index[i] = orig[i] = i;
+      std::sort(index.begin(), index.end(), [&](int a, int b) { return hr[a] < hr[b]; });
+      for (int i = 0; i < n1max; i++) {
+        if (index[i] != i) {
+          const int j = index[i];
+          std::swap(orig[i], orig[j]);    // points1Spherical.row(i).swap(points1Spherical.row(index[i]))
+          std::swap(index[i], index[j]);  // std::swap(index[i], index[index[i]])
+        }
+      }
+      for (int i = 0; i < n1max; i++) pos[orig[i]] = i;
+      CK(cudaMemcpyAsync(ck.pos1, pos.data(), (size_t)n1max * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+      LAUNCH(2, k_off_shipped<<<P, 256, 0, st>>>(ck));
+      LAUNCH(2, k_scatter_shipped<<<g1, 256, 0, st>>>(ck));
+      LAUNCH(3, k_cluster_shipped<<<dim3(std::max(1, std::min(ncell, 1024)), P), 128, 0, st>>>(ck));
+    } else {
     LAUNCH(2, k_scatter<<<g1, 256, 0, st>>>(ck));
     // one warp per listed cell; enough CTAs to cover a typical work list (~25 % of the cells) in one pass
     int gx = std::max(1, std::min((ncell + CLUSTER_WARPS - 1) / CLUSTER_WARPS,
                                   std::max(32, (ctx->sm_count * 16 + P - 1) / P)));
     LAUNCH(3, k_cluster<<<dim3(gx, P), CLUSTER_WARPS * 32, 0, st>>>(ck));
+    }
     if (small_batch) {  // latency shape: 128 points per warp
       const int tile_s = pass_tile_points(PASS_K_SMALL);
       LAUNCH(4, k_pass<false, PASS_K_SMALL, 3, 1, PASS_K_SMALL><<<dim3((n1max + tile_s - 1) / tile_s, P), PASS_THREADS, psm2, st>>>(ck));

@@ -10,6 +10,7 @@
 
 bool ICET::fillVisualization = true;
 int ICET::device = 0;
+bool ICET::shippedRowOrder = false;
 
 namespace {
 
@@ -50,6 +51,7 @@ ICET::ICET(Eigen::MatrixXf& scan1, Eigen::MatrixXf& scan2, int runlen, Eigen::Ve
   p.n = n_;
   p.thresh = thresh_;
   p.buff = buff_;
+  p.flags = shippedRowOrder ? ICET_B200_FLAG_SHIPPED_ORDER : 0;
   float x0[6];
   for (int k = 0; k < 6; k++) x0[k] = X0[k];
   icet_b200_result res;

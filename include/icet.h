@@ -76,6 +76,11 @@ class ICET {
   static bool fillVisualization;
   // CUDA device used by the calling thread's context (default 0).  Set before the first construction.
   static int device;
+  // false (default): findCluster sees each cell's points in ascending range order, which is what the reference's
+  // comments intend (src/icet.cpp:71).  true: in the row order the reference's permutation loop really leaves
+  // (src/icet.cpp:78-83 is not a valid permutation application) -- reproduces an unmodified reference build
+  // (several times fewer voxels get a Gaussian), at the price of one host round trip (ICET_B200_FLAG_SHIPPED_ORDER).
+  static bool shippedRowOrder;
 };
 
 #endif

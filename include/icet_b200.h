@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ICET_B200_VERSION 102
+#define ICET_B200_VERSION 103
 
 /* status codes (return values; also icet_b200_result.status for per-pair conditions) */
 enum {
@@ -63,7 +63,16 @@ enum {
   /* Odometry chaining (odometry.cpp:82 `X0 << X[0], X[1], ...`): the pairs of a batch / sequence call are
    * registered in order and pair k+1 starts from the solution of pair k.  `x0` then holds ONE seed (6 floats, pair 0)
    * or NULL.  Runs as the persistent kernel with pair-major task order; nothing returns to the host in between. */
-  ICET_B200_FLAG_CHAIN_X0 = 8
+  ICET_B200_FLAG_CHAIN_X0 = 8,
+  /* Compatibility / validation mode, single pair only (icet_b200_register, icet_b200_register_clouds): findCluster
+   * walks the points of each cell in the row order the reference ACTUALLY ends up with.  Its "radial sort"
+   * (src/icet.cpp:72-83) index-sorts by range and then applies the permutation with a loop that is not a valid
+   * permutation application, so the rows stay in a pseudo-random order; findCluster (:557-607) then finds far fewer
+   * clusters than the sorted order the comments intend (89 instead of 336 Gaussians on the bundled pair).  The default
+   * of this library is the intended, sorted order.  With this flag the host reproduces the shipped row order (the very
+   * same std::sort call and swap loop, on the ranges the device computed) and the device clusters in that order --
+   * slower (one host round trip), for checking results against an unmodified reference build. */
+  ICET_B200_FLAG_SHIPPED_ORDER = 16
 };
 
 /* per-pair result: the members callers of `class ICET` read (X: all four callers; pred_stds:

@@ -522,3 +522,40 @@ def test_big_cells_bucket_clustering(ctx, po):
         np.testing.assert_array_equal(g["has1"], o.has1)
         o2, o64, nbad = oracle_with_gpu_signs(po, big, host[2], g, o, **kw)
         check_final(r, o2, o64)
+
+
+@pytest.mark.parametrize("name", ["frame", "sample_pc"])
+def test_shipped_order_mode_matches_reference_as_shipped(ctx, po, name):
+    """ICET_B200_FLAG_SHIPPED_ORDER: clustering in the row order the reference's permutation loop really leaves
+    (src/icet.cpp:72-83 is not a valid permutation application).  Against the oracle in
+    REF_SHIPPED mode and the committed golden vectors of that mode: cell counts, cluster bounds and the set of
+    voxels with a Gaussian are bit-identical (far fewer than in the sorted order), the transform is within the usual
+    tolerances of the golden X whenever the registration is well conditioned."""
+    import os
+    from conftest import GOLDEN, load_pair
+    from icet_b200 import api
+    s1, s2 = load_pair(name)
+    p = params(flags=api.FLAG_SHIPPED_ORDER)
+    r, g = ctx.register(s1, s2, params=p, dump=True)
+    o = po.run(s1, s2, dumps="small", order_mode=1)
+    gold = np.load(os.path.join(GOLDEN, "golden_%s_shipped.npz" % name))
+    np.testing.assert_array_equal(g["cnt1"], o.cnt1)
+    np.testing.assert_array_equal(g["bounds"], o.bounds)
+    np.testing.assert_array_equal(g["bounds"], gold["bounds"])
+    np.testing.assert_array_equal(g["has1"], o.has1)
+    np.testing.assert_array_equal(g["has1"], gold["has1"])
+    has = o.has1 > 0
+    np.testing.assert_array_equal(g["nin1"][has], o.nin1[has])
+    # the sorted default finds several times as many clusters on the same pair
+    rs = ctx.register(s1, s2)
+    assert int(has.sum()) == r["n_gauss1"] < 0.5 * rs["n_gauss1"]
+    print("%s: Gaussians shipped order %d, sorted order %d" % (name, r["n_gauss1"], rs["n_gauss1"]))
+    ov = None
+    bad = unstable_voxels(g, o)
+    if bad.any():
+        ov = (g["evec1"], bad.astype(np.uint8))
+    o2 = po.run(s1, s2, dumps=None, order_mode=1, evec_override=ov)
+    assert np.abs(r["X"][:3] - o2.X[:3]).max() < TOL_M and np.abs(r["X"][3:] - o2.X[3:]).max() < TOL_RAD
+    # batches cannot use the mode
+    with pytest.raises(Exception):
+        ctx.register_batch([s1, s1], [s2, s2], None, p)
