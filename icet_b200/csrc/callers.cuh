@@ -114,6 +114,16 @@ __global__ void __launch_bounds__(FILT_THREADS) k_range_scatter(const FilterJob*
   if (blockIdx.x == (unsigned)ntile - 1 && threadIdx.x == 0) *j.kept = run;
 }
 
+// prev_pcl_matrix = pcl_matrix (odometry.cpp:89): the rows that exist (device-resident count), not the whole capacity
+__global__ void __launch_bounds__(256) k_copy_cloud(const float* src, float* dst, int ld, const int32_t* n_dev) {
+  const int n = min(*n_dev, ld);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    dst[i] = src[i];
+    dst[ld + i] = src[ld + i];
+    dst[2 * (size_t)ld + i] = src[2 * (size_t)ld + i];
+  }
+}
+
 // Pair descriptors of a sequence of filtered clouds held back to back: slot k at slots + k*3*cap, kept[k] rows.
 __global__ void k_seq_desc(PairDesc* desc, int npairs, const float* slots, int cap, const int32_t* kept) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;

@@ -151,8 +151,9 @@ int icet_b200_node_push_device(icet_b200_node* nd, int32_t nscans, const float* 
     nd->have_result = true;
   }
   // prev_pcl_matrix = pcl_matrix (odometry.cpp:89, simpleMapMaker.cpp:162)
-  CK(cudaMemcpyAsync(nd->prev.p, slots + (size_t)(nslots - 1) * 3 * cap, (size_t)3 * cap * sizeof(float),
-                     cudaMemcpyDeviceToDevice, st));
+  k_copy_cloud<<<std::max(1, std::min((cap + 255) / 256, c->sm_count * 4)), 256, 0, st>>>(
+      slots + (size_t)(nslots - 1) * 3 * cap, (float*)nd->prev.p, cap, kept + (nslots - 1));
+  c->launches++;
   CK(cudaMemcpyAsync(&stt->prev_n, kept + (nslots - 1), sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   CK(cudaGetLastError());
   nd->initialized = true;
