@@ -2,7 +2,7 @@
 // (include/icet_nodes.h): what `rosbag play` + odometry_node / map_maker_node do in the reference
 // (src/odometry.cpp, src/simpleMapMaker.cpp), printing what they would publish.
 //
-// usage: nodes_headless odometry|map points_per_scan file.f32 [map_size downsample]
+// usage: nodes_headless odometry|map|match points_per_scan file.f32 [map_size downsample]
 //   file.f32: consecutive scans, each the x | y | z planes of points_per_scan float32 values.
 #include <cstdio>
 #include <fstream>
@@ -24,13 +24,16 @@ int main(int argc, char** argv) {
   try {
     OdometryNode* odo = nullptr;
     MapMakerNode* mm = nullptr;
-    if (mode == "map") mm = new MapMakerNode((int)n, argc > 4 ? std::stoi(argv[4]) : 600000, argc > 5 ? std::stoi(argv[5]) : 2000);
+    ScanMatcherNode* sm = nullptr;
+    if (mode == "match") sm = new ScanMatcherNode((int)n);
+    else if (mode == "map") mm = new MapMakerNode((int)n, argc > 4 ? std::stoi(argv[4]) : 600000, argc > 5 ? std::stoi(argv[5]) : 2000);
     else odo = new OdometryNode((int)n);
+    if (sm) { delete odo; odo = nullptr; }
     for (long k = 0; k < nscans; k++) {
       Eigen::MatrixXf cloud(n, 3);
       f.read(reinterpret_cast<char*>(cloud.data()), n * 12);
       NodeOutput o;
-      const bool got = mm ? mm->pointcloudCallback(cloud, &o) : odo->pointcloudCallback(cloud, &o);
+      const bool got = sm ? sm->pointcloudCallback(cloud, &o) : (mm ? mm->pointcloudCallback(cloud, &o) : odo->pointcloudCallback(cloud, &o));
       if (!got) continue;
       std::printf("POSE %ld X [%.9g, %.9g, %.9g, %.9g, %.9g, %.9g] pos [%.9g, %.9g, %.9g] quat [%.9g, %.9g, %.9g, %.9g] "
                   "points %d guarded %d\n", k, o.X[0], o.X[1], o.X[2], o.X[3], o.X[4], o.X[5], o.position[0],
@@ -44,6 +47,11 @@ int main(int argc, char** argv) {
       std::printf("MAP rows %ld sum [%.9g, %.9g, %.9g] sample0 %d\n", (long)m.rows(), sx, sy, sz,
                   mm->lastSample.empty() ? -1 : mm->lastSample[0]);
     }
+    if (sm) {
+      const Eigen::MatrixXf& a = sm->scan2_in_scan1_frame;
+      std::printf("ALIGNED rows %ld first [%.9g, %.9g, %.9g] trail %ld\n", (long)a.rows(), a(0, 0), a(0, 1), a(0, 2), (long)sm->snailTrail.rows());
+    }
+    delete sm;
     delete mm;
     delete odo;
   } catch (const std::exception& e) {

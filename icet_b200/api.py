@@ -109,7 +109,8 @@ EXPORTS = ["icet_b200_version", "icet_b200_last_error", "icet_b200_create", "ice
            "icet_b200_node_create", "icet_b200_node_destroy", "icet_b200_node_push_device", "icet_b200_node_push",
            "icet_b200_node_current_scan", "icet_b200_node_last_result", "icet_b200_map_create",
            "icet_b200_map_destroy", "icet_b200_map_add_scan_device", "icet_b200_map_get", "icet_b200_map_get_device",
-           "icet_b200_ingest", "icet_b200_register_clouds", "icet_b200_node_push_cloud"]
+           "icet_b200_ingest", "icet_b200_register_clouds", "icet_b200_node_push_cloud",
+           "icet_b200_transform_cloud_device", "icet_b200_transform_cloud"]
 NKERNELS = 11
 
 _LIB = None
@@ -169,6 +170,8 @@ def load_library() -> C.CDLL:
                                                 C.c_float]
     L.icet_b200_map_get.argtypes = [vp, vp, C.c_int32, C.POINTER(C.c_int32)]
     L.icet_b200_map_get_device.argtypes = [vp, vp, C.c_int32, vp]
+    L.icet_b200_transform_cloud_device.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp, C.c_int32, vp, C.c_int32]
+    L.icet_b200_transform_cloud.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, C.c_int32, vp, C.c_int32]
     L.icet_b200_ingest.argtypes = [vp, C.POINTER(Cloud), vp, C.c_int32]
     L.icet_b200_register_clouds.argtypes = [vp, C.POINTER(Params), C.POINTER(Cloud), C.POINTER(Cloud), vp,
                                             C.POINTER(Result)]
@@ -278,6 +281,14 @@ class Context:
         self._check(self._L.icet_b200_register_clouds(self._h, C.byref(p), C.byref(c1), C.byref(c2), x0.ctypes.data,
                                                       C.byref(res)))
         return np.frombuffer(bytes(res), dtype=RESULT_DTYPE)[0]
+
+    def transform_cloud_device(self, cloud_ptr: int, n: int, ld: int, X_ptr: int, mode: int, out_ptr: int, ld_out: int,
+                               n_dev_ptr: int = 0):
+        """mode 0: (cloud * R^-1) - t (scanMatcher.cpp:73); mode 1: (cloud - t) * R^-1 (simpleMapMaker.cpp:41);
+        X (6 floats) in device memory."""
+        self._check(self._L.icet_b200_transform_cloud_device(self._h, C.c_void_p(cloud_ptr), n, ld,
+                                                             C.c_void_p(n_dev_ptr) if n_dev_ptr else None,
+                                                             C.c_void_p(X_ptr), mode, C.c_void_p(out_ptr), ld_out))
 
     def ingest(self, cloud, out_ptr: int, ld: int, divide: float = 0.0):
         c, keep = cloud if isinstance(cloud, tuple) else cloud_desc(cloud, divide)

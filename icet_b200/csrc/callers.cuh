@@ -376,3 +376,31 @@ __global__ void __launch_bounds__(256) k_ingest(const IngestDesc d, float* out, 
     out[(size_t)k * ld + i] = ingest_elem(p, d.dtype, d.divide);
   }
 }
+
+// ----------------------------------------------------------------------------------------------
+// Whole-cloud re-expressions of the nodes (scanMatcher.cpp:73,76; simpleMapMaker.cpp:41,222), X read on the device.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_transform_cloud(const float* src, int n, int ld, const int32_t* n_dev,
+                                                         const float* X, int mode, float* dst, int ld_out) {
+  __shared__ float s_m[12];
+  if (threadIdx.x == 0) {
+    float R[9];
+    icet::rotR(X[3], X[4], X[5], R);
+    inv3_cofactor(R, s_m);
+    s_m[9] = X[0]; s_m[10] = X[1]; s_m[11] = X[2];
+  }
+  __syncthreads();
+  const int rows = n_dev ? min(n, *n_dev) : n;
+  const float tx = s_m[9], ty = s_m[10], tz = s_m[11];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += gridDim.x * blockDim.x) {
+    float x = src[i], y = src[ld + i], z = src[2 * (size_t)ld + i];
+    if (mode == 1) { x = __fsub_rn(x, tx); y = __fsub_rn(y, ty); z = __fsub_rn(z, tz); }
+    float ox = __fadd_rn(__fadd_rn(__fmul_rn(x, s_m[0]), __fmul_rn(y, s_m[3])), __fmul_rn(z, s_m[6]));
+    float oy = __fadd_rn(__fadd_rn(__fmul_rn(x, s_m[1]), __fmul_rn(y, s_m[4])), __fmul_rn(z, s_m[7]));
+    float oz = __fadd_rn(__fadd_rn(__fmul_rn(x, s_m[2]), __fmul_rn(y, s_m[5])), __fmul_rn(z, s_m[8]));
+    if (mode == 0) { ox = __fsub_rn(ox, tx); oy = __fsub_rn(oy, ty); oz = __fsub_rn(oz, tz); }
+    dst[i] = ox;
+    dst[ld_out + i] = oy;
+    dst[2 * (size_t)ld_out + i] = oz;
+  }
+}

@@ -308,6 +308,37 @@ int icet_b200_map_get(icet_b200_map* m, float* out, int32_t ld_out, int32_t* n_o
   return 0;
 }
 
+int icet_b200_transform_cloud_device(icet_b200_ctx* c, const float* cloud, int32_t n, int32_t ld, const int32_t* n_dev,
+                                     const float* X, int32_t mode, float* out, int32_t ld_out) {
+  if (!c || !X) return fail(ICET_B200_E_INVALID, "NULL argument");
+  if (n < 0 || ld < n || ld_out < n || (mode != 0 && mode != 1) || (n > 0 && (!cloud || !out)))
+    return fail(ICET_B200_E_INVALID, "bad argument");
+  if (n == 0) return 0;
+  CK(cudaSetDevice(c->device));
+  const int grid = std::max(1, std::min((n + 255) / 256, c->sm_count * 8));
+  k_transform_cloud<<<grid, 256, 0, c->stream>>>(cloud, n, ld, n_dev, X, mode, out, ld_out);
+  c->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int icet_b200_transform_cloud(icet_b200_ctx* c, const float* cloud, int32_t n, int32_t ld, const float* X, int32_t mode,
+                              float* out, int32_t ld_out) {
+  if (!c || !out) return fail(ICET_B200_E_INVALID, "NULL argument");
+  if (n < 0 || ld_out < n) return fail(ICET_B200_E_INVALID, "bad argument");
+  if (n == 0) return 0;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  int rc = c->rawbuf[1].ensure((size_t)3 * n * sizeof(float));
+  if (rc) return rc;
+  rc = icet_b200_transform_cloud_device(c, cloud, n, ld, nullptr, X, mode, (float*)c->rawbuf[1].p, n);
+  if (rc) return rc;
+  CK(cudaMemcpy2DAsync(out, (size_t)ld_out * sizeof(float), c->rawbuf[1].p, (size_t)n * sizeof(float),
+                       (size_t)n * sizeof(float), 3, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 // -- ingest ------------------------------------------------------------------------------------------------------
 static int cloud_bytes(const icet_b200_cloud* c, size_t* bytes) {
   if (!c) return fail(ICET_B200_E_INVALID, "cloud is NULL");

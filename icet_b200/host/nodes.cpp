@@ -4,6 +4,7 @@
 #include "icet_nodes.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 
@@ -126,4 +127,53 @@ Eigen::MatrixXf MapMakerNode::getQueue() {
   for (int c = 0; c < 3; c++)
     for (int i = 0; i < rows; i++) m(i, c) = planes[(std::size_t)c * map_size_ + i];
   return m;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+ScanMatcherNode::ScanMatcherNode(int max_points, int run_length, int numBinsPhi, int numBinsTheta, int device)
+    : OdometryNode(max_points, -1.f, run_length, numBinsPhi, numBinsTheta, device, false, 0.f, 0.f) {
+  snailTrail = Eigen::MatrixXf::Zero(1, 3);  // scanMatcher.cpp:25-26
+}
+
+ScanMatcherNode::~ScanMatcherNode() {}
+
+bool ScanMatcherNode::pointcloudCallback(const Eigen::MatrixXf& pcl_matrix, NodeOutput* out) {
+  if (pcl_matrix.rows() == 0) return false;  // "Received an empty point cloud" (:41-44)
+  NodeOutput tmp;
+  NodeOutput* o = out ? out : &tmp;
+  if (!OdometryNode::pointcloudCallback(pcl_matrix, o)) return false;  // first cloud (:47-51)
+  for (int k = 0; k < 6; k++) X0[k] = 0.f;                              // :58-62
+  const int n = (int)pcl_matrix.rows();
+  const float* scan = nullptr;
+  const int32_t* n_dev = nullptr;
+  int32_t ld = 0;
+  check(icet_b200_node_current_scan(node_, &scan, &n_dev, &ld));
+  const icet_b200_result* res_dev = nullptr;
+  check(icet_b200_node_last_result(node_, &res_dev));
+  // scan2_in_scan1_frame = (pcl_matrix * rot_mat.inverse()).rowwise() - trans   (:73)
+  // Eigen::MatrixXf is column-major: data() is the plane layout the C ABI writes
+  scan2_in_scan1_frame.resize(n, 3);
+  check(icet_b200_transform_cloud(ctx_, scan, n, ld, res_dev->X, 0, scan2_in_scan1_frame.data(), n));
+  // snail trail (:76-80): a handful of rows, on the host like the reference.  rot_mat.inverse() by cofactors.
+  const float phi = o->X[3], th = o->X[4], psi = o->X[5];
+  const float sph = std::sin(phi), cph = std::cos(phi), sth = std::sin(th), cth = std::cos(th), sps = std::sin(psi),
+              cps = std::cos(psi);
+  const float R[9] = {cth * cps, sps * cph + sph * sth * cps, sph * sps - sth * cph * cps,
+                      -sps * cth, cph * cps - sph * sth * sps, sph * cps + sth * sps * cph,
+                      sth, -sph * cth, cph * cth};  // utils::R, src/utils.cpp:144-152
+  float Ri[9];
+  {
+    const float c00 = R[4] * R[8] - R[5] * R[7], c10 = R[5] * R[6] - R[3] * R[8], c20 = R[3] * R[7] - R[4] * R[6];
+    const float id = 1.0f / (c00 * R[0] + c10 * R[1] + c20 * R[2]);
+    Ri[0] = c00 * id; Ri[3] = c10 * id; Ri[6] = c20 * id;
+    Ri[1] = (R[2] * R[7] - R[1] * R[8]) * id; Ri[4] = (R[0] * R[8] - R[2] * R[6]) * id; Ri[7] = (R[1] * R[6] - R[0] * R[7]) * id;
+    Ri[2] = (R[1] * R[5] - R[2] * R[4]) * id; Ri[5] = (R[2] * R[3] - R[0] * R[5]) * id; Ri[8] = (R[0] * R[4] - R[1] * R[3]) * id;
+  }
+  const long rows = snailTrail.rows();
+  Eigen::MatrixXf next = Eigen::MatrixXf::Zero(rows + 1, 3);
+  for (long i = 0; i < rows; i++)
+    for (int c = 0; c < 3; c++)
+      next(i, c) = snailTrail(i, 0) * Ri[c] + snailTrail(i, 1) * Ri[3 + c] + snailTrail(i, 2) * Ri[6 + c] - o->X[c];
+  snailTrail = next;  // new row (0, 0, 0) appended (:77-80)
+  return true;
 }

@@ -1,6 +1,7 @@
 """Host-side mirror of the reference's two ROS nodes, minus ROS:
 
     OdometryNode   reference src/odometry.cpp:23-214       scan in -> pose / covariance diagonal / twist out
+    ScanMatcherNode reference src/scanMatcher.cpp:18-150    scan in -> scan 2 in the frame of scan 1 + snail trail out
     MapMakerNode   reference src/simpleMapMaker.cpp:60-291  scan in -> pose + 600 000-point FIFO map out
 
 Both are thin: every step between two scans (min-range filter, registration, seeding of the next registration, pose
@@ -181,3 +182,54 @@ class MapMakerNode:
 
     def map_points(self) -> np.ndarray:
         return self.q.get()
+
+
+class ScanMatcherNode:
+    """Mirror of ScanMatcherNode (src/scanMatcher.cpp:18-150): every cloud is registered against its predecessor as it
+    came (no range filter), X0 = 0 (:58-62), run_length 7, 24 x 75 bins (:55-57); publishes scan 2 re-expressed in
+    the frame of scan 1, `(pcl_matrix * rot_mat.inverse()).rowwise() - trans` (:73), and the snail trail (:76-80).
+    The re-expression of the cloud runs on the device from the device-resident result."""
+
+    def __init__(self, ctx: Context | None = None, max_points: int = 131072, runlen: int = 7, num_bins_phi: int = 24,
+                 num_bins_theta: int = 75):
+        import torch
+        self.ctx = ctx or api.default_context()
+        self.node = Node(self.ctx, api.make_params(runlen, num_bins_phi, num_bins_theta),
+                         OdometryParams(-1.0, 0, 10.0, 0.0, 0.0), max_points)
+        self._torch = torch
+        self._out = torch.empty((3, max_points), dtype=torch.float32, device="cuda")
+        self.snailTrail = np.zeros((1, 3), np.float32)   # scanMatcher.cpp:25-26
+        self.frameCount = 0
+
+    def callback(self, scan):
+        self.frameCount += 1
+        s = as_planes(scan)
+        if s.shape[1] == 0:           # "Received an empty point cloud" (:41-44)
+            return None
+        out = self.node.push(s)
+        if out is None:               # "Previous point cloud is empty, skipping this frame" (:47-51)
+            return None
+        res, pose = out
+        X = res["X"].copy()
+        scan_ptr, n_ptr, ld = self.node.current_scan()
+        n = s.shape[1]
+        self.ctx.transform_cloud_device(scan_ptr, n, ld, self.node.last_result_ptr(), 0, self._out.data_ptr(),
+                                        self._out.shape[1])
+        self.ctx.synchronize()
+        aligned = self._out[:, :n].cpu().numpy().T.copy()
+        # snail trail (:76-80): a handful of rows, host side like the reference
+        from numpy.linalg import inv
+        R = _rot_R(X[3], X[4], X[5])
+        self.snailTrail = ((self.snailTrail @ inv(R.astype(np.float64)).astype(np.float32)) - X[:3]).astype(np.float32)
+        self.snailTrail = np.vstack([self.snailTrail, np.zeros((1, 3), np.float32)])
+        return {"X": X, "scan2_in_scan1_frame": aligned, "snailTrail": self.snailTrail.copy()}
+
+
+def _rot_R(phi, theta, psi) -> np.ndarray:
+    """utils::R (reference src/utils.cpp:144-152), float32, row-major."""
+    f = np.float32
+    sph, cph, sth, cth, sps, cps = (np.sin(f(phi)), np.cos(f(phi)), np.sin(f(theta)), np.cos(f(theta)),
+                                    np.sin(f(psi)), np.cos(f(psi)))
+    return np.array([[cth * cps, sps * cph + sph * sth * cps, sph * sps - sth * cph * cps],
+                     [-sps * cth, cph * cps - sph * sth * sps, sph * cps + sth * sps * cph],
+                     [sth, -sph * cth, cph * cth]], dtype=f)

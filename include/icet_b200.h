@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ICET_B200_VERSION 103
+#define ICET_B200_VERSION 104
 
 /* status codes (return values; also icet_b200_result.status for per-pair conditions) */
 enum {
@@ -238,6 +238,19 @@ int icet_b200_node_push(icet_b200_node* node, const float* scan, int32_t n, int3
 int icet_b200_node_current_scan(icet_b200_node* node, const float** scan, const int32_t** n_dev, int32_t* ld);
 /* The device-resident result of the most recent registration (NULL before the first one). */
 int icet_b200_node_last_result(icet_b200_node* node, const icet_b200_result** res_dev);
+
+/* The rigid re-expressions the nodes apply to whole clouds, with trans / rot_mat taken from X = (x y z phi theta psi) in
+ * DEVICE memory (e.g. &result->X), rot_mat.inverse() by cofactors like Eigen's 3x3 inverse:
+ *   mode 0:  out = (cloud * rot_mat.inverse()).rowwise() - trans   scan 2 in the frame of scan 1, scanMatcher.cpp:73;
+ *                                                                   the snail trails, scanMatcher.cpp:76, simpleMapMaker.cpp:222
+ *   mode 1:  out = (cloud.rowwise() - trans) * rot_mat.inverse()   EigenQueue::add_new_scan, simpleMapMaker.cpp:41
+ * cloud / out: DEVICE planes (leading dimensions ld / ld_out; out may alias cloud), n rows or *n_dev rows when n_dev is
+ * given (device-resident count, clipped to n).  Asynchronous on the context's stream. */
+int icet_b200_transform_cloud_device(icet_b200_ctx* ctx, const float* cloud, int32_t n, int32_t ld, const int32_t* n_dev,
+                                     const float* X, int32_t mode, float* out, int32_t ld_out);
+/* Same with the result in HOST memory (planes, leading dimension ld_out >= n), blocking: what a node publishes. */
+int icet_b200_transform_cloud(icet_b200_ctx* ctx, const float* cloud, int32_t n, int32_t ld, const float* X, int32_t mode,
+                              float* out, int32_t ld_out);
 
 /* EigenQueue (simpleMapMaker.cpp:18-58): FIFO of map points (600 000 in the reference, :62), re-expressed in the
  * newest sensor frame at every insertion. */

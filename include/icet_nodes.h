@@ -4,6 +4,7 @@
  *
  *   OdometryNode::pointcloudCallback   reference src/odometry.cpp:38-168
  *   MapMakerNode::pointcloudCallback   reference src/simpleMapMaker.cpp:78-240   (+ EigenQueue, :18-58)
+ *   ScanMatcherNode::pointcloudCallback reference src/scanMatcher.cpp:30-112
  *
  * A ROS wrapper only has to convert sensor_msgs::PointCloud2 to the Eigen::MatrixXf the reference's
  * convertPCLtoEigen produces (odometry.cpp:186-192) and to copy the fields of NodeOutput into nav_msgs::Odometry /
@@ -54,6 +55,19 @@ class OdometryNode {
                float trans_thresh, float rot_thresh);
   icet_b200_ctx* ctx_ = nullptr;
   icet_b200_node* node_ = nullptr;
+};
+
+class ScanMatcherNode : public OdometryNode {
+ public:
+  // src/scanMatcher.cpp:18-150: clouds as they come (no range filter), X0 = 0 (:58-62), run_length 7, 24 x 75 bins
+  explicit ScanMatcherNode(int max_points = 262144, int run_length = 7, int numBinsPhi = 24, int numBinsTheta = 75,
+                           int device = 0);
+  ~ScanMatcherNode();
+  // returns false for an empty cloud (:41-44) and for the first cloud (:47-51); otherwise fills out->X and
+  // scan2_in_scan1_frame = (pcl_matrix * rot_mat.inverse()).rowwise() - trans (:73), computed on the device
+  bool pointcloudCallback(const Eigen::MatrixXf& pcl_matrix, NodeOutput* out);
+  Eigen::MatrixXf scan2_in_scan1_frame;  // N x 3
+  Eigen::MatrixXf snailTrail;            // (:25-26, :76-80) grows by one row per registration
 };
 
 class MapMakerNode : public OdometryNode {

@@ -154,3 +154,28 @@ class MapMakerOracle:
         self.q.add_new_scan(cur[idx], X[:3], rot_R(X[3], X[4], X[5]))   # :139-160
         out["sample"] = idx
         return out
+
+
+class ScanMatcherOracle:
+    """ScanMatcherNode::pointcloudCallback, src/scanMatcher.cpp:30-112 (ROS publishing removed)."""
+
+    def __init__(self, runlen=7, bins_phi=24, bins_theta=75, **kw):
+        self.runlen, self.bins_phi, self.bins_theta, self.kw = runlen, bins_phi, bins_theta, kw
+        self.prev = None
+        self.snail = np.zeros((1, 3), F)             # :25-26
+
+    def callback(self, cloud):
+        cloud = np.ascontiguousarray(np.asarray(cloud, F))
+        if cloud.shape[0] == 0:                      # :41-44
+            return None
+        if self.prev is None:                        # :47-51
+            self.prev = cloud
+            return None
+        it = po.run(self.prev, cloud, runlen=self.runlen, X0=np.zeros(6, F), bins_phi=self.bins_phi,
+                    bins_theta=self.bins_theta, dumps=None, **self.kw)   # :55-63
+        X = np.asarray(it.X, F).copy()
+        self.prev = cloud                            # :68
+        rinv = np.linalg.inv(rot_R(X[3], X[4], X[5]).astype(np.float64)).astype(F)
+        aligned = ((cloud @ rinv) - X[:3]).astype(F)                     # :73
+        self.snail = np.vstack([((self.snail @ rinv) - X[:3]).astype(F), np.zeros((1, 3), F)])   # :76-80
+        return {"X": X, "scan2_in_scan1_frame": aligned, "snailTrail": self.snail.copy()}

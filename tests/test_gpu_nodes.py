@@ -191,6 +191,20 @@ def test_cpp_node_classes(ctx, scans, tmp_path):
     ml = [l for l in out.stdout.splitlines() if l.startswith("MAP")][0]
     assert "rows 5000" in ml
 
+    from icet_b200 import ScanMatcherNode
+    out = subprocess.run([exe, "match", str(n), str(f)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    sm = ScanMatcherNode(ctx)
+    py = [sm.callback(s) for s in use][1:]
+    cpp = poses(out.stdout)
+    assert len(cpp) == len(py) == 3
+    for (x, p, q, npts), g in zip(cpp, py):
+        np.testing.assert_array_equal(x, g["X"])
+    al = [l for l in out.stdout.splitlines() if l.startswith("ALIGNED")][0]
+    first = np.float32(json.loads(al[al.index("first [") + 6: al.index("] trail") + 1]))
+    np.testing.assert_array_equal(first, py[-1]["scan2_in_scan1_frame"][0])
+    assert "rows %d" % n in al and al.endswith("trail 4")
+
 
 def test_ingest_native_layouts(ctx, frame_pair):
     """clouds in the layouts the reference's callers hold them in -- float64 .npy arrays in C and
@@ -234,3 +248,27 @@ def test_ingest_native_layouts(ctx, frame_pair):
     assert ra[0]["X"].tobytes() == rb[0]["X"].tobytes() and ra[1]["X_homo"].tobytes() == rb[1]["X_homo"].tobytes()
     with pytest.raises(Exception):
         ctx.register_clouds(api.cloud_desc(rec.tobytes(), point_step=16, offsets=(0, 4, 14)), a64)
+
+
+def test_scan_matcher_node_matches_oracle(ctx, scans):
+    """ScanMatcherNode (src/scanMatcher.cpp:30-112): unfiltered consecutive pairs, X0 = 0, scan 2 re-expressed in the
+    frame of scan 1 on the device, snail trail."""
+    from icet_b200 import ScanMatcherNode
+    from oracle import nodes_oracle as no
+    node, orc = ScanMatcherNode(ctx), no.ScanMatcherOracle()
+    assert node.callback(np.zeros((0, 3), np.float32)) is None and orc.callback(np.zeros((0, 3), np.float32)) is None
+    for k, s in enumerate(scans[:3]):
+        g, o = node.callback(s), orc.callback(s)
+        if k == 0:
+            assert g is None and o is None
+            continue
+        assert np.abs(g["X"][:3] - o["X"][:3]).max() < TOL_M and np.abs(g["X"][3:] - o["X"][3:]).max() < TOL_RAD
+        a, b = g["scan2_in_scan1_frame"], o["scan2_in_scan1_frame"]
+        assert a.shape == b.shape == s.shape
+        assert np.abs(a - b).max() < TOL_M + 120.0 * TOL_RAD
+        # the re-expression itself, from the GPU's own X: exact to rounding
+        Rinv = np.linalg.inv(no.rot_R(*g["X"][3:]).astype(np.float64))
+        ref = s.astype(np.float64) @ Rinv - g["X"][:3].astype(np.float64)
+        assert np.abs(a - ref).max() < 6e-5   # fp32 evaluation on coordinates up to 120 m (ulp 7.6e-6)
+        assert g["snailTrail"].shape == o["snailTrail"].shape == (k + 1, 3)
+        assert np.abs(g["snailTrail"] - o["snailTrail"]).max() < k * (TOL_M + 5.0 * TOL_RAD)
