@@ -105,3 +105,23 @@ def test_cpp_nodes_compile_and_fail_loudly_without_gpu(tmp_path):
         r = subprocess.run([os.path.join(ROOT, "examples", "_build", "nodes_headless"), mode, "64", str(f)],
                            capture_output=True, text=True)
         assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+def test_scan_matcher_oracle(po, frame_pair):
+    """ScanMatcherNode (scanMatcher.cpp:30-112): empty cloud and first cloud produce nothing; then X0 = 0 registration
+    of unfiltered clouds, scan 2 re-expressed as (cloud * R^-1) - t, snail trail one row longer per registration."""
+    from oracle import nodes_oracle as no
+    s1, s2 = frame_pair
+    a, b = np.ascontiguousarray(s1[:, ::4].T), np.ascontiguousarray(s2[:, ::4].T)
+    o = no.ScanMatcherOracle(runlen=3)
+    assert o.callback(np.zeros((0, 3), np.float32)) is None
+    assert o.callback(a) is None
+    r = o.callback(b)
+    ref = po.run(a, b, runlen=3, dumps=None)
+    np.testing.assert_array_equal(r["X"], np.asarray(ref.X, np.float32))
+    R = no.rot_R(*r["X"][3:]).astype(np.float64)
+    np.testing.assert_allclose(r["scan2_in_scan1_frame"], b.astype(np.float64) @ np.linalg.inv(R) - r["X"][:3], atol=2e-5)
+    assert r["snailTrail"].shape == (2, 3) and not r["snailTrail"][-1].any()
+    np.testing.assert_allclose(r["snailTrail"][0], -r["X"][:3], atol=1e-7)
+    r2 = o.callback(a)
+    assert r2["snailTrail"].shape == (3, 3)
