@@ -49,3 +49,16 @@ extern "C" void synth_host_motion(uint64_t seed, int k, double d[6]) {
   }
   synth::drive_step(seed, k, P, d);
 }
+
+// the motions of `n` consecutive steps k0, k0+1, ... in one walk of the trajectory
+extern "C" void synth_host_motions(uint64_t seed, int k0, int n, double* out /* [n][6] */) {
+  synth::Pose P;
+  synth::pose_identity(P);
+  double e[6];
+  for (int j = 0; j < k0 + n; j++) {
+    synth::drive_step(seed, j, P, e);
+    if (j >= k0)
+      for (int c = 0; c < 6; c++) out[(size_t)(j - k0) * 6 + c] = e[c];
+    synth::advance(P, e);
+  }
+}

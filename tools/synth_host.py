@@ -25,6 +25,7 @@ def _lib():
         _LIB = C.CDLL(build())
         _LIB.synth_host_scans.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _LIB.synth_host_motion.argtypes = [C.c_uint64, C.c_int, C.c_void_p]
+        _LIB.synth_host_motions.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_void_p]
     return _LIB
 
 
@@ -41,4 +42,11 @@ def scans(nscans, first_scan=0, seed=20240, rings=64, azim=2048, nthreads=None) 
 def motion(k, seed=20240) -> np.ndarray:
     d = np.zeros(6, np.float64)
     _lib().synth_host_motion(seed, k, d.ctypes.data)
+    return d
+
+
+def motions(k0, n, seed=20240) -> np.ndarray:
+    """[n, 6] generator motions (dx dy dz roll pitch yaw) of the steps k0 .. k0+n-1: the ground truth of the pairs."""
+    d = np.zeros((n, 6), np.float64)
+    _lib().synth_host_motions(seed, k0, n, d.ctypes.data)
     return d
