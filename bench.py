@@ -359,8 +359,8 @@ def main():
         host_out = torch.zeros((P, 56), dtype=torch.float32, pin_memory=True)
         ptr0 = host_scans.data_ptr()
         stride = 3 * NPTS * 4
-        p1 = [ptr0 + i * stride for i in range(P)]
-        p2 = [ptr0 + (i + 1) * stride for i in range(P)]
+        p1 = np.array([ptr0 + i * stride for i in range(P)], np.uint64)        # the caller's pointer tables, built once
+        p2 = np.array([ptr0 + (i + 1) * stride for i in range(P)], np.uint64)
         nn = np.full(P, NPTS, np.int32)
 
         def e2e_step():

@@ -319,12 +319,14 @@ class Context:
         """Raw-pointer form (host or device pointers; `out_ptr` likewise)."""
         p = params or make_params()
         npairs = len(ptrs1)
-        a1 = (C.c_void_p * npairs)(*ptrs1)
-        a2 = (C.c_void_p * npairs)(*ptrs2)
+        # pointer tables: a uint64 numpy array IS a `const float* const*` (pass one to skip the per-call conversion)
+        a1 = ptrs1 if isinstance(ptrs1, np.ndarray) else np.array(ptrs1, np.uint64)
+        a2 = ptrs2 if isinstance(ptrs2, np.ndarray) else np.array(ptrs2, np.uint64)
+        assert a1.dtype == np.uint64 and a2.dtype == np.uint64 and a1.flags["C_CONTIGUOUS"] and a2.flags["C_CONTIGUOUS"]
         n1 = np.ascontiguousarray(n1, np.int32)
         n2 = np.ascontiguousarray(n2, np.int32)
         f = self._L.icet_b200_register_batch_device if device else self._L.icet_b200_register_batch
-        self._check(f(self._h, C.byref(p), npairs, a1, n1.ctypes.data, a2, n2.ctypes.data,
+        self._check(f(self._h, C.byref(p), npairs, a1.ctypes.data, n1.ctypes.data, a2.ctypes.data, n2.ctypes.data,
                       C.c_void_p(x0_ptr) if x0_ptr else None, C.c_void_p(out_ptr)))
 
     # -- device-resident registration ----------------------------------------------------------
