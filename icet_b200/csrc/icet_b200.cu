@@ -4,13 +4,15 @@
 // Replaces the work of the reference constructor ICET::ICET (src/icet.cpp:29-63):
 //   fitScan1  (:68-107)  -> k_scan1_bin, k_cell_scan, k_scatter, k_cluster, k_pass<false>, k_fit1
 //   prepScan2 (:254-277) -> k_prep2
-//   fitScan2  (:372-436) -> per iteration: k_pass<true>, k_solve
+//   fitScan2  (:372-436) -> per iteration: k_pass<true>, k_vox2, k_solve6 (batches), or all iterations in the
+//                           persistent k_loop (single pairs, chained pairs)
 // All pairs of a chunk advance together through these kernels (bulk-synchronous over the batch),
 // everything stays on the device between iterations; the host only enqueues.
+// callers.cuh / callers_abi.inl (included below) hold the thin callers around the path: range filter, pose
+// bookkeeping, FIFO map, cloud re-expression, ingest.
 //
-// Determinism: per-voxel statistics are accumulated as 64-bit fixed-point integers
-// (warp-aggregated with REDUX, then RED.64 to L2), so results do not depend on thread / block /
-// GPU partitioning or on atomic ordering.
+// Determinism: per-voxel statistics are accumulated as 64-bit fixed-point integers (run sums in registers, then
+// RED.64 to L2), so results do not depend on thread / block / GPU partitioning or on atomic ordering.
 #include <cuda_runtime.h>
 
 #include <algorithm>
