@@ -272,3 +272,53 @@ def test_scan_matcher_node_matches_oracle(ctx, scans):
         assert np.abs(a - ref).max() < 6e-5   # fp32 evaluation on coordinates up to 120 m (ulp 7.6e-6)
         assert g["snailTrail"].shape == o["snailTrail"].shape == (k + 1, 3)
         assert np.abs(g["snailTrail"] - o["snailTrail"]).max() < k * (TOL_M + 5.0 * TOL_RAD)
+
+
+def test_callers_edge_cases(ctx, scans):
+    """Empty / tiny / NaN clouds, zero iterations, odd map capacities: defined behaviour, no device faults."""
+    import torch
+    from icet_b200 import Node, PointMap, api
+    op = api.OdometryParams(2.0, 1, 10.0, 0.0, 0.0)
+    # empty and tiny clouds through a chained node: X stays the seed, pose stays the identity
+    nd = Node(ctx, api.make_params(), op, 1024)
+    assert nd.push(np.zeros((0, 3), np.float32)) is None
+    for cloud in (np.zeros((0, 3), np.float32), np.ones((5, 3), np.float32) * 3, np.full((40, 3), np.nan, np.float32)):
+        res, pose = nd.push(cloud)
+        assert res["status"] == 0 and not res["X"].any() and np.isfinite(pose["X_homo"]).all()
+        np.testing.assert_array_equal(pose["X_homo"], np.eye(4, dtype=np.float32))
+    assert int(pose["n_points"]) == 0            # NaN rows never pass `distance > minD`
+    nd.close()
+    # zero iterations: the chain hands the seed through unchanged
+    seed = np.array([0.1, 0, 0, 0, 0, 0.01], np.float32)
+    nd = Node(ctx, api.make_params(runlen=0), op, scans[0].shape[0], X0=seed)
+    nd.push(scans[0])
+    for s in scans[1:3]:
+        res, pose = nd.push(s)
+        np.testing.assert_array_equal(res["X"], seed)
+    nd.close()
+    # a clouds larger than the node's capacity is refused, the node stays usable
+    nd = Node(ctx, api.make_params(), op, 1000)
+    with pytest.raises(Exception):
+        nd.push(np.zeros((2000, 3), np.float32))
+    assert nd.push(np.zeros((10, 3), np.float32)) is None
+    nd.close()
+    # map: capacity that is not a multiple of 4, insertions of 0 rows and of more rows than the ring holds
+    pm = PointMap(ctx, 1003)
+    X = torch.zeros(6, dtype=torch.float32, device="cuda")
+    pts = torch.arange(3 * 2500, dtype=torch.float32, device="cuda").reshape(3, 2500).contiguous()
+    pm.add_scan_device(pts.data_ptr(), 2500, 2500, X.data_ptr(), count=0)
+    assert pm.get().shape == (0, 3)
+    pm.add_scan_device(pts.data_ptr(), 2500, 2500, X.data_ptr(), count=2500)
+    m = pm.get()
+    assert m.shape == (1003, 3)
+    np.testing.assert_array_equal(m[:, 0], np.arange(2500 - 1003, 2500, dtype=np.float32))   # the newest 1003 rows, oldest first
+    pm.close()
+    # ingest of an empty cloud, registration of empty clouds
+    r = ctx.register_clouds(np.zeros((0, 3), np.float64), np.zeros((0, 3), np.float32))
+    assert r["status"] == 0 and not r["X"].any()
+    # shipped-order mode with NaN rows and dropped returns in scan 1
+    c = scans[0].copy()
+    c[::97] = np.nan
+    r = ctx.register(c, scans[1], params=api.make_params(flags=api.FLAG_SHIPPED_ORDER))
+    assert np.isfinite(r["X"]).all()
+    ctx.synchronize()
