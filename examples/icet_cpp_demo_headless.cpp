@@ -4,7 +4,8 @@
 // print the solution, the 1-sigma bounds and the timing, plus the sizes of the members the demo hands to its
 // visualisation (icet_cpp_demo.cpp:48-57).
 //
-// usage: icet_cpp_demo_headless scan1 scan2 [ouster|txt|f32] [x0_x]
+// usage: icet_cpp_demo_headless scan1 scan2 [ouster|txt|f32] [x0_x] [shipped]
+//   "shipped": ICET::shippedRowOrder = true -- cluster in the row order an unmodified reference build ends up with
 //   "f32": raw float32 file holding the x | y | z planes (column-major N x 3), the tests' exchange format.
 #include <chrono>
 #include <cstdio>
@@ -40,6 +41,7 @@ int main(int argc, char** argv) {
   X0.resize(6);
   X0 << (argc > 4 ? std::stof(argv[4]) : 1.f), 0., 0., 0., 0., 0.;  // the demo's initial estimate
 
+  if (argc > 5 && std::string(argv[5]) == "shipped") ICET::shippedRowOrder = true;
   try {
     Eigen::MatrixXf scan1 = type == "f32" ? load_f32(argv[1]) : utils::loadPointCloudCSV(argv[1], type);
     Eigen::MatrixXf scan2 = type == "f32" ? load_f32(argv[2]) : utils::loadPointCloudCSV(argv[2], type);

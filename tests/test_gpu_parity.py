@@ -461,6 +461,15 @@ def test_cpp_class_dropin_demo(ctx, po, frame_pair, tmp_path):
     inv = np.argsort(o.perm2)
     np.testing.assert_allclose(p2, o.points2_final[:, inv], atol=5e-5)
     assert "ellipsoids 336" in out.stdout and "clusterBounds 1800x6" in out.stdout
+    # ICET::shippedRowOrder: the reference's shipped (unsorted) row order through the C++ class
+    from icet_b200 import api
+    out = subprocess.run([os.path.join(ROOT, "examples", "_build", "icet_cpp_demo_headless"), str(a), str(b), "f32", "1",
+                          "shipped"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    Xs = np.array(json.loads([l for l in out.stdout.splitlines() if l.startswith("X_JSON")][0][7:]), np.float32)
+    rs = ctx.register(s1, s2, X0=x0, params=params(flags=api.FLAG_SHIPPED_ORDER))
+    np.testing.assert_array_equal(Xs, rs["X"])
+    assert "ellipsoids %d" % rs["n_gauss1"] in out.stdout and rs["n_gauss1"] < 150
 
 
 def test_chained_batch_equals_seeded_single_calls(ctx):
