@@ -1,0 +1,122 @@
+// icet_b200/csrc/chunk.cuh -- error reporting helpers, per-chunk device state (Chunk and its records), constants and
+// the explicit-address-space atomics.  Included by icet_b200.cu inside its anonymous namespace.
+#pragma once
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(ICET_B200_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+  } while (0)
+
+constexpr int FPB = 21;                 // fixed-point: |d * scale| <= 2^FPB
+constexpr int FP_LIM = (1 << FPB);
+constexpr unsigned FULL = 0xffffffffu;
+constexpr uint32_t F_STAT1 = 1u;        // scan-1 statistics wanted for this cell
+constexpr uint32_t F_ACTIVE2 = 2u;      // voxel takes part in the scan-2 loop
+constexpr int SORT_SMEM = 4096;         // cells up to this many points are sorted in shared memory
+constexpr int NQ = 12;                  // accumulator words per cell
+constexpr int CLUSTER_WARPS = 4;
+constexpr int WSORT_MAX = 1024;         // cells up to this many non-zero ranges are sorted by one warp in registers
+
+struct PairDesc {
+  const float* s1;
+  const float* s2;
+  int n1, ld1, n2, ld2;
+};
+
+struct __align__(16) CellRec {  // read by the pass kernels: first half by every point, second half per run of inside points
+  float inner, outer;           // clusterBounds columns 4,5 (src/icet.cpp:149)
+  uint32_t flags;
+  float scale;                  // power-of-two scale of the voxel's fixed-point frame
+  float refx, refy, refz;       // reference point of the fixed-point frame
+  int32_t cnt1;                 // points of scan 1 in this angular bin
+};
+
+struct Vox1 {     // scan-1 Gaussian, constants of the iteration loop (sigma1/mu1/U/L, include/icet.h:89-94)
+  double mu[3];
+  double S1n[6];  // sigma1 / (cnt1 - 1), upper triangle xx xy xz yy yz zz
+  double LV[9];   // L * U^T = L * V  (rows of V, zeroed where L is 0)
+  int lmask;      // bit k: L(k,k) == 1
+  int pad;
+};
+
+struct Dump {  // optional per-voxel recording (device memory), single-pair debugging only
+  int32_t* nin1; uint8_t* has1; float* mu1; float* sigma1; float* evec1; float* eval1; uint8_t* lmask;
+  int32_t* cnt2; int32_t* nin2; uint8_t* used2; float* mu2; float* sigma2; float* Xit; float* HTWH; float* HTWdz;
+  unsigned long long* tl;  // [runlen][16] globaltimer stamps of the loop kernel (debug) + per-tile stamps of iteration 3
+};
+
+struct Chunk {  // everything a kernel needs, passed by value
+  const PairDesc* desc;
+  int npairs, ncell, nT, nP, n, runlen, flags;
+  float thresh, buff;
+  int n1max, n2max;
+  // scan 1
+  int32_t* cellid1;  // [P][n1max]
+  float* r1;         // [P][n1max]
+  float* th1;        // [P][n1max]  theta, phi of scan 1 (K1 -> K3: the second pass over scan 1 does not redo the
+  float* ph1;        // [P][n1max]  spherical conversion)
+  float* rbuf;       // [P][n1max]  non-zero ranges grouped by cell
+  unsigned long long* kbuf;  // [n1max]  ICET_B200_FLAG_SHIPPED_ORDER: (row position << 32 | range bits) grouped by cell
+  int32_t* pos1;     // [n1max]  ... position of every row of scan 1 in the reference's shipped row order
+  int32_t* cnt1;     // [P][ncell]
+  int32_t* cntz;     // [P][ncell]  zero-range points
+  int32_t* off;      // [P][ncell]
+  int32_t* cursor;   // [P][ncell]
+  int32_t* work;     // [P][ncell]  cells with cnt1 >= n
+  int32_t* nwork;    // [P]
+  int32_t* nbig;     // [P]  cells of the work list with more than WSORT_MAX non-zero ranges
+  CellRec* rec;      // [P][ncell]
+  unsigned long long* acc;  // [P][ncell][NQ]
+  Vox1* vox;         // [P][ncell]
+  const float* azE;  // [nT+1] float azimuth bin edges  (src/icet.cpp:136-137)
+  const float* elE;  // [nP+1] float elevation bin edges (src/icet.cpp:138-139)
+  icet::BinTable bth, bph;  // exact bin lookup tables (src/icet.cpp:545-546)
+  const float* binrec;      // [(nT+1) + (nP+1)][4] bin + box records of the pass kernels (see bin_box)
+  float* TR;         // [P][12] translation (3) and rotation R(X) (9) of the current iteration
+  float* TRprev;     // [P][12] transform the LAST iteration used (the reference's public `points2`)
+  float* J;          // [P][27] get_H derivative matrices Jx | Jy | Jz of the current iteration
+  double* part;      // [P][nblk][NRED] per-block partial sums of the voxel contributions
+  // scan 2
+  float* pog;        // [P][3][n2max]  points2_OG without the dropped returns (compacted, any order)
+  int32_t* n2c;      // [P] points stored in pog
+  int32_t* nz2;      // [P] dropped returns of scan 2 (points2_OG == 0)
+  float* X;          // [P][6]
+  const float* x0;   // [P][6] or null
+  icet_b200_result* res;  // [P] device
+  // control words of the persistent Gauss-Newton kernel (k_loop)
+  unsigned* ticket;      // [1]  next task
+  unsigned* tiles_done;  // [P]  scan-2 tiles finished so far (all iterations)
+  int* iter_done;        // [P]  iterations whose solve has been published
+  unsigned* vox_done;    // [P][runlen] vox tasks finished per iteration
+  unsigned* vmask;       // [P][ceil(vt/32)] vox groups that wrote a partial sum (current iteration)
+  int* dbg;              // [8] watchdog record of k_loop: {tripped, kind, pair, iter, seen, need, ticket, -}
+  Dump dump;
+  int dump_on;
+};
+
+// Atomics on Chunk memory, with the address space spelled out.  Kernels that hand the Chunk to non-inlined device
+// functions by reference (k_loop) keep it in local memory, and the compiler then no longer knows which address space
+// the pointers it loads from there refer to: atomicAdd() becomes a GENERIC atomic that waits for a predicate from the
+// memory system (one L2 round trip each instead of a fire-and-forget RED) plus a shared-memory CAS fallback.
+__device__ __forceinline__ void red_add(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_add(unsigned* p, unsigned v) {
+  asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_or(unsigned* p, unsigned v) {
+  asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned atom_add(unsigned* p, unsigned v) {
+  unsigned r;
+  asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v) : "memory");
+  return r;
+}
+

@@ -1,0 +1,535 @@
+// icet_b200/csrc/kernels_scan1.cuh -- K1, K2a, K2b, K2c: spherical coordinates and voxel indices of scan 1, cell
+// bookkeeping, grouping of the ranges by cell, radial clustering (fitScan1 up to findCluster, src/icet.cpp:68-107,
+// :557-607), and the shipped-row-order validation kernels.  Included by icet_b200.cu inside its anonymous namespace.
+#pragma once
+// ----------------------------------------------------------------------------------------------
+// Fixed-point accumulators acc[cell][NQ] (64-bit integers, RED.64 to L2):
+//   q[0] += points in the angular bin, q[1] += points inside the cluster box,
+//   q[2..4] += sum d, q[5..10] += sum d d^T (xx xy xz yy yz zz),   d = round((p - ref) * scale)
+// Exact integer arithmetic => the sums do not depend on the order or grouping of the additions.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cell_of(const Chunk& ck, float th, float ph, int& bt, int& bp) {
+  bt = icet::bin_lookup(th, ck.bth, 2 * M_PI);
+  bp = icet::bin_lookup(ph, ck.bph, M_PI);
+}
+// ----------------------------------------------------------------------------------------------
+// K1: scan 1 -> spherical, cell index, per-cell histogram.
+// utils::cartesianToSpherical (src/utils.cpp:93-119) + sortSphericalCoordinates (src/icet.cpp:534-554)
+// ----------------------------------------------------------------------------------------------
+constexpr int32_t CELL_INBOX = 0x40000000;  // cellid1 flag: the point passes the fp32 az / el box test of its own bin
+__device__ __forceinline__ int bin_box(float a, const float4* rec, const icet::BinTable& bt, bool& inbox);
+
+__global__ void __launch_bounds__(256) k_scan1_bin(const Chunk ck) {
+  const int pair = blockIdx.y;
+  const PairDesc d = ck.desc[pair];
+  if ((int)(blockIdx.x * blockDim.x) >= d.n1) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int cell = -1;
+  bool zero = false;
+  if (i < d.n1) {
+    float x = __ldg(d.s1 + i), y = __ldg(d.s1 + d.ld1 + i), z = __ldg(d.s1 + 2 * (size_t)d.ld1 + i);
+    float r, th, ph;
+    icet::c2s(x, y, z, r, th, ph);
+    // bin and box test in one look-up (same records as the pass kernels, read through L1 here)
+    const float4* tth = reinterpret_cast<const float4*>(ck.binrec);
+    const float4* tph = tth + ck.nT + 2;
+    bool bt_in, bp_in;
+    const int bt = bin_box(th, tth, ck.bth, bt_in);
+    const int bp = bin_box(ph, tph, ck.bph, bp_in);
+    cell = ck.nT * bp + bt;
+    zero = (r == 0.0f);
+    const size_t o = (size_t)pair * ck.n1max + i;
+    ck.cellid1[o] = cell | ((bt_in && bp_in) ? CELL_INBOX : 0);
+    ck.r1[o] = r;
+    ck.th1[o] = th;
+    ck.ph1[o] = ph;
+  }
+  // warp-aggregated histogram
+  const int lane = threadIdx.x & 31;
+  const unsigned act = __ballot_sync(FULL, cell >= 0);
+  if (cell >= 0) {
+    const unsigned m = __match_any_sync(act, cell);
+    const unsigned mz = __ballot_sync(m, zero);
+    if (lane == __ffs(m) - 1) {
+      atomicAdd(&ck.cnt1[(size_t)pair * ck.ncell + cell], __popc(m));
+      if (mz) atomicAdd(&ck.cntz[(size_t)pair * ck.ncell + cell], __popc(mz));
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K2a: per pair: exclusive scan of the non-zero counts (offsets into rbuf), work list of cells with
+// cnt1 >= n (src/icet.cpp:115), default cell records (the else-branch :243-251: inner = outer = 0).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cell_scan(const Chunk ck) {
+  const int pair = blockIdx.x;
+  __shared__ int s_ws[8], s_ww[8];
+  const int per = (ck.ncell + 255) / 256;
+  const int c0 = threadIdx.x * per, c1 = min(ck.ncell, c0 + per);
+  const int32_t* cnt1 = ck.cnt1 + (size_t)pair * ck.ncell;
+  const int32_t* cntz = ck.cntz + (size_t)pair * ck.ncell;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int s = 0, w = 0, big = 0;
+  for (int c = c0; c < c1; c++) {
+    const int m = cnt1[c] - cntz[c];
+    s += m;
+    w += (cnt1[c] >= ck.n) ? 1 : 0;
+    big += (cnt1[c] >= ck.n && m > WSORT_MAX) ? 1 : 0;
+  }
+  {
+    const int anybig = __syncthreads_count(big > 0);  // (number of threads that own a big cell: only zero / non-zero matters)
+    if (threadIdx.x == 0) ck.nbig[pair] = anybig;
+  }
+  // exclusive block scan of (s, w): inclusive warp scans, then the warp totals
+  int is = s, iw = w;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int ts = __shfl_up_sync(FULL, is, o), tw = __shfl_up_sync(FULL, iw, o);
+    if (lane >= o) { is += ts; iw += tw; }
+  }
+  if (lane == 31) { s_ws[warp] = is; s_ww[warp] = iw; }
+  // meanwhile: the per-pair state.  Warp 1 owns the result record, thread 0 the transform.
+  if (warp == 1) {
+    icet_b200_result* R = ck.res + pair;
+    // chained pairs (ICET_B200_FLAG_CHAIN_X0, odometry.cpp:82): x0 holds ONE seed, that of pair 0; the later pairs are
+    // seeded by the last solve of their predecessor (chain_seed_next).  Without iterations the seed is the answer.
+    const bool chain = (ck.flags & ICET_B200_FLAG_CHAIN_X0) != 0;
+    const bool seeded = ck.x0 && (!chain || pair == 0 || ck.runlen == 0);
+    if (lane < 6) {
+      const float x = seeded ? ck.x0[(chain ? 0 : pair * 6) + lane] : 0.f;
+      ck.X[pair * 6 + lane] = x;
+      R->X[lane] = x;
+      R->pred_stds[lane] = 0.f;
+    }
+    for (int k = lane; k < 36; k += 32) R->Q[k] = 0.f;
+    if (lane == 6) { R->status = 0; R->n_gauss1 = 0; R->n_used = 0; R->n_dropped = 0; R->cond = 0.f; }
+    if (lane >= 7 && lane < 10) R->reserved[lane - 7] = 0;
+  }
+  if (threadIdx.x == 0) {
+    const bool chain = (ck.flags & ICET_B200_FLAG_CHAIN_X0) != 0;
+    const bool seeded = ck.x0 && (!chain || pair == 0 || ck.runlen == 0);
+    float X[6];
+    for (int k = 0; k < 6; k++) X[k] = seeded ? ck.x0[(chain ? 0 : pair * 6) + k] : 0.f;
+    float* TR = ck.TR + (size_t)pair * 12;
+    TR[0] = X[0]; TR[1] = X[1]; TR[2] = X[2];
+    icet::rotR(X[3], X[4], X[5], TR + 3);
+    icet::getH_J(X[3], X[4], X[5], ck.J + (size_t)pair * 27);
+    for (int k = 0; k < 12; k++) ck.TRprev[(size_t)pair * 12 + k] = TR[k];
+  }
+  __syncthreads();
+  int a = is - s, b = iw - w;
+  for (int q = 0; q < warp; q++) { a += s_ws[q]; b += s_ww[q]; }
+  if (threadIdx.x == 255) ck.nwork[pair] = b + w;
+  for (int c = c0; c < c1; c++) {
+    ck.off[(size_t)pair * ck.ncell + c] = a;
+    a += cnt1[c] - cntz[c];
+    if (cnt1[c] >= ck.n) ck.work[(size_t)pair * ck.ncell + (b++)] = c;
+    CellRec rc;
+    rc.inner = 0.f; rc.outer = 0.f; rc.refx = rc.refy = rc.refz = 0.f; rc.scale = 0.f;
+    rc.flags = 0; rc.cnt1 = cnt1[c];
+    ck.rec[(size_t)pair * ck.ncell + c] = rc;
+  }
+}
+
+// K2b: group the non-zero ranges by cell
+__global__ void __launch_bounds__(256) k_scatter(const Chunk ck) {
+  const int pair = blockIdx.y;
+  const PairDesc d = ck.desc[pair];
+  if ((int)(blockIdx.x * blockDim.x) >= d.n1) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int cell = -1;
+  float r = 0.f;
+  if (i < d.n1) {
+    r = ck.r1[(size_t)pair * ck.n1max + i];
+    if (r != 0.0f) cell = ck.cellid1[(size_t)pair * ck.n1max + i] & ~CELL_INBOX;
+  }
+  const int lane = threadIdx.x & 31;
+  const unsigned act = __ballot_sync(FULL, cell >= 0);
+  if (cell >= 0) {
+    const unsigned m = __match_any_sync(act, cell);
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&ck.cursor[(size_t)pair * ck.ncell + cell], __popc(m));
+    base = __shfl_sync(m, base, leader);
+    const int rank = __popc(m & ((1u << lane) - 1));
+    ck.rbuf[(size_t)pair * ck.n1max + ck.off[(size_t)pair * ck.ncell + cell] + base + rank] = r;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K2c: per cell with cnt1 >= n: sort the ranges ascending (what src/icet.cpp:71-83 intends) and run
+// ICET::findCluster (src/icet.cpp:557-607) on them; write the cell record.
+// ----------------------------------------------------------------------------------------------
+// Bitonic-style network with all comparators ascending ("mirror" first step): works for any m,
+// indices >= m behave as +inf and are never touched.
+template <class Ptr>
+__device__ inline void block_sort_asc(Ptr a, int m) {
+  int p2 = 1;
+  while (p2 < m) p2 <<= 1;
+  for (int k = 2; k <= p2; k <<= 1) {
+    // mirror step: i with partner i ^ (k-1)
+    for (int t = threadIdx.x; t < p2 / 2; t += blockDim.x) {
+      int blk = t / (k / 2), o = t % (k / 2);
+      int i = blk * k + o, j = blk * k + (k - 1 - o);
+      if (j < m) {
+        auto x = a[i];
+        auto y = a[j];
+        if (y < x) { a[i] = y; a[j] = x; }
+      }
+    }
+    __syncthreads();
+    for (int j2 = k / 4; j2 >= 1; j2 >>= 1) {
+      for (int t = threadIdx.x; t < p2 / 2; t += blockDim.x) {
+        int i = (t / j2) * (2 * j2) + (t % j2), j = i + j2;
+        if (j < m) {
+          auto x = a[i];
+          auto y = a[j];
+          if (y < x) { a[i] = y; a[j] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// findCluster over the virtual sequence seq = [0 x nz, a[0..m)] (ascending); executed by warp 0,
+// every lane computes the same result.  A "break" at position i means seq[i] does not extend the
+// current run (reference :572); the run before a break is returned if it has >= n points (:577-582,
+// no zero check), the run that reaches the end of the data goes through the zero check (:592-603).
+template <class Ptr>
+__device__ inline void find_cluster_warp(Ptr a, int m, int nz, int n, float thresh, float buff, float& inner,
+                                         float& outer) {
+  const int lane = threadIdx.x & 31;
+  const int total = nz + m;
+  auto seq = [&](int i) -> float { return i < nz ? 0.0f : a[i - nz]; };
+  int start = 0;  // first element of the current run; the nz leading zeros never break (thresh >= 0)
+  bool found = false;
+  float fi = 0.f, fo = 0.f;
+  for (int base = nz; base < total && !found; base += 32) {
+    const int i = base + lane;
+    bool brk = false;
+    if (i < total && i > 0) brk = !(fabsf(seq(i - 1) - seq(i)) <= thresh);
+    unsigned mask = __ballot_sync(FULL, brk);
+    while (mask && !found) {
+      const int pos = base + __ffs(mask) - 1;
+      mask &= mask - 1;
+      if (pos - start >= n) {
+        fi = seq(start) - buff;
+        fo = seq(pos - 1) + buff;
+        found = true;
+      } else {
+        start = pos;
+      }
+    }
+  }
+  if (!found && total > 0 && total - start >= n) {
+    if (seq(start) != 0.0f) {
+      fi = seq(start) - buff;
+      fo = seq(total - 1) + buff;
+    }
+  }
+  inner = fi;
+  outer = fo;
+}
+
+// writes the cell record of a clustered cell (clusterBounds columns 4,5 + the voxel's fixed-point frame)
+__device__ inline void write_cluster_rec(const Chunk& ck, int pair, int cell, int cnt, float inner, float outer) {
+  const int bt = cell % ck.nT, bp = cell / ck.nT;
+  CellRec rc;
+  rc.inner = inner;
+  rc.outer = outer;
+  rc.cnt1 = cnt;
+  rc.flags = ((double)outer > 0.1) ? F_STAT1 : 0u;  // `outerDistance > 0.1` src/icet.cpp:158
+  // fixed-point frame of the voxel: reference point = centre of the spherical box, scale from
+  // a bound on the box diameter
+  const float azl = ck.azE[bt], azh = ck.azE[bt + 1], ell = ck.elE[bp], elh = ck.elE[bp + 1];
+  const float rm = 0.5f * (inner + outer), tm = 0.5f * (azl + azh), pm = 0.5f * (ell + elh);
+  icet::s2c(rm, tm, pm, rc.refx, rc.refy, rc.refz);
+  float D = (outer - inner) + fabsf(outer) * ((azh - azl) + (elh - ell));
+  int e;
+  frexpf(fmaxf(D, 1e-20f), &e);          // D < 2^e
+  rc.scale = ldexpf(1.0f, FPB - e - 1);  // |d| <= D  =>  |d*scale| < 2^(FPB-1)
+  ck.rec[(size_t)pair * ck.ncell + cell] = rc;
+}
+
+// Bitonic sort of 32*EPL floats held EPL per lane; element index = lane*EPL + j.  Compare-exchange distances
+// below EPL stay inside a lane (registers), larger ones are one shuffle per element.  Fully unrolled.
+template <int EPL>
+__device__ __forceinline__ void warp_sort_regs(float (&v)[EPL]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 2; k <= 32 * EPL; k <<= 1) {
+#pragma unroll
+    for (int d = k >> 1; d > 0; d >>= 1) {
+      if (d >= EPL) {
+        const int ld = d / EPL;                                             // partner lane distance
+        const bool asc = (k >= 32 * EPL) || ((lane & (k / EPL)) == 0);
+        const bool keep_min = (((lane & ld) == 0) == asc);
+#pragma unroll
+        for (int j = 0; j < EPL; j++) {
+          const float o = __shfl_xor_sync(FULL, v[j], ld);
+          v[j] = keep_min ? fminf(v[j], o) : fmaxf(v[j], o);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < EPL; j++) {
+          if ((j & d) == 0) {
+            // direction bit k of the element index: in the register index for k < EPL, in the lane above
+            const bool asc = (k >= 32 * EPL) || (k < EPL ? ((j & k) == 0) : ((lane & (k / EPL)) == 0));
+            const float lo = fminf(v[j], v[j ^ d]), hi = fmaxf(v[j], v[j ^ d]);
+            v[j] = asc ? lo : hi;
+            v[j ^ d] = asc ? hi : lo;
+          }
+        }
+      }
+    }
+  }
+}
+
+// loads the m ranges of a cell (any order), sorts them in registers and leaves them ascending in the warp's
+// shared-memory row (index i stored at i + i/32: conflict-free for the blocked write and for consecutive reads)
+template <int EPL>
+__device__ __forceinline__ void warp_sort_cell(const float* __restrict__ g, int m, float* srow) {
+  const int lane = threadIdx.x & 31;
+  float v[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; j++) {
+    const int i = j * 32 + lane;  // coalesced; which register an unsorted value lands in is irrelevant
+    v[j] = i < m ? __ldg(g + i) : INFINITY;
+  }
+  warp_sort_regs<EPL>(v);
+#pragma unroll
+  for (int j = 0; j < EPL; j++) {
+    const int i = lane * EPL + j;
+    srow[i + (i >> 5)] = v[j];
+  }
+  __syncwarp();
+}
+
+struct PaddedRow {  // view of a shared-memory row written by warp_sort_cell
+  const float* p;
+  __device__ __forceinline__ float operator[](int i) const { return p[i + (i >> 5)]; }
+};
+
+// K2c: ONE WARP per cell with cnt1 >= n (a cell of a 64-ring scan holds ~260 ranges): register bitonic sort, then
+// ICET::findCluster on the sorted row.  Cells with more than WSORT_MAX ranges take the CTA path at the end of the kernel.
+__global__ void __launch_bounds__(CLUSTER_WARPS * 32) k_cluster(const Chunk ck) {
+  const int pair = blockIdx.y;
+  constexpr int ROW = WSORT_MAX + WSORT_MAX / 32;
+  constexpr int SM_FLOATS = CLUSTER_WARPS * ROW > SORT_SMEM ? CLUSTER_WARPS * ROW : SORT_SMEM;
+  __shared__ float s_all[SM_FLOATS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* srow = s_all + warp * ROW;
+  const int nw = ck.nwork[pair];
+  for (int w = blockIdx.x * CLUSTER_WARPS + warp; w < nw; w += gridDim.x * CLUSTER_WARPS) {
+    const int cell = ck.work[(size_t)pair * ck.ncell + w];
+    const int cnt = ck.cnt1[(size_t)pair * ck.ncell + cell];
+    const int nz = ck.cntz[(size_t)pair * ck.ncell + cell];
+    const int m = cnt - nz;
+    if (m > WSORT_MAX) continue;
+    const float* g = ck.rbuf + (size_t)pair * ck.n1max + ck.off[(size_t)pair * ck.ncell + cell];
+    if (m <= 128) warp_sort_cell<4>(g, m, srow);
+    else if (m <= 256) warp_sort_cell<8>(g, m, srow);
+    else if (m <= 512) warp_sort_cell<16>(g, m, srow);
+    else warp_sort_cell<32>(g, m, srow);
+    float inner, outer;
+    find_cluster_warp(PaddedRow{srow}, m, nz, ck.n, ck.thresh, ck.buff, inner, outer);
+    if (lane == 0) write_cluster_rec(ck, pair, cell, cnt, inner, outer);
+    __syncwarp();
+  }
+  // The big cells (more than WSORT_MAX ranges: an accumulated map as scan 1; k_cell_scan counted them), the whole CTA per
+  // cell.  findCluster only needs to know where consecutive SORTED ranges are more than `thresh` apart, so no sort:
+  // the ranges are dropped into buckets half a threshold wide (count, min, max per bucket; ranges inside one bucket
+  // are closer than the threshold by construction), windows of NBKT buckets are walked in ascending order, and the
+  // walk stops at the first run that qualifies.  O(m) per window instead of the O(m log^2 m) of a bitonic network
+  // (a 2 M-point map: 217 ms -> well under 1 ms).  Fallback for thresholds / ranges the buckets cannot cover: sort.
+  if (ck.nbig[pair] == 0) return;  // block-uniform
+  __syncthreads();
+  constexpr int NBKT = (SM_FLOATS - 8) / 3;
+  int* b_cnt = reinterpret_cast<int*>(s_all);
+  int* b_min = b_cnt + NBKT;
+  int* b_max = b_min + NBKT;
+  int* s_ctl = b_max + NBKT;  // [0] points seen so far, [1] done, [2..3] result bits
+  for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+    const int cell = ck.work[(size_t)pair * ck.ncell + w];
+    const int cnt = ck.cnt1[(size_t)pair * ck.ncell + cell];
+    const int nz = ck.cntz[(size_t)pair * ck.ncell + cell];
+    const int m = cnt - nz;
+    if (m <= WSORT_MAX) continue;  // block-uniform
+    float* g = ck.rbuf + (size_t)pair * ck.n1max + ck.off[(size_t)pair * ck.ncell + cell];
+    // largest range of the cell (the ranges are >= 0: their bit patterns order like the values)
+    __syncthreads();
+    if (threadIdx.x == 0) s_ctl[0] = 0;
+    __syncthreads();
+    {
+      int mx = 0;
+      for (int i0 = threadIdx.x; i0 < m; i0 += 8 * blockDim.x) {  // eight loads in flight per thread
+        int v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int i = i0 + u * blockDim.x;
+          v[u] = i < m ? __float_as_int(g[i]) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) mx = max(mx, v[u]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+      if (lane == 0) atomicMax(&s_ctl[0], mx);
+    }
+    __syncthreads();
+    const float rmax = __int_as_float(s_ctl[0]);
+    const float wdt = 0.5f * ck.thresh, inv_w = 1.0f / wdt;
+    const bool buckets_ok = ck.thresh > 1e-6f && rmax * inv_w < 64.0f * NBKT;  // false for inf / NaN as well
+    float inner = 0.f, outer = 0.f;
+    if (buckets_ok) {
+      // state of the walk (warp 0, uniform across its lanes)
+      int idx = nz, start = 0;
+      float start_val = 0.f, prev_val = 0.f;
+      bool found = false;
+      __syncthreads();
+      if (threadIdx.x == 0) { s_ctl[0] = 0; s_ctl[1] = 0; }
+      for (int win = 0;; win++) {
+        for (int k = threadIdx.x; k < NBKT; k += blockDim.x) { b_cnt[k] = 0; b_min[k] = 0x7f800000; b_max[k] = 0; }
+        __syncthreads();
+        if (s_ctl[1]) break;  // found, or every range has been walked
+        const int lo = win * NBKT;
+        for (int i0 = threadIdx.x; i0 < m; i0 += 8 * blockDim.x) {  // eight loads in flight per thread
+          float rv[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int i = i0 + u * blockDim.x;
+            rv[u] = i < m ? g[i] : -1.0f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const float r = rv[u];
+            const int k = __float2int_rd(r * inv_w) - lo;
+            if (r >= 0.0f && k >= 0 && k < NBKT) {
+              atomicAdd(&b_cnt[k], 1);
+              atomicMin(&b_min[k], __float_as_int(r));
+              atomicMax(&b_max[k], __float_as_int(r));
+            }
+          }
+        }
+        __syncthreads();
+        if (warp == 0) {
+          int seen = 0;
+          for (int base = 0; base < NBKT && !found; base += 32) {
+            const int k = base + lane;
+            const int c = k < NBKT ? b_cnt[k] : 0;
+            unsigned mask = __ballot_sync(FULL, c > 0);
+            while (mask && !found) {
+              const int kb = base + __ffs(mask) - 1;
+              mask &= mask - 1;
+              const int bc = b_cnt[kb];
+              const float mn = __int_as_float(b_min[kb]), mxv = __int_as_float(b_max[kb]);
+              if (idx > 0) {
+                if (!(fabsf(prev_val - mn) <= ck.thresh)) {  // a break in front of this bucket (reference :572)
+                  if (idx - start >= ck.n) {
+                    inner = start_val - ck.buff;             // :577-582, no zero check
+                    outer = prev_val + ck.buff;
+                    found = true;
+                    break;
+                  }
+                  start = idx;
+                  start_val = mn;
+                }
+              } else {
+                start_val = mn;
+              }
+              idx += bc;
+              seen += bc;
+              prev_val = mxv;
+            }
+          }
+          if (lane == 0) {
+            s_ctl[0] += seen;
+            if (found || s_ctl[0] >= m) s_ctl[1] = 1;
+          }
+        }
+        __syncthreads();
+      }
+      if (warp == 0 && !found && nz + m - start >= ck.n && start_val != 0.0f) {  // end of the data (:592-603)
+        inner = start_val - ck.buff;
+        outer = prev_val + ck.buff;
+      }
+    } else {
+      float* s_r = s_all;
+      if (m <= SORT_SMEM) {
+        for (int i = threadIdx.x; i < m; i += blockDim.x) s_r[i] = g[i];
+        __syncthreads();
+        block_sort_asc(s_r, m);
+        if (threadIdx.x < 32) find_cluster_warp(s_r, m, nz, ck.n, ck.thresh, ck.buff, inner, outer);
+      } else {
+        __syncthreads();
+        block_sort_asc(g, m);
+        if (threadIdx.x < 32) find_cluster_warp(g, m, nz, ck.n, ck.thresh, ck.buff, inner, outer);
+      }
+    }
+    if (threadIdx.x == 0) write_cluster_rec(ck, pair, cell, cnt, inner, outer);
+    __syncthreads();
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// ICET_B200_FLAG_SHIPPED_ORDER (single pair, validation): clustering in the row order the reference ends up with
+// after its broken permutation loop (src/icet.cpp:72-83); ck.pos1 holds that position for every row of scan 1.
+// Zero ranges are ordinary members of the sequence here.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_off_shipped(const Chunk ck) {  // offsets of ALL points per cell
+  const int pair = blockIdx.x;
+  __shared__ int s_part[256];
+  const int per = (ck.ncell + 255) / 256;
+  const int c0 = threadIdx.x * per, c1 = min(ck.ncell, c0 + per);
+  const int32_t* cnt1 = ck.cnt1 + (size_t)pair * ck.ncell;
+  int s = 0;
+  for (int c = c0; c < c1; c++) s += cnt1[c];
+  s_part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int a = 0;
+    for (int t = 0; t < 256; t++) { const int v = s_part[t]; s_part[t] = a; a += v; }
+  }
+  __syncthreads();
+  int a = s_part[threadIdx.x];
+  for (int c = c0; c < c1; c++) {
+    ck.off[(size_t)pair * ck.ncell + c] = a;
+    ck.cursor[(size_t)pair * ck.ncell + c] = 0;
+    a += cnt1[c];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_scatter_shipped(const Chunk ck) {
+  const int pair = blockIdx.y;
+  const PairDesc d = ck.desc[pair];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.n1) return;
+  const size_t o = (size_t)pair * ck.n1max + i;
+  const int cell = ck.cellid1[o] & ~CELL_INBOX;
+  const int slot = atomicAdd(&ck.cursor[(size_t)pair * ck.ncell + cell], 1);
+  const unsigned long long key = ((unsigned long long)(unsigned)ck.pos1[o] << 32) | (unsigned)__float_as_uint(ck.r1[o]);
+  ck.kbuf[(size_t)pair * ck.n1max + ck.off[(size_t)pair * ck.ncell + cell] + slot] = key;
+}
+
+struct KeyRanges {  // the ranges of a cell in row order: low words of the keys sorted by position
+  const unsigned long long* k;
+  __device__ __forceinline__ float operator[](int i) const { return __uint_as_float((unsigned)(k[i] & 0xffffffffull)); }
+};
+
+__global__ void __launch_bounds__(128) k_cluster_shipped(const Chunk ck) {
+  const int pair = blockIdx.y;
+  const int nw = ck.nwork[pair];
+  for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+    const int cell = ck.work[(size_t)pair * ck.ncell + w];
+    const int m = ck.cnt1[(size_t)pair * ck.ncell + cell];
+    unsigned long long* g = ck.kbuf + (size_t)pair * ck.n1max + ck.off[(size_t)pair * ck.ncell + cell];
+    __syncthreads();
+    block_sort_asc(g, m);  // by row position (the high word is unique)
+    float inner = 0.f, outer = 0.f;
+    if (threadIdx.x < 32) find_cluster_warp(KeyRanges{g}, m, 0, ck.n, ck.thresh, ck.buff, inner, outer);
+    if (threadIdx.x == 0) write_cluster_rec(ck, pair, cell, m, inner, outer);
+    __syncthreads();
+  }
+}
+

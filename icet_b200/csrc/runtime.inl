@@ -1,0 +1,452 @@
+// icet_b200/csrc/runtime.inl -- host side: device buffers, the context, workspace layout, bin tables and the per-chunk
+// launch sequence (run_chunk).  Included by icet_b200.cu INSIDE its anonymous namespace; the context struct lives at
+// global scope (it is the opaque type of the C ABI), so this file closes and reopens the namespace around it.
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+      if (e != cudaSuccess) return fail(ICET_B200_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+constexpr int ICET_LOOP_MAX_PAIRS = 1;  // chunks up to this size run the Gauss-Newton loop as one persistent kernel
+constexpr int ICET_NSLOT = 4;  // staging slots of the host-buffer pipeline
+constexpr int ICET_NLANE = 4;  // compute lanes: consecutive chunks rotate over up to four streams (each with its own
+                               // workspace) so that the latency-bound ends of one chunk's kernels overlap the other's
+
+struct icet_b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;
+  cudaStream_t lanes[ICET_NLANE] = {};  // compute lanes 1.. (lane 0 is `stream`)
+  cudaEvent_t ev_fork = nullptr, ev_join[ICET_NLANE] = {};
+  cudaEvent_t ev_aux[2] = {};  // single-pair chunks: prepScan2 runs beside the scan-1 kernels on lane 1
+  int nlanes_default = 4;
+  int nlanes = 4;
+  cudaEvent_t ev_copy[ICET_NSLOT] = {};
+  cudaEvent_t ev_done[ICET_NSLOT] = {};
+  int chunk_pairs = 256;
+  int host_chunk = 64;  // pairs per chunk of the host-buffer pipeline (upload of chunk k+1 || registration of chunk k)
+  int64_t launches = 0;
+  int dump_on = 0;
+  int sm_count = 148;
+  int pass_smem_set = 0;  // dynamic shared memory the pass kernels are currently allowed
+  int* loop_dbg[ICET_NLANE] = {};  // watchdog record of the last k_loop launch per lane
+  int loop_occ[2] = {0, 0};  // resident blocks per SM of k_loop<PASS_K>, k_loop<PASS_K_SMALL>
+  // per-kernel timing (icet_b200_set_profile): events around every launch, summed on request
+  int profile_on = 0;
+  std::vector<cudaEvent_t> prof_ev;   // pairs (begin, end)
+  std::vector<int> prof_id;
+  size_t prof_used = 0;
+  double prof_ms[ICET_B200_NKERNELS] = {0};
+  int64_t prof_n[ICET_B200_NKERNELS] = {0};
+  // workspace
+  DevBuf ws[ICET_NLANE];  // one slab per compute lane, carved per chunk
+  DevBuf zero_ws;   // (part of ws) -- region that must be cleared per chunk is contiguous
+  DevBuf edges;     // azE | elE
+  int edges_nT = -1, edges_nP = -1;
+  DevBuf stage[ICET_NSLOT];  // host-input staging of scans (double buffered)
+  DevBuf descbuf[ICET_NSLOT];
+  DevBuf x0buf[ICET_NSLOT];
+  DevBuf resbuf;    // device results for host-facing calls
+  DevBuf dumpbuf;
+  DevBuf posebuf;
+  DevBuf rawbuf[2];  // ingest: device copies of the callers' raw records
+  DevBuf planebuf;   // ingest: planes of the two clouds of icet_b200_register_clouds
+  void* pinned = nullptr;  // pinned host bounce for results / descriptors
+  size_t pinned_cap = 0;
+  // dump bookkeeping
+  icet_b200_params dump_params{};
+  bool dump_valid = false;
+  Dump dump_ptrs{};
+  // the most recent single-pair chunk (for icet_b200_get_points2)
+  bool last_valid = false;
+  int last_n2 = 0, last_runlen = 0;
+  char last_ck[640];
+};
+
+namespace {
+
+struct Carve {
+  char* base;
+  size_t off = 0;
+  explicit Carve(void* b) : base((char*)b) {}
+  template <class T>
+  T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? (T*)(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+// Layout of the chunk workspace.  The first region (cnt1, cntz, cursor, acc) must be zero at chunk start.
+size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runlen, Chunk& ck, size_t* zero_bytes,
+                   bool shipped = false) {
+  const int vt = (ncell + 31) / 32;
+  Carve c(base);
+  ck.cnt1 = c.take<int32_t>((size_t)P * ncell);
+  ck.cntz = c.take<int32_t>((size_t)P * ncell);
+  ck.cursor = c.take<int32_t>((size_t)P * ncell);
+  ck.acc = c.take<unsigned long long>((size_t)P * ncell * NQ);
+  ck.n2c = c.take<int32_t>((size_t)P);
+  ck.nz2 = c.take<int32_t>((size_t)P);
+  ck.ticket = c.take<unsigned>(1);
+  ck.tiles_done = c.take<unsigned>((size_t)P);
+  ck.iter_done = c.take<int>((size_t)P);
+  ck.vox_done = c.take<unsigned>((size_t)P * std::max(1, runlen));
+  ck.vmask = c.take<unsigned>((size_t)P * ((vt + 31) / 32));
+  ck.dbg = c.take<int>(8);
+  c.off = (c.off + 255) & ~(size_t)255;
+  if (zero_bytes) *zero_bytes = c.off;
+  ck.off = c.take<int32_t>((size_t)P * ncell);
+  ck.work = c.take<int32_t>((size_t)P * ncell);
+  ck.nwork = c.take<int32_t>((size_t)P);
+  ck.nbig = c.take<int32_t>((size_t)P);
+  ck.rec = c.take<CellRec>((size_t)P * ncell);
+  ck.vox = c.take<Vox1>((size_t)P * ncell);
+  ck.cellid1 = c.take<int32_t>((size_t)P * n1max);
+  ck.r1 = c.take<float>((size_t)P * n1max);
+  ck.th1 = c.take<float>((size_t)P * n1max);
+  ck.ph1 = c.take<float>((size_t)P * n1max);
+  ck.rbuf = c.take<float>((size_t)P * n1max);
+  ck.kbuf = shipped ? c.take<unsigned long long>((size_t)P * n1max) : nullptr;
+  ck.pos1 = shipped ? c.take<int32_t>((size_t)P * n1max) : nullptr;
+  ck.pog = c.take<float>((size_t)P * 3 * n2max);
+  ck.X = c.take<float>((size_t)P * 6);
+  ck.TR = c.take<float>((size_t)P * 12);
+  ck.TRprev = c.take<float>((size_t)P * 12);
+  ck.J = c.take<float>((size_t)P * 27);
+  ck.part = c.take<double>((size_t)P * vt * 28);  // per vox group (k_loop) / per 64-voxel block (split loop)
+  return (c.off + 255) & ~(size_t)255;
+}
+
+int validate(const icet_b200_params* p) {
+  if (!p) return fail(ICET_B200_E_INVALID, "params is NULL");
+  if (p->runlen < 0 || p->runlen > 10000) return fail(ICET_B200_E_INVALID, "runlen out of range");
+  if (p->bins_phi < 1 || p->bins_theta < 1 || p->bins_phi + p->bins_theta > 4096 ||
+      (long long)p->bins_phi * p->bins_theta > (1 << 20))
+    return fail(ICET_B200_E_INVALID, "bins_phi/bins_theta out of range");
+  if (p->n < 1) return fail(ICET_B200_E_INVALID, "n must be >= 1");
+  if (!(p->thresh >= 0.f) || !(p->buff >= 0.f)) return fail(ICET_B200_E_INVALID, "thresh/buff must be >= 0");
+  return 0;
+}
+
+// smallest fp32 a >= 0 with int((double(a)/period)*nb) >= k  (binary search over the fp32 bit patterns,
+// which are ordered like the values for a >= 0)
+float bin_threshold(int k, double period, int nb) {
+  auto f = [&](float a) { return static_cast<int>(((double)a / period) * nb); };
+  uint32_t lo = 0, hi = 0x41000000u;  // +0.0f .. 8.0f
+  while (lo < hi) {
+    uint32_t mid = lo + (hi - lo) / 2;
+    float a;
+    memcpy(&a, &mid, 4);
+    if (f(a) >= k) hi = mid; else lo = mid + 1;
+  }
+  float a;
+  memcpy(&a, &lo, 4);
+  return a;
+}
+
+// device tables that depend only on the bin counts: fp32 box edges (src/icet.cpp:136-139) and the
+// exact bin-lookup thresholds (src/icet.cpp:545-546)
+int ensure_edges(icet_b200_ctx* ctx, int nT, int nP) {
+  if (ctx->edges_nT == nT && ctx->edges_nP == nP) return 0;
+  const size_t nbase = (size_t)2 * (nT + nP) + 6;
+  std::vector<float> e(((nbase + 3) & ~(size_t)3) + (size_t)4 * (nT + nP + 4));
+  float* azE = e.data();
+  float* elE = azE + nT + 1;
+  float* Tth = elE + nP + 1;
+  float* Tph = Tth + nT + 2;
+  // src/icet.cpp:136-139: float divide, double multiply, float store
+  for (int t = 0; t <= nT; t++) azE[t] = (static_cast<float>(t) / nT) * (2 * M_PI);
+  for (int q = 0; q <= nP; q++) elE[q] = (static_cast<float>(q) / nP) * (M_PI);
+  for (int k = 0; k <= nT; k++) Tth[k] = bin_threshold(k, 2 * M_PI, nT);
+  for (int k = 0; k <= nP; k++) Tph[k] = bin_threshold(k, M_PI, nP);
+  Tth[nT + 1] = INFINITY;
+  Tph[nP + 1] = INFINITY;
+  // bin + box records (bin_box): {T[k], T[k+1], max(T[k], E[k]), min(pred(T[k+1]), E[k+1])}; record nb is empty
+  float* rec = e.data() + ((nbase + 3) & ~(size_t)3);
+  auto fill = [](float* out, const float* T, const float* E, int nb, double period) {
+    const float beyond = std::nextafterf((float)period, INFINITY);
+    for (int k = 0; k < nb; k++) {
+      out[4 * k + 0] = T[k];
+      out[4 * k + 1] = T[k + 1];
+      out[4 * k + 2] = std::max(T[k], E[k]);
+      out[4 * k + 3] = std::min(std::nextafterf(T[k + 1], -INFINITY), E[k + 1]);
+    }
+    out[4 * nb + 0] = T[nb];
+    out[4 * nb + 1] = beyond;
+    out[4 * nb + 2] = INFINITY;
+    out[4 * nb + 3] = -INFINITY;
+    out[4 * nb + 4] = beyond;
+    out[4 * nb + 5] = INFINITY;
+    out[4 * nb + 6] = INFINITY;
+    out[4 * nb + 7] = -INFINITY;
+  };
+  fill(rec, Tth, azE, nT, 2 * M_PI);
+  fill(rec + 4 * (nT + 2), Tph, elE, nP, M_PI);
+  int rc = ctx->edges.ensure(e.size() * sizeof(float));
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->edges.p, e.data(), e.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->edges_nT = nT;
+  ctx->edges_nP = nP;
+  return 0;
+}
+
+void fill_tables(icet_b200_ctx* ctx, int nT, int nP, const float** azE, const float** elE, icet::BinTable* bth,
+                 icet::BinTable* bph, const float** binrec = nullptr) {
+  const float* base = (const float*)ctx->edges.p;
+  if (binrec) *binrec = base + ((((size_t)2 * (nT + nP) + 6) + 3) & ~(size_t)3);
+  *azE = base;
+  *elE = base + nT + 1;
+  bth->T = base + nT + 1 + nP + 1;
+  bth->nb = nT;
+  bth->scale = (float)((double)nT / (2 * M_PI));
+  bth->amax = (float)(2 * M_PI);
+  bth->acap = (float)((nT + 1.25) / ((double)nT / (2 * M_PI)));
+  bth->sbin = static_cast<int>(((double)1000.0f / (2 * M_PI)) * nT) % nT;
+  bph->T = bth->T + nT + 2;
+  bph->nb = nP;
+  bph->scale = (float)((double)nP / M_PI);
+  bph->amax = (float)M_PI;
+  bph->acap = (float)((nP + 1.25) / ((double)nP / M_PI));
+  bph->sbin = static_cast<int>(((double)1000.0f / M_PI) * nP) % nP;
+}
+
+int prof_events(icet_b200_ctx* ctx, int id, cudaEvent_t* e0, cudaEvent_t* e1) {
+  if (ctx->prof_used + 2 > ctx->prof_ev.size()) {
+    for (int k = 0; k < 2; k++) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return fail(ICET_B200_E_CUDA, "cudaEventCreate failed");
+      ctx->prof_ev.push_back(e);
+    }
+  }
+  *e0 = ctx->prof_ev[ctx->prof_used];
+  *e1 = ctx->prof_ev[ctx->prof_used + 1];
+  ctx->prof_used += 2;
+  ctx->prof_id.push_back(id);
+  return 0;
+}
+
+// Enqueue the whole registration of one chunk (descriptors already on the device).
+int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDesc* d_desc, int n1max, int n2max,
+              const float* d_x0, icet_b200_result* d_res, bool dump, int lane = 0) {
+  const int nT = p->bins_theta, nP = p->bins_phi, ncell = nT * nP;
+  int rc = ensure_edges(ctx, nT, nP);
+  if (rc) return rc;
+  Chunk ck;
+  memset(&ck, 0, sizeof(ck));
+  size_t zero_bytes = 0;
+  const bool shipped = (p->flags & ICET_B200_FLAG_SHIPPED_ORDER) != 0;
+  if (shipped && P != 1)
+    return fail(ICET_B200_E_INVALID, "ICET_B200_FLAG_SHIPPED_ORDER is a single-pair validation mode");
+  size_t need = carve_chunk(nullptr, P, ncell, n1max, n2max, p->runlen, ck, &zero_bytes, shipped);
+  rc = ctx->ws[lane].ensure(need);
+  if (rc) return rc;
+  carve_chunk(ctx->ws[lane].p, P, ncell, n1max, n2max, p->runlen, ck, &zero_bytes, shipped);
+  ck.desc = d_desc;
+  ck.npairs = P; ck.ncell = ncell; ck.nT = nT; ck.nP = nP; ck.n = p->n; ck.runlen = p->runlen;
+  ck.flags = p->flags; ck.thresh = p->thresh; ck.buff = p->buff;
+  ck.n1max = n1max; ck.n2max = n2max;
+  fill_tables(ctx, nT, nP, &ck.azE, &ck.elE, &ck.bth, &ck.bph, &ck.binrec);
+  ck.x0 = d_x0;
+  ck.res = d_res;
+  ck.dump_on = dump ? 1 : 0;
+  if (dump) ck.dump = ctx->dump_ptrs;
+  cudaStream_t st = lane == 0 ? ctx->stream : ctx->lanes[lane];
+  CK(cudaMemsetAsync(ctx->ws[lane].p, 0, zero_bytes, st));
+  const dim3 g1((n1max + 255) / 256, P), g2((n2max + 255) / 256, P);
+  const int nblk = (ncell + VOX_THREADS - 1) / VOX_THREADS;
+  // shape of the loop kernel: big tiles (16 points per lane) for throughput; small tiles (4 points per lane) when
+  // the chunk has too few big tiles to keep every resident block busy for several rounds
+  // pass kernels of the split loop: 12 rows per warp tile, 4 blocks / SM, coordinates prefetched 2 rows ahead
+  // (measured against 8 / 12 rows with 4-5 blocks and against no prefetch: profiles/r01_pass_variants.txt)
+  const int tile1 = pass_tile_points(PASS_K);
+  const dim3 gp1((n1max + tile1 - 1) / tile1, P), gp2((n2max + tile1 - 1) / tile1, P);
+  const int psm = pass_smem_bytes(nT, nP, PASS_K);
+  if (psm > ctx->pass_smem_set) {
+    CK(cudaFuncSetAttribute(k_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
+    CK(cudaFuncSetAttribute(k_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
+    CK(cudaFuncSetAttribute(k_loop<PASS_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
+    CK(cudaFuncSetAttribute(k_loop<PASS_K_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->loop_occ[0], k_loop<PASS_K>, PASS_THREADS, psm));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->loop_occ[1], k_loop<PASS_K_SMALL>, PASS_THREADS,
+                                                     pass_smem_bytes(nT, nP, PASS_K_SMALL)));
+    ctx->pass_smem_set = psm;
+  }
+  // warp tiles: 32*K points.  Small K when the chunk has too few big tiles to keep every resident warp busy for
+  // several rounds per iteration (small batches, single-pair latency).
+  const int wt_big = 32 * PASS_K;
+  const long long big_tiles = (long long)P * ((n2max + wt_big - 1) / wt_big);
+  const bool chain = (p->flags & ICET_B200_FLAG_CHAIN_X0) != 0;  // one pair at a time is in flight: latency shape
+  const bool small_batch = big_tiles < 4LL * ctx->sm_count * std::max(1, ctx->loop_occ[0]) * PASS_WARPS;
+  const bool small = chain || small_batch;
+  const int K2 = small ? PASS_K_SMALL : PASS_K;
+  const int tiles2 = std::max(1, (n2max + 32 * K2 - 1) / (32 * K2));  // >= 1: tile 0 carries the dropped returns
+  const int vt = (ncell + 31) / 32;
+  const int psm2 = pass_smem_bytes(nT, nP, K2);
+  // LAUNCH(id, kernel<<<...>>>(...)): counts the launch and, when profiling, brackets it with events
+#define LAUNCH(id, ...)                                                   \
+  do {                                                                    \
+    cudaEvent_t e0_ = nullptr, e1_ = nullptr;                             \
+    if (ctx->profile_on) {                                                \
+      if (prof_events(ctx, id, &e0_, &e1_)) return ICET_B200_E_CUDA;      \
+      cudaEventRecord(e0_, st);                                           \
+    }                                                                     \
+    __VA_ARGS__;                                                          \
+    if (e1_) cudaEventRecord(e1_, st);                                    \
+    ctx->launches++;                                                      \
+  } while (0)
+  // Latency shape (one pair): prepScan2 does not depend on the scan-1 kernels, so it runs beside them on lane 1.
+  const bool prep_aside = P == 1 && n2max > 0 && lane == 0 && !ctx->profile_on && ctx->lanes[1] != nullptr;
+  if (prep_aside) {
+    CK(cudaEventRecord(ctx->ev_aux[0], st));  // after the workspace has been cleared and the descriptor uploaded
+    CK(cudaStreamWaitEvent(ctx->lanes[1], ctx->ev_aux[0], 0));
+    k_prep2<<<g2, 256, 0, ctx->lanes[1]>>>(ck);
+    ctx->launches++;
+    CK(cudaEventRecord(ctx->ev_aux[1], ctx->lanes[1]));
+  }
+  if (n1max > 0) LAUNCH(0, k_scan1_bin<<<g1, 256, 0, st>>>(ck));
+  LAUNCH(1, k_cell_scan<<<P, 256, 0, st>>>(ck));
+  if (n1max > 0) {
+    if (shipped) {
+      // The row order the reference ends up with (src/icet.cpp:72-83), reproduced on the host from the ranges the
+      // device computed: the same index sort by range (std::sort; the reference's std::execution::par falls back
+      // to it without TBB) and the same swap loop, which is NOT a valid permutation application.
+      std::vector<float> hr((size_t)n1max);
+      CK(cudaMemcpyAsync(hr.data(), ck.r1, (size_t)n1max * sizeof(float), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      std::vector<int> index((size_t)n1max), orig((size_t)n1max), pos((size_t)n1max);
+      for (int i = 0; i < n1max; i++) index[i] = orig[i] = i;
+      std::sort(index.begin(), index.end(), [&](int a, int b) { return hr[a] < hr[b]; });
+      for (int i = 0; i < n1max; i++) {
+        if (index[i] != i) {
+          const int j = index[i];
+          std::swap(orig[i], orig[j]);    // points1Spherical.row(i).swap(points1Spherical.row(index[i]))
+          std::swap(index[i], index[j]);  // std::swap(index[i], index[index[i]])
+        }
+      }
+      for (int i = 0; i < n1max; i++) pos[orig[i]] = i;
+      CK(cudaMemcpyAsync(ck.pos1, pos.data(), (size_t)n1max * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+      LAUNCH(2, k_off_shipped<<<P, 256, 0, st>>>(ck));
+      LAUNCH(2, k_scatter_shipped<<<g1, 256, 0, st>>>(ck));
+      LAUNCH(3, k_cluster_shipped<<<dim3(std::max(1, std::min(ncell, 1024)), P), 128, 0, st>>>(ck));
+    } else {
+    LAUNCH(2, k_scatter<<<g1, 256, 0, st>>>(ck));
+    // one warp per listed cell; enough CTAs to cover a typical work list (~25 % of the cells) in one pass
+    int gx = std::max(1, std::min((ncell + CLUSTER_WARPS - 1) / CLUSTER_WARPS,
+                                  std::max(32, (ctx->sm_count * 16 + P - 1) / P)));
+    LAUNCH(3, k_cluster<<<dim3(gx, P), CLUSTER_WARPS * 32, 0, st>>>(ck));
+    }
+    if (small_batch) {  // latency shape: 128 points per warp
+      const int tile_s = pass_tile_points(PASS_K_SMALL);
+      LAUNCH(4, k_pass<false, PASS_K_SMALL, 3, 1, PASS_K_SMALL><<<dim3((n1max + tile_s - 1) / tile_s, P), PASS_THREADS, psm2, st>>>(ck));
+    } else {
+      LAUNCH(4, k_pass<false><<<gp1, PASS_THREADS, psm, st>>>(ck));
+    }
+  }
+  LAUNCH(5, k_fit1<<<dim3((ncell + 127) / 128, P), 128, 0, st>>>(ck));
+  if (prep_aside) CK(cudaStreamWaitEvent(st, ctx->ev_aux[1], 0));
+  else if (n2max > 0) LAUNCH(6, k_prep2<<<g2, 256, 0, st>>>(ck));
+  const bool use_loop = chain || (p->flags & ICET_B200_FLAG_PERSISTENT_LOOP) ||
+                        (!(p->flags & ICET_B200_FLAG_UNFUSED_LOOP) && P <= ICET_LOOP_MAX_PAIRS);
+  if (!use_loop) {
+    for (int it = 0; it < p->runlen; it++) {
+      if (n2max > 0) LAUNCH(7, k_pass<true><<<gp2, PASS_THREADS, psm, st>>>(ck));
+      LAUNCH(8, k_vox2<<<dim3(nblk, P), VOX_THREADS, 0, st>>>(ck, it));
+      LAUNCH(9, k_solve6<<<P, 32, 0, st>>>(ck, it, nblk));
+    }
+  } else if (p->runlen > 0) {
+    // persistent: as many blocks as can be resident (more would only queue behind them)
+    const long long tasks = (long long)P * (tiles2 + vt) * p->runlen;
+    if (tasks >= (1LL << 32)) return fail(ICET_B200_E_INVALID, "chunk too large: reduce icet_b200_set_chunk");
+    const int occ = std::max(1, ctx->loop_occ[small ? 1 : 0]);
+    const int grid = (int)std::min<long long>((tasks + PASS_WARPS - 1) / PASS_WARPS, (long long)ctx->sm_count * occ);
+    ctx->loop_dbg[lane] = ck.dbg;
+    if (small) LAUNCH(10, k_loop<PASS_K_SMALL><<<grid, PASS_THREADS, psm2, st>>>(ck, tiles2, vt));
+    else LAUNCH(10, k_loop<PASS_K><<<grid, PASS_THREADS, psm2, st>>>(ck, tiles2, vt));
+  }
+#undef LAUNCH
+  CK(cudaGetLastError());
+  static_assert(sizeof(Chunk) <= 640, "Chunk too large for last_ck");
+  ctx->last_valid = (P == 1);
+  if (P == 1) memcpy(ctx->last_ck, &ck, sizeof(Chunk));
+  return 0;
+}
+
+// after a blocking call: did a wait inside k_loop give up?  (never expected; turns a would-be hang into an error)
+int check_loop_watchdog(icet_b200_ctx* ctx) {
+  for (int lane = 0; lane < ICET_NLANE; lane++) {
+    if (!ctx->loop_dbg[lane]) continue;
+    int d[8];
+    CK(cudaMemcpy(d, ctx->loop_dbg[lane], sizeof(d), cudaMemcpyDeviceToHost));
+    ctx->loop_dbg[lane] = nullptr;
+    if (d[0])
+      return fail(ICET_B200_E_CUDA, "persistent loop kernel: wait timed out (kind " + std::to_string(d[1]) + ", pair " +
+                                        std::to_string(d[2]) + ", iteration " + std::to_string(d[3]) + ", seen " +
+                                        std::to_string(d[4]) + ", need " + std::to_string(d[5]) + ", ticket " +
+                                        std::to_string(d[6]) + ")");
+  }
+  return 0;
+}
+
+int ensure_pinned(icet_b200_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->pinned_cap) return 0;
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  ctx->pinned = nullptr;
+  ctx->pinned_cap = 0;
+  CK(cudaMallocHost(&ctx->pinned, bytes));
+  ctx->pinned_cap = bytes;
+  return 0;
+}
+
+int ensure_dump(icet_b200_ctx* ctx, const icet_b200_params* p) {
+  const size_t ncell = (size_t)p->bins_phi * p->bins_theta, rl = (size_t)std::max(1, p->runlen);
+  Carve c(nullptr);
+  auto lay = [&](Carve& cv, Dump& d) {
+    d.nin1 = cv.take<int32_t>(ncell); d.has1 = cv.take<uint8_t>(ncell); d.mu1 = cv.take<float>(ncell * 3);
+    d.sigma1 = cv.take<float>(ncell * 9); d.evec1 = cv.take<float>(ncell * 9); d.eval1 = cv.take<float>(ncell * 3);
+    d.lmask = cv.take<uint8_t>(ncell * 3);
+    d.cnt2 = cv.take<int32_t>(rl * ncell); d.nin2 = cv.take<int32_t>(rl * ncell); d.used2 = cv.take<uint8_t>(rl * ncell);
+    d.mu2 = cv.take<float>(rl * ncell * 3); d.sigma2 = cv.take<float>(rl * ncell * 9);
+    d.Xit = cv.take<float>(rl * 6); d.HTWH = cv.take<float>(rl * 36); d.HTWdz = cv.take<float>(rl * 6);
+    d.tl = cv.take<unsigned long long>(rl * 16 + 6144);  // + begin / end / mid of up to 2048 tiles of iteration 3
+  };
+  Dump tmp;
+  lay(c, tmp);
+  size_t need = c.off + 256;
+  int rc = ctx->dumpbuf.ensure(need);
+  if (rc) return rc;
+  Carve c2(ctx->dumpbuf.p);
+  lay(c2, ctx->dump_ptrs);
+  CK(cudaMemsetAsync(ctx->dumpbuf.p, 0, need, ctx->stream));
+  return 0;
+}
+

@@ -40,8 +40,9 @@ def test_library_links_no_cpu_fallback():
     assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
     ldd = subprocess.run(["ldd", lib], capture_output=True, text=True).stdout
     assert "oracle" not in ldd
-    src = open(os.path.join(ROOT, "icet_b200", "csrc", "icet_b200.cu")).read() + \
-        open(os.path.join(ROOT, "icet_b200", "api.py")).read()
+    csrc = os.path.join(ROOT, "icet_b200", "csrc")
+    src = "".join(open(os.path.join(csrc, f)).read() for f in sorted(os.listdir(csrc))) + \
+        open(os.path.join(ROOT, "icet_b200", "api.py")).read() + open(os.path.join(ROOT, "icet_b200", "nodes.py")).read()
     assert "pyoracle" not in src and "icet_oracle" not in src  # the product never references the checker
 
 
