@@ -423,51 +423,28 @@ __global__ void __launch_bounds__(128) k_fit1(const Chunk ck) {
 __global__ void __launch_bounds__(256) k_prep2(const Chunk ck) {
   const int pair = blockIdx.y;
   const PairDesc d = ck.desc[pair];
-  if ((int)(blockIdx.x * blockDim.x) >= d.n2) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  float x = 0.f, y = 0.f, z = 0.f;
-  bool keep = false, zero = false;
-  // Consecutive pairs of a sequence share a scan: scan 2 of this pair is scan 1 of the next one, whose spherical
-  // coordinates K1 has already stored (same function, same inputs) -- read them instead of converting again.
-  bool shared = false;
+  // scan 2 of this pair is scan 1 of the next one (sequences): k_scan1_bin of that pair has done this work already
   if (pair + 1 < ck.npairs) {
     const PairDesc nx = ck.desc[pair + 1];
-    shared = nx.s1 == d.s2 && nx.n1 == d.n2 && nx.ld1 == d.ld2;
+    if (nx.s1 == d.s2 && nx.n1 == d.n2 && nx.ld1 == d.ld2) return;
   }
-  if (i < d.n2) {
-    float r, th, ph;
-    if (shared) {
-      const size_t o = (size_t)(pair + 1) * ck.n1max + i;
-      r = __ldg(ck.r1 + o); th = __ldg(ck.th1 + o); ph = __ldg(ck.ph1 + o);
-    } else {
+  // (few blocks per pair in big chunks, where most pairs return above: the grid stays small)
+  for (int b0 = blockIdx.x * blockDim.x; b0 < d.n2; b0 += gridDim.x * blockDim.x) {  // block-uniform
+    const int i = b0 + threadIdx.x;
+    float x = 0.f, y = 0.f, z = 0.f;
+    bool keep = false, zero = false;
+    if (i < d.n2) {
       x = __ldg(d.s2 + i); y = __ldg(d.s2 + d.ld2 + i); z = __ldg(d.s2 + 2 * (size_t)d.ld2 + i);
+      float r, th, ph;
       icet::c2s(x, y, z, r, th, ph);
+      icet::s2c(r, th, ph, x, y, z);
+      // Dropped returns: (0,0,0) stays (+0,+0,+0).  They are all the same point in every iteration, so they are
+      // counted here and evaluated once per iteration by k_pass<true> instead of being stored.
+      zero = (__float_as_uint(x) | __float_as_uint(y) | __float_as_uint(z)) == 0u;
+      keep = !zero;
     }
-    icet::s2c(r, th, ph, x, y, z);
-    // Dropped returns: (0,0,0) stays (+0,+0,+0).  They are all the same point in every iteration, so they are
-    // counted here and evaluated once per iteration by k_pass<true> instead of being stored.
-    zero = (__float_as_uint(x) | __float_as_uint(y) | __float_as_uint(z)) == 0u;
-    keep = !zero;
-  }
-  // block-level compaction (the order of points2_OG is irrelevant: all sums over it are exact integers)
-  __shared__ int s_cnt[8], s_zero[8], s_base;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned mk = __ballot_sync(FULL, keep), mz = __ballot_sync(FULL, zero);
-  if (lane == 0) { s_cnt[warp] = __popc(mk); s_zero[warp] = __popc(mz); }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int tot = 0, totz = 0;
-    for (int w = 0; w < 8; w++) { const int c = s_cnt[w]; s_cnt[w] = tot; tot += c; totz += s_zero[w]; }
-    s_base = tot ? atomicAdd(&ck.n2c[pair], tot) : 0;
-    if (totz) atomicAdd(&ck.nz2[pair], totz);
-  }
-  __syncthreads();
-  if (keep) {
-    const int o = s_base + s_cnt[warp] + __popc(mk & ((1u << lane) - 1));
-    float* pg = ck.pog + (size_t)pair * 3 * ck.n2max;
-    pg[o] = x;
-    pg[ck.n2max + o] = y;
-    pg[2 * (size_t)ck.n2max + o] = z;
+    prep2_compact(ck, pair, x, y, z, keep, zero);
+    __syncthreads();  // the shared scratch of prep2_compact is reused by the next round
   }
 }
 

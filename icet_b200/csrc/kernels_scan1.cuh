@@ -16,6 +16,30 @@ __device__ __forceinline__ void cell_of(const Chunk& ck, float th, float ph, int
 // K1: scan 1 -> spherical, cell index, per-cell histogram.
 // utils::cartesianToSpherical (src/utils.cpp:93-119) + sortSphericalCoordinates (src/icet.cpp:534-554)
 // ----------------------------------------------------------------------------------------------
+// Block-level compaction of points2_OG into pog[pair] (the order of points2_OG is irrelevant: all sums over it are
+// exact integers); dropped returns are counted, not stored.  Called by every thread of a 256-thread block.
+__device__ __forceinline__ void prep2_compact(const Chunk& ck, int pair, float x, float y, float z, bool keep, bool zero) {
+  __shared__ int s_cnt[8], s_zero[8], s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned mk = __ballot_sync(FULL, keep), mz = __ballot_sync(FULL, zero);
+  if (lane == 0) { s_cnt[warp] = __popc(mk); s_zero[warp] = __popc(mz); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0, totz = 0;
+    for (int w = 0; w < 8; w++) { const int c = s_cnt[w]; s_cnt[w] = tot; tot += c; totz += s_zero[w]; }
+    s_base = tot ? atomicAdd(&ck.n2c[pair], tot) : 0;
+    if (totz) atomicAdd(&ck.nz2[pair], totz);
+  }
+  __syncthreads();
+  if (keep) {
+    const int o = s_base + s_cnt[warp] + __popc(mk & ((1u << lane) - 1));
+    float* pg = ck.pog + (size_t)pair * 3 * ck.n2max;
+    pg[o] = x;
+    pg[ck.n2max + o] = y;
+    pg[2 * (size_t)ck.n2max + o] = z;
+  }
+}
+
 constexpr int32_t CELL_INBOX = 0x40000000;  // cellid1 flag: the point passes the fp32 az / el box test of its own bin
 __device__ __forceinline__ int bin_box(float a, const float4* rec, const icet::BinTable& bt, bool& inbox);
 
@@ -26,10 +50,25 @@ __global__ void __launch_bounds__(256) k_scan1_bin(const Chunk ck) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int cell = -1;
   bool zero = false;
+  // Consecutive pairs of a sequence share a scan: scan 1 of this pair is scan 2 of the previous one.  Its spherical
+  // coordinates are computed here anyway, so prepScan2 of the previous pair (round trip + compaction, see k_prep2)
+  // is done in the same pass and k_prep2 skips that pair.
+  bool prev_shares = false;
+  if (pair > 0) {
+    const PairDesc pv = ck.desc[pair - 1];
+    prev_shares = pv.s2 == d.s1 && pv.n2 == d.n1 && pv.ld2 == d.ld1;
+  }
+  float px = 0.f, py = 0.f, pz = 0.f;
+  bool pkeep = false, pzero = false;
   if (i < d.n1) {
     float x = __ldg(d.s1 + i), y = __ldg(d.s1 + d.ld1 + i), z = __ldg(d.s1 + 2 * (size_t)d.ld1 + i);
     float r, th, ph;
     icet::c2s(x, y, z, r, th, ph);
+    if (prev_shares) {
+      icet::s2c(r, th, ph, px, py, pz);
+      pzero = (__float_as_uint(px) | __float_as_uint(py) | __float_as_uint(pz)) == 0u;
+      pkeep = !pzero;
+    }
     // bin and box test in one look-up (same records as the pass kernels, read through L1 here)
     const float4* tth = reinterpret_cast<const float4*>(ck.binrec);
     const float4* tph = tth + ck.nT + 2;
@@ -55,6 +94,7 @@ __global__ void __launch_bounds__(256) k_scan1_bin(const Chunk ck) {
       if (mz) atomicAdd(&ck.cntz[(size_t)pair * ck.ncell + cell], __popc(mz));
     }
   }
+  if (prev_shares) prep2_compact(ck, pair - 1, px, py, pz, pkeep, pzero);  // block-uniform
 }
 
 // ----------------------------------------------------------------------------------------------

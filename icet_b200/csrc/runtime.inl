@@ -281,7 +281,8 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   if (dump) ck.dump = ctx->dump_ptrs;
   cudaStream_t st = lane == 0 ? ctx->stream : ctx->lanes[lane];
   CK(cudaMemsetAsync(ctx->ws[lane].p, 0, zero_bytes, st));
-  const dim3 g1((n1max + 255) / 256, P), g2((n2max + 255) / 256, P);
+  // (k_prep2 strides over its pair: one block per 256 points for small chunks, at least 32 blocks per pair always)
+  const dim3 g1((n1max + 255) / 256, P), g2(std::max(1, std::min((n2max + 255) / 256, std::max(32, 8192 / P))), P);
   const int nblk = (ncell + VOX_THREADS - 1) / VOX_THREADS;
   // shape of the loop kernel: big tiles (16 points per lane) for throughput; small tiles (4 points per lane) when
   // the chunk has too few big tiles to keep every resident block busy for several rounds
