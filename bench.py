@@ -126,12 +126,14 @@ def run_reference(args, rank: int, world: int):
             times.append(sample / pps)
     t = float(np.mean(times))
     value = sample / t
+    one_core, _ = cpu_time_sequence(scans[:5], 1)  # one instance on one core
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": value / README_PAIRS_PER_S, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.pairs_per_gpu, args.gpus),
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "one_core_value": one_core,
                          "sample": "%d consecutive synthetic 64-ch pairs per step, %d threads (one pair per thread "
                                    "at a time); the reference C++ cannot be compiled here (no Eigen), this is the "
                                    "oracle restatement built -O3 -march=native" % (sample, cores)},
@@ -438,7 +440,8 @@ def main():
         sample = max(2, min(2 * cores, P, 256))
         hs = scans[: sample + 1].cpu().numpy()
         pps, ores = cpu_time_sequence(hs, cores)
-        cpu_baseline = {"value": pps, "unit": "pairs/s", "cores": cores, "kind": "port",
+        one_core, _ = cpu_time_sequence(hs[:5], 1)  # one instance on one core
+        cpu_baseline = {"value": pps, "unit": "pairs/s", "cores": cores, "kind": "port", "one_core_value": one_core,
                         "sample": "first %d pairs of the same synthetic sequence, %d host threads (one pair per thread "
                                   "at a time); oracle restatement built -O3 -march=native (the reference cannot be "
                                   "compiled here: no Eigen)" % (sample, cores)}
