@@ -37,11 +37,15 @@ FLAG_FULL_EIG = 1
 FLAG_UNFUSED_LOOP = 2
 FLAG_PERSISTENT_LOOP = 4
 FLAG_SHIPPED_ORDER = 16  # validation: cluster in the row order the reference's broken permutation loop leaves (single pair)
+FLAG_EXACT_PASS = 32  # scan 2: the reference's per-point pipeline in every iteration (validation form)
+FLAG_FULL_REBUILD = 64  # scan 2: incremental bookkeeping, every point re-evaluated in every iteration (diagnostic)
+FLAG_VERIFY_INCREMENTAL = 128  # self-check: result["reserved"][0] counts stable points whose class changed (must be 0)
 FLAG_CHAIN_X0 = 8  # odometry.cpp:82: pair k+1 starts from the solution of pair k; X0 = one seed (pair 0)
 
 _DUMP_FIELDS = [("cnt1", _IP), ("bounds", _FP), ("nin1", _IP), ("has1", _BP), ("mu1", _FP), ("sigma1", _FP),
                 ("evec1", _FP), ("eval1", _FP), ("lmask", _BP), ("cnt2", _IP), ("nin2", _IP), ("used2", _BP),
-                ("mu2", _FP), ("sigma2", _FP), ("Xit", _FP), ("HTWH", _FP), ("HTWdz", _FP)]
+                ("mu2", _FP), ("sigma2", _FP), ("Xit", _FP), ("HTWH", _FP), ("HTWdz", _FP), ("TRit", _FP),
+                ("testPoints", _FP)]
 
 
 class OdometryParams(C.Structure):
@@ -104,6 +108,7 @@ EXPORTS = ["icet_b200_version", "icet_b200_last_error", "icet_b200_create", "ice
            "icet_b200_set_stream", "icet_b200_set_chunk", "icet_b200_set_host_chunk", "icet_b200_set_lanes", "icet_b200_debug_timeline", "icet_b200_register", "icet_b200_register_batch",
            "icet_b200_register_batch_device", "icet_b200_register_sequence_device", "icet_b200_synchronize",
            "icet_b200_set_dump", "icet_b200_get_dump", "icet_b200_get_points2", "icet_b200_spherical_bins",
+           "icet_b200_classify_scan2",
            "icet_b200_synth_scans_device", "icet_b200_kernel_launches", "icet_b200_set_profile",
            "icet_b200_get_profile", "icet_b200_kernel_name",
            "icet_b200_node_create", "icet_b200_node_destroy", "icet_b200_node_push_device", "icet_b200_node_push",
@@ -150,6 +155,7 @@ def load_library() -> C.CDLL:
     L.icet_b200_set_dump.argtypes = [vp, C.c_int32]
     L.icet_b200_get_dump.argtypes = [vp, C.POINTER(_Dump)]
     L.icet_b200_get_points2.argtypes = [vp, vp, C.c_int32]
+    L.icet_b200_classify_scan2.argtypes = [vp, C.c_int32, vp, vp, C.c_int32]
     L.icet_b200_spherical_bins.argtypes = [vp, C.POINTER(Params), vp, C.c_int32, C.c_int32, vp, vp]
     L.icet_b200_synth_scans_device.argtypes = [vp, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     L.icet_b200_kernel_launches.argtypes = [vp]
@@ -358,6 +364,14 @@ class Context:
         self._check(self._L.icet_b200_get_points2(self._h, out.ctypes.data, n2))
         return out
 
+    def classify_scan2(self, it: int, n2: int):
+        """(cell [n2] int32, in [n2] uint8): class of every point of scan 2 of the last dumped `register` call in
+        iteration `it` by the per-point pipeline, in the caller's point order."""
+        cell = np.zeros(n2, np.int32)
+        inb = np.zeros(n2, np.uint8)
+        self._check(self._L.icet_b200_classify_scan2(self._h, it, cell.ctypes.data, inb.ctypes.data, n2))
+        return cell, inb
+
     def debug_timeline(self, runlen: int) -> np.ndarray:
         """%globaltimer stamps [runlen, 16] (ns) of the loop kernel for the last dumped single-pair call."""
         out = np.zeros(runlen * 16 + 6144, np.uint64)
@@ -374,7 +388,8 @@ class Context:
                   "lmask": ((ncell, 3), np.uint8), "cnt2": ((rl, ncell), np.int32), "nin2": ((rl, ncell), np.int32),
                   "used2": ((rl, ncell), np.uint8), "mu2": ((rl, ncell, 3), np.float32),
                   "sigma2": ((rl, ncell, 3, 3), np.float32), "Xit": ((rl, 6), np.float32),
-                  "HTWH": ((rl, 6, 6), np.float32), "HTWdz": ((rl, 6), np.float32)}
+                  "HTWH": ((rl, 6, 6), np.float32), "HTWdz": ((rl, 6), np.float32),
+                  "TRit": ((rl, 12), np.float32), "testPoints": ((ncell * 6, 3), np.float32)}
         arrs = {k: np.zeros(s, d) for k, (s, d) in shapes.items()}
         d = _Dump()
         for name, ct in _DUMP_FIELDS:

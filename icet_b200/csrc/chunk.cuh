@@ -46,9 +46,24 @@ struct Vox1 {     // scan-1 Gaussian, constants of the iteration loop (sigma1/mu
   int pad;
 };
 
+// Per-pair control block of the incremental scan-2 loop (kernels_pass2.cuh): written by k_cell_scan (first iteration:
+// rebuild) and by the 6x6 solve for the iteration that follows it.
+struct __align__(16) PairMode {
+  int set;        // accumulator set (0 / 1) the current iteration reads and updates
+  int rebuild;    // 1: every point is evaluated and the set is built from zero; 0: only points whose margin is used up
+  float SA, C;    // motion odometers since the last rebuild: SA = sum |R_j+1 - R_j|_F, C = SB + SA * SB, SB = sum |t_j+1 - t_j|
+  float SB;
+  int zcls;       // class word of the dropped-return point (0,0,0) in the previous iteration
+  int pad[2];
+  float TRb[12];  // transform of the last rebuild: the voxels' fixed-point frames of scan 2 are anchored to it
+  int pad2[4];
+};
+
 struct Dump {  // optional per-voxel recording (device memory), single-pair debugging only
   int32_t* nin1; uint8_t* has1; float* mu1; float* sigma1; float* evec1; float* eval1; uint8_t* lmask;
   int32_t* cnt2; int32_t* nin2; uint8_t* used2; float* mu2; float* sigma2; float* Xit; float* HTWH; float* HTWdz;
+  float* TRit;      // [runlen][12] t | R(X) every iteration used (src/icet.cpp:375-376)
+  float* testpts;   // [ncell*6][3] the reference's public `testPoints` (src/icet.cpp:214-232): sigma points of suppressed axes
   unsigned long long* tl;  // [runlen][16] globaltimer stamps of the loop kernel (debug) + per-tile stamps of iteration 3
 };
 
@@ -73,7 +88,7 @@ struct Chunk {  // everything a kernel needs, passed by value
   int32_t* nwork;    // [P]
   int32_t* nbig;     // [P]  cells of the work list with more than WSORT_MAX non-zero ranges
   CellRec* rec;      // [P][ncell]
-  unsigned long long* acc;  // [P][ncell][NQ]
+  unsigned long long* acc;  // [2][P][ncell][NQ]  (set 1 is used by the incremental scan-2 loop only)
   Vox1* vox;         // [P][ncell]
   const float* azE;  // [nT+1] float azimuth bin edges  (src/icet.cpp:136-137)
   const float* elE;  // [nP+1] float elevation bin edges (src/icet.cpp:138-139)
@@ -87,6 +102,10 @@ struct Chunk {  // everything a kernel needs, passed by value
   float* pog;        // [P][3][n2max]  points2_OG without the dropped returns (compacted, any order)
   int32_t* n2c;      // [P] points stored in pog
   int32_t* nz2;      // [P] dropped returns of scan 2 (points2_OG == 0)
+  float2* marg;      // [P][n2max]  incremental loop: {u, r_e} of every stored point: its class cannot have changed while
+                     //               r_e * SA + C < u   (kernels_pass2.cuh)
+  uint32_t* cls2;    // [P][n2max]  incremental loop: cell | CLS_IN | CLS_ACTIVE of the point's last evaluation
+  PairMode* pm;      // [P]
   float* X;          // [P][6]
   const float* x0;   // [P][6] or null
   icet_b200_result* res;  // [P] device

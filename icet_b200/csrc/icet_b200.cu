@@ -32,6 +32,7 @@ namespace {
 #include "chunk.cuh"
 #include "kernels_scan1.cuh"
 #include "kernels_pass.cuh"
+#include "kernels_pass2.cuh"
 #include "kernels_loop.cuh"
 #include "runtime.inl"
 #include "callers.cuh"
@@ -516,7 +517,7 @@ int icet_b200_get_dump(icet_b200_ctx* c, icet_b200_voxel_dump* o) {
   CP(evec1, evec1, ncell * 36); CP(eval1, eval1, ncell * 12); CP(lmask, lmask, ncell * 3);
   CP(cnt2, cnt2, rl * ncell * 4); CP(nin2, nin2, rl * ncell * 4); CP(used2, used2, rl * ncell);
   CP(mu2, mu2, rl * ncell * 12); CP(sigma2, sigma2, rl * ncell * 36); CP(Xit, Xit, rl * 24);
-  CP(HTWH, HTWH, rl * 144); CP(HTWdz, HTWdz, rl * 24);
+  CP(HTWH, HTWH, rl * 144); CP(HTWdz, HTWdz, rl * 24); CP(TRit, TRit, rl * 48); CP(testPoints, testpts, ncell * 72);
 #undef CP
   return 0;
 }
@@ -547,6 +548,29 @@ int icet_b200_get_points2(icet_b200_ctx* c, float* out, int32_t n2) {
   c->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, d_out, (size_t)3 * n2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int icet_b200_classify_scan2(icet_b200_ctx* c, int32_t iter, int32_t* cell, uint8_t* in, int32_t n2) {
+  if (!c || !cell || !in) return fail(ICET_B200_E_INVALID, "NULL argument");
+  if (!c->last_valid || !c->dump_valid) return fail(ICET_B200_E_INVALID, "no dumped single-pair registration to classify");
+  if (n2 != c->last_n2) return fail(ICET_B200_E_INVALID, "n2 does not match the last registration");
+  if (iter < 0 || iter >= c->dump_params.runlen) return fail(ICET_B200_E_INVALID, "iteration out of range");
+  if (n2 == 0) return 0;
+  CK(cudaSetDevice(c->device));
+  Chunk ck;
+  memcpy(&ck, c->last_ck, sizeof(Chunk));
+  CK(cudaStreamSynchronize(c->stream));
+  int rc = c->resbuf.ensure((size_t)5 * n2 + 1024);
+  if (rc) return rc;
+  int32_t* d_cell = (int32_t*)c->resbuf.p;
+  uint8_t* d_in = (uint8_t*)(d_cell + n2);
+  k_classify2<<<(n2 + 255) / 256, 256, 0, c->stream>>>(ck, n2, c->dump_ptrs.TRit + (size_t)iter * 12, d_cell, d_in);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(cell, d_cell, (size_t)n2 * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(in, d_in, (size_t)n2, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }

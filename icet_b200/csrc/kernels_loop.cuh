@@ -70,6 +70,9 @@ __device__ __forceinline__ bool vox_gate(const Chunk& ck, int pair, int cell, in
   return use;
 }
 
+__device__ __forceinline__ void vox_algebra_core(const Chunk& ck, int pair, int cell, int iter, const float* Jm,
+                                                 long long nbin, const double mean[3], const double cov[6], double acc[NRED]);
+
 // The algebra of one contributing voxel; takes (and clears) its accumulators.
 __device__ __forceinline__ void vox_algebra(const Chunk& ck, int pair, int cell, int iter, const float* Jm /* 27 */,
                                             double acc[NRED]) {
@@ -85,9 +88,16 @@ __device__ __forceinline__ void vox_algebra(const Chunk& ck, int pair, int cell,
   }
 #pragma unroll
   for (int k = 0; k < NQ; k++) qp[k] = 0ull;
-  const long long nbin = (long long)q[0];
   double mean[3], cov[6];
   stats_from_acc(q, rc, mean, cov);
+  vox_algebra_core(ck, pair, cell, iter, Jm, (long long)q[0], mean, cov, acc);
+}
+
+// from the scan-2 mean / covariance of a voxel to its contributions H^T W H_j, H^T W dz_j (src/icet.cpp:308-338)
+__device__ __forceinline__ void vox_algebra_core(const Chunk& ck, int pair, int cell, int iter, const float* Jm,
+                                                 long long nbin, const double mean[3], const double cov[6],
+                                                 double acc[NRED]) {
+  const size_t ci = (size_t)pair * ck.ncell + cell;
   const Vox1 v = ck.vox[ci];
   if (ck.dump_on) {
     float* m2 = ck.dump.mu2 + ((size_t)iter * ck.ncell + cell) * 3;
@@ -163,9 +173,120 @@ __device__ __forceinline__ void vox_algebra(const Chunk& ck, int pair, int cell,
   acc[27] += 1.0;
 }
 
+// ---- incremental loop (kernels_pass2.cuh): the accumulators hold exact moments of the UNTRANSFORMED members of the
+// voxel, in the set the pair currently uses; nothing is cleared except, right after a rebuild, the other set.
+struct VoxMode {
+  int set, rebuild;
+  float trb[12], tr[12];
+};
+__device__ __forceinline__ void load_vox_mode(const Chunk& ck, int pair, VoxMode& vm) {
+  const PairMode* pm = ck.pm + pair;
+  const int2 h = __ldcg(reinterpret_cast<const int2*>(pm));
+  vm.set = h.x;
+  vm.rebuild = h.y;
+  const float4* tb = reinterpret_cast<const float4*>(pm->TRb);
+  const float4* tp = reinterpret_cast<const float4*>(ck.TR + (size_t)pair * 12);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float4 a = __ldcg(tb + k), b = __ldcg(tp + k);
+    vm.trb[4 * k] = a.x; vm.trb[4 * k + 1] = a.y; vm.trb[4 * k + 2] = a.z; vm.trb[4 * k + 3] = a.w;
+    vm.tr[4 * k] = b.x; vm.tr[4 * k + 1] = b.y; vm.tr[4 * k + 2] = b.z; vm.tr[4 * k + 3] = b.w;
+  }
+}
+
+__device__ __forceinline__ bool vox_gate2(const Chunk& ck, int pair, int cell, int iter, const VoxMode& vm) {
+  const size_t ci = (size_t)pair * ck.ncell + cell;
+  const uint32_t flags = ck.rec[ci].flags;
+  if (!(flags & F_ACTIVE2)) {
+    if (ck.dump_on) {
+      ck.dump.cnt2[(size_t)iter * ck.ncell + cell] = -1;
+      ck.dump.nin2[(size_t)iter * ck.ncell + cell] = -1;
+      ck.dump.used2[(size_t)iter * ck.ncell + cell] = 0;
+    }
+    return false;
+  }
+  if (vm.rebuild) {  // the set the pair has just left becomes the clean target of the next rebuild
+    unsigned long long* sp = ck.acc + ((size_t)(vm.set ^ 1) * ck.npairs * ck.ncell + ci) * NQ;
+#pragma unroll
+    for (int k = 0; k < NQ; k += 2) *reinterpret_cast<ulonglong2*>(sp + k) = make_ulonglong2(0ull, 0ull);
+  }
+  const unsigned long long* qp = ck.acc + ((size_t)vm.set * ck.npairs * ck.ncell + ci) * NQ;
+  const ulonglong2 q01 = __ldcg(reinterpret_cast<const ulonglong2*>(qp));
+  const long long nbin = (long long)q01.x, nin = (long long)q01.y;
+  const bool use = nbin > ck.n && nin > ck.n;
+  if (ck.dump_on) {
+    ck.dump.cnt2[(size_t)iter * ck.ncell + cell] = (int)nbin;
+    ck.dump.nin2[(size_t)iter * ck.ncell + cell] = (nbin > ck.n) ? (int)nin : -1;
+    ck.dump.used2[(size_t)iter * ck.ncell + cell] = use ? 1 : 0;
+  }
+  return use;
+}
+
+// mean / covariance of the voxel's scan-2 members at the current transform, from the moments of the untransformed
+// points:  mu2 = (mean_OG + t) R,  Sigma2 = R^T Cov_OG R   (what src/icet.cpp:375-378 + :303-306 compute point by point)
+__device__ __forceinline__ void stats2_from_moments(const unsigned long long* q, const CellRec* recs, int cell,
+                                                    const VoxMode& vm, double mean[3], double cov[6]) {
+  float ax, ay, az, sc;
+  vox_anchor2(recs, cell, vm.trb, ax, ay, az, sc);
+  const double nin = (double)(long long)q[1];
+  const double inv = 1.0 / (double)sc;  // exact: the scale is a power of two
+  const double in_ = 1.0 / nin;
+  const double sx = (double)(long long)q[2], sy = (double)(long long)q[3], sz = (double)(long long)q[4];
+  const double mx = sx * in_, my = sy * in_, mz = sz * in_;
+  const double po[3] = {((double)ax + mx * inv) + (double)vm.tr[0], ((double)ay + my * inv) + (double)vm.tr[1],
+                        ((double)az + mz * inv) + (double)vm.tr[2]};
+  const double f = inv * inv / (nin - 1.0);
+  double co[9];
+  co[0] = ((double)(long long)q[5] - sx * mx) * f;
+  co[1] = co[3] = ((double)(long long)q[6] - sx * my) * f;
+  co[2] = co[6] = ((double)(long long)q[7] - sx * mz) * f;
+  co[4] = ((double)(long long)q[8] - sy * my) * f;
+  co[5] = co[7] = ((double)(long long)q[9] - sy * mz) * f;
+  co[8] = ((double)(long long)q[10] - sz * mz) * f;
+  double R[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) R[k] = (double)vm.tr[3 + k];
+#pragma unroll
+  for (int i = 0; i < 3; i++) mean[i] = po[0] * R[i] + po[1] * R[3 + i] + po[2] * R[6 + i];
+  double T[9];  // T = Cov_OG R
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) T[3 * a + j] = co[3 * a] * R[j] + co[3 * a + 1] * R[3 + j] + co[3 * a + 2] * R[6 + j];
+  int t = 0;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = i; j < 3; j++) cov[t++] = R[i] * T[j] + R[3 + i] * T[3 + j] + R[6 + i] * T[6 + j];
+}
+
+__device__ __forceinline__ void vox_algebra2(const Chunk& ck, int pair, int cell, int iter, const float* Jm, const VoxMode& vm,
+                                             double acc[NRED]) {
+  const size_t ci = (size_t)pair * ck.ncell + cell;
+  unsigned long long q[NQ];
+  const unsigned long long* qp = ck.acc + ((size_t)vm.set * ck.npairs * ck.ncell + ci) * NQ;
+#pragma unroll
+  for (int k = 0; k < NQ; k += 2) {
+    const ulonglong2 t = __ldcg(reinterpret_cast<const ulonglong2*>(qp + k));
+    q[k] = t.x;
+    q[k + 1] = t.y;
+  }
+  double mean[3], cov[6];
+  stats2_from_moments(q, ck.rec + (size_t)pair * ck.ncell, cell, vm, mean, cov);
+  vox_algebra_core(ck, pair, cell, iter, Jm, (long long)q[0], mean, cov, acc);
+}
+
+__device__ __forceinline__ bool loop_incremental(const Chunk& ck) { return !(ck.flags & ICET_B200_FLAG_EXACT_PASS); }
+
 __device__ __forceinline__ void vox_contrib(const Chunk& ck, int pair, int cell, int iter, const float* Jm,
                                             double acc[NRED]) {
-  if (vox_gate(ck, pair, cell, iter)) vox_algebra(ck, pair, cell, iter, Jm, acc);
+  if (loop_incremental(ck)) {
+    VoxMode vm;
+    load_vox_mode(ck, pair, vm);
+    if (vox_gate2(ck, pair, cell, iter, vm)) vox_algebra2(ck, pair, cell, iter, Jm, vm, acc);
+  } else if (vox_gate(ck, pair, cell, iter)) {
+    vox_algebra(ck, pair, cell, iter, Jm, acc);
+  }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -185,6 +306,31 @@ __device__ __forceinline__ void chain_seed_next(const Chunk& ck, int pair, const
     ck.TRprev[(size_t)q * 12 + k] = v;
   }
   for (int k = 0; k < 27; k++) ck.J[(size_t)q * 27 + k] = ck.J[(size_t)pair * 27 + k];
+  for (int k = 0; k < 12; k++) ck.pm[q].TRb[k] = ck.TR[(size_t)pair * 12 + k];  // its first iteration rebuilds at this transform
+}
+
+// Incremental loop: after the solve of an iteration, decide how the next one runs (see kernels_pass2.cuh).  tro / trn:
+// the transform this iteration used / the next one will use.
+__device__ __forceinline__ void mode_after_solve(const Chunk& ck, int pair, const float* tro, const float* trn) {
+  PairMode* pm = ck.pm + pair;
+  float a2 = 0.f, b2 = 0.f;
+  for (int k = 0; k < 3; k++) b2 += (trn[k] - tro[k]) * (trn[k] - tro[k]);
+  for (int k = 3; k < 12; k++) a2 += (trn[k] - tro[k]) * (trn[k] - tro[k]);
+  const float SA = __ldcg(&pm->SA) + 1.001f * sqrtf(a2), SB = __ldcg(&pm->SB) + 1.001f * sqrtf(b2);
+  const bool delta = !(ck.flags & ICET_B200_FLAG_FULL_REBUILD) && SA <= INC_MAX_SA && SB <= INC_MAX_SB;  // false for NaN
+  if (delta) {
+    pm->rebuild = 0;
+    pm->SA = SA;
+    pm->SB = SB;
+    pm->C = (SB + SA * SB) * 1.0001f;
+  } else {
+    pm->set = __ldcg(&pm->set) ^ 1;
+    pm->rebuild = 1;
+    pm->SA = 0.f;
+    pm->SB = 0.f;
+    pm->C = 0.f;
+    for (int k = 0; k < 12; k++) pm->TRb[k] = trn[k];
+  }
 }
 
 __device__ __noinline__ void solve_pair(const Chunk& ck, int pair, int iter, const double* tot) {
@@ -275,11 +421,16 @@ __device__ __noinline__ void solve_pair(const Chunk& ck, int pair, int iter, con
   for (int k = 0; k < 6; k++) X[k] = Xn[k];
   {  // trigonometry of the next iteration: utils::R (src/icet.cpp:375-376) and get_H (:507-527)
     float* TR = ck.TR + (size_t)pair * 12;
+    float tro[12];
+    for (int k = 0; k < 12; k++) tro[k] = __ldcg(TR + k);
     if (iter == ck.runlen - 1)
-      for (int k = 0; k < 12; k++) ck.TRprev[(size_t)pair * 12 + k] = __ldcg(TR + k);
+      for (int k = 0; k < 12; k++) ck.TRprev[(size_t)pair * 12 + k] = tro[k];
+    if (ck.dump_on)
+      for (int k = 0; k < 12; k++) ck.dump.TRit[iter * 12 + k] = tro[k];
     TR[0] = Xn[0]; TR[1] = Xn[1]; TR[2] = Xn[2];
     icet::rotR(Xn[3], Xn[4], Xn[5], TR + 3);
     icet::getH_J(Xn[3], Xn[4], Xn[5], ck.J + (size_t)pair * 27);
+    if (loop_incremental(ck) && iter < ck.runlen - 1) mode_after_solve(ck, pair, tro, TR);
     if (iter == ck.runlen - 1) chain_seed_next(ck, pair, Xn);
   }
   if (ck.dump_on) {
@@ -304,7 +455,7 @@ __device__ __forceinline__ bool solve_pair_warp(const Chunk& ck, int pair, int i
   const int lane = threadIdx.x & 31;
   // requested now, used after the elimination: the current X and (last iteration) the transform it started from
   const float x_old = lane < 6 ? __ldcg(ck.X + pair * 6 + lane) : 0.f;
-  const float tr_old = (lane < 12 && iter == ck.runlen - 1) ? __ldcg(ck.TR + (size_t)pair * 12 + lane) : 0.f;
+  const float tr_old = lane < 12 ? __ldcg(ck.TR + (size_t)pair * 12 + lane) : 0.f;
   double col[6];
   {
     // lane j < 6: column j of A; lane 6 + j: column j of I; lane 12: b
@@ -375,8 +526,19 @@ __device__ __forceinline__ bool solve_pair_warp(const Chunk& ck, int pair, int i
   }
   if (lane < 12) {
     if (last) ck.TRprev[(size_t)pair * 12 + lane] = tr_old;  // the transform the LAST iteration used (`points2`)
+    if (ck.dump_on) ck.dump.TRit[iter * 12 + lane] = tr_old;
     ck.TR[(size_t)pair * 12 + lane] = trv;
-    if (seed) { ck.TR[(size_t)(pair + 1) * 12 + lane] = trv; ck.TRprev[(size_t)(pair + 1) * 12 + lane] = trv; }
+    if (seed) {
+      ck.TR[(size_t)(pair + 1) * 12 + lane] = trv;
+      ck.TRprev[(size_t)(pair + 1) * 12 + lane] = trv;
+      ck.pm[pair + 1].TRb[lane] = trv;  // its first iteration rebuilds at this transform
+    }
+  }
+  if (loop_incremental(ck) && !last) {  // how the next iteration runs (same arithmetic as mode_after_solve)
+    float tro[12], trn[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) { tro[k] = __shfl_sync(FULL, tr_old, k); trn[k] = __shfl_sync(FULL, trv, k); }
+    if (lane == 0) mode_after_solve(ck, pair, tro, trn);
   }
   if (lane < 27) {
     ck.J[(size_t)pair * 27 + lane] = jv;
@@ -476,7 +638,7 @@ __device__ __noinline__ void vox_task(const Chunk& ck, int iter, int pair, int g
     double acc[NRED];
 #pragma unroll
     for (int k = 0; k < NRED; k++) acc[k] = 0.0;
-    if (cell < ck.ncell && vox_gate(ck, pair, cell, iter)) vox_algebra(ck, pair, cell, iter, w_J, acc);
+    if (cell < ck.ncell) vox_contrib(ck, pair, cell, iter, w_J, acc);
     TL(8);
     if (__any_sync(FULL, acc[27] != 0.0)) {
       double* out = ck.part + ((size_t)pair * vt + grp) * NRED;
@@ -490,7 +652,8 @@ __device__ __noinline__ void vox_task(const Chunk& ck, int iter, int pair, int g
     }
     TL(2);
   } else if (ck.dump_on && cell < ck.ncell) {
-    vox_gate(ck, pair, cell, iter);  // records the "inactive" markers
+    double none[NRED];
+    vox_contrib(ck, pair, cell, iter, w_J, none);  // records the "inactive" markers (no voxel of the group is active)
   }
   __threadfence();  // every lane: partial sums, cleared accumulators, the group's vmask bit
   __syncwarp();
@@ -637,11 +800,22 @@ __global__ void __launch_bounds__(PASS_THREADS, 3) k_loop(const Chunk ck, int ti
         unsigned long long* accp = ck.acc + (size_t)pair * ck.ncell * NQ;
         if (tile == 0) TL(6);
         if (ck.dump_on && iter == 3 && tile < 2048 && lane == 0) ck.dump.tl[(size_t)ck.runlen * 16 + 2 * tile] = gtime();
+        if (loop_incremental(ck)) {
+          Pass2Mode md;
+          load_pass2_mode(ck, pair, md);
+          pass2_warp_tile<K>(ck, went, tab, recs, tr, md, ck.pog + (size_t)pair * 3 * ck.n2max, (size_t)ck.n2max, n, w0,
+                             ck.marg + (size_t)pair * ck.n2max, ck.cls2 + (size_t)pair * ck.n2max,
+                             (ck.flags & ICET_B200_FLAG_VERIFY_INCREMENTAL) ? &ck.res[pair].reserved[0] : nullptr);
+          if (tile == 0 && lane == 0)
+            pass2_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 2,
+                                  recs, tr, md, pair, __ldg(ck.nz2 + pair));
+        } else {
         pass_warp_tile<true, K, 2, (K <= 4 ? K : 1)>(ck, went, tab, recs, tr, ck.pog + (size_t)pair * 3 * ck.n2max, (size_t)ck.n2max, n, w0,
                                 accp, (ck.dump_on && iter == 3 && tile < 2048) ? ck.dump.tl + (size_t)ck.runlen * 16 + 4096 + tile : nullptr);
         if (tile == 0 && lane == 0)
           pass_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 2,
                                recs, tr, accp, __ldg(ck.nz2 + pair));
+        }
         if (tile == 0) TL(7);
         if (ck.dump_on && iter == 3 && tile < 2048 && lane == 0) ck.dump.tl[(size_t)ck.runlen * 16 + 2 * tile + 1] = gtime();
         __threadfence();  // every lane: its accumulator updates are visible before the tile is counted
@@ -710,6 +884,25 @@ __global__ void k_points2(const Chunk ck, int n2, float* out) {
   out[i] = x;
   out[n2 + i] = y;
   out[2 * (size_t)n2 + i] = z;
+}
+
+// parity-test entry (icet_b200_classify_scan2): class of every point of scan 2 of pair 0 under the transform `tr`
+__global__ void k_classify2(const Chunk ck, int n2, const float* trp, int32_t* cell, uint8_t* in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n2) return;
+  const PairDesc d = ck.desc[0];
+  float tr[12];
+  for (int k = 0; k < 12; k++) tr[k] = trp[k];
+  float x = d.s2[i], y = d.s2[d.ld2 + i], z = d.s2[2 * (size_t)d.ld2 + i];
+  float r, th, ph;
+  icet::c2s(x, y, z, r, th, ph);   // points2_OG (prepScan2, src/icet.cpp:263-275)
+  icet::s2c(r, th, ph, x, y, z);
+  const float4* tth = reinterpret_cast<const float4*>(ck.binrec);
+  int c;
+  bool active, inb;
+  point_stage1<true>(ck, tth, tth + ck.nT + 2, ck.rec, tr, x, y, z, c, active, inb, r, th, ph);
+  cell[i] = c;
+  in[i] = inb ? 1 : 0;
 }
 
 // spherical coordinates + cell index of a cloud (parity-test entry point)

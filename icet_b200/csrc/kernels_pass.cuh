@@ -377,14 +377,17 @@ __global__ void __launch_bounds__(128) k_fit1(const Chunk ck) {
       const int bt = cell % ck.nT, bp = cell / ck.nT;
       const float azl = ck.azE[bt], azh = ck.azE[bt + 1], ell = ck.elE[bp], elh = ck.elE[bp + 1];
       bool inside[6] = {false, false, false, false, false, false};
+      float sp[6][3];
       for (int j = 0; j < 6; j++) {
         const int k = j >> 1;
         const float al = 2.0f * sqrtf(ev[k]);
-        float p[3];
         for (int c = 0; c < 3; c++) {
           float rot = al * V[3 * k + c];
-          p[c] = (j & 1) ? mu[c] - rot : mu[c] + rot;
+          sp[j][c] = (j & 1) ? mu[c] - rot : mu[c] + rot;
         }
+      }
+      for (int j = 0; j < 6; j++) {
+        const float* p = sp[j];
         float r, th, ph;
         icet::c2s(p[0], p[1], p[2], r, th, ph);
         if (th >= azl && th <= azh && ph >= ell && ph <= elh && r >= rc.inner && r <= rc.outer) inside[j] = true;
@@ -402,6 +405,10 @@ __global__ void __launch_bounds__(128) k_fit1(const Chunk ck) {
         for (int k = 0; k < 3; k++) { ck.dump.mu1[3 * cell + k] = (float)mean[k]; ck.dump.eval1[3 * cell + k] = ev[k]; }
         for (int k = 0; k < 9; k++) { ck.dump.sigma1[9 * cell + k] = A[k]; ck.dump.evec1[9 * cell + k] = V[k]; }
         for (int k = 0; k < 3; k++) ck.dump.lmask[3 * cell + k] = (lm >> k) & 1;
+        // public member testPoints (src/icet.cpp:214-232): the sigma points of the axes found extended
+        for (int j = 0; j < 6; j++)
+          if (!((lm >> (j >> 1)) & 1))
+            for (int c = 0; c < 3; c++) ck.dump.testpts[(size_t)(6 * cell + j) * 3 + c] = sp[j][c];
       }
     }
   }

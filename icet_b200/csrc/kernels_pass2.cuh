@@ -1,0 +1,336 @@
+// icet_b200/csrc/kernels_pass2.cuh -- K5i: the INCREMENTAL pass over scan 2 (default form of the Gauss-Newton loop).
+// Included by icet_b200.cu inside its anonymous namespace.
+//
+// What the reference does per iteration (src/icet.cpp:372-403): transform every point of scan 2, convert it to spherical
+// coordinates, bin it, test it against the cluster box of its cell, convert the survivors back (sphericalToCartesian)
+// and take mean / covariance per voxel.  From the second or third iteration on the transform moves the points by
+// millimetres and almost none of them changes its voxel or its side of a cluster box.  This pass therefore keeps, per
+// voxel, EXACT integer moments (count, sum, sum of products) of the UNTRANSFORMED members (points2_OG, prepScan2) and,
+// per point, the class (cell | in-box) of its last evaluation together with a margin: a bound on how far the point can
+// move before ANY comparison that decided its class can change.  An iteration then
+//   * REBUILD (first iteration, or when the transform has moved by more than INC_MAX_SA / INC_MAX_SB since the last
+//     rebuild): evaluates every point like the per-point pass (transform, spherical, bin + box look-up, range test),
+//     records class and margin, and accumulates the moments of the inside points from zero;
+//   * DELTA: re-evaluates only the points whose margin is used up by the motion since their evaluation (one 8-byte
+//     load, one FMA, one compare for all the others) and moves the few points whose class changed from one voxel's
+//     moments to another's.
+// The per-voxel algebra (vox_algebra2, kernels_loop.cuh) transforms the moments analytically:
+//     mu2 = (mean_OG + t) R,   Sigma2 = R^T Cov_OG R        (src/icet.cpp:375-378 applied to the moments).
+//
+// Parity (DESIGN.md "incremental scan-2 loop"): the CLASS of every point in every iteration is the one the per-point
+// fp32 pipeline computes (the margins are conservative bounds that include the fp32 rounding of that pipeline; tested
+// against the forced-rebuild form and against the per-point form ICET_B200_FLAG_EXACT_PASS), so voxel indices, bin
+// counts and in-box counts are unchanged.  Mean / covariance of scan 2 no longer go through the per-point fp32 round
+// trip: they differ from the reference's by that round trip's own rounding noise (<= a few ulp of the coordinates per
+// point, averaged over the voxel) and are closer to the exact statistics of the transformed points.
+#pragma once
+
+constexpr uint32_t CLS_IN = 0x40000000u;      // the point passes filterPointsInsideCluster of its cell
+constexpr uint32_t CLS_ACTIVE = 0x80000000u;  // its cell takes part in the loop (F_ACTIVE2)
+constexpr uint32_t CLS_CELL = 0x000fffffu;
+constexpr uint32_t CLS_NONE = 0x000fffffu;    // "no class yet"
+constexpr float INC_MAX_SA = 1.0e-3f;         // delta iterations while sum |dR|_F  <= this
+constexpr float INC_MAX_SB = 0.05f;           //                  and   sum |dt|    <= this (metres) since the last rebuild
+constexpr float INC_SCALE2 = 0.25f;           // fixed-point scale of scan-2 moments relative to CellRec::scale: the
+                                              // members of a voxel may sit up to 8 box diameters from the anchor
+
+struct Pass2Mode {  // block-uniform copy of the pair's PairMode + accumulator set
+  bool rebuild;
+  float SA, SB, C;
+  float trb[12];
+  unsigned long long* accp;
+};
+
+// bin + box look-up (see bin_box) that also returns the distance of the angle to the nearest threshold that decided it
+__device__ __forceinline__ int bin_box_m(float a, const float4* rec, const icet::BinTable& bt, bool& inbox, float& dist) {
+  int k = __float2int_rz(fminf(a, bt.acap) * bt.scale);
+  float4 e = rec[k];
+  if (a < e.x || a >= e.y) {
+    k += (a < e.x) ? -1 : 1;
+    e = rec[k];
+  }
+  inbox = a >= e.z && a <= e.w;
+  dist = fminf(fminf(fabsf(a - e.x), fabsf(e.y - a)), fminf(fabsf(a - e.z), fabsf(e.w - a)));
+  return k < bt.nb ? k : (k == bt.nb ? 0 : bt.sbin);
+}
+
+// Full evaluation of one point of scan 2: class word and {u, r_e}.
+//   The class can only change when the computed theta / phi / r crosses one of the thresholds it was compared with.
+//   A displacement delta of the transformed point changes theta by <= asin(delta / rho), phi by <= asin(delta / r) and
+//   r by <= delta; the fp32 evaluation itself is within (2e-6 rad * rho + 3e-6 r) / (4e-6 rad * r / rho) / 4e-6 r of
+//   exact for theta / phi / r (transform: 3 roundings per coordinate; own atan2 / acos within 1 ulp; IEEE sqrt, div),
+//   counted twice (evaluation now, evaluation then).  m = the smallest distance to a threshold in metres minus that
+//   slop, capped at rho / 4 (asin(x) <= 1.011 x there); the class is safe while delta < 0.9 m.
+//   delta(e -> k) <= r_e (SA_k - SA_e) + SB_k SA_k + (SB_k - SB_e), hence the stored u = 0.9 m + r_e SA_e + SB_e and the
+//   test r_e SA_k + C_k < u with C_k = SB_k + SA_k SB_k.
+__device__ __forceinline__ void point_eval2(const Chunk& ck, const float4* tth, const float4* tph, const CellRec* recs,
+                                            const float* tr, float SA, float SB, float px, float py, float pz,
+                                            uint32_t& cls, float2& mg) {
+  float x, y, z;
+  icet::transform(px, py, pz, tr, tr + 3, x, y, z);
+  const float sxy = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));
+  float r, th, ph;
+  icet::c2s(x, y, z, r, th, ph);
+  bool bt_in, bp_in;
+  float dth, dph;
+  const int bt = bin_box_m(th, tth, ck.bth, bt_in, dth);
+  const int bp = bin_box_m(ph, tph, ck.bph, bp_in, dph);
+  const int c = ck.nT * bp + bt;
+  const float4 ra = __ldg(reinterpret_cast<const float4*>(recs + c));  // inner, outer, flags, scale
+  const bool active = (__float_as_uint(ra.z) & F_ACTIVE2) != 0;
+  const bool in = active && bt_in && bp_in && r >= ra.x && r <= ra.y;
+  cls = (uint32_t)c | (in ? CLS_IN : 0u) | (active ? CLS_ACTIVE : 0u);
+  float irho;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(irho) : "f"(sxy));
+  const float rho = sxy * irho * 0.999f;
+  const float k = r * irho * 1.001f;
+  float m = fminf((dth - 2e-6f) * rho - 3e-6f * r, (dph - 4e-6f * k) * r);
+  m = fminf(m, 0.25f * rho);
+  if (active) m = fminf(m, fminf(fabsf(r - ra.x), fabsf(ra.y - r)) - 4e-6f * r);
+  float u = fmaf(0.9f, m, -1e-6f) + fmaf(r, SA, SB);
+  // non-finite coordinates (NaN rows take the 1000.0 sentinels, :116): evaluated every time
+  if (!(__fadd_rn(sxy, __fmul_rn(z, z)) < 3e38f) || !(sxy > 1e-30f) || !(u == u)) u = 0.f;
+  mg = make_float2(u, r);
+}
+
+// anchor of a voxel's scan-2 fixed-point frame: the centre of its box, taken back through the transform of the last
+// rebuild (p = q R^T - t), and the scale
+__device__ __forceinline__ void vox_anchor2(const CellRec* recs, int cell, const float* trb, float& ax, float& ay, float& az,
+                                            float& sc) {
+  const float4* rp = reinterpret_cast<const float4*>(recs + cell);
+  const float4 ra = __ldg(rp), rb = __ldg(rp + 1);
+  const float* R = trb + 3;
+  sc = ra.w * INC_SCALE2;
+  ax = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(rb.x, R[0]), __fmul_rn(rb.y, R[1])), __fmul_rn(rb.z, R[2])), -trb[0]);
+  ay = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(rb.x, R[3]), __fmul_rn(rb.y, R[4])), __fmul_rn(rb.z, R[5])), -trb[1]);
+  az = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(rb.x, R[6]), __fmul_rn(rb.y, R[7])), __fmul_rn(rb.z, R[8])), -trb[2]);
+}
+__device__ __forceinline__ void fix2(float px, float py, float pz, float ax, float ay, float az, float sc, int& fx, int& fy,
+                                     int& fz) {
+  fx = max(-FP_LIM, min(FP_LIM, __float2int_rn(__fmul_rn(__fadd_rn(px, -ax), sc))));
+  fy = max(-FP_LIM, min(FP_LIM, __float2int_rn(__fmul_rn(__fadd_rn(py, -ay), sc))));
+  fz = max(-FP_LIM, min(FP_LIM, __float2int_rn(__fmul_rn(__fadd_rn(pz, -az), sc))));
+}
+
+// adds (w = +n) or removes (w = -n) n copies of an inside point to / from the moments of its voxel
+__device__ __forceinline__ void moments_add(unsigned long long* accp, const CellRec* recs, int cell, const float* trb,
+                                            float px, float py, float pz, long long w) {
+  float ax, ay, az, sc;
+  vox_anchor2(recs, cell, trb, ax, ay, az, sc);
+  int ix, iy, iz;
+  fix2(px, py, pz, ax, ay, az, sc, ix, iy, iz);
+  const long long fx = ix, fy = iy, fz = iz;
+  unsigned long long* q = accp + (size_t)cell * NQ;
+  red_add(q + 1, (unsigned long long)w);
+  red_add(q + 2, (unsigned long long)(w * fx));
+  red_add(q + 3, (unsigned long long)(w * fy));
+  red_add(q + 4, (unsigned long long)(w * fz));
+  red_add(q + 5, (unsigned long long)(w * fx * fx));
+  red_add(q + 6, (unsigned long long)(w * fx * fy));
+  red_add(q + 7, (unsigned long long)(w * fx * fz));
+  red_add(q + 8, (unsigned long long)(w * fy * fy));
+  red_add(q + 9, (unsigned long long)(w * fy * fz));
+  red_add(q + 10, (unsigned long long)(w * fz * fz));
+}
+
+// moves `w` copies of a point from class `oc` to class `nc` (either may be CLS_NONE / inactive)
+__device__ __forceinline__ void class_move(unsigned long long* accp, const CellRec* recs, const float* trb, uint32_t oc,
+                                           uint32_t nc, float px, float py, float pz, long long w) {
+  if (oc == nc) return;
+  const int ocell = (int)(oc & CLS_CELL), ncell_ = (int)(nc & CLS_CELL);
+  const bool oact = (oc & CLS_ACTIVE) != 0, nact = (nc & CLS_ACTIVE) != 0;
+  if (ocell != ncell_) {
+    if (oact) red_add(accp + (size_t)ocell * NQ, (unsigned long long)(-w));
+    if (nact) red_add(accp + (size_t)ncell_ * NQ, (unsigned long long)w);
+  }
+  if (oc & CLS_IN) moments_add(accp, recs, ocell, trb, px, py, pz, -w);
+  if (nc & CLS_IN) moments_add(accp, recs, ncell_, trb, px, py, pz, w);
+}
+
+// The dropped returns of scan 2 (points2_OG == (0,0,0) for all nz of them): one point with weight nz,
+// evaluated every iteration by one thread.
+__device__ inline void pass2_dropped_returns(const Chunk& ck, const float4* tth, const float4* tph, const CellRec* recs,
+                                             const float* tr, const Pass2Mode& md, int pair, long long nz) {
+  if (nz <= 0) return;
+  uint32_t cls;
+  float2 mg;
+  point_eval2(ck, tth, tph, recs, tr, 0.f, 0.f, 0.f, 0.f, 0.f, cls, mg);
+  const uint32_t old = md.rebuild ? CLS_NONE : (uint32_t)__ldcg(&ck.pm[pair].zcls);
+  class_move(md.accp, recs, md.trb, old, cls, 0.f, 0.f, 0.f, nz);
+  ck.pm[pair].zcls = (int)cls;
+}
+
+// One warp tile of 32*K consecutive stored points of scan 2.  `went`: the warp's pass_wslots(K) 16-byte slots.
+template <int K>
+__device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, const float* tab, const CellRec* recs,
+                                                const float* tr, const Pass2Mode& md, const float* pog, size_t ld, int n,
+                                                int w0, float2* marg, uint32_t* cls2, int* violations) {
+  const int lane = threadIdx.x & 31;
+  if (w0 >= n) return;
+  const float4* tth = reinterpret_cast<const float4*>(tab);
+  const float4* tph = tth + ck.nT + 2;
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned long long* accp = md.accp;
+  if (md.rebuild) {
+    // ---- phase A: every point.  Coordinates of row j + 2 are requested before row j is worked on.
+    int nin_tile = 0;
+    float bx[2], by[2], bz[2];
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      const int i = w0 + p * 32 + lane;
+      bx[p] = by[p] = bz[p] = 0.f;
+      if (p < K && i < n) { bx[p] = __ldg(pog + i); by[p] = __ldg(pog + ld + i); bz[p] = __ldg(pog + 2 * ld + i); }
+    }
+#pragma unroll(K % 4 == 0 ? 4 : 2)
+    for (int j = 0; j < K; j++) {
+      const int i = w0 + j * 32 + lane;
+      const float x = bx[j & 1], y = by[j & 1], z = bz[j & 1];
+      const int ip = i + 64;
+      if (j + 2 < K && ip < n) { bx[j & 1] = __ldg(pog + ip); by[j & 1] = __ldg(pog + ld + ip); bz[j & 1] = __ldg(pog + 2 * ld + ip); }
+      uint32_t cls = CLS_NONE;
+      if (i < n) {
+        float2 mg;
+        point_eval2(ck, tth, tph, recs, tr, 0.f, 0.f, x, y, z, cls, mg);
+        marg[i] = mg;
+        cls2[i] = cls;
+      }
+      // bin counts: one RED per run of equal (participating) cell in this row
+      const int key = (cls & CLS_ACTIVE) ? (int)(cls & CLS_CELL) : -1;
+      const int prev = __shfl_up_sync(FULL, key, 1);
+      const bool head = (lane == 0) || (key != prev);
+      const unsigned hm = __ballot_sync(FULL, head);
+      if (head && key >= 0) {
+        const unsigned nh = (lane == 31) ? 0u : (hm >> (lane + 1));
+        const int len = nh ? __ffs(nh) : 32 - lane;
+        red_add(accp + (size_t)key * NQ, (unsigned long long)len);
+      }
+      const bool in = (cls & CLS_IN) != 0;
+      const unsigned im = __ballot_sync(FULL, in);
+      if (in) went[nin_tile + __popc(im & lt)] = make_int4((int)(cls & CLS_CELL), __float_as_int(x), __float_as_int(y), __float_as_int(z));
+      nin_tile += __popc(im);
+    }
+    __syncwarp();
+    // ---- phase B: lane takes entries [lane*q, lane*q + q); q odd => conflict-free 16-byte shared loads
+    const int q = ((nin_tile + 31) >> 5) | 1;
+    const int e0 = lane * q, e1 = min(nin_tile, e0 + q);
+    int cur = -1, nin = 0, sx = 0, sy = 0, sz = 0;
+    long long pxx = 0, pxy = 0, pxz = 0, pyy = 0, pyz = 0, pzz = 0;
+    float ax = 0.f, ay = 0.f, az = 0.f, sc = 0.f;
+#pragma unroll 2
+    for (int e = e0; e < e1; e++) {
+      const int4 v = went[e];
+      if (v.x != cur) {
+        flush_in_run(accp, cur, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
+        cur = v.x;
+        nin = sx = sy = sz = 0;
+        pxx = pxy = pxz = pyy = pyz = pzz = 0;
+        vox_anchor2(recs, cur, md.trb, ax, ay, az, sc);
+      }
+      int fx, fy, fz;
+      fix2(__int_as_float(v.y), __int_as_float(v.z), __int_as_float(v.w), ax, ay, az, sc, fx, fy, fz);
+      nin++;
+      sx += fx; sy += fy; sz += fz;
+      pxx += (long long)fx * fx; pxy += (long long)fx * fy; pxz += (long long)fx * fz;
+      pyy += (long long)fy * fy; pyz += (long long)fy * fz; pzz += (long long)fz * fz;
+    }
+    flush_in_run(accp, cur, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
+    __syncwarp();
+    return;
+  }
+  // ---- DELTA, phase T: which points have used up their margin?  (8 bytes per point, all rows requested up front in
+  // groups of 4)
+  int* list = reinterpret_cast<int*>(went);  // indices of the points to re-evaluate (<= 32*K)
+  int nre = 0;
+  constexpr int R = (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1);
+#pragma unroll 1
+  for (int j0 = 0; j0 < K; j0 += R) {
+    float2 mg[R];
+#pragma unroll
+    for (int g = 0; g < R; g++) {
+      const int i = w0 + (j0 + g) * 32 + lane;
+      mg[g] = make_float2(3e38f, 0.f);
+      if (i < n) mg[g] = __ldcg(marg + i);  // (L2: written by another SM in the previous iteration)
+    }
+#pragma unroll
+    for (int g = 0; g < R; g++) {
+      const int i = w0 + (j0 + g) * 32 + lane;
+      const bool stable = fmaf(mg[g].y, md.SA, md.C) < mg[g].x;
+      // ICET_B200_FLAG_VERIFY_INCREMENTAL: evaluate the stable points as well and count those whose class changed
+      const bool redo = i < n && (!stable || violations != nullptr);
+      const unsigned rm = __ballot_sync(FULL, redo);
+      if (redo) list[nre + __popc(rm & lt)] = stable ? (i | (int)0x80000000) : i;
+      nre += __popc(rm);
+    }
+  }
+  __syncwarp();
+  // ---- phase E: full evaluation of the listed points, lane per point
+  for (int e0 = 0; e0 < nre; e0 += 32) {
+    const int e = e0 + lane;
+    if (e < nre) {
+      const bool was_stable = list[e] < 0;
+      const int i = list[e] & 0x7fffffff;
+      const float x = __ldg(pog + i), y = __ldg(pog + ld + i), z = __ldg(pog + 2 * ld + i);
+      const uint32_t old = __ldcg(cls2 + i);
+      uint32_t cls;
+      float2 mg;
+      point_eval2(ck, tth, tph, recs, tr, md.SA, md.SB, x, y, z, cls, mg);
+      marg[i] = mg;
+      if (cls != old) {
+        if (was_stable) atomicAdd(violations, 1);
+        cls2[i] = cls;
+        class_move(accp, recs, md.trb, old, cls, x, y, z, 1);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void load_pass2_mode(const Chunk& ck, int pair, Pass2Mode& md) {
+  const PairMode* pm = ck.pm + pair;
+  const int4 h = __ldcg(reinterpret_cast<const int4*>(pm));             // set, rebuild, SA, C
+  md.rebuild = h.y != 0;
+  md.SA = __int_as_float(h.z);
+  md.C = __int_as_float(h.w);
+  md.SB = __ldcg(&pm->SB);
+  const float4* tb = reinterpret_cast<const float4*>(pm->TRb);
+  const float4 a = __ldcg(tb), b = __ldcg(tb + 1), c = __ldcg(tb + 2);
+  md.trb[0] = a.x; md.trb[1] = a.y; md.trb[2] = a.z; md.trb[3] = a.w; md.trb[4] = b.x; md.trb[5] = b.y; md.trb[6] = b.z;
+  md.trb[7] = b.w; md.trb[8] = c.x; md.trb[9] = c.y; md.trb[10] = c.z; md.trb[11] = c.w;
+  md.accp = ck.acc + ((size_t)h.x * ck.npairs + pair) * ck.ncell * NQ;
+}
+
+template <int K = PASS_K, int MINB = PASS_MINB>
+__global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass2(const Chunk ck) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int4* ent = reinterpret_cast<int4*>(smem_raw);
+  float* tab = reinterpret_cast<float*>(smem_raw + PASS_WARPS * pass_wslots(K) * 16);
+  const int pair = blockIdx.y;
+  const int n = ck.n2c[pair];
+  const int tile0 = blockIdx.x * pass_tile_points(K);
+  if (tile0 >= n && blockIdx.x != 0) return;
+  Pass2Mode md;
+  load_pass2_mode(ck, pair, md);
+  // delta iterations only read the look-up tables for the few points they re-evaluate: straight from global memory
+  const float* tabp = ck.binrec;
+  if (md.rebuild) {
+    const int ntab = pass_tab_floats(ck.nT, ck.nP);
+    for (int k = threadIdx.x; k < ntab; k += PASS_THREADS) tab[k] = __ldg(ck.binrec + k);
+    tabp = tab;
+    __syncthreads();
+  }
+  float tr[12];
+  {
+    const float4* tp = reinterpret_cast<const float4*>(ck.TR + (size_t)pair * 12);
+    const float4 a = __ldcg(tp), b = __ldcg(tp + 1), c = __ldcg(tp + 2);
+    tr[0] = a.x; tr[1] = a.y; tr[2] = a.z; tr[3] = a.w; tr[4] = b.x; tr[5] = b.y; tr[6] = b.z; tr[7] = b.w;
+    tr[8] = c.x; tr[9] = c.y; tr[10] = c.z; tr[11] = c.w;
+  }
+  const CellRec* recs = ck.rec + (size_t)pair * ck.ncell;
+  pass2_warp_tile<K>(ck, ent + (threadIdx.x >> 5) * pass_wslots(K), tabp, recs, tr, md, ck.pog + (size_t)pair * 3 * ck.n2max,
+                     (size_t)ck.n2max, n, tile0 + (threadIdx.x >> 5) * 32 * K, ck.marg + (size_t)pair * ck.n2max,
+                     ck.cls2 + (size_t)pair * ck.n2max,
+                     (ck.flags & ICET_B200_FLAG_VERIFY_INCREMENTAL) ? &ck.res[pair].reserved[0] : nullptr);
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    pass2_dropped_returns(ck, reinterpret_cast<const float4*>(tabp), reinterpret_cast<const float4*>(tabp) + ck.nT + 2, recs,
+                          tr, md, pair, ck.nz2[pair]);
+}

@@ -155,6 +155,10 @@ __global__ void __launch_bounds__(256) k_cell_scan(const Chunk ck) {
     icet::rotR(X[3], X[4], X[5], TR + 3);
     icet::getH_J(X[3], X[4], X[5], ck.J + (size_t)pair * 27);
     for (int k = 0; k < 12; k++) ck.TRprev[(size_t)pair * 12 + k] = TR[k];
+    // incremental scan-2 loop: the first iteration builds the moments from zero in set 0, anchored at this transform
+    PairMode* pm = ck.pm + pair;
+    pm->set = 0; pm->rebuild = 1; pm->SA = 0.f; pm->C = 0.f; pm->SB = 0.f; pm->zcls = (int)0x000fffff;
+    for (int k = 0; k < 12; k++) pm->TRb[k] = TR[k];
   }
   __syncthreads();
   int a = is - s, b = iw - w;

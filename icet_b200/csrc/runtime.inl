@@ -112,7 +112,7 @@ size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runle
   ck.cnt1 = c.take<int32_t>((size_t)P * ncell);
   ck.cntz = c.take<int32_t>((size_t)P * ncell);
   ck.cursor = c.take<int32_t>((size_t)P * ncell);
-  ck.acc = c.take<unsigned long long>((size_t)P * ncell * NQ);
+  ck.acc = c.take<unsigned long long>((size_t)2 * P * ncell * NQ);
   ck.n2c = c.take<int32_t>((size_t)P);
   ck.nz2 = c.take<int32_t>((size_t)P);
   ck.ticket = c.take<unsigned>(1);
@@ -127,6 +127,7 @@ size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runle
   ck.work = c.take<int32_t>((size_t)P * ncell);
   ck.nwork = c.take<int32_t>((size_t)P);
   ck.nbig = c.take<int32_t>((size_t)P);
+  ck.pm = c.take<PairMode>((size_t)P);
   ck.rec = c.take<CellRec>((size_t)P * ncell);
   ck.vox = c.take<Vox1>((size_t)P * ncell);
   ck.cellid1 = c.take<int32_t>((size_t)P * n1max);
@@ -137,6 +138,8 @@ size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runle
   ck.kbuf = shipped ? c.take<unsigned long long>((size_t)P * n1max) : nullptr;
   ck.pos1 = shipped ? c.take<int32_t>((size_t)P * n1max) : nullptr;
   ck.pog = c.take<float>((size_t)P * 3 * n2max);
+  ck.marg = c.take<float2>((size_t)P * n2max);
+  ck.cls2 = c.take<uint32_t>((size_t)P * n2max);
   ck.X = c.take<float>((size_t)P * 6);
   ck.TR = c.take<float>((size_t)P * 12);
   ck.TRprev = c.take<float>((size_t)P * 12);
@@ -294,6 +297,7 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   if (psm > ctx->pass_smem_set) {
     CK(cudaFuncSetAttribute(k_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
     CK(cudaFuncSetAttribute(k_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
+    CK(cudaFuncSetAttribute(k_pass2<>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
     CK(cudaFuncSetAttribute(k_loop<PASS_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
     CK(cudaFuncSetAttribute(k_loop<PASS_K_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->loop_occ[0], k_loop<PASS_K>, PASS_THREADS, psm));
@@ -380,7 +384,10 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
                         (!(p->flags & ICET_B200_FLAG_UNFUSED_LOOP) && P <= ICET_LOOP_MAX_PAIRS);
   if (!use_loop) {
     for (int it = 0; it < p->runlen; it++) {
-      if (n2max > 0) LAUNCH(7, k_pass<true><<<gp2, PASS_THREADS, psm, st>>>(ck));
+      if (n2max > 0) {
+        if (p->flags & ICET_B200_FLAG_EXACT_PASS) LAUNCH(7, k_pass<true><<<gp2, PASS_THREADS, psm, st>>>(ck));
+        else LAUNCH(7, k_pass2<><<<gp2, PASS_THREADS, psm, st>>>(ck));
+      }
       LAUNCH(8, k_vox2<<<dim3(nblk, P), VOX_THREADS, 0, st>>>(ck, it));
       LAUNCH(9, k_solve6<<<P, 32, 0, st>>>(ck, it, nblk));
     }
@@ -438,6 +445,7 @@ int ensure_dump(icet_b200_ctx* ctx, const icet_b200_params* p) {
     d.cnt2 = cv.take<int32_t>(rl * ncell); d.nin2 = cv.take<int32_t>(rl * ncell); d.used2 = cv.take<uint8_t>(rl * ncell);
     d.mu2 = cv.take<float>(rl * ncell * 3); d.sigma2 = cv.take<float>(rl * ncell * 9);
     d.Xit = cv.take<float>(rl * 6); d.HTWH = cv.take<float>(rl * 36); d.HTWdz = cv.take<float>(rl * 6);
+    d.TRit = cv.take<float>(rl * 12); d.testpts = cv.take<float>(ncell * 18);
     d.tl = cv.take<unsigned long long>(rl * 16 + 6144);  // + begin / end / mid of up to 2048 tiles of iteration 3
   };
   Dump tmp;

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ICET_B200_VERSION 104
+#define ICET_B200_VERSION 105
 
 /* status codes (return values; also icet_b200_result.status for per-pair conditions) */
 enum {
@@ -72,7 +72,22 @@ enum {
    * of this library is the intended, sorted order.  With this flag the host reproduces the shipped row order (the very
    * same std::sort call and swap loop, on the ranges the device computed) and the device clusters in that order --
    * slower (one host round trip), for checking results against an unmodified reference build. */
-  ICET_B200_FLAG_SHIPPED_ORDER = 16
+  ICET_B200_FLAG_SHIPPED_ORDER = 16,
+  /* Scan 2 in the Gauss-Newton loop.  Default: INCREMENTAL -- exact integer moments of the untransformed members of
+   * every voxel are kept across iterations, a point is re-evaluated (transform, spherical coordinates, voxel, cluster
+   * box) only when the transform has moved it further than its margin to the nearest deciding threshold, and the
+   * voxel mean / covariance follow from the moments analytically ((mean + t) R, R^T Cov R).  Voxel membership is the
+   * per-point pipeline's in every iteration; mean / covariance differ from the reference's by the rounding noise of
+   * its per-point fp32 round trip.
+   * EXACT_PASS: every iteration runs the reference's per-point pipeline on every point (transform, c2s, filter,
+   * sphericalToCartesian, src/icet.cpp:375-403 + :303-306) -- the validation form, about 3x slower in the loop.
+   * FULL_REBUILD (diagnostic): incremental bookkeeping, but every iteration re-evaluates every point. */
+  ICET_B200_FLAG_EXACT_PASS = 32,
+  ICET_B200_FLAG_FULL_REBUILD = 64,
+  /* Self-check of the incremental loop (tests): every point is re-evaluated in every iteration, and a point that the
+   * margin test would have skipped but whose class changed is counted in icet_b200_result.reserved[0] (must stay 0).
+   * Results are bit-identical to the default form. */
+  ICET_B200_FLAG_VERIFY_INCREMENTAL = 128
 };
 
 /* per-pair result: the members callers of `class ICET` read (X: all four callers; pred_stds:
@@ -166,6 +181,11 @@ typedef struct {
   float* Xit;        /* [runlen*6]  X after each iteration     */
   float* HTWH;       /* [runlen*36] */
   float* HTWdz;      /* [runlen*6]  */
+  float* TRit;       /* [runlen*12] trans (3) | rot_mat (9, row-major) every iteration used (src/icet.cpp:375-376) */
+  float* testPoints; /* [ncell*6*3] the reference's public member testPoints (include/icet.h:84), row-major 6*ncell x 3:
+                        rows 6*cell+2k, +2k+1 hold the two 2-sigma test points of axis k when that axis was found
+                        extended (L(k,k) = 0, src/icet.cpp:214-232); all other rows are 0 (uninitialised in the
+                        reference)                                                                               */
 } icet_b200_voxel_dump;
 
 /* Enable (1) / disable (0) recording of the per-voxel state for subsequent icet_b200_register calls. */
@@ -177,6 +197,13 @@ int icet_b200_get_dump(icet_b200_ctx* ctx, icet_b200_voxel_dump* out);
  * before :433), in the caller's point order (the reference leaves it in its internal permuted order).
  * out: HOST buffer of 3*n2 floats (planes), n2 must equal the registered size. */
 int icet_b200_get_points2(icet_b200_ctx* ctx, float* out, int32_t n2);
+
+/* Parity-test entry: the class the per-point pipeline (transform, cartesianToSpherical, sortSphericalCoordinates,
+ * filterPointsInsideCluster; src/icet.cpp:375-388, :290-300) gives every point of scan 2 of the most recent DUMPED
+ * icet_b200_register call in iteration `iter`, in the caller's point order: cell[n2] = bins_theta*phi + theta,
+ * in[n2] = 1 if the point is inside the cluster box of a voxel that has a scan-1 Gaussian and passes the scan-1 gates
+ * of fitCells2 (`indices1.size() > n`, `outer > 1`).  HOST buffers, blocking. */
+int icet_b200_classify_scan2(icet_b200_ctx* ctx, int32_t iter, int32_t* cell, uint8_t* in, int32_t n2);
 
 /* Stage outputs used by the parity tests (HOST buffers, blocking):
  * spherical coordinates [3*n] (r | theta | phi) and the cell index of each point,

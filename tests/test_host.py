@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), "missing export " + name
     assert sorted(api.EXPORTS) == declared
-    assert L.icet_b200_version() == 104
+    assert L.icet_b200_version() == 105
     assert C.sizeof(api.Result) == 224 and C.sizeof(api.Params) == 32
     m = re.search(r"#define ICET_B200_NKERNELS (\d+)", hdr)
     assert int(m.group(1)) == api.NKERNELS
