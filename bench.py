@@ -4,11 +4,13 @@
     python bench.py --gpus N --steps K --warmup W             (N > 1: launched under torchrun)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-A "step" registers --pairs-per-gpu consecutive scan pairs (64 rings x 2048 azimuth steps = 131 072
-points per scan, 75 x 24 spherical voxels, 7 iterations, X0 = 0) per GPU; scans are resident in HBM
-when the timed region starts (`value`), or start in pinned host memory (`e2e`).  Pairs are sharded by
-contiguous pair range across ranks (no data-path collective; one all_gather of 48 floats per pair
-closes each step), so scaling is weak: total pairs = N * pairs-per-gpu.
+A "step" registers the BASELINE.json configs[2] batch: --pairs-total (default 4096) consecutive scan pairs (64 rings x
+2048 azimuth steps = 131 072 points per scan, 75 x 24 spherical voxels, 7 iterations, X0 = 0), pair-sharded by contiguous
+range over the N ranks (strong scaling: 4096 / N pairs per GPU; no data-path collective, one all_gather of 48 floats per
+pair closes each step).  --pairs-per-gpu P selects the weak-scaling form instead (N * P pairs).  Scans are resident in
+HBM when the timed region starts (`value`), or start in pinned host memory (`e2e`, with a copy-only control that
+measures what the host->device link of this box sustains with all ranks copying at once).  `configs` holds the other
+BASELINE.json configurations (latency of one 64-channel pair, the 128-channel pair, scan-to-submap at 2 M points).
 
 Prints ONE JSON line on rank 0.
 """
@@ -109,9 +111,57 @@ def cpu_time_sequence(scans_host: np.ndarray, threads: int):
     return (scans_host.shape[0] - 1) / dt, res
 
 
+def ref_time_sequence(scans_host: np.ndarray, threads: int):
+    """Time the REFERENCE's own code (oracle/_ref: its unmodified src/icet.cpp, utils.cpp, ThreadPool.cpp compiled in the
+    build container against the Eigen-API shim, see oracle/Makefile), one `ICET` object per pair like its callers.
+    Returns pairs/s, or None when the library did not travel to this box."""
+    from oracle import pyref
+    for native in (True, False):
+        if not os.path.exists(pyref.so_path(native)) and not os.path.isdir(os.path.join(pyref.REFERENCE, "src")):
+            continue
+        try:
+            _, dt = pyref.run_sequence(scans_host, nthreads=threads, native=native, **oracle_params())
+            return (scans_host.shape[0] - 1) / dt
+        except Exception:
+            continue
+    return None
+
+
+def cpu_baseline_measure(scans_host: np.ndarray, cores: int, warmup: int = 1, steps: int = 2):
+    """The CPU baseline both arms report: `warmup` + `steps` passes over the sample with all host threads, the
+    reference's own code when oracle/_ref is present (kind "reference"), else the oracle port (kind "port").  The
+    port is timed as well (it is also the parity checker of the GPU results)."""
+    sample = scans_host.shape[0] - 1
+    ref_t, port_t, ores = [], [], None
+    for s in range(warmup + steps):
+        v = ref_time_sequence(scans_host, cores)
+        pps, ores = cpu_time_sequence(scans_host, cores)
+        if s >= warmup:
+            port_t.append(sample / pps)
+            if v:
+                ref_t.append(sample / v)
+    port = sample / float(np.mean(port_t))
+    one_core, _ = cpu_time_sequence(scans_host[:5], 1)  # SURVEY.md 8(d)(i): one instance on one core
+    if ref_t:
+        value, kind = sample / float(np.mean(ref_t)), "reference"
+        one_ref = ref_time_sequence(scans_host[:3], 1)
+        note = ("%d consecutive synthetic 64-ch pairs per pass, %d host threads (one ICET object per pair, one pair per "
+                "thread at a time), %d warm-up + %d timed passes; the reference's own sources (src/icet.cpp, utils.cpp, "
+                "ThreadPool.cpp) built -O3 -march=x86-64-v3 in the build container against oracle/eigen_shim -- Eigen "
+                "itself is not in the image: the reference's logic, allocations and libm calls are its own, Eigen's dense "
+                "kernels are plain loops" % (sample, cores, warmup, steps))
+    else:
+        value, kind, one_ref = port, "port", None
+        note = ("%d consecutive synthetic 64-ch pairs per pass, %d host threads, %d warm-up + %d timed passes; oracle "
+                "restatement built -O3 -march=native (oracle/_ref did not travel to this box)" % (sample, cores, warmup, steps))
+    cb = {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": note,
+          "one_core_value": one_ref if one_ref else one_core, "port_value": port, "port_one_core_value": one_core}
+    return cb, ores
+
+
 def run_reference(args, rank: int, world: int):
-    """Reference arm: the reference's own CPU implementation of the path.  The reference cannot be built here
-    (Eigen3 absent), so this times oracle/ (the CPU restatement, kind = "port") with all host threads."""
+    """Reference arm: the reference's own CPU implementation of the path on the box's host cores (oracle/_ref when it
+    travelled, else the oracle port), all host threads, bounded sample of the same workload."""
     if rank != 0:
         return
     from tools import synth_host
@@ -119,33 +169,35 @@ def run_reference(args, rank: int, world: int):
     # one step = `sample` pairs: 2 per host thread (bounded so that the whole run ends within minutes)
     sample = max(2, min(2 * cores, 256))
     scans = synth_host.scans(sample + 1, first_scan=0, seed=SEED, rings=RINGS, azim=AZIM)
-    times = []
-    for s in range(args.warmup + args.steps):
-        pps, _ = cpu_time_sequence(scans, cores)
-        if s >= args.warmup:
-            times.append(sample / pps)
-    t = float(np.mean(times))
-    value = sample / t
-    one_core, _ = cpu_time_sequence(scans[:5], 1)  # one instance on one core
+    cb, _ = cpu_baseline_measure(scans, cores, warmup=max(1, args.warmup), steps=max(1, args.steps))
+    value = cb["value"]
+    t = sample / value
+    total, per_gpu, scaling = resolve_pairs(args, world)
+    cfg = workload_config(per_gpu, world, scaling)
+    cfg["pairs_per_step"] = sample          # what this arm really registers per step (a bounded sample of the batch)
+    cfg["pairs_per_step_note"] = "bounded CPU sample of the %d-pair batch the GPU arm registers per step" % total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": value / README_PAIRS_PER_S, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.pairs_per_gpu, args.gpus),
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "one_core_value": one_core,
-                         "sample": "%d consecutive synthetic 64-ch pairs per step, %d threads (one pair per thread "
-                                   "at a time); the reference C++ cannot be compiled here (no Eigen), this is the "
-                                   "oracle restatement built -O3 -march=native" % (sample, cores)},
+        "scaling": scaling, "vs_baseline": value / README_PAIRS_PER_S, "dtype": "f32", "data": "synthetic",
+        "config": cfg, "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(pairs_per_gpu: int, n_gpus: int) -> dict:
-    return {"workload": "BASELINE.json configs[2] shape: synthetic 64-channel odometry sequence, consecutive pairs "
-                        "(k,k+1), X0=0, pair-sharded by contiguous range",
+def resolve_pairs(args, world: int):
+    """(total pairs per step, pairs per GPU, "strong" | "weak")"""
+    if args.pairs_per_gpu:
+        return args.pairs_per_gpu * world, args.pairs_per_gpu, "weak"
+    per = max(1, args.pairs_total // world)
+    return per * world, per, "strong"
+
+
+def workload_config(pairs_per_gpu: int, n_gpus: int, scaling: str = "strong") -> dict:
+    return {"workload": "BASELINE.json configs[2]: batched synthetic 64-channel odometry sequence, consecutive pairs "
+                        "(k,k+1), X0=0, pair-sharded by contiguous range (%s scaling)" % scaling,
             "points_per_scan": NPTS, "rings": RINGS, "azimuth_steps": AZIM, "voxels": "75x24",
             "iterations": RUNLEN, "pairs_per_gpu_per_step": pairs_per_gpu, "pairs_per_step": pairs_per_gpu * n_gpus,
             "l2_policy": "inputs larger than L2 (%d scans x 1.5 MiB per GPU)" % (pairs_per_gpu + 1),
@@ -210,13 +262,70 @@ def bench_callers(ctx, scans, stream, M):
     return out
 
 
+def bench_configs(ctx, stream, dev, latency):
+    """The BASELINE.json configurations that are not the headline batch, one device-resident pair each:
+    p50 / p95 of the call (CUDA events), the algorithmic bytes of SURVEY.md 8(d) (12 B per input point + 192 B of
+    results) and the fraction of the HBM roofline they amount to."""
+    import torch
+    from icet_b200 import api
+    from tools import synth_host
+    peak, _ = peaks()
+
+    def p50(s1, n1, s2, n2, p, reps):
+        res = torch.zeros((1, 56), dtype=torch.float32, device=dev)
+        lat = []
+        for i in range(reps + 20):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            ctx.register_batch_ptrs([s1.data_ptr()], [n1], [s2.data_ptr()], [n2], res.data_ptr(), params=p, device=True)
+            b.record(stream)
+            torch.cuda.synchronize()
+            if i >= 20:
+                lat.append(a.elapsed_time(b))
+        r = res.cpu().numpy().view(api.RESULT_DTYPE).reshape(-1)[0]
+        return float(np.median(lat)), float(np.percentile(lat, 95)), r
+
+    def entry(workload, n1, n2, m, q, r):
+        b_alg = 12 * (n1 + n2) + 192
+        return {"workload": workload, "p50_ms": m, "p95_ms": q, "algorithmic_bytes": b_alg,
+                "achieved_gbs": b_alg / (m * 1e-3) / 1e9, "frac_of_hbm_peak": b_alg / (m * 1e-3) / 1e9 / peak,
+                "gaussians": int(r["n_gauss1"]), "voxels_used": int(r["n_used"]), "status": int(r["status"])}
+
+    out = {}
+    if latency:
+        b_alg = 12 * 2 * NPTS + 192
+        out["latency_64ch"] = {"workload": "configs[1]: one synthetic 64-ch pair (131 072 points per scan), 75x24, 7 it",
+                               "p50_ms": latency["device_resident_p50_ms"], "p95_ms": latency["device_resident_p95_ms"],
+                               "host_api_pinned_p50_ms": latency["host_api_pinned_p50_ms"], "algorithmic_bytes": b_alg,
+                               "achieved_gbs": b_alg / (latency["device_resident_p50_ms"] * 1e-3) / 1e9,
+                               "frac_of_hbm_peak": b_alg / (latency["device_resident_p50_ms"] * 1e-3) / 1e9 / peak}
+    n128 = 128 * 2048
+    b = torch.empty((2, 3, n128), dtype=torch.float32, device=dev)
+    ctx.synth_scans_device(b.data_ptr(), 2, first_scan=10, seed=SEED, rings=128, azim=2048)
+    m, q, r = p50(b[0], n128, b[1], n128, api.make_params(10, 48, 150, NMIN, THRESH, BUFF), 100)
+    out["ouster_128ch"] = entry("configs[3]: synthetic 128-channel pair (262 144 points per scan), 150x48, 10 it",
+                                n128, n128, m, q, r)
+    del b
+    mp_h, cur_h = synth_host.submap()
+    mp = torch.from_numpy(mp_h).to(dev)
+    cur = torch.from_numpy(cur_h).to(dev)
+    m, q, r = p50(mp, mp.shape[1], cur, NPTS, api.make_params(RUNLEN, BINS_PHI, BINS_THETA, NMIN, THRESH, BUFF), 50)
+    out["submap_2M"] = entry("configs[4]: scan-to-submap, %d-point accumulated map (1240 scans x 2000 rays, exact "
+                             "generator poses) vs one 64-ch scan, 75x24, 7 it" % mp.shape[1], mp.shape[1], NPTS, m, q, r)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs-per-gpu", type=int, default=512)
+    ap.add_argument("--pairs-total", type=int, default=4096,
+                    help="pairs per step over ALL ranks (BASELINE.json configs[2]: 4096; strong scaling)")
+    ap.add_argument("--pairs-per-gpu", type=int, default=0,
+                    help="weak-scaling form: this many pairs per step on every rank (overrides --pairs-total)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the 128-channel / submap configuration lines")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -254,7 +363,7 @@ def main():
     if world != args.gpus and rank == 0:
         print("bench.py: warning: --gpus %d but WORLD_SIZE=%d" % (args.gpus, world), file=sys.stderr)
 
-    P = args.pairs_per_gpu
+    total_pairs, P, scaling = resolve_pairs(args, world)
     ctx = icet_b200.Context(local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
@@ -273,7 +382,9 @@ def main():
     first_scan, nscans = sharding.shard_scans(world * P, rank, world)
     assert nscans == P + 1
     scans = torch.empty((P + 1, 3, NPTS), dtype=torch.float32, device=dev)
-    ctx.synth_scans_device(scans.data_ptr(), P + 1, first_scan=first_scan, seed=SEED, rings=RINGS, azim=AZIM)
+    for c0 in range(0, P + 1, 512):   # 512-scan slabs keep the generator's pose table small
+        ctx.synth_scans_device(scans[c0].data_ptr(), min(512, P + 1 - c0), first_scan=first_scan + c0, seed=SEED,
+                               rings=RINGS, azim=AZIM)
     results = torch.zeros((P, 56), dtype=torch.float32, device=dev)
     torch.cuda.synchronize()
 
@@ -357,7 +468,6 @@ def main():
         host_scans = torch.empty((P + 1, 3, NPTS), dtype=torch.float32, pin_memory=True)
         host_scans.copy_(scans)
         torch.cuda.synchronize()
-        hs = host_scans.numpy()
         host_out = torch.zeros((P, 56), dtype=torch.float32, pin_memory=True)
         ptr0 = host_scans.data_ptr()
         stride = 3 * NPTS * 4
@@ -372,23 +482,43 @@ def main():
             e2e_step()
         barrier()
         t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        nst = max(2, min(args.steps, 5))
+        nst = max(2, args.steps)
         for _ in range(nst):
             e2e_step()
-        e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
-        tw = torch.tensor([wall], dtype=torch.float64, device=dev)
+        # copy-only control: the very same host buffer -> device memory, no kernels, all ranks at once: what the
+        # host->device path of THIS box sustains (PCIe link, host memory / NUMA placement, shared root ports)
+        sink = torch.empty((min(P + 1, 512), 3, NPTS), dtype=torch.float32, device=dev)
+        def copy_only():
+            for c0 in range(0, P + 1, sink.shape[0]):
+                m = min(sink.shape[0], P + 1 - c0)
+                sink[:m].copy_(host_scans[c0:c0 + m], non_blocking=True)
+        copy_only()
+        barrier()
+        c0t = time.perf_counter()
+        ncp = 3
+        for _ in range(ncp):
+            copy_only()
+        barrier()
+        cwall = time.perf_counter() - c0t
+        tw = torch.tensor([wall, cwall], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * P * nst / float(tw[0]), "unit": "pairs/s",
-               "h2d_bytes_per_step": int((P + 1) * stride + P * 24) * world, "d2h_bytes_per_step": int(P * 224) * world,
+        del sink
+        h2d = int((P + 1) * stride + P * 24)
+        e2e_v = world * P * nst / float(tw[0])
+        ceil_gbs = world * (P + 1) * stride * ncp / float(tw[1]) / 1e9
+        ceil_pairs = world * P * ncp / float(tw[1])
+        e2e = {"value": e2e_v, "unit": "pairs/s", "steps": nst,
+               "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": int(P * 224) * world,
+               "h2d_gbs_achieved": h2d * world * nst / float(tw[0]) / 1e9,
+               "h2d_ceiling_gbs": ceil_gbs, "h2d_ceiling_pairs_per_s": ceil_pairs, "frac_of_h2d_ceiling": e2e_v / ceil_pairs,
                "note": "icet_b200_register_batch on pinned host scans (each scan uploaded once), results copied back; "
-                       "host wall clock around blocking calls, max over ranks"}
-        del hs
-
+                       "host wall clock around blocking calls, max over ranks.  h2d_ceiling_*: copy-only control (the same "
+                       "pinned buffers copied to the device by all ranks at once, no kernels): the limiter of e2e is the "
+                       "host->device path, not the kernels (value) and not NCCL"}
+        del host_scans
     # ---- single-pair latency (BASELINE.json configs[1]) -----------------------------------------------------
     latency = None
     if rank == 0 and not args.no_latency:
@@ -432,32 +562,34 @@ def main():
     if rank == 0 and not args.no_callers:
         callers = bench_callers(ctx, scans, stream, max(1, min(P // 4, 128)))
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle on the box's host cores ------------------------
+    # ---- the other BASELINE.json configurations (rank 0) ------------------------------------------------------------
+    configs = None
+    if rank == 0 and not args.no_configs:
+        configs = bench_configs(ctx, stream, dev, latency)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's CPU path on the box's host cores ---------------
     cpu_baseline = None
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         sample = max(2, min(2 * cores, P, 256))
         hs = scans[: sample + 1].cpu().numpy()
-        pps, ores = cpu_time_sequence(hs, cores)
-        one_core, _ = cpu_time_sequence(hs[:5], 1)  # one instance on one core
-        cpu_baseline = {"value": pps, "unit": "pairs/s", "cores": cores, "kind": "port", "one_core_value": one_core,
-                        "sample": "first %d pairs of the same synthetic sequence, %d host threads (one pair per thread "
-                                  "at a time); oracle restatement built -O3 -march=native (the reference cannot be "
-                                  "compiled here: no Eigen)" % (sample, cores)}
+        cpu_baseline, ores = cpu_baseline_measure(hs, cores)
         g = results[:sample].cpu().numpy()
         parity = {"pairs_checked": sample, "max_abs_dX_m": float(np.abs(g[:, :3] - ores[:, :3]).max()),
-                  "max_abs_dX_rad": float(np.abs(g[:, 3:6] - ores[:, 3:6]).max())}
+                  "max_abs_dX_rad": float(np.abs(g[:, 3:6] - ores[:, 3:6]).max()),
+                  "note": "GPU results of the timed batch against the oracle port (sorted order, like the product's default)"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": value / README_PAIRS_PER_S,
             "baseline_note": "reference README.md:59: 35 ms/pair (28.6 pairs/s) on a Ryzen 5800X CPU",
-            "dtype": "f32", "data": "synthetic", "config": workload_config(P, world), "clocks": clocks,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(P, world, scaling), "clocks": clocks,
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_path": roofline_path,
-            "cpu_baseline": cpu_baseline, "latency": latency, "parity_vs_oracle": parity, "callers": callers,
+            "cpu_baseline": cpu_baseline, "latency": latency, "configs": configs, "parity_vs_oracle": parity,
+            "callers": callers,
             "kernel_ms_per_step": {k: round(v[0], 4) for k, v in prof.items()},
         }
         print(json.dumps(line), flush=True)

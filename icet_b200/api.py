@@ -115,7 +115,9 @@ EXPORTS = ["icet_b200_version", "icet_b200_last_error", "icet_b200_create", "ice
            "icet_b200_node_current_scan", "icet_b200_node_last_result", "icet_b200_map_create",
            "icet_b200_map_destroy", "icet_b200_map_add_scan_device", "icet_b200_map_get", "icet_b200_map_get_device",
            "icet_b200_ingest", "icet_b200_register_clouds", "icet_b200_node_push_cloud",
-           "icet_b200_transform_cloud_device", "icet_b200_transform_cloud"]
+           "icet_b200_transform_cloud_device", "icet_b200_transform_cloud",
+           "icet_b200_multi_create", "icet_b200_multi_destroy", "icet_b200_multi_devices", "icet_b200_multi_context",
+           "icet_b200_register_batch_multi", "icet_b200_register_sequence_multi_device", "icet_b200_multi_gathered"]
 NKERNELS = 11
 
 _LIB = None
@@ -183,6 +185,14 @@ def load_library() -> C.CDLL:
                                             C.POINTER(Result)]
     L.icet_b200_node_push_cloud.argtypes = [vp, C.POINTER(Cloud), C.POINTER(Result), C.POINTER(Pose)]
     L.icet_b200_kernel_name.restype = C.c_char_p
+    L.icet_b200_multi_create.argtypes = [vp, C.c_int32, C.POINTER(vp)]
+    L.icet_b200_multi_destroy.argtypes = [vp]
+    L.icet_b200_multi_devices.argtypes = [vp]
+    L.icet_b200_multi_context.argtypes = [vp, C.c_int32]
+    L.icet_b200_multi_context.restype = vp
+    L.icet_b200_register_batch_multi.argtypes = [vp, C.POINTER(Params), C.c_int32, vp, vp, vp, vp, vp, vp]
+    L.icet_b200_register_sequence_multi_device.argtypes = [vp, C.POINTER(Params), C.c_int32, vp, C.c_int32]
+    L.icet_b200_multi_gathered.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(C.c_int32)]
     _LIB = L
     return L
 
@@ -396,6 +406,68 @@ class Context:
             setattr(d, name, arrs[name].ctypes.data_as(ct))
         self._check(self._L.icet_b200_get_dump(self._h, C.byref(d)))
         return arrs
+
+
+class MultiContext:
+    """icet_b200_multi: one process, one context per device, batches sharded by contiguous pair range, one
+    ncclAllGather of 48 floats per pair at the end (include/icet_b200.h "multi-GPU")."""
+
+    def __init__(self, devices=None, ndev=None):
+        self._L = load_library()
+        devs = list(devices) if devices is not None else list(range(ndev or 1))
+        arr = np.array(devs, np.int32)
+        h = C.c_void_p()
+        self._h = None
+        rc = self._L.icet_b200_multi_create(arr.ctypes.data, len(devs), C.byref(h))
+        if rc < 0:
+            raise IcetError("icet_b200 error %d: %s" % (rc, self._L.icet_b200_last_error().decode()))
+        self._h = h
+        self.devices = devs
+
+    def _check(self, rc):
+        if rc < 0:
+            raise IcetError("icet_b200 error %d: %s" % (rc, self._L.icet_b200_last_error().decode()))
+        return rc
+
+    def close(self):
+        if self._h is not None:
+            self._L.icet_b200_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def register_batch(self, scans1, scans2, X0=None, params: Params | None = None) -> np.ndarray:
+        """HOST planes, like Context.register_batch; pairs [P d / G, P (d+1) / G) run on device slot d."""
+        p = params or make_params()
+        npairs = len(scans1)
+        p1 = np.array([a.ctypes.data for a in scans1], np.uint64)
+        p2 = np.array([a.ctypes.data for a in scans2], np.uint64)
+        n1 = np.array([a.shape[1] for a in scans1], np.int32)
+        n2 = np.array([a.shape[1] for a in scans2], np.int32)
+        x0p = None
+        if X0 is not None:
+            x0 = np.ascontiguousarray(X0, np.float32).reshape(npairs, 6)
+            x0p = x0.ctypes.data
+        out = np.zeros(npairs, RESULT_DTYPE)
+        self._check(self._L.icet_b200_register_batch_multi(self._h, C.byref(p), npairs, p1.ctypes.data, n1.ctypes.data,
+                                                           p2.ctypes.data, n2.ctypes.data, x0p, out.ctypes.data))
+        return out
+
+    def register_sequence_device(self, shard_ptrs, nscans: int, n: int, params: Params | None = None):
+        """shard_ptrs[d]: device pointer (on device slot d) to that device's scans of the sequence."""
+        p = params or make_params()
+        ptrs = np.array(shard_ptrs, np.uint64)
+        self._check(self._L.icet_b200_register_sequence_multi_device(self._h, C.byref(p), nscans, ptrs.ctypes.data, n))
+
+    def gathered(self, d: int):
+        """(device pointer to [ndev][rows_per_shard][48] floats on device slot d, rows_per_shard)"""
+        ptr, rows = C.c_void_p(), C.c_int32()
+        self._check(self._L.icet_b200_multi_gathered(self._h, d, C.byref(ptr), C.byref(rows)))
+        return ptr.value, rows.value
 
 
 _DEFAULT_CTX: Context | None = None

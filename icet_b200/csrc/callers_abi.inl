@@ -420,6 +420,7 @@ int icet_b200_register_clouds(icet_b200_ctx* c, const icet_b200_params* p, const
   if (dump) { c->dump_params = *p; c->dump_valid = true; }
   c->last_n2 = n2;
   c->last_runlen = p->runlen;
+  c->last_valid = true;  // (the planes of both clouds stay in planebuf until the next call)
   CK(cudaMemcpyAsync(out, dres, sizeof(icet_b200_result), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return check_loop_watchdog(c);

@@ -116,6 +116,7 @@ struct Chunk {  // everything a kernel needs, passed by value
   unsigned* vox_done;    // [P][runlen] vox tasks finished per iteration
   unsigned* vmask;       // [P][ceil(vt/32)] vox groups that wrote a partial sum (current iteration)
   int* dbg;              // [8] watchdog record of k_loop: {tripped, kind, pair, iter, seen, need, ticket, -}
+  unsigned long long loop_timeout_ns;  // a wait inside k_loop gives up after this long
   Dump dump;
   int dump_on;
 };

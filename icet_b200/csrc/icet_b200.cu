@@ -14,13 +14,17 @@
 // Determinism: per-voxel statistics are accumulated as 64-bit fixed-point integers (run sums in registers, then
 // RED.64 to L2), so results do not depend on thread / block / GPU partitioning or on atomic ordering.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/icet_b200.h"
@@ -69,6 +73,10 @@ int icet_b200_create(int device, icet_b200_ctx** out) {
   icet_b200_ctx* c = new icet_b200_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("ICET_B200_LOOP_TIMEOUT_MS")) {
+    const long long ms = atoll(e);
+    if (ms > 0) c->loop_timeout_ns = (unsigned long long)ms * 1000000ull;
+  }
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->own_stream = true;
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -452,6 +460,7 @@ int icet_b200_register_batch(icet_b200_ctx* c, const icet_b200_params* p, int32_
     if (npairs == 1) {
       c->last_n2 = n2[0];
       c->last_runlen = p->runlen;
+      c->last_valid = true;
     }
   }
   if (two) {
@@ -632,5 +641,6 @@ int icet_b200_synth_scans_device(icet_b200_ctx* c, uint64_t seed, int32_t first_
 }
 
 #include "callers_abi.inl"
+#include "multi_abi.inl"
 
 }  // extern "C"

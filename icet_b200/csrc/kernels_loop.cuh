@@ -583,8 +583,9 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// Spin until *p >= need.  A protocol failure must not hang the GPU: after ~2 s the wait gives up, records what it
-// was waiting for in ck.dbg and marks the pair (results of the chunk are then invalid; the host reports an error).
+// Spin until *p >= need.  A protocol failure must not hang the GPU: after ck.loop_timeout_ns (default 20 s of
+// %globaltimer, ICET_B200_LOOP_TIMEOUT_MS overrides: long enough for compute-sanitizer / time-sliced GPUs) the wait gives
+// up, records what it was waiting for in ck.dbg and marks EVERY pair of the chunk (the host reports an error).
 // The polling itself uses RELAXED loads: an acquire load is followed by an invalidation of the SM's whole L1
 // (CCTL.IVALL), and thousands of spinning warps would keep every L1 of the GPU empty for the warps that do the work.
 // One acquire load after the condition has been seen orders the reads that follow.
@@ -604,10 +605,12 @@ __device__ __noinline__ void loop_wait(const Chunk& ck, const int* p, int need, 
       ld_acquire(p);
       return;
     }
-    if ((++spins & 1023u) == 0 && gtime() - t0 > 2000000000ull) {
+    if ((++spins & 1023u) == 0 && (gtime() - t0 > ck.loop_timeout_ns || ld_relaxed(ck.dbg) != 0)) {
+      // give up (or another warp already has): every result of the chunk is poisoned, not only the waiting pair's --
+      // tasks that proceed past a failed wait work on unfinished accumulators
       if ((threadIdx.x & 31) == 0 && atomicCAS(ck.dbg, 0, 1) == 0) {
         ck.dbg[1] = kind; ck.dbg[2] = pair; ck.dbg[3] = iter; ck.dbg[4] = seen; ck.dbg[5] = need; ck.dbg[6] = (int)ticket;
-        ck.res[pair].status = ICET_B200_LOOP_TIMEOUT;
+        for (int q = 0; q < ck.npairs; q++) ck.res[q].status = ICET_B200_LOOP_TIMEOUT;
       }
       return;
     }
@@ -877,10 +880,12 @@ __global__ void k_points2(const Chunk ck, int n2, float* out) {
   if (i >= n2) return;
   const PairDesc d = ck.desc[0];
   float x = d.s2[i], y = d.s2[d.ld2 + i], z = d.s2[2 * (size_t)d.ld2 + i];
-  float r, th, ph;
-  icet::c2s(x, y, z, r, th, ph);   // points2_OG (prepScan2, src/icet.cpp:263-275), recomputed: the workspace
-  icet::s2c(r, th, ph, x, y, z);   // copy is compacted
-  icet::transform(x, y, z, ck.TRprev, ck.TRprev + 3, x, y, z);
+  if (ck.runlen > 0) {  // without an iteration the member is still the constructor's copy of scan 2 (src/icet.cpp:30)
+    float r, th, ph;
+    icet::c2s(x, y, z, r, th, ph);   // points2_OG (prepScan2, src/icet.cpp:263-275), recomputed: the workspace
+    icet::s2c(r, th, ph, x, y, z);   // copy is compacted
+    icet::transform(x, y, z, ck.TRprev, ck.TRprev + 3, x, y, z);
+  }
   out[i] = x;
   out[n2 + i] = y;
   out[2 * (size_t)n2 + i] = z;

@@ -18,7 +18,8 @@ constexpr int PASS_K_SMALL = 4;  // same for small batches (latency shape: more,
 __host__ __device__ constexpr int pass_wslots(int K) { return 32 * K; }  // 16-byte entry slots per warp tile
 __host__ __device__ constexpr int pass_tile_points(int K) { return PASS_WARPS * 32 * K; }
 // shared memory: entry tiles, then the angular tables: (nT + 2) + (nP + 2) records {T[k], T[k+1], lo[k], hi[k]}
-__host__ __device__ inline int pass_tab_floats(int nT, int nP) { return 4 * (nT + nP + 4); }
+// (+ the "sure" intervals of the filtered evaluation of the incremental loop: {lo, hi} per record)
+__host__ __device__ inline int pass_tab_floats(int nT, int nP) { return 6 * (nT + nP + 4); }
 __host__ __device__ inline int pass_smem_bytes(int nT, int nP, int K) {
   return PASS_WARPS * pass_wslots(K) * 16 + pass_tab_floats(nT, nP) * 4;
 }

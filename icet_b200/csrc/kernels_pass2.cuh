@@ -93,6 +93,89 @@ __device__ __forceinline__ void point_eval2(const Chunk& ck, const float4* tth, 
   mg = make_float2(u, r);
 }
 
+// ---- Filtered evaluation.  The incremental loop needs the CLASS of a point and a conservative margin, not the values
+// of theta / phi / r themselves.  Approximate angles (reciprocal / rsqrt approximations, fp32 octant fix-up; each
+// within TAU of the exactly evaluated fp32 pipeline) decide the class whenever they are further than TAU from every
+// threshold they are compared with -- then the exact pipeline cannot decide differently -- and only the remaining
+// points (a few in 10^4) go through the exact evaluation point_eval2.  Less than half the instructions per point.
+constexpr float TAU_TH = 3.0e-6f;  // |theta_fast - theta_exact| < 2e-6 (rcp.approx 1e-7 rel, polynomial 1e-7, three fp32
+                                   // subtractions <= 6e-7, constants 2e-7; exact side: own atan2 within 1 ulp = 4.8e-7)
+constexpr float TAU_PH = 1.5e-6f;  // |phi_fast - phi_exact| < 1e-6 for |z/r| <= 0.5 (rsqrt.approx 2e-7 rel, polynomial 1e-7)
+constexpr float TAU_R = 1.0e-6f;   // |r_fast - r_exact| < 5e-7 r (rsqrt.approx; the exact side is IEEE sqrt)
+
+__device__ __forceinline__ float fast_theta(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const bool steep = ay > ax;
+  const float mx = steep ? ay : ax, mn = steep ? ax : ay;
+  float rc;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(mx));
+  const float t = mn * rc;  // NaN for (0, 0): every comparison below fails and the point takes the exact path
+  const float s = t * t;
+  float p = -0.0019267977913841605f;
+  p = fmaf(p, s, 0.01150327268987894f);
+  p = fmaf(p, s, -0.03226083889603615f);
+  p = fmaf(p, s, 0.059030335396528244f);
+  p = fmaf(p, s, -0.08465225994586945f);
+  p = fmaf(p, s, 0.10972991585731506f);
+  p = fmaf(p, s, -0.14268141984939575f);
+  p = fmaf(p, s, 0.19998906552791595f);
+  p = fmaf(p, s, -0.3333331048488617f);
+  float v = fmaf(t * s, p, t);
+  v = steep ? (1.57079632679489662f - v) : v;
+  v = (x < 0.0f) ? (3.14159265358979324f - v) : v;
+  v = (y < 0.0f) ? (6.28318530717958648f - v) : v;
+  return v;
+}
+
+__device__ __forceinline__ void point_eval2_fast(const Chunk& ck, const float4* tth, const float4* tph, const CellRec* recs,
+                                                 const float* tr, float SA, float SB, float px, float py, float pz,
+                                                 uint32_t& cls, float2& mg) {
+  float x, y, z;
+  icet::transform(px, py, pz, tr, tr + 3, x, y, z);
+  const float sxy = fmaf(y, y, x * x);
+  const float s = fmaf(z, z, sxy);
+  float irs, irho;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(irs) : "f"(s));
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(irho) : "f"(sxy));
+  const float r = s * irs;
+  const float q = z * irs;
+  const float th = fast_theta(y, x);
+  const float q2 = q * q;
+  float pp = 0.0435001514852047f;
+  pp = fmaf(pp, q2, 0.023313719779253006f);
+  pp = fmaf(pp, q2, 0.045668356120586395f);
+  pp = fmaf(pp, q2, 0.07493448257446289f);
+  pp = fmaf(pp, q2, 0.166668102145195f);
+  const float ph = 1.57079632679489662f - fmaf(q * q2, pp, q);
+  // "sure" intervals (host: ensure_edges): strictly inside (lo + TAU, hi - TAU) of record k the exact pipeline finds
+  // bin k and passes the bin's fp32 box test as well.  NaN indexes record 0 and fails every comparison.
+  const float2* sth = reinterpret_cast<const float2*>(tth + ck.nT + ck.nP + 4);
+  const float2* sph = sth + ck.nT + 2;
+  const int bt = min(__float2int_rz(th * ck.bth.scale), ck.nT + 1);
+  const int bp = min(__float2int_rz(ph * ck.bph.scale), ck.nP + 1);
+  const float2 et = sth[bt], ep = sph[bp];
+  const float dth = fminf(th - et.x, et.y - th), dph = fminf(ph - ep.x, ep.y - ph);
+  const int c = ck.nT * min(bp, ck.nP - 1) + min(bt, ck.nT - 1);  // (clamped only so that the load below is in range)
+  const float4 ra = __ldg(reinterpret_cast<const float4*>(recs + c));  // inner, outer, flags, scale
+  const bool active = (__float_as_uint(ra.z) & F_ACTIVE2) != 0;
+  const float dr = fminf(fabsf(r - ra.x), fabsf(ra.y - r));
+  // (written so that NaN / inf anywhere fails the test)
+  const bool sure = dth > 0.f && dph > 0.f && fabsf(q) <= 0.5f && s < 3e38f && sxy > 1e-30f && (!active || dr > TAU_R * r);
+  if (!sure) {
+    point_eval2(ck, tth, tph, recs, tr, SA, SB, px, py, pz, cls, mg);
+    return;
+  }
+  const bool in = active && r >= ra.x && r <= ra.y;
+  cls = (uint32_t)c | (in ? CLS_IN : 0u) | (active ? CLS_ACTIVE : 0u);
+  // margin as in point_eval2, every distance reduced by the approximation error as well (TAU is in the table already)
+  const float rho = sxy * irho * 0.999f;
+  const float k = r * irho * 1.001f;
+  float m = fminf((dth - 2e-6f) * rho - 3e-6f * r, (dph - 4e-6f * k) * r);
+  m = fminf(m, 0.25f * rho);
+  if (active) m = fminf(m, dr - (TAU_R + 4e-6f) * r);
+  mg = make_float2(fmaf(0.9f, m, -1e-6f) + fmaf(r * 1.000001f, SA, SB), r * 1.000001f);
+}
+
 // anchor of a voxel's scan-2 fixed-point frame: the centre of its box, taken back through the transform of the last
 // rebuild (p = q R^T - t), and the scale
 __device__ __forceinline__ void vox_anchor2(const CellRec* recs, int cell, const float* trb, float& ax, float& ay, float& az,
@@ -190,7 +273,13 @@ __device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, con
       uint32_t cls = CLS_NONE;
       if (i < n) {
         float2 mg;
-        point_eval2(ck, tth, tph, recs, tr, 0.f, 0.f, x, y, z, cls, mg);
+        point_eval2_fast(ck, tth, tph, recs, tr, 0.f, 0.f, x, y, z, cls, mg);
+        if (violations) {  // self-check: the filtered evaluation must give the class of the exact pipeline
+          uint32_t cx;
+          float2 mx;
+          point_eval2(ck, tth, tph, recs, tr, 0.f, 0.f, x, y, z, cx, mx);
+          if (cx != cls) atomicAdd(violations + 1, 1);
+        }
         marg[i] = mg;
         cls2[i] = cls;
       }
@@ -273,7 +362,13 @@ __device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, con
       const uint32_t old = __ldcg(cls2 + i);
       uint32_t cls;
       float2 mg;
-      point_eval2(ck, tth, tph, recs, tr, md.SA, md.SB, x, y, z, cls, mg);
+      point_eval2_fast(ck, tth, tph, recs, tr, md.SA, md.SB, x, y, z, cls, mg);
+      if (violations) {
+        uint32_t cx;
+        float2 mx;
+        point_eval2(ck, tth, tph, recs, tr, md.SA, md.SB, x, y, z, cx, mx);
+        if (cx != cls) atomicAdd(violations + 1, 1);
+      }
       marg[i] = mg;
       if (cls != old) {
         if (was_stable) atomicAdd(violations, 1);

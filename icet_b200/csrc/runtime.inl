@@ -56,6 +56,7 @@ struct icet_b200_ctx {
   int sm_count = 148;
   int pass_smem_set = 0;  // dynamic shared memory the pass kernels are currently allowed
   int* loop_dbg[ICET_NLANE] = {};  // watchdog record of the last k_loop launch per lane
+  unsigned long long loop_timeout_ns = 20000000000ull;  // ICET_B200_LOOP_TIMEOUT_MS
   int loop_occ[2] = {0, 0};  // resident blocks per SM of k_loop<PASS_K>, k_loop<PASS_K_SMALL>
   // per-kernel timing (icet_b200_set_profile): events around every launch, summed on request
   int profile_on = 0;
@@ -86,7 +87,7 @@ struct icet_b200_ctx {
   // the most recent single-pair chunk (for icet_b200_get_points2)
   bool last_valid = false;
   int last_n2 = 0, last_runlen = 0;
-  char last_ck[640];
+  char last_ck[768];
 };
 
 namespace {
@@ -180,7 +181,7 @@ float bin_threshold(int k, double period, int nb) {
 int ensure_edges(icet_b200_ctx* ctx, int nT, int nP) {
   if (ctx->edges_nT == nT && ctx->edges_nP == nP) return 0;
   const size_t nbase = (size_t)2 * (nT + nP) + 6;
-  std::vector<float> e(((nbase + 3) & ~(size_t)3) + (size_t)4 * (nT + nP + 4));
+  std::vector<float> e(((nbase + 3) & ~(size_t)3) + (size_t)6 * (nT + nP + 4));
   float* azE = e.data();
   float* elE = azE + nT + 1;
   float* Tth = elE + nP + 1;
@@ -213,6 +214,18 @@ int ensure_edges(icet_b200_ctx* ctx, int nT, int nP) {
   };
   fill(rec, Tth, azE, nT, 2 * M_PI);
   fill(rec + 4 * (nT + 2), Tph, elE, nP, M_PI);
+  // "sure" intervals of the filtered evaluation (kernels_pass2.cuh): an approximate angle strictly inside
+  // (lo + tau, hi - tau) of record k is in bin k AND inside the bin's fp32 box for the exact pipeline as well
+  float* sure = rec + 4 * (nT + nP + 4);
+  auto fill_sure = [](float* out, const float* r4, int nb, float tau) {
+    for (int k = 0; k < nb + 2; k++) {
+      const float lo = r4[4 * k + 2], hi = r4[4 * k + 3];
+      out[2 * k + 0] = (k < nb) ? std::nextafterf(lo + tau, INFINITY) : INFINITY;
+      out[2 * k + 1] = (k < nb) ? std::nextafterf(hi - tau, -INFINITY) : -INFINITY;
+    }
+  };
+  fill_sure(sure, rec, nT, 3.0e-6f);                          // TAU_TH
+  fill_sure(sure + 2 * (nT + 2), rec + 4 * (nT + 2), nP, 1.5e-6f);  // TAU_PH
   int rc = ctx->edges.ensure(e.size() * sizeof(float));
   if (rc) return rc;
   CK(cudaMemcpyAsync(ctx->edges.p, e.data(), e.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -267,8 +280,6 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   memset(&ck, 0, sizeof(ck));
   size_t zero_bytes = 0;
   const bool shipped = (p->flags & ICET_B200_FLAG_SHIPPED_ORDER) != 0;
-  if (shipped && P != 1)
-    return fail(ICET_B200_E_INVALID, "ICET_B200_FLAG_SHIPPED_ORDER is a single-pair validation mode");
   size_t need = carve_chunk(nullptr, P, ncell, n1max, n2max, p->runlen, ck, &zero_bytes, shipped);
   rc = ctx->ws[lane].ensure(need);
   if (rc) return rc;
@@ -280,6 +291,7 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   fill_tables(ctx, nT, nP, &ck.azE, &ck.elE, &ck.bth, &ck.bph, &ck.binrec);
   ck.x0 = d_x0;
   ck.res = d_res;
+  ck.loop_timeout_ns = ctx->loop_timeout_ns;
   ck.dump_on = dump ? 1 : 0;
   if (dump) ck.dump = ctx->dump_ptrs;
   cudaStream_t st = lane == 0 ? ctx->stream : ctx->lanes[lane];
@@ -344,21 +356,42 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
       // The row order the reference ends up with (src/icet.cpp:72-83), reproduced on the host from the ranges the
       // device computed: the same index sort by range (std::sort; the reference's std::execution::par falls back
       // to it without TBB) and the same swap loop, which is NOT a valid permutation application.
-      std::vector<float> hr((size_t)n1max);
-      CK(cudaMemcpyAsync(hr.data(), ck.r1, (size_t)n1max * sizeof(float), cudaMemcpyDeviceToHost, st));
+      // One host round trip per chunk (this mode is for validation / strict reference compatibility, not for speed);
+      // the pairs of the chunk are ordered on all host threads.
+      std::vector<float> hr((size_t)P * n1max);
+      std::vector<PairDesc> hd((size_t)P);
+      CK(cudaMemcpyAsync(hr.data(), ck.r1, hr.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(hd.data(), d_desc, hd.size() * sizeof(PairDesc), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
-      std::vector<int> index((size_t)n1max), orig((size_t)n1max), pos((size_t)n1max);
-      for (int i = 0; i < n1max; i++) index[i] = orig[i] = i;
-      std::sort(index.begin(), index.end(), [&](int a, int b) { return hr[a] < hr[b]; });
-      for (int i = 0; i < n1max; i++) {
-        if (index[i] != i) {
-          const int j = index[i];
-          std::swap(orig[i], orig[j]);    // points1Spherical.row(i).swap(points1Spherical.row(index[i]))
-          std::swap(index[i], index[j]);  // std::swap(index[i], index[index[i]])
+      std::vector<int32_t> pos((size_t)P * n1max, 0);
+      auto order_pair = [&](int pr) {
+        const int n1 = std::min(hd[pr].n1, n1max);
+        const float* r = hr.data() + (size_t)pr * n1max;
+        std::vector<int> index((size_t)n1), orig((size_t)n1);
+        for (int i = 0; i < n1; i++) index[i] = orig[i] = i;
+        std::sort(index.begin(), index.end(), [&](int a, int b) { return r[a] < r[b]; });
+        for (int i = 0; i < n1; i++) {
+          if (index[i] != i) {
+            const int j = index[i];
+            std::swap(orig[i], orig[j]);    // points1Spherical.row(i).swap(points1Spherical.row(index[i]))
+            std::swap(index[i], index[j]);  // std::swap(index[i], index[index[i]])
+          }
+        }
+        int32_t* ps = pos.data() + (size_t)pr * n1max;
+        for (int i = 0; i < n1; i++) ps[orig[i]] = i;
+      };
+      {
+        const int nth = std::max(1, std::min(P, (int)std::thread::hardware_concurrency()));
+        if (nth == 1) {
+          for (int pr = 0; pr < P; pr++) order_pair(pr);
+        } else {
+          std::vector<std::thread> th;
+          for (int t = 0; t < nth; t++)
+            th.emplace_back([&, t]() { for (int pr = t; pr < P; pr += nth) order_pair(pr); });
+          for (auto& t : th) t.join();
         }
       }
-      for (int i = 0; i < n1max; i++) pos[orig[i]] = i;
-      CK(cudaMemcpyAsync(ck.pos1, pos.data(), (size_t)n1max * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ck.pos1, pos.data(), pos.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
       CK(cudaStreamSynchronize(st));
       LAUNCH(2, k_off_shipped<<<P, 256, 0, st>>>(ck));
       LAUNCH(2, k_scatter_shipped<<<g1, 256, 0, st>>>(ck));
@@ -403,8 +436,11 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   }
 #undef LAUNCH
   CK(cudaGetLastError());
-  static_assert(sizeof(Chunk) <= 640, "Chunk too large for last_ck");
-  ctx->last_valid = (P == 1);
+  static_assert(sizeof(Chunk) <= sizeof(icet_b200_ctx::last_ck), "Chunk too large for last_ck");
+  // icet_b200_get_points2 / classify_scan2 refer to the most recent single-pair icet_b200_register call only: that
+  // entry point validates the record (together with last_n2 / last_runlen) after this returns; any other chunk --
+  // the 1-pair tail of a batch, a node push -- invalidates it (its descriptors point into buffers that get reused)
+  ctx->last_valid = false;
   if (P == 1) memcpy(ctx->last_ck, &ck, sizeof(Chunk));
   return 0;
 }

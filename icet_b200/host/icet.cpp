@@ -73,14 +73,29 @@ ICET::ICET(Eigen::MatrixXf& scan1, Eigen::MatrixXf& scan2, int runlen, Eigen::Ve
 
   const int ncell = num_bins_phi * num_bins_theta;
   clusterBounds = Eigen::MatrixXf::Zero(ncell, 6);
+  testPoints = Eigen::MatrixXf::Zero((long)6 * ncell, 3);
+  HTWH_i = Eigen::MatrixXf::Zero(6, 6);
+  HTWdz_i = Eigen::MatrixXf::Zero(6, 1);
+  dx = Eigen::VectorXf(6);
+  dx.setZero();
   if (!fillVisualization) return;
 
   // members only the visualisation reads
   if (n2 > 0) check(icet_b200_get_points2(ctx, points2.data(), n2));
   std::vector<float> bounds((size_t)ncell * 6), mu((size_t)ncell * 3), sig((size_t)ncell * 9), vec((size_t)ncell * 9);
   std::vector<uint8_t> has(ncell), lm((size_t)ncell * 3);
+  const size_t rlz = (size_t)(runlen > 0 ? runlen : 1);
+  std::vector<float> tp((size_t)ncell * 18), hh(rlz * 36), hz(rlz * 6), xit(rlz * 6), mu2v(rlz * ncell * 3), sg2v(rlz * ncell * 9);
+  std::vector<uint8_t> used(rlz * ncell);
   icet_b200_voxel_dump d;
   std::memset(&d, 0, sizeof(d));
+  d.testPoints = tp.data();
+  d.HTWH = hh.data();
+  d.HTWdz = hz.data();
+  d.Xit = xit.data();
+  d.mu2 = mu2v.data();
+  d.sigma2 = sg2v.data();
+  d.used2 = used.data();
   d.bounds = bounds.data();
   d.mu1 = mu.data();
   d.sigma1 = sig.data();
@@ -90,6 +105,29 @@ ICET::ICET(Eigen::MatrixXf& scan1, Eigen::MatrixXf& scan2, int runlen, Eigen::Ve
   check(icet_b200_get_dump(ctx, &d));
   for (int c = 0; c < ncell; c++)
     for (int k = 0; k < 6; k++) clusterBounds(c, k) = bounds[(size_t)c * 6 + k];
+  for (long r = 0; r < (long)6 * ncell; r++)
+    for (int k = 0; k < 3; k++) testPoints(r, k) = tp[(size_t)r * 3 + k];
+  if (runlen > 0) {
+    const size_t last = (size_t)runlen - 1;
+    for (int i = 0; i < 6; i++) {
+      HTWdz_i(i, 0) = hz[last * 6 + i];
+      dx[i] = xit[last * 6 + i] - (runlen > 1 ? xit[(last - 1) * 6 + i] : x0[i]);
+      for (int j = 0; j < 6; j++) HTWH_i(i, j) = hh[last * 36 + 6 * i + j];
+    }
+    for (int phi = 0; phi < num_bins_phi; phi++)
+      for (int theta = 0; theta < num_bins_theta; theta++) {
+        const size_t c = (size_t)num_bins_theta * phi + theta;
+        if (!used[last * ncell + c]) continue;
+        Eigen::Vector3f m2;
+        CovarianceMatrix S2;
+        for (int i = 0; i < 3; i++) {
+          m2[i] = mu2v[(last * ncell + c) * 3 + i];
+          for (int j = 0; j < 3; j++) S2(i, j) = sg2v[(last * ncell + c) * 9 + 3 * i + j];
+        }
+        mu2[theta][phi] = m2;
+        sigma2[theta][phi] = S2;
+      }
+  }
   // the reference visits cells phi-major, theta-minor (src/icet.cpp:95-101): same order for the viz vectors
   for (int phi = 0; phi < num_bins_phi; phi++)
     for (int theta = 0; theta < num_bins_theta; theta++) {

@@ -32,9 +32,11 @@ Eigen::MatrixXf loadPointCloudCSV(std::string filename, std::string datasetType)
   std::vector<float> xyz;
   std::string line;
   if (datasetType == "ouster") {
-    // two header rows, then integer millimetres in columns 8, 9, 10
-    std::getline(file, line);
-    std::getline(file, line);
+    // Integer millimetres in columns 8, 9, 10.  FOUR lines are consumed before the first point, like in the reference:
+    // csv-parser with header_row(1) drops lines 0 and 1, then the two read_row() calls "skip the first / second row"
+    // (src/utils.cpp:20-30) -- i.e. the first two data rows are dropped as well (checked against the reference's own
+    // loader compiled from its sources: tests/test_host.py::test_utils_loader_formats).
+    for (int k = 0; k < 4; k++) std::getline(file, line);
     while (std::getline(file, line)) {
       if (line.empty()) continue;
       std::vector<std::string> f = split(line, ',');
@@ -42,6 +44,8 @@ Eigen::MatrixXf loadPointCloudCSV(std::string filename, std::string datasetType)
       for (int k = 8; k <= 10; k++) xyz.push_back(static_cast<float>(std::stoi(f[k])) / 1000);
     }
   } else {
+    // tab-separated x y z; csv-parser takes line 0 as the header, so the reference never sees the first point (:64-78)
+    std::getline(file, line);
     while (std::getline(file, line)) {
       if (line.empty()) continue;
       std::vector<std::string> f = split(line, '\t');

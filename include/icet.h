@@ -7,7 +7,13 @@
  *
  * Differences a caller can observe:
  *   - the CPU-only helper methods (fitScan1, fitCells1, findCluster, ... include/icet.h:44-68) and the 4-thread
- *     ThreadPool member (:113) do not exist: their work happens inside the kernels;
+ *     ThreadPool member (:113) do not exist: their work happens inside the kernels; the per-point scratch members no
+ *     caller reads (points1Spherical, points2Spherical, points2_OG, pointIndices1/2, include/icet.h:79-82, :95-96) are
+ *     not materialised on the host (two more N x 3 downloads and 1800 index lists per registration);
+ *   - DEFAULT ROW ORDER: the voxels of scan 1 are clustered in ascending range order -- what the reference's comments
+ *     intend -- whereas an unmodified reference build walks them in the order its broken permutation loop leaves
+ *     (src/icet.cpp:78-83) and finds several times fewer clusters (89 instead of 336 Gaussians on the bundled pair), so
+ *     X and pred_stds DIFFER from an upstream build unless ICET::shippedRowOrder = true (bit-identical voxels then);
  *   - `points2` is returned in the caller's row order (the reference leaves it in its internal radial order);
  *   - new member `Q`: the 6x6 error-bound covariance the reference computes and drops (src/icet.cpp:410-411);
  *   - a failed registration throws std::runtime_error (scanMatcher.cpp:98-104 already catches std::exception).
@@ -46,6 +52,10 @@ class ICET {
   Eigen::MatrixXf points1;
   Eigen::MatrixXf points2;        // scan 2 as transformed by the last iteration (src/icet.cpp:375-378)
   Eigen::MatrixXf clusterBounds;  // (numBinsPhi*numBinsTheta) x 6, row = numBinsTheta*phi + theta
+  Eigen::MatrixXf testPoints;     // (6*numBinsPhi*numBinsTheta) x 3: the 2-sigma test points of the axes found extended
+                                  // (src/icet.cpp:214-232); rows the reference never writes are 0 here
+  Eigen::MatrixXf HTWH_i;         // 6 x 6 H^T W H of the last iteration (src/icet.cpp:383, :401)
+  Eigen::MatrixXf HTWdz_i;        // 6 x 1 H^T W dz of the last iteration (:385, :402)
   Eigen::VectorXf pred_stds;
 
   // per-voxel scan-1 state, keyed [theta][phi] like the reference (include/icet.h:89-94)
@@ -53,8 +63,13 @@ class ICET {
   MeanMap mu1;
   CovarianceMap L;
   CovarianceMap U;
+  // scan-2 Gaussians of the LAST iteration for the voxels that contributed.  (The reference declares these maps but
+  // never fills them -- the assignments at src/icet.cpp:308-310 are commented out; here they are filled.)
+  CovarianceMap sigma2;
+  MeanMap mu2;
 
   Eigen::VectorXf X;   // solution vector [x y z phi theta psi]
+  Eigen::VectorXf dx;  // the last update of X (src/icet.cpp:430-433)
   Eigen::MatrixXf Q;   // 6x6 pinv(H^T W H) of the last iteration (not in the reference)
 
   // for viz (reference include/icet.h:102-107); ellipsoid2* stay empty like in the reference (src/icet.cpp:49-61)

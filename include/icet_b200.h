@@ -85,8 +85,9 @@ enum {
   ICET_B200_FLAG_EXACT_PASS = 32,
   ICET_B200_FLAG_FULL_REBUILD = 64,
   /* Self-check of the incremental loop (tests): every point is re-evaluated in every iteration, and a point that the
-   * margin test would have skipped but whose class changed is counted in icet_b200_result.reserved[0] (must stay 0).
-   * Results are bit-identical to the default form. */
+   * margin test would have skipped but whose class changed is counted in icet_b200_result.reserved[0]; every point
+   * whose filtered (approximate-angle) evaluation disagrees with the exact fp32 pipeline in reserved[1].  Both must
+   * stay 0.  Results are bit-identical to the default form. */
   ICET_B200_FLAG_VERIFY_INCREMENTAL = 128
 };
 
@@ -323,6 +324,34 @@ int icet_b200_register_clouds(icet_b200_ctx* ctx, const icet_b200_params* p, con
 /* icet_b200_node_push for a cloud in its native layout, e.g. straight from a sensor_msgs::PointCloud2 (blocking). */
 int icet_b200_node_push_cloud(icet_b200_node* node, const icet_b200_cloud* cloud, icet_b200_result* res,
                               icet_b200_pose* pose);
+
+/* -- multi-GPU ---------------------------------------------------------------------------------------
+ * The reference's registrations are independent objects ("run multiple ICETs at once", include/icet.h:43), so a batch
+ * shards by scan pair: ONE process, one context per device, device d of G registers the contiguous pair range
+ * [P d / G, P (d+1) / G); nothing is exchanged during the registration; ONE ncclAllGather of 48 floats per pair
+ * (X 6 | pred_stds 6 | Q 36) closes the call, after which every device holds every result.  NCCL is loaded at run time
+ * (libnccl.so.2); creation fails without it. */
+typedef struct icet_b200_multi icet_b200_multi;
+/* devices: ndev distinct CUDA device indices (NULL: 0 .. ndev-1).  Creates one context per device and the communicator
+ * (ncclCommInitAll). */
+int icet_b200_multi_create(const int32_t* devices, int32_t ndev, icet_b200_multi** multi);
+int icet_b200_multi_destroy(icet_b200_multi* multi);
+int icet_b200_multi_devices(icet_b200_multi* multi);
+/* the context of device slot d (to configure chunks / lanes / streams per device) */
+icet_b200_ctx* icet_b200_multi_context(icet_b200_multi* multi, int32_t d);
+/* icet_b200_register_batch over all devices: HOST buffers, blocking; `out` (HOST, npairs records) is written by the
+ * devices' own downloads; the gathered rows stay on every device (icet_b200_multi_gathered). */
+int icet_b200_register_batch_multi(icet_b200_multi* multi, const icet_b200_params* p, int32_t npairs,
+                                   const float* const* scan1, const int32_t* n1, const float* const* scan2,
+                                   const int32_t* n2, const float* x0, icet_b200_result* out);
+/* icet_b200_register_sequence_device over all devices: a sequence of nscans clouds of n points whose consecutive pairs
+ * are sharded as above; shard_scans[d] is DEVICE memory on device d holding the scans lo_d .. hi_d of its pair range
+ * ([hi_d - lo_d + 1][3][n], one boundary scan is duplicated on the next device).  Blocking. */
+int icet_b200_register_sequence_multi_device(icet_b200_multi* multi, const icet_b200_params* p, int32_t nscans,
+                                             const float* const* shard_scans, int32_t n);
+/* The all-gathered results on device slot d: DEVICE pointer to [ndev][rows_per_shard][48] floats (shard s holds the pairs
+ * of device s in order; shards shorter than rows_per_shard are zero padded). */
+int icet_b200_multi_gathered(icet_b200_multi* multi, int32_t d, const float** rows, int32_t* rows_per_shard);
 
 /* -- synthetic 64-channel scans (bench / test utility) --------------------------- */
 /* Writes nscans consecutive scans (index first_scan ...) of rings x azim points each to DEVICE memory

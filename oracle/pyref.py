@@ -57,7 +57,9 @@ def build(native: bool = False, eigen_include: str | None = None) -> str:
             if eigen_include:
                 cmd.append("EIGEN_INCLUDE=" + eigen_include)
             if native:
-                cmd += ["REF_OPT=-O3 -march=native", "REF_LIB=libicet_ref_native.so"]
+                # the reference's CMakeLists.txt:18,38 says -O3 -march=native; its sources exist only in the build
+                # container, so the timing build targets the x86-64-v3 level (AVX2 + FMA) every GPU-box host has
+                cmd += ["REF_OPT=-O3 -march=x86-64-v3", "REF_LIB=libicet_ref_native.so"]
             subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
     if not os.path.exists(target):
         raise RuntimeError("%s is missing and %s is not available to build it" % (target, REFERENCE))

@@ -114,4 +114,13 @@ double icet_ref_run_sequence(const float* scans, int32_t n, int32_t npairs, int3
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+/* utils::loadPointCloudCSV of the reference (src/utils.cpp:12-91): returns the number of rows; copies up to `cap` rows
+ * (row-major x y z) into out. */
+int icet_ref_load_csv(const char* filename, const char* dataset_type, float* out, int32_t cap) {
+  Eigen::MatrixXf m = utils::loadPointCloudCSV(filename, dataset_type);
+  for (int i = 0; i < m.rows() && i < cap; i++)
+    for (int j = 0; j < 3; j++) out[3 * i + j] = m(i, j);
+  return (int)m.rows();
+}
+
 }  // extern "C"

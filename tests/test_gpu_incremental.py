@@ -46,6 +46,7 @@ def test_margin_invariant_selfcheck(ctx, parity):
             r = ctx.register(a, b, X0=x0, params=params(flags=extra, **kw))
             v = ctx.register(a, b, X0=x0, params=params(flags=extra | api.FLAG_VERIFY_INCREMENTAL, **kw))
             assert v["reserved"][0] == 0, "%s: %d stable points changed class" % (name, v["reserved"][0])
+            assert v["reserved"][1] == 0, "%s: filtered evaluation != exact pipeline for %d points" % (name, v["reserved"][1])
             assert v["X"].tobytes() == r["X"].tobytes() and v["Q"].tobytes() == r["Q"].tobytes(), name
         parity.add("incremental_invariant", name, violations=0)
     from tools import synth_host
@@ -54,7 +55,7 @@ def test_margin_invariant_selfcheck(ctx, parity):
     for fl in (0, api.FLAG_CHAIN_X0, api.FLAG_PERSISTENT_LOOP):
         r = ctx.register_batch(s1, s2, None, params(flags=fl))
         v = ctx.register_batch(s1, s2, None, params(flags=fl | api.FLAG_VERIFY_INCREMENTAL))
-        assert (v["reserved"][:, 0] == 0).all()
+        assert (v["reserved"][:, :2] == 0).all()
         assert v["X"].tobytes() == r["X"].tobytes() and v["Q"].tobytes() == r["Q"].tobytes()
 
 
@@ -87,11 +88,9 @@ def test_incremental_matches_per_point_form(ctx, parity):
             nvox += int(same.sum())
             for c, v in zip(np.where(same)[0][sg_e >= 1e-5], sg_e[sg_e >= 1e-5]):
                 over.append((it, int(c), float(v), int(g["nin2"][it][c])))
-        # north_star: per-voxel means and covariances within 1e-5 relative.  Both sides are this library here (moments vs
-        # per-point fp32 round trip); voxels beyond 1e-5 are listed: thin clusters whose covariance carries the round
-        # trip's own rounding noise (~1 ulp of the coordinates per point)
-        assert worst_mu < 1e-5, (name, worst_mu)
-        assert len(over) <= max(3, nvox // 500) and worst_sg < 5e-5, (name, worst_sg, over)
+        # both sides are this library here (moments vs per-point fp32 round trip with CUDA's sincosf); the comparison with
+        # north_star's 1e-5 is made against the ORACLE in test_scan2_statistics_vs_oracle
+        assert worst_mu < 1e-5 and worst_sg < 5e-5, (name, worst_mu, worst_sg)
         # voxels whose counts differ in later iterations: X differs by ~1e-7 m between the forms, a boundary point may flip
         assert flips <= 4 * p.runlen, (name, flips)
         dm, dr = np.abs(r["X"][:3] - e["X"][:3]).max(), np.abs(r["X"][3:] - e["X"][3:]).max()
@@ -102,7 +101,7 @@ def test_incremental_matches_per_point_form(ctx, parity):
         assert r["n_used"] == f["n_used"]
         parity.add("incremental_vs_per_point", name, dX_m=float(dm), dX_rad=float(dr), dQ_rel=float(dq),
                    mu2_rel_max=float(worst_mu), sigma2_rel_max=float(worst_sg), voxel_iterations=nvox,
-                   sigma2_over_1e5=[dict(iter=a, cell=b, rel=c, points=d) for a, b, c, d in over],
+                   sigma2_voxel_iterations_over_1e5=len(over),
                    voxels_with_flipped_counts=flips,
                    dX_m_vs_full_rebuild=float(dmf))
         print("%s: incremental vs per-point |dX| %.1e m %.1e rad |dQ| %.1e; mu2 %.1e sigma2 %.1e; count flips %d"
@@ -179,3 +178,49 @@ def test_scan2_classes_vs_oracle_listed(ctx, po, parity, name):
     parity.add("scan2_classes_vs_oracle", name, points=n2, iterations=p.runlen, differing=total,
                listed=[dict(iter=a, point=b, cell_gpu=c, cell_oracle=d, in_gpu=e, in_oracle=f, ulps_to_edge=h, cause=k)
                        for a, b, c, d, e, f, h, k in listed])
+
+
+@pytest.mark.parametrize("name", ["frame", "sample_pc", "synth"])
+def test_scan2_statistics_vs_oracle(ctx, po, parity, name):
+    """north_star: per-voxel means and covariances within 1e-5 relative -- the incremental loop's scan-2 statistics (exact
+    moments of the untransformed members carried through the transform) against the ORACLE's per-point fp32 round trip
+    (src/icet.cpp:303-306), every iteration, every voxel with the same member count on both sides.  Voxels beyond 1e-5
+    are listed by id; the oracle's own `moments` twin (same membership, exact statistics) says which side carries the
+    rounding noise."""
+    from conftest import load_pair
+    from tools import synth_host
+    if name == "synth":
+        sc = synth_host.scans(2, first_scan=100)
+        s1, s2 = sc[0], sc[1]
+    else:
+        s1, s2 = load_pair(name)
+    p = params()
+    r, g = ctx.register(s1, s2, params=p, dump=True)
+    o = po.run(s1, s2, dumps="small")
+    bad = (o.has1 > 0) & (g["has1"] > 0) & (np.abs(g["evec1"] - o.evec1).reshape(-1, 9).max(1) > 1e-3)
+    ov = (g["evec1"], bad.astype(np.uint8)) if bad.any() else None
+    o = po.run(s1, s2, dumps="small", evec_override=ov)
+    om = po.run(s1, s2, dumps="small", evec_override=ov, stats2_mode=po.STATS2_MOMENTS, precise=True)
+    over, nvox, wmu, wsg, wsg_m = [], 0, 0.0, 0.0, 0.0
+    for it in range(p.runlen):
+        same = (g["used2"][it] > 0) & (o.used2[it] > 0) & (g["nin2"][it] == o.nin2[it]) & (g["cnt2"][it] == o.cnt2[it])
+        nvox += int(same.sum())
+        mu_e = np.abs(g["mu2"][it][same] - o.mu2[it][same]).max(1) / np.abs(o.mu2[it][same]).max(1)
+        sg_e = np.abs(g["sigma2"][it][same] - o.sigma2[it][same]).reshape(-1, 9).max(1) / \
+            np.abs(o.sigma2[it][same]).reshape(-1, 9).max(1)
+        wmu, wsg = max(wmu, float(mu_e.max())), max(wsg, float(sg_e.max()))
+        sm = same & (om.used2[it] > 0) & (om.nin2[it] == g["nin2"][it])
+        sg_m = np.abs(g["sigma2"][it][sm] - om.sigma2[it][sm]).reshape(-1, 9).max(1) / \
+            np.abs(om.sigma2[it][sm]).reshape(-1, 9).max(1)
+        wsg_m = max(wsg_m, float(sg_m.max()))
+        for c, v in zip(np.where(same)[0][sg_e >= 1e-5], sg_e[sg_e >= 1e-5]):
+            over.append(dict(iter=it, cell=int(c), rel=float(v), points=int(g["nin2"][it][c]),
+                             cause="fp32 round-trip noise of the reference path (thin cluster)"))
+    assert wmu < 1e-5, wmu
+    assert len(over) <= 3 and wsg < 3e-5, (wsg, over)
+    # against the exact statistics of the same members the GPU is an order of magnitude tighter
+    assert wsg_m < 3e-6, wsg_m
+    print("%s: %d voxel-iterations: mu2 rel max %.1e, sigma2 rel max %.1e (vs exact moments twin %.1e), over 1e-5: %s"
+          % (name, nvox, wmu, wsg, wsg_m, over))
+    parity.add("scan2_statistics_vs_oracle", name, voxel_iterations=nvox, mu2_rel_max=wmu, sigma2_rel_max=wsg,
+               sigma2_rel_max_vs_moments_twin=wsg_m, sigma2_over_1e5=over)

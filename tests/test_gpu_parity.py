@@ -369,6 +369,45 @@ def test_submap_config_properties(ctx):
     assert r0["n_gauss1"] > 100
 
 
+def test_submap_full_size_vs_golden(ctx, po, parity):
+    """BASELINE.json configs[4] at FULL size: the 2 002 756-point accumulated map (1240 scans x 2000 rays, exact generator
+    poses, tools/synth_host.submap) as scan 1 against one 64-channel scan.  The map is regenerated bit for bit from the
+    seed (hash checked); the GPU is compared with the committed oracle outputs (tests/golden/golden_submap_2M.npz,
+    written offline by tools/make_fixtures.py) and with the oracle run live: cell counts, cluster bounds (the largest
+    cell holds 800 000 ranges: bucket clustering) and the set of Gaussians bit for bit, X / Q within north_star's
+    tolerances."""
+    import hashlib
+    import os
+    from conftest import GOLDEN
+    from tools import synth_host
+    gold = np.load(os.path.join(GOLDEN, "golden_submap_2M.npz"))
+    mp, cur = synth_host.submap()
+    assert mp.shape[1] == int(gold["n_map"]) == 2002756
+    assert hashlib.sha256(mp.tobytes()).hexdigest() == str(gold["map_sha256"])
+    assert hashlib.sha256(cur.tobytes()).hexdigest() == str(gold["scan_sha256"])
+    r, g = ctx.register(mp, cur, dump=True)
+    assert r["status"] == 0
+    np.testing.assert_array_equal(g["cnt1"], gold["cnt1"])
+    np.testing.assert_array_equal(g["bounds"], gold["bounds"])
+    np.testing.assert_array_equal(g["has1"], gold["has1"])
+    has = gold["has1"] > 0
+    np.testing.assert_array_equal(g["nin1"][has], gold["nin1"][has])
+    assert int(g["cnt1"].max()) > 500000
+    o = po.run(mp, cur, dumps="small")
+    np.testing.assert_array_equal(o.X, gold["X"])             # the oracle has not drifted from its stored outputs
+    o2, o64, nbad = oracle_with_gpu_signs(po, mp, cur, g, o)
+    dm, dr, dq = check_final(r, o2, o64)
+    # shuffled map rows: not a bit changes (integer statistics, value-based clustering)
+    rng = np.random.default_rng(5)
+    r2 = ctx.register(np.ascontiguousarray(mp[:, rng.permutation(mp.shape[1])]), cur)
+    assert r2["X"].tobytes() == r["X"].tobytes() and r2["Q"].tobytes() == r["Q"].tobytes()
+    print("submap 2M: gaussians %d, used %d, sign-unstable %d, |dX| %.1e m %.1e rad |dQ| %.1e"
+          % (r["n_gauss1"], r["n_used"], nbad, dm, dr, dq))
+    parity.add("submap_2M_vs_oracle", "configs[4]", map_points=int(mp.shape[1]), gaussians=int(r["n_gauss1"]),
+               voxels_used=int(r["n_used"]), sign_unstable_voxels=nbad, dX_m=dm, dX_rad=dr, dQ_rel=dq,
+               bounds_bit_identical=True, largest_cell=int(g["cnt1"].max()))
+
+
 # ---------------------------------------------------------------------------------------------------------
 # edge cases of the boundary
 # ---------------------------------------------------------------------------------------------------------
@@ -565,9 +604,28 @@ def test_shipped_order_mode_matches_reference_as_shipped(ctx, po, name):
         ov = (g["evec1"], bad.astype(np.uint8))
     o2 = po.run(s1, s2, dumps=None, order_mode=1, evec_override=ov)
     assert np.abs(r["X"][:3] - o2.X[:3]).max() < TOL_M and np.abs(r["X"][3:] - o2.X[3:]).max() < TOL_RAD
-    # batches cannot use the mode
-    with pytest.raises(Exception):
-        ctx.register_batch([s1, s1], [s2, s2], None, p)
+    # against the REFERENCE BUILD itself (tests/golden/ref_*_shipped.npz: the reference's own sources, tools/pin_against_ref.py)
+    ref = np.load(os.path.join(GOLDEN, "ref_%s_shipped.npz" % name))
+    np.testing.assert_array_equal(g["bounds"], ref["clusterBounds"])
+    np.testing.assert_array_equal(g["cnt1"], ref["cnt1"])
+    np.testing.assert_array_equal(g["has1"], ref["has1"])
+    assert r["n_gauss1"] == int(ref["n_ellipsoids"])
+    if not bad.any():
+        assert np.abs(r["X"][:3] - ref["X"][:3]).max() < TOL_M and np.abs(r["X"][3:] - ref["X"][3:]).max() < TOL_RAD
+        np.testing.assert_allclose(r["pred_stds"], ref["pred_stds"], rtol=5e-3)
+    # public member testPoints (src/icet.cpp:214-232): written exactly where the reference writes it
+    tp, tr = g["testPoints"].reshape(-1, 6, 3), ref["testPoints"].reshape(-1, 6, 3)
+    stable = has & ~bad
+    np.testing.assert_array_equal(np.abs(tp[stable]).sum(2) > 0, np.abs(tr[stable]).sum(2) > 0)
+    np.testing.assert_allclose(tp[stable], tr[stable], atol=2e-4)
+    assert (np.abs(tr[stable]).sum(2) > 0).sum() > 20
+    # the mode works for batches too (one host round trip per chunk): bit-identical to the single-pair calls
+    rb = ctx.register_batch([s1, s2, s1], [s2, s1, s2], None, p)
+    assert rb[0]["X"].tobytes() == r["X"].tobytes() and rb[2]["Q"].tobytes() == r["Q"].tobytes()
+    r_rev = ctx.register(s2, s1, params=p)
+    assert rb[1]["X"].tobytes() == r_rev["X"].tobytes()
+    o_rev = po.run(s2, s1, dumps=None, order_mode=1)
+    assert np.abs(r_rev["X"][:3] - o_rev.X[:3]).max() < 5 * TOL_M     # (no eigenvector injection for this one)
 
 
 def test_full_size_sequence_properties(ctx):
@@ -645,3 +703,77 @@ def test_full_size_sequence_properties(ctx):
         assert np.abs(o.X[:3] - gt[k, :3]).max() > 0.5 * et[k] - 1e-3   # the oracle misses the truth as well
         if et[k] < 0.05:
             assert d[:3].max() < TOL_M and d[3:].max() < TOL_RAD
+
+
+# ---------------------------------------------------------------------------------------------------------
+# multi-GPU behind the C ABI
+# ---------------------------------------------------------------------------------------------------------
+def test_multi_gpu_c_abi(ctx):
+    """icet_b200_register_batch_multi / icet_b200_register_sequence_multi_device: one process, one context per device,
+    contiguous pair ranges, ONE ncclAllGather of 48 floats per pair.  Runs over every visible device (a single-device
+    communicator on a 1-GPU box exercises the same code, including the collective; with >= 2 GPUs the shards really
+    live on different devices).  Results are bit-identical to the single-context batch."""
+    import torch
+    import icet_b200
+    from icet_b200 import api
+    from tools import synth_host
+    ndev = torch.cuda.device_count()
+    sc = synth_host.scans(8, first_scan=200)
+    s1, s2 = [sc[k] for k in range(7)], [sc[k + 1] for k in range(7)]
+    ref = ctx.register_batch(s1, s2)
+    for devs in ([0], list(range(min(ndev, 2))), list(range(ndev))):
+        m = icet_b200.MultiContext(devs)
+        out = m.register_batch(s1, s2)
+        assert out["X"].tobytes() == ref["X"].tobytes() and out["Q"].tobytes() == ref["Q"].tobytes()
+        G = len(devs)
+        for d in range(G):
+            ptr, rows = m.gathered(d)
+            assert rows == -(-7 // G)
+            with torch.cuda.device(devs[d]):
+                hostrows = np.zeros((G, rows, 48), np.float32)
+                rc = torch.cuda.cudart().cudaMemcpy(hostrows.ctypes.data, ptr, hostrows.nbytes, 2)  # cudaMemcpyDeviceToHost
+                assert int(rc) == 0
+            for s in range(G):
+                lo, hi = 7 * s // G, 7 * (s + 1) // G
+                np.testing.assert_array_equal(hostrows[s, :hi - lo, :6], ref["X"][lo:hi])
+                np.testing.assert_array_equal(hostrows[s, :hi - lo, 6:12], ref["pred_stds"][lo:hi])
+                np.testing.assert_array_equal(hostrows[s, :hi - lo, 12:], ref["Q"][lo:hi].reshape(-1, 36))
+                assert not hostrows[s, hi - lo:].any()
+        # device-resident shards of the same sequence
+        shards, ptrs = [], []
+        for d in range(G):
+            lo, hi = 7 * d // G, 7 * (d + 1) // G
+            t = torch.from_numpy(sc[lo:hi + 1]).to("cuda:%d" % devs[d])
+            shards.append(t)
+            ptrs.append(t.data_ptr())
+        torch.cuda.synchronize()
+        m.register_sequence_device(ptrs, 8, sc.shape[2])
+        ptr, rows = m.gathered(0)
+        hostrows = np.zeros((G, rows, 48), np.float32)
+        with torch.cuda.device(devs[0]):
+            assert int(torch.cuda.cudart().cudaMemcpy(hostrows.ctypes.data, ptr, hostrows.nbytes, 2)) == 0
+        for s in range(G):
+            lo, hi = 7 * s // G, 7 * (s + 1) // G
+            np.testing.assert_array_equal(hostrows[s, :hi - lo, :6], ref["X"][lo:hi])
+        with pytest.raises(icet_b200.IcetError):
+            m.register_batch(s1, s2, params=params(flags=api.FLAG_CHAIN_X0))
+        m.close()
+
+
+def test_multi_gpu_cpp_example(ctx, tmp_path):
+    """examples/multi_gpu_batch.cpp: a C++ caller sharding a batch over the visible devices through the C ABI alone."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "examples"), "_build/multi_gpu_batch"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = subprocess.run([os.path.join(ROOT, "examples", "_build", "multi_gpu_batch"), "6"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    lines = [l for l in out.stdout.splitlines() if l.startswith("pair")]
+    assert len(lines) >= 2
+    # pair 0 of the synthetic sequence through the Python path: same library, same bits (printed with 5 decimals)
+    from tools import synth_host
+    sc = synth_host.scans(2, first_scan=0)
+    r0 = ctx.register(sc[0], sc[1])
+    x = [float(v) for v in lines[0].split("X =")[1].split("pred_stds")[0].split()]
+    np.testing.assert_allclose(x, r0["X"], atol=2e-5)

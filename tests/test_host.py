@@ -195,15 +195,28 @@ int main(int argc, char** argv) {
     assert r.returncode == 0, r.stderr
     csv = tmp_path / "o.csv"
     hdr = ",".join("c%d" % i for i in range(12))
+    # two header lines + 5 data rows: the reference drops the two header lines AND the first two data rows
     csv.write_text(hdr + "\n" + hdr + "\n" + "\n".join(
-        ",".join(["0"] * 8 + [str(1000 * (i + 1)), str(-250 * i), str(3), "9"]) for i in range(3)) + "\n")
+        ",".join(["0"] * 8 + [str(1000 * (i + 1)), str(-250 * i), str(3), "9"]) for i in range(5)) + "\n")
     out = subprocess.run([str(exe), str(csv), "ouster"], capture_output=True, text=True).stdout.split()
     assert out[:2] == ["3", "3"]
-    np.testing.assert_allclose([float(v) for v in out[2:11]], [1, 0, 0.003, 2, -0.25, 0.003, 3, -0.5, 0.003], atol=1e-6)
+    np.testing.assert_allclose([float(v) for v in out[2:11]], [3, -0.5, 0.003, 4, -0.75, 0.003, 5, -1.0, 0.003], atol=1e-6)
     tsv = tmp_path / "t.txt"
-    tsv.write_text("1.5\t2.5\t-3\n4\t5\t6\n")
+    tsv.write_text("0\t0\t0\n1.5\t2.5\t-3\n4\t5\t6\n")   # line 0 is taken as the header
     out = subprocess.run([str(exe), str(tsv), "txt"], capture_output=True, text=True).stdout.split()
     assert out[:2] == ["2", "3"] and float(out[4]) == -3.0
+    # the same files through the REFERENCE's own loader (src/utils.cpp + csv.hpp, compiled by `make -C oracle ref`)
+    from oracle import pyref
+    if pyref.available():
+        import ctypes as C
+        L = pyref.lib()
+        L.icet_ref_load_csv.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int32]
+        buf = np.zeros((16, 3), np.float32)
+        for path, kind in ((csv, "ouster"), (tsv, "txt")):
+            n = L.icet_ref_load_csv(str(path).encode(), kind.encode(), buf.ctypes.data, 16)
+            mine = subprocess.run([str(exe), str(path), kind], capture_output=True, text=True).stdout.split()
+            assert int(mine[0]) == n
+            np.testing.assert_allclose([float(v) for v in mine[2:2 + 3 * n]], buf[:n].reshape(-1), atol=1e-6)
     # utils::R (reference src/utils.cpp:144-152): R(0,0) = cos(theta) cos(psi), R(2,2) = cos(phi) cos(theta)
     i = out.index("R")
     np.testing.assert_allclose([float(v) for v in out[i + 1:i + 4]],

@@ -185,3 +185,20 @@ def test_golden_vectors(po, name, tag, kw):
     np.testing.assert_allclose(r.pred_stds, g["pred_stds"], rtol=1e-4)
     np.testing.assert_allclose(r.Q, g["Q"], rtol=0, atol=1e-4 * abs(g["Q"]).max())
     np.testing.assert_allclose(r.mu2[[0, -1]], g["mu2"], rtol=0, atol=1e-5)
+
+
+def test_submap_golden_full_size(po):
+    """BASELINE.json configs[4] at full size (2 002 756-point map): the map generator is bit-reproducible and the oracle
+    reproduces the stored outputs (tests/golden/golden_submap_2M.npz, tools/make_fixtures.py)."""
+    import hashlib
+    from tools import synth_host
+    gold = np.load(os.path.join(GOLDEN, "golden_submap_2M.npz"))
+    mp, cur = synth_host.submap()
+    assert mp.shape[1] == int(gold["n_map"])
+    assert hashlib.sha256(mp.tobytes()).hexdigest() == str(gold["map_sha256"])
+    o = po.run(mp, cur, dumps="small")
+    np.testing.assert_array_equal(o.X, gold["X"])
+    np.testing.assert_array_equal(o.bounds, gold["bounds"])
+    np.testing.assert_array_equal(o.cnt1, gold["cnt1"])
+    np.testing.assert_array_equal(o.has1, gold["has1"])
+    assert np.abs(o.X[:3]).max() < 0.02        # the map is expressed in the frame of the scan: the true transform is 0

@@ -17,9 +17,9 @@ fi
 if [ "${SKIP_NCU:-0}" != "1" ]; then
   echo "== ncu launch list"
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
-    python bench.py --steps 1 --warmup 3 --pairs-per-gpu 256 --lanes 1 --no-cpu-baseline --no-latency --no-e2e --no-callers > $OUT/ncu_bench.log 2>&1
+    python bench.py --steps 1 --warmup 3 --pairs-per-gpu 256 --lanes 1 --no-cpu-baseline --no-latency --no-e2e --no-callers --no-configs > $OUT/ncu_bench.log 2>&1
   echo "== ncu full capture of k_pass<scan2>, k_pass<scan1>"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pass -s 3 -c 2 -f -o $OUT/prof_kpass \
-    python bench.py --steps 1 --warmup 3 --pairs-per-gpu 256 --lanes 1 --no-cpu-baseline --no-latency --no-e2e --no-callers > $OUT/ncu_full.log 2>&1
+    python bench.py --steps 1 --warmup 3 --pairs-per-gpu 256 --lanes 1 --no-cpu-baseline --no-latency --no-e2e --no-callers --no-configs > $OUT/ncu_full.log 2>&1
   cp icet_b200/lib/libicet_b200.so $OUT/libicet_b200.so; ls -la $OUT
 fi

@@ -49,5 +49,24 @@ def main():
             print(name, tag, r.X, int(r.has1.sum()), int(r.used2[-1].sum()))
 
 
+def submap_golden():
+    """BASELINE.json configs[4] at FULL size: the 2 M-point accumulated map of tools/synth_host.submap() against one
+    64-channel scan.  Only outputs are stored (the map is regenerated bit for bit from the seed; its hash is kept)."""
+    import hashlib
+    from tools import synth_host
+    mp, cur = synth_host.submap()
+    r = po.run(mp, cur, dumps="small")
+    np.savez_compressed(os.path.join(OUT, "golden_submap_2M.npz"), X=r.X, pred_stds=r.pred_stds, Q=r.Q,
+                        cnt1=r.cnt1, bounds=r.bounds, has1=r.has1, nin1=r.nin1, used2_last=r.used2[-1],
+                        Xit=r.Xit, n_map=np.int64(mp.shape[1]),
+                        map_sha256=hashlib.sha256(mp.tobytes()).hexdigest(),
+                        scan_sha256=hashlib.sha256(cur.tobytes()).hexdigest())
+    print("submap", mp.shape, r.X, int(r.has1.sum()), int(r.used2[-1].sum()), "largest cell", int(r.cnt1.max()))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "submap":
+        submap_golden()
+        sys.exit(0)
     main()
+    submap_golden()

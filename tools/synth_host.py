@@ -26,6 +26,8 @@ def _lib():
         _LIB.synth_host_scans.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _LIB.synth_host_motion.argtypes = [C.c_uint64, C.c_int, C.c_void_p]
         _LIB.synth_host_motions.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+        _LIB.synth_host_map.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long]
+        _LIB.synth_host_map.restype = C.c_long
     return _LIB
 
 
@@ -50,3 +52,18 @@ def motions(k0, n, seed=20240) -> np.ndarray:
     d = np.zeros((n, 6), np.float64)
     _lib().synth_host_motions(seed, k0, n, d.ctypes.data)
     return d
+
+
+def submap(nscans=1240, per_scan=2000, first_scan=20, seed=20240, rings=64, azim=2048, nthreads=None):
+    """BASELINE.json configs[4]: (map [3, M] float32, current scan [3, rings*azim]).  The map holds `per_scan` returns of
+    each of `nscans` consecutive scans (the simpleMapMaker.cpp:150-160 recipe) expressed in the frame of the scan that
+    follows them, which is returned as the scan to match.  1240 x 2000 rays minus the dropped returns and the rays without a hit = 2.0 M points.
+    Bit-reproducible (pure function of the arguments, double-precision poses of the generator)."""
+    cap = nscans * per_scan
+    buf = np.zeros((3, cap), np.float32)
+    nthreads = nthreads or os.cpu_count() or 1
+    n = _lib().synth_host_map(seed, first_scan, nscans, per_scan, rings, azim, nthreads, buf.ctypes.data, cap)
+    if n < 0:
+        raise RuntimeError("synth_host_map failed: %d" % n)
+    cur = scans(1, first_scan=first_scan + nscans, seed=seed, rings=rings, azim=azim, nthreads=nthreads)[0]
+    return np.ascontiguousarray(buf[:, :n]), cur
