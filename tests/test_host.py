@@ -139,13 +139,17 @@ def test_pair_sharding_world2_gloo(tmp_path):
 
 
 def test_bench_reference_arm_runs():
-    """`bench.py --impl reference` times the CPU restatement on the host cores and prints one JSON line."""
+    """`bench.py --impl reference` times the reference's CPU path on the host cores and prints one JSON line."""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    from oracle import pyref
+    # the reference's own sources when oracle/_ref exists (or can be built: /root/reference), else the oracle port
+    assert line["cpu_baseline"]["kind"] == ("reference" if pyref.available(True) or pyref.available(False) else "port")
+    assert line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["port_value"] > 0
+    assert line["config"]["pairs_per_step"] == max(2, min(2 * (os.cpu_count() or 1), 256))   # what really ran
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
 
 
