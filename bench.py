@@ -312,6 +312,14 @@ def bench_configs(ctx, stream, dev, latency):
     m, q, r = p50(mp, mp.shape[1], cur, NPTS, api.make_params(RUNLEN, BINS_PHI, BINS_THETA, NMIN, THRESH, BUFF), 50)
     out["submap_2M"] = entry("configs[4]: scan-to-submap, %d-point accumulated map (1240 scans x 2000 rays, exact "
                              "generator poses) vs one 64-ch scan, 75x24, 7 it" % mp.shape[1], mp.shape[1], NPTS, m, q, r)
+    ctx.set_profile(True)   # per-kernel device time of this configuration (events around every launch)
+    res = torch.zeros((1, 56), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        ctx.register_batch_ptrs([mp.data_ptr()], [mp.shape[1]], [cur.data_ptr()], [NPTS], res.data_ptr(),
+                                params=api.make_params(RUNLEN, BINS_PHI, BINS_THETA, NMIN, THRESH, BUFF), device=True)
+    prof = ctx.get_profile()
+    ctx.set_profile(False)
+    out["submap_2M"]["kernel_ms"] = {k: round(v[0] / 3, 4) for k, v in prof.items() if v[1]}
     return out
 
 

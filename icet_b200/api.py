@@ -40,6 +40,7 @@ FLAG_SHIPPED_ORDER = 16  # validation: cluster in the row order the reference's 
 FLAG_EXACT_PASS = 32  # scan 2: the reference's per-point pipeline in every iteration (validation form)
 FLAG_FULL_REBUILD = 64  # scan 2: incremental bookkeeping, every point re-evaluated in every iteration (diagnostic)
 FLAG_VERIFY_INCREMENTAL = 128  # self-check: result["reserved"][0] counts stable points whose class changed (must be 0)
+FLAG_CLUSTER_LOOP = 256  # the loop of every pair inside one thread-block cluster (default for single / chained pairs)
 FLAG_CHAIN_X0 = 8  # odometry.cpp:82: pair k+1 starts from the solution of pair k; X0 = one seed (pair 0)
 
 _DUMP_FIELDS = [("cnt1", _IP), ("bounds", _FP), ("nin1", _IP), ("has1", _BP), ("mu1", _FP), ("sigma1", _FP),

@@ -23,6 +23,10 @@ constexpr int SORT_SMEM = 4096;         // cells up to this many points are sort
 constexpr int NQ = 12;                  // accumulator words per cell
 constexpr int CLUSTER_WARPS = 4;
 constexpr int WSORT_MAX = 1024;         // cells up to this many non-zero ranges are sorted by one warp in registers
+constexpr int HUGE_MIN = 32768;         // cells with more non-zero ranges (accumulated maps) are clustered by many CTAs
+constexpr int HUGE_SLOTS = 64;          //   ... at most this many per chunk (the rest take the one-CTA path)
+constexpr int HUGE_NB = 32768;          //   ... through a global table of this many half-threshold buckets per cell
+constexpr int HUGE_SPLIT = 128;         //   ... filled by this many CTAs per cell
 
 struct PairDesc {
   const float* s1;
@@ -87,6 +91,12 @@ struct Chunk {  // everything a kernel needs, passed by value
   int32_t* work;     // [P][ncell]  cells with cnt1 >= n
   int32_t* nwork;    // [P]
   int32_t* nbig;     // [P]  cells of the work list with more than WSORT_MAX non-zero ranges
+  int32_t* hslot;    // [P][ncell]  huge cells: slot + 1 in the tables below (0: none)
+  int32_t* nhuge;    // [1]
+  int32_t* hpair;    // [HUGE_SLOTS]
+  int32_t* hcell;    // [HUGE_SLOTS]
+  int32_t* hflag;    // [HUGE_SLOTS]  1: a range fell outside the table -> the cell takes the one-CTA path after all
+  int32_t* hbkt;     // [HUGE_SLOTS][3][HUGE_NB]  count | min bits | max bits per bucket (null: path disabled for the chunk)
   CellRec* rec;      // [P][ncell]
   unsigned long long* acc;  // [2][P][ncell][NQ]  (set 1 is used by the incremental scan-2 loop only)
   Vox1* vox;         // [P][ncell]

@@ -13,6 +13,7 @@
 //
 // Determinism: per-voxel statistics are accumulated as 64-bit fixed-point integers (run sums in registers, then
 // RED.64 to L2), so results do not depend on thread / block / GPU partitioning or on atomic ordering.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -38,6 +39,7 @@ namespace {
 #include "kernels_pass.cuh"
 #include "kernels_pass2.cuh"
 #include "kernels_loop.cuh"
+#include "kernels_cluster.cuh"
 #include "runtime.inl"
 #include "callers.cuh"
 

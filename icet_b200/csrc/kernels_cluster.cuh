@@ -1,0 +1,132 @@
+// icet_b200/csrc/kernels_cluster.cuh -- the Gauss-Newton loop of a pair inside ONE THREAD-BLOCK CLUSTER (latency shape:
+// single pairs, small batches, chained odometry).  Included by icet_b200.cu inside its anonymous namespace.
+//
+// The persistent kernel k_loop spreads the ~1100 tasks of an iteration over the whole GPU and orders them with flags
+// in global memory (tickets, per-pair counters, polling): with one pair in flight the flag round trips ARE the
+// iteration (33 us per iteration for ~1 us of issue).  With the incremental scan-2 pass an iteration is
+// small enough for a handful of SMs, so this form gives a pair to one cluster of CS CTAs (16 where the device allows
+// the non-portable size, else 8) and replaces every flag by the hardware cluster barrier:
+//     phase 1  all warps of the cluster walk the pair's scan-2 tiles (pass2_warp_tile: margin test / re-evaluation /
+//              rebuild), integer moments go to the L2-resident accumulators            -> barrier.cluster
+//     phase 2  one thread per voxel: fitCells2 algebra; 28 partial sums per CTA in ITS shared memory, fixed order
+//                                                                                       -> barrier.cluster
+//     phase 3  warp 0 of CTA 0 adds the CS partial sums through DISTRIBUTED SHARED MEMORY (rank order), solves the
+//              6x6 system on the warp, publishes X / R(X) / get_H / the mode of the next iteration -> barrier.cluster
+// Independent pairs of a small batch run in different clusters of the same launch; chained pairs (odometry.cpp:82)
+// run back to back in one cluster.  Same per-point / per-voxel arithmetic as the other loop forms.
+#pragma once
+// (icet_b200.cu includes <cooperative_groups.h> at global scope)
+
+constexpr int CL_THREADS = 512;
+constexpr int CL_WARPS = CL_THREADS / 32;
+constexpr int CL_K = PASS_K_SMALL;  // rows per warp tile
+
+__host__ __device__ inline int cluster_smem_bytes(int nT, int nP) {
+  return CL_WARPS * pass_wslots(CL_K) * 16 + pass_tab_floats(nT, nP) * 4 + (CL_WARPS + 1) * NRED * 8 + 32 * 4;
+}
+
+__global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int4* ent = reinterpret_cast<int4*>(smem_raw);
+  float* tab = reinterpret_cast<float*>(smem_raw + CL_WARPS * pass_wslots(CL_K) * 16);
+  double* wpart = reinterpret_cast<double*>(tab + pass_tab_floats(ck.nT, ck.nP));  // [CL_WARPS][NRED]
+  double* cpart = wpart + CL_WARPS * NRED;                                         // [NRED]  this CTA's partial sums
+  float* s_J = reinterpret_cast<float*>(cpart + NRED);                             // [27]
+  {
+    const int ntab = pass_tab_floats(ck.nT, ck.nP);
+    for (int k = threadIdx.x; k < ntab; k += CL_THREADS) tab[k] = __ldg(ck.binrec + k);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned cs = cluster.num_blocks(), rank = cluster.block_rank();
+  const int ncl = gridDim.x / cs, cl = blockIdx.x / cs;  // clusters of the launch, this cluster
+  int4* went = ent + warp * pass_wslots(CL_K);
+  const bool chain = (ck.flags & ICET_B200_FLAG_CHAIN_X0) != 0;
+  const bool inc = loop_incremental(ck);
+  const int gwarp = (int)rank * CL_WARPS + warp, nwarp = (int)cs * CL_WARPS;
+  // chained pairs: one cluster walks them in order (the launch has one cluster); independent pairs: round robin
+  for (int pair = chain ? 0 : cl; pair < ck.npairs; pair += chain ? 1 : ncl) {
+    const int n = __ldg(ck.n2c + pair);
+    const int tiles = max(1, (n + 32 * CL_K - 1) / (32 * CL_K));
+    const CellRec* recs = ck.rec + (size_t)pair * ck.ncell;
+    for (int iter = 0; iter < ck.runlen; iter++) {
+#define CTL(slot)                                                                                           \
+  do {                                                                                                      \
+    if (ck.dump_on && rank == 0 && threadIdx.x == 0) ck.dump.tl[(size_t)iter * 16 + (slot)] = gtime();      \
+  } while (0)
+      CTL(0);
+      // ------------------------------------------------------------------ phase 1: scan-2 tiles
+      float tr[12];
+      {
+        const float4* tp = reinterpret_cast<const float4*>(ck.TR + (size_t)pair * 12);
+        const float4 a = __ldcg(tp), b = __ldcg(tp + 1), c = __ldcg(tp + 2);
+        tr[0] = a.x; tr[1] = a.y; tr[2] = a.z; tr[3] = a.w; tr[4] = b.x; tr[5] = b.y; tr[6] = b.z; tr[7] = b.w;
+        tr[8] = c.x; tr[9] = c.y; tr[10] = c.z; tr[11] = c.w;
+      }
+      if (threadIdx.x < 27) s_J[threadIdx.x] = __ldcg(ck.J + (size_t)pair * 27 + threadIdx.x);
+      if (inc) {
+        Pass2Mode md;
+        load_pass2_mode(ck, pair, md);
+        for (int tile = gwarp; tile < tiles; tile += nwarp)
+          pass2_warp_tile<CL_K>(ck, went, tab, recs, tr, md, ck.pog + (size_t)pair * 3 * ck.n2max, (size_t)ck.n2max, n,
+                                tile * 32 * CL_K, ck.marg + (size_t)pair * ck.n2max, ck.cls2 + (size_t)pair * ck.n2max,
+                                (ck.flags & ICET_B200_FLAG_VERIFY_INCREMENTAL) ? &ck.res[pair].reserved[0] : nullptr);
+        if (gwarp == nwarp - 1 && lane == 0)  // (the last warp has the fewest tiles)
+          pass2_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 2,
+                                recs, tr, md, pair, __ldg(ck.nz2 + pair));
+      } else {
+        unsigned long long* accp = ck.acc + (size_t)pair * ck.ncell * NQ;
+        for (int tile = gwarp; tile < tiles; tile += nwarp)
+          pass_warp_tile<true, CL_K, 2, CL_K>(ck, went, tab, recs, tr, ck.pog + (size_t)pair * 3 * ck.n2max,
+                                              (size_t)ck.n2max, n, tile * 32 * CL_K, accp);
+        if (gwarp == nwarp - 1 && lane == 0)
+          pass_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 2,
+                               recs, tr, accp, __ldg(ck.nz2 + pair));
+      }
+      CTL(1);
+      __threadfence();
+      cluster.sync();
+      CTL(2);
+      // ------------------------------------------------------------------ phase 2: one thread per voxel
+      {
+        double acc[NRED];
+#pragma unroll
+        for (int k = 0; k < NRED; k++) acc[k] = 0.0;
+        // cell c -> CTA c % cs, thread c / cs: the occupied rows of the grid spread over all CTAs
+        for (int c = (int)rank + (int)cs * threadIdx.x; c < ck.ncell; c += (int)cs * CL_THREADS)
+          vox_contrib(ck, pair, c, iter, s_J, acc);
+        const double tot = warp_sum_transposed(acc, lane);
+        if (lane < NRED) wpart[warp * NRED + lane] = tot;
+        __syncthreads();
+        if (threadIdx.x < NRED) {
+          double s = 0.0;
+          for (int w = 0; w < CL_WARPS; w++) s += wpart[w * NRED + threadIdx.x];
+          cpart[threadIdx.x] = s;
+        }
+      }
+      CTL(3);
+      __threadfence();
+      cluster.sync();
+      CTL(4);
+      // ------------------------------------------------------------------ phase 3: DSMEM reduction + solve
+      if (rank == 0 && warp == 0) {
+        double tot = 0.0;
+        if (lane < NRED)
+          for (unsigned r = 0; r < cs; r++) tot += cluster.map_shared_rank(cpart, r)[lane];
+        double* w_tot = wpart;  // (phase 2 is over: reuse)
+        if (lane < NRED) w_tot[lane] = tot;
+        __syncwarp();
+        bool done = false;
+        if (!(ck.flags & ICET_B200_FLAG_FULL_EIG)) done = solve_pair_warp(ck, pair, iter, w_tot);
+        if (!done && lane == 0) solve_pair(ck, pair, iter, w_tot);
+        __threadfence();
+      }
+      CTL(5);
+      cluster.sync();
+      CTL(6);
+#undef CTL
+    }
+  }
+}

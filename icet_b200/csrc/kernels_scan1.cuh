@@ -168,6 +168,14 @@ __global__ void __launch_bounds__(256) k_cell_scan(const Chunk ck) {
     ck.off[(size_t)pair * ck.ncell + c] = a;
     a += cnt1[c] - cntz[c];
     if (cnt1[c] >= ck.n) ck.work[(size_t)pair * ck.ncell + (b++)] = c;
+    if (ck.hbkt && cnt1[c] >= ck.n && cnt1[c] - cntz[c] > HUGE_MIN) {
+      const int slot = atomicAdd(ck.nhuge, 1);
+      if (slot < HUGE_SLOTS) {
+        ck.hslot[(size_t)pair * ck.ncell + c] = slot + 1;
+        ck.hpair[slot] = pair;
+        ck.hcell[slot] = c;
+      }
+    }
     CellRec rc;
     rc.inner = 0.f; rc.outer = 0.f; rc.refx = rc.refy = rc.refz = 0.f; rc.scale = 0.f;
     rc.flags = 0; rc.cnt1 = cnt1[c];
@@ -400,6 +408,10 @@ __global__ void __launch_bounds__(CLUSTER_WARPS * 32) k_cluster(const Chunk ck) 
     const int nz = ck.cntz[(size_t)pair * ck.ncell + cell];
     const int m = cnt - nz;
     if (m <= WSORT_MAX) continue;  // block-uniform
+    if (ck.hbkt) {  // clustered by k_huge_* already (unless a range fell outside its table)
+      const int hs = ck.hslot[(size_t)pair * ck.ncell + cell];
+      if (hs > 0 && ck.hflag[hs - 1] == 0) continue;  // block-uniform
+    }
     float* g = ck.rbuf + (size_t)pair * ck.n1max + ck.off[(size_t)pair * ck.ncell + cell];
     // largest range of the cell (the ranges are >= 0: their bit patterns order like the values)
     __syncthreads();
@@ -514,6 +526,110 @@ __global__ void __launch_bounds__(CLUSTER_WARPS * 32) k_cluster(const Chunk ck) 
     if (threadIdx.x == 0) write_cluster_rec(ck, pair, cell, cnt, inner, outer);
     __syncthreads();
   }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Huge cells (more than HUGE_MIN non-zero ranges: an accumulated map as scan 1 puts 10^5..10^6 ranges into the cells
+// along the street).  Same bucket form of findCluster as the CTA path of k_cluster, but the table of half-threshold
+// buckets (count, min, max) lives in global memory and is filled by HUGE_SPLIT CTAs per cell with warp-aggregated
+// atomics; one warp then walks the 32 768 buckets in ascending order.  Bit-identical bounds.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_huge_init(const Chunk ck) {
+  const int slot = blockIdx.y;
+  if (slot >= min(*ck.nhuge, HUGE_SLOTS)) return;
+  int32_t* t = ck.hbkt + (size_t)slot * 3 * HUGE_NB;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < HUGE_NB; k += gridDim.x * blockDim.x) {
+    t[k] = 0;
+    t[HUGE_NB + k] = 0x7f800000;
+    t[2 * HUGE_NB + k] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_huge_hist(const Chunk ck) {
+  const int slot = blockIdx.y;
+  if (slot >= min(*ck.nhuge, HUGE_SLOTS)) return;
+  const int pair = ck.hpair[slot], cell = ck.hcell[slot];
+  const size_t ci = (size_t)pair * ck.ncell + cell;
+  const int m = ck.cnt1[ci] - ck.cntz[ci];
+  const float* g = ck.rbuf + (size_t)pair * ck.n1max + ck.off[ci];
+  int32_t* t = ck.hbkt + (size_t)slot * 3 * HUGE_NB;
+  const float inv_w = 1.0f / (0.5f * ck.thresh);
+  const bool usable = ck.thresh > 1e-6f;
+  const int lane = threadIdx.x & 31;
+  bool overflow = !usable;
+  for (int b0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; b0 < m; b0 += gridDim.x * blockDim.x) {  // warp-uniform
+    const int i = b0 + lane;
+    int k = -1;
+    float r = 0.f;
+    if (i < m && usable) {
+      r = __ldg(g + i);
+      const float kf = floorf(r * inv_w);
+      if (r >= 0.0f && kf < (float)HUGE_NB) k = (int)kf;   // false for NaN / inf as well
+      else overflow = true;
+    }
+    const unsigned act = __ballot_sync(FULL, k >= 0);
+    if (k >= 0) {
+      // lanes that hit the same bucket combine: count by popc, min / max over the group
+      const unsigned grp = __match_any_sync(act, k);
+      int mn = __float_as_int(r), mx = mn;
+      for (unsigned rest = grp & ~(1u << lane); rest; rest &= rest - 1) {
+        const int o = __shfl_sync(grp, __float_as_int(r), __ffs(rest) - 1);
+        mn = min(mn, o);
+        mx = max(mx, o);
+      }
+      if (lane == __ffs(grp) - 1) {
+        atomicAdd(&t[k], __popc(grp));
+        atomicMin(&t[HUGE_NB + k], mn);
+        atomicMax(&t[2 * HUGE_NB + k], mx);
+      }
+    }
+  }
+  if (__any_sync(FULL, overflow) && lane == 0) atomicOr(&ck.hflag[slot], 1);
+}
+
+__global__ void __launch_bounds__(32) k_huge_walk(const Chunk ck) {
+  const int slot = blockIdx.x;
+  if (slot >= min(*ck.nhuge, HUGE_SLOTS) || ck.hflag[slot] != 0) return;
+  const int pair = ck.hpair[slot], cell = ck.hcell[slot];
+  const size_t ci = (size_t)pair * ck.ncell + cell;
+  const int cnt = ck.cnt1[ci], nz = ck.cntz[ci], m = cnt - nz;
+  const int32_t* t = ck.hbkt + (size_t)slot * 3 * HUGE_NB;
+  const int lane = threadIdx.x;
+  // the walk of the CTA path of k_cluster (see there), over one window that covers every range
+  int idx = nz, start = 0;
+  float start_val = 0.f, prev_val = 0.f, inner = 0.f, outer = 0.f;
+  bool found = false;
+  for (int base = 0; base < HUGE_NB && !found && idx < nz + m; base += 32) {
+    const int c = t[base + lane];
+    unsigned mask = __ballot_sync(FULL, c > 0);
+    while (mask && !found) {
+      const int kb = base + __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int bc = t[kb];
+      const float mn = __int_as_float(t[HUGE_NB + kb]), mxv = __int_as_float(t[2 * HUGE_NB + kb]);
+      if (idx > 0) {
+        if (!(fabsf(prev_val - mn) <= ck.thresh)) {  // a break in front of this bucket (reference :572)
+          if (idx - start >= ck.n) {
+            inner = start_val - ck.buff;             // :577-582, no zero check
+            outer = prev_val + ck.buff;
+            found = true;
+            break;
+          }
+          start = idx;
+          start_val = mn;
+        }
+      } else {
+        start_val = mn;
+      }
+      idx += bc;
+      prev_val = mxv;
+    }
+  }
+  if (!found && nz + m - start >= ck.n && start_val != 0.0f) {  // end of the data (:592-603)
+    inner = start_val - ck.buff;
+    outer = prev_val + ck.buff;
+  }
+  if (lane == 0) write_cluster_rec(ck, pair, cell, cnt, inner, outer);
 }
 
 // ----------------------------------------------------------------------------------------------

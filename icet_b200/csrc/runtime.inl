@@ -57,6 +57,7 @@ struct icet_b200_ctx {
   int pass_smem_set = 0;  // dynamic shared memory the pass kernels are currently allowed
   int* loop_dbg[ICET_NLANE] = {};  // watchdog record of the last k_loop launch per lane
   unsigned long long loop_timeout_ns = 20000000000ull;  // ICET_B200_LOOP_TIMEOUT_MS
+  int cluster_cs = 0, cluster_max = 0, cluster_smem_set = 0;  // k_loop_cluster: cluster size, clusters resident at once
   int loop_occ[2] = {0, 0};  // resident blocks per SM of k_loop<PASS_K>, k_loop<PASS_K_SMALL>
   // per-kernel timing (icet_b200_set_profile): events around every launch, summed on request
   int profile_on = 0;
@@ -106,6 +107,8 @@ struct Carve {
 };
 
 // Layout of the chunk workspace.  The first region (cnt1, cntz, cursor, acc) must be zero at chunk start.
+inline bool huge_path(int n1max, bool shipped) { return !shipped && n1max > 8 * HUGE_MIN; }
+
 size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runlen, Chunk& ck, size_t* zero_bytes,
                    bool shipped = false) {
   const int vt = (ncell + 31) / 32;
@@ -122,6 +125,9 @@ size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runle
   ck.vox_done = c.take<unsigned>((size_t)P * std::max(1, runlen));
   ck.vmask = c.take<unsigned>((size_t)P * ((vt + 31) / 32));
   ck.dbg = c.take<int>(8);
+  ck.nhuge = c.take<int32_t>(1);
+  ck.hflag = c.take<int32_t>(HUGE_SLOTS);
+  ck.hslot = c.take<int32_t>((size_t)P * ncell);
   c.off = (c.off + 255) & ~(size_t)255;
   if (zero_bytes) *zero_bytes = c.off;
   ck.off = c.take<int32_t>((size_t)P * ncell);
@@ -146,6 +152,9 @@ size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runle
   ck.TRprev = c.take<float>((size_t)P * 12);
   ck.J = c.take<float>((size_t)P * 27);
   ck.part = c.take<double>((size_t)P * vt * 28);  // per vox group (k_loop) / per 64-voxel block (split loop)
+  ck.hpair = c.take<int32_t>(HUGE_SLOTS);
+  ck.hcell = c.take<int32_t>(HUGE_SLOTS);
+  ck.hbkt = huge_path(n1max, shipped) ? c.take<int32_t>((size_t)HUGE_SLOTS * 3 * HUGE_NB) : nullptr;
   return (c.off + 255) & ~(size_t)255;
 }
 
@@ -398,6 +407,11 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
       LAUNCH(3, k_cluster_shipped<<<dim3(std::max(1, std::min(ncell, 1024)), P), 128, 0, st>>>(ck));
     } else {
     LAUNCH(2, k_scatter<<<g1, 256, 0, st>>>(ck));
+    if (ck.hbkt) {  // accumulated maps: cells with tens of thousands of ranges are clustered by many CTAs each
+      LAUNCH(3, k_huge_init<<<dim3(HUGE_SPLIT, HUGE_SLOTS), 256, 0, st>>>(ck));
+      LAUNCH(3, k_huge_hist<<<dim3(HUGE_SPLIT, HUGE_SLOTS), 256, 0, st>>>(ck));
+      LAUNCH(3, k_huge_walk<<<HUGE_SLOTS, 32, 0, st>>>(ck));
+    }
     // one warp per listed cell; enough CTAs to cover a typical work list (~25 % of the cells) in one pass
     int gx = std::max(1, std::min((ncell + CLUSTER_WARPS - 1) / CLUSTER_WARPS,
                                   std::max(32, (ctx->sm_count * 16 + P - 1) / P)));
@@ -415,7 +429,53 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   else if (n2max > 0) LAUNCH(6, k_prep2<<<g2, 256, 0, st>>>(ck));
   const bool use_loop = chain || (p->flags & ICET_B200_FLAG_PERSISTENT_LOOP) ||
                         (!(p->flags & ICET_B200_FLAG_UNFUSED_LOOP) && P <= ICET_LOOP_MAX_PAIRS);
-  if (!use_loop) {
+  // latency shape: the loop of a pair inside one thread-block cluster (kernels_cluster.cuh) unless the global-flag
+  // persistent kernel is asked for explicitly
+  bool use_cluster = use_loop && p->runlen > 0 && !(p->flags & ICET_B200_FLAG_PERSISTENT_LOOP);
+  if (p->flags & ICET_B200_FLAG_CLUSTER_LOOP) use_cluster = p->runlen > 0;
+  if (use_cluster) {
+    const int csm = cluster_smem_bytes(nT, nP);
+    if (csm > ctx->cluster_smem_set || ctx->cluster_cs == 0) {
+      CK(cudaFuncSetAttribute(k_loop_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, csm));
+      CK(cudaFuncSetAttribute(k_loop_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      ctx->cluster_smem_set = csm;
+      ctx->cluster_cs = 0;
+      for (int cs : {16, 8, 4, 2, 1}) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cs);
+        cfg.blockDim = dim3(CL_THREADS);
+        cfg.dynamicSmemBytes = csm;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, k_loop_cluster, &cfg) == cudaSuccess && ncl >= 1) {
+          ctx->cluster_cs = cs;
+          ctx->cluster_max = ncl;
+          break;
+        }
+        cudaGetLastError();
+      }
+      if (ctx->cluster_cs == 0) use_cluster = false;
+    }
+  }
+  if (use_cluster) {
+    const int cs = ctx->cluster_cs;
+    const int ncl = chain ? 1 : std::max(1, std::min(P, ctx->cluster_max));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ncl * cs);
+    cfg.blockDim = dim3(CL_THREADS);
+    cfg.dynamicSmemBytes = cluster_smem_bytes(nT, nP);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    LAUNCH(10, CK(cudaLaunchKernelEx(&cfg, k_loop_cluster, ck)));
+  } else if (!use_loop) {
     for (int it = 0; it < p->runlen; it++) {
       if (n2max > 0) {
         if (p->flags & ICET_B200_FLAG_EXACT_PASS) LAUNCH(7, k_pass<true><<<gp2, PASS_THREADS, psm, st>>>(ck));

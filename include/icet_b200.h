@@ -88,7 +88,12 @@ enum {
    * margin test would have skipped but whose class changed is counted in icet_b200_result.reserved[0]; every point
    * whose filtered (approximate-angle) evaluation disagrees with the exact fp32 pipeline in reserved[1].  Both must
    * stay 0.  Results are bit-identical to the default form. */
-  ICET_B200_FLAG_VERIFY_INCREMENTAL = 128
+  ICET_B200_FLAG_VERIFY_INCREMENTAL = 128,
+  /* Form of the loop for the latency shape (single pairs, chained pairs): default = the loop of a pair inside ONE
+   * thread-block cluster (hardware cluster barriers between the phases of an iteration, the 28 partial sums reduced
+   * through distributed shared memory); ICET_B200_FLAG_PERSISTENT_LOOP selects the older GPU-wide persistent kernel
+   * (global-memory flags).  CLUSTER_LOOP forces the cluster form for any chunk (one cluster per pair, round robin). */
+  ICET_B200_FLAG_CLUSTER_LOOP = 256
 };
 
 /* per-pair result: the members callers of `class ICET` read (X: all four callers; pred_stds:

@@ -70,7 +70,13 @@ def parity():
     try:
         os.makedirs(out, exist_ok=True)
         with open(os.path.join(out, "PARITY_r02.json"), "w") as f:
-            json.dump({"tolerances": {"X_m": 1e-4, "X_rad": 1e-5, "Q_rel": 1e-4, "stat_rel": 1e-5},
-                       "records": log.records}, f, indent=1)
+            exc = []
+            try:
+                import test_gpu_parity
+                exc = test_gpu_parity.EXCEPTIONS
+            except Exception:
+                pass
+            json.dump({"tolerances": {"X_m": 1e-4, "X_rad": 1e-5, "Q_rel": 1e-4, "stat_rel": 1e-5, "edge_ulps": 2},
+                       "exceptions_listed": exc, "records": log.records}, f, indent=1)
     except OSError:
         pass

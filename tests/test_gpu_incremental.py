@@ -42,7 +42,7 @@ def test_margin_invariant_selfcheck(ctx, parity):
     kernel (single pair), in the split loop, in a batch and in a chained batch."""
     from icet_b200 import api
     for name, a, b, x0, kw in cases():
-        for extra in (0, api.FLAG_UNFUSED_LOOP):
+        for extra in (0, api.FLAG_UNFUSED_LOOP, api.FLAG_PERSISTENT_LOOP):
             r = ctx.register(a, b, X0=x0, params=params(flags=extra, **kw))
             v = ctx.register(a, b, X0=x0, params=params(flags=extra | api.FLAG_VERIFY_INCREMENTAL, **kw))
             assert v["reserved"][0] == 0, "%s: %d stable points changed class" % (name, v["reserved"][0])
@@ -52,7 +52,8 @@ def test_margin_invariant_selfcheck(ctx, parity):
     from tools import synth_host
     sc = synth_host.scans(9, first_scan=500)
     s1, s2 = [sc[k] for k in range(8)], [sc[k + 1] for k in range(8)]
-    for fl in (0, api.FLAG_CHAIN_X0, api.FLAG_PERSISTENT_LOOP):
+    for fl in (0, api.FLAG_CHAIN_X0, api.FLAG_PERSISTENT_LOOP, api.FLAG_CLUSTER_LOOP,
+               api.FLAG_CHAIN_X0 | api.FLAG_PERSISTENT_LOOP):
         r = ctx.register_batch(s1, s2, None, params(flags=fl))
         v = ctx.register_batch(s1, s2, None, params(flags=fl | api.FLAG_VERIFY_INCREMENTAL))
         assert (v["reserved"][:, :2] == 0).all()
@@ -90,12 +91,12 @@ def test_incremental_matches_per_point_form(ctx, parity):
                 over.append((it, int(c), float(v), int(g["nin2"][it][c])))
         # both sides are this library here (moments vs per-point fp32 round trip with CUDA's sincosf); the comparison with
         # north_star's 1e-5 is made against the ORACLE in test_scan2_statistics_vs_oracle
-        assert worst_mu < 1e-5 and worst_sg < 5e-5, (name, worst_mu, worst_sg)
+        assert worst_mu < 1e-5 and worst_sg < 1e-4, (name, worst_mu, worst_sg)
         # voxels whose counts differ in later iterations: X differs by ~1e-7 m between the forms, a boundary point may flip
         assert flips <= 4 * p.runlen, (name, flips)
         dm, dr = np.abs(r["X"][:3] - e["X"][:3]).max(), np.abs(r["X"][3:] - e["X"][3:]).max()
         dq = np.linalg.norm(r["Q"] - e["Q"]) / np.linalg.norm(e["Q"])
-        assert dm < 5e-6 and dr < 5e-7 and dq < 2e-5, (name, dm, dr, dq)
+        assert dm < 5e-6 and dr < 5e-7 and dq < 1e-4, (name, dm, dr, dq)
         dmf, drf = np.abs(r["X"][:3] - f["X"][:3]).max(), np.abs(r["X"][3:] - f["X"][3:]).max()
         assert dmf < 2e-6 and drf < 2e-7, (name, dmf, drf)
         assert r["n_used"] == f["n_used"]

@@ -67,7 +67,9 @@ def test_odometry_node_matches_oracle(ctx, scans):
         assert abs(np.linalg.norm(q) - 1) < 1e-5 and min(np.abs(q - qo).max(), np.abs(q + qo).max()) < 1e-5 * k
         np.testing.assert_allclose(g["twist"], 10.0 * g["X"], rtol=1e-6)
         np.testing.assert_allclose(g["covariance_diag"], g["pred_stds"])
-        np.testing.assert_allclose(g["pred_stds"], o["pred_stds"], rtol=2e-2)
+        # (fp32 oracle without its double twin here: its small rotational entries carry ~1e-3 of fp32 COD noise, see
+        # check_final in test_gpu_parity.py for the rule with the twin)
+        np.testing.assert_allclose(g["pred_stds"], o["pred_stds"], rtol=5e-3)
     # chaining is what the node does: the last registration started from the previous solution
     assert np.abs(node.X0 - orc.X0).max() < 1e-3
 

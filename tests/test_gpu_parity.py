@@ -64,13 +64,16 @@ def oracle_with_gpu_signs(po, s1, s2, g, o, **kw):
     return o32, o64, int(bad.sum())
 
 
-def check_final(r, o, o64):
-    """north_star tolerances.  X is compared with the fp32 oracle.  For the 6x6 error-bound covariance the fp32
-    reference path carries its own rounding noise (fp32 COD inverses of R_noise with cond ~1e4, fp32 sums over ~350
-    voxels: |Q32 - Q64| / |Q64| reaches 1e-4..1e-3 on some pairs), and the double twin can in turn
-    take a different discrete path (a boundary point flipping after X moved by 1e-7).  The GPU computes these steps
-    in double on the fp32 geometry, so Q must be within 1e-4 of the oracle evaluated in fp32 OR in double, and never
-    further from the fp32 oracle than the tolerance plus the oracle's own fp32-vs-double spread."""
+EXCEPTIONS = []   # (test, what, cause): every place a north_star tolerance is exceeded, listed instead of widened
+
+
+def check_final(r, o, o64, where="?"):
+    """north_star tolerances AS WRITTEN: X within 1e-4 m / 1e-5 rad and Q within 1e-4 relative (Frobenius) of the fp32
+    oracle.  The fp32 reference path carries rounding noise of its own in Q (fp32 COD inverses of R_noise with cond
+    ~1e4, fp32 sums over ~350 voxels: |Q32 - Q64| / |Q64| reaches 1e-4..1e-3 on some pairs), while the GPU
+    computes those steps in double on the fp32 geometry.  A pair whose Q is further than 1e-4 from the fp32 oracle is
+    therefore not failed but LISTED (EXCEPTIONS, PARITY_r02.json) -- and must then be within 1e-4 of the oracle's
+    double-precision twin and no further from the fp32 oracle than the oracle's own fp32-vs-double spread explains."""
     dm = float(np.abs(r["X"][:3] - o.X[:3]).max())
     dr = float(np.abs(r["X"][3:] - o.X[3:]).max())
     dq32 = float(np.linalg.norm(r["Q"] - o.Q) / np.linalg.norm(o.Q))
@@ -78,10 +81,21 @@ def check_final(r, o, o64):
     spread = float(np.linalg.norm(o.Q - o64.Q) / np.linalg.norm(o64.Q))
     assert dm < TOL_M, "translation differs by %.3e m" % dm
     assert dr < TOL_RAD, "rotation differs by %.3e rad" % dr
-    assert min(dq32, dq64) < TOL_Q, "error-bound covariance: %.3e vs fp32 oracle, %.3e vs double twin" % (dq32, dq64)
-    assert dq32 < TOL_Q + 1.5 * spread, "error-bound covariance %.3e vs fp32 oracle (oracle spread %.3e)" % (dq32, spread)
-    # pred_stds = sqrt|diag Q|: the small rotational entries of the fp32 oracle's inverse carry ~1e-3 relative noise
-    np.testing.assert_allclose(r["pred_stds"], np.sqrt(np.abs(np.diag(o.Q))), rtol=5e-3)
+    if dq32 >= TOL_Q:
+        assert dq64 < TOL_Q, "error-bound covariance: %.3e vs fp32 oracle, %.3e vs double twin" % (dq32, dq64)
+        assert dq32 < TOL_Q + 1.5 * spread, "error-bound covariance %.3e vs fp32 oracle (oracle spread %.3e)" % (dq32, spread)
+        EXCEPTIONS.append(dict(where=where, what="Q", rel_vs_fp32_oracle=dq32, rel_vs_double_twin=dq64,
+                               oracle_fp32_vs_double=spread, cause="fp32 COD / summation noise of the reference path itself"))
+    # pred_stds = sqrt|diag Q|: same rule, entry by entry
+    s32, s64 = np.sqrt(np.abs(np.diag(o.Q))), np.sqrt(np.abs(np.diag(o64.Q)))
+    e32, e64 = np.abs(r["pred_stds"] - s32) / s32, np.abs(r["pred_stds"] - s64) / s64
+    sp = np.abs(s32 - s64) / s64
+    for k in range(6):
+        if e32[k] >= TOL_Q:
+            assert e64[k] < TOL_Q and e32[k] < TOL_Q + 1.5 * sp[k], (k, e32[k], e64[k], sp[k])
+            EXCEPTIONS.append(dict(where=where, what="pred_stds[%d]" % k, rel_vs_fp32_oracle=float(e32[k]),
+                                   rel_vs_double_twin=float(e64[k]), oracle_fp32_vs_double=float(sp[k]),
+                                   cause="fp32 COD / summation noise of the reference path itself"))
     return dm, dr, min(dq32, dq64)
 
 
@@ -96,7 +110,8 @@ def test_spherical_and_bins(ctx, po, name):
         ref = po.c2s(scan)
         # r and z/r are IEEE operations in the same order on both sides: bit-exact
         np.testing.assert_array_equal(sph[0].view(np.int32), ref[0].view(np.int32))
-        assert ulp_diff(sph[1], ref[1]).max() <= 3 and ulp_diff(sph[2], ref[2]).max() <= 2
+        # own atan2 / acos: within 1 ulp of correctly rounded; glibc's likewise => at most 2 ulp apart
+        assert ulp_diff(sph[1], ref[1]).max() <= 2 and ulp_diff(sph[2], ref[2]).max() <= 2
         # the bin function itself is exact: GPU cells == reference formula applied to the GPU's own angles
         np.testing.assert_array_equal(cell, po.bins(sph))
         # against the oracle's angles only "edge points" may differ; count and list them
@@ -108,7 +123,7 @@ def test_spherical_and_bins(ctx, po, name):
             kt, kp = th / (2 * np.pi) * 75, ph / np.pi * 24
             near = min(abs(kt - round(kt)) / 75 * 2 * np.pi / np.spacing(np.float32(th)),
                        abs(kp - round(kp)) / 24 * np.pi / np.spacing(np.float32(ph)))
-            assert near <= 3, "point %d changed voxel but is %.1f ulp from an edge" % (i, near)
+            assert near <= 2, "point %d changed voxel but is %.1f ulp from an edge" % (i, near)
         print("%s: %d points, %d edge points %s" % (name, scan.shape[1], len(edge), edge.tolist()))
 
 
@@ -183,7 +198,7 @@ def test_bins_zero_and_nan_rows(ctx, po):
 # scan-1 voxel stage (K2-K4) and the iteration loop (K5-K6) on the bundled pairs
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name,x0", [("frame", None), ("frame", [1, 0, 0, 0, 0, 0]), ("sample_pc", None)])
-def test_stage_parity_fixture(ctx, po, name, x0):
+def test_stage_parity_fixture(ctx, po, parity, name, x0):
     from conftest import load_pair
     s1, s2 = load_pair(name)
     p = params()
@@ -203,8 +218,18 @@ def test_stage_parity_fixture(ctx, po, name, x0):
     sg_err = np.abs(g["sigma1"][has] - o.sigma1[has]).reshape(-1, 9).max(1) / \
         np.abs(o.sigma1[has]).reshape(-1, 9).max(1)
     assert mu_err.max() < TOL_STAT
-    # libm: a 2-ulp azimuth difference moves a point by ~5e-5 m at 50 m; allow 2x on the worst voxel, 1x on 99 %
-    assert np.percentile(sg_err, 99) < TOL_STAT and sg_err.max() < 2 * TOL_STAT
+    # north_star: covariances within 1e-5 relative.  Voxels beyond it are LISTED with their cause, not tolerated
+    # silently: CUDA's sinf / cosf differ from glibc's by <= 2 ulp on a few % of inputs, which moves a point at 50 m by
+    # ~5e-5 m; on a thin cluster that is visible in the covariance.  Their number and size are bounded.
+    over = np.where(sg_err >= TOL_STAT)[0]
+    assert len(over) <= 3 and sg_err.max() < 3 * TOL_STAT, (len(over), sg_err.max())
+    for k in over:
+        c = int(np.where(has)[0][k])
+        EXCEPTIONS.append(dict(where="%s x0=%s" % (name, x0), what="sigma1 of voxel %d" % c, rel=float(sg_err[k]),
+                               points=int(o.nin1[c]), cause="sincosf (CUDA) vs sinf/cosf (glibc), <= 2 ulp, thin cluster"))
+    parity.add("scan1_statistics", "%s x0=%s" % (name, x0), voxels=int(has.sum()), mu1_rel_max=float(mu_err.max()),
+               sigma1_rel_max=float(sg_err.max()), sigma1_rel_p99=float(np.percentile(sg_err, 99)),
+               sigma1_over_1e5=[int(np.where(has)[0][k]) for k in over])
     # --- eigen stage: the CUDA port of Eigen's 3x3 solver is bit-identical to the oracle's on the same input
     for c in np.where(has)[0][::7]:
         ev, V = po.eig3(g["sigma1"][c])
@@ -220,7 +245,9 @@ def test_stage_parity_fixture(ctx, po, name, x0):
     for it in range(p.runlen):
         act = g["cnt2"][it] >= 0
         cnt_mism = int((g["cnt2"][it][act] != o2.cnt2[it][act]).sum())
-        assert cnt_mism <= 0.15 * act.sum()  # boundary points (libm) move between neighbouring voxels
+        # edge points (within 2-3 ulp of a bin edge, listed one by one in test_scan2_classes_vs_oracle_listed) move
+        # between neighbouring voxels: each changes the count of two cells
+        assert cnt_mism <= 24, (it, cnt_mism)
         both = (g["used2"][it] > 0) & (o2.used2[it] > 0)
         assert (g["used2"][it] != o2.used2[it]).sum() <= 3
         same_n = both & (g["nin2"][it] == o2.nin2[it])
@@ -229,8 +256,10 @@ def test_stage_parity_fixture(ctx, po, name, x0):
             e = np.abs(g["mu2"][it][same_n] - o2.mu2[it][same_n]).max(1) / np.abs(o2.mu2[it][same_n]).max(1)
             assert np.percentile(e, 99) < TOL_STAT
     # --- result
-    dm, dr, dq = check_final(r, o2, o64)
+    dm, dr, dq = check_final(r, o2, o64, "%s x0=%s" % (name, x0))
     print("%s x0=%s: sign-unstable voxels %d; |dX| %.2e m %.2e rad, |dQ|/|Q| %.2e" % (name, x0, nbad, dm, dr, dq))
+    parity.add("final", "%s x0=%s" % (name, x0), dX_m=dm, dX_rad=dr, dQ_rel=dq, sign_unstable_voxels_injected=nbad,
+               dX_m_without_injection=float(np.abs(r["X"][:3] - o.X[:3]).max()))
     # without the injection the transform still agrees within tolerance on these pairs
     assert np.abs(r["X"][:3] - o.X[:3]).max() < TOL_M and np.abs(r["X"][3:] - o.X[3:]).max() < TOL_RAD
 
@@ -261,7 +290,7 @@ def test_python_icet_class_mirror(ctx, po, frame_pair):
 # ---------------------------------------------------------------------------------------------------------
 # synthetic 64-channel sequence (BASELINE.json configs[1], [2]): batch API, determinism, invariances
 # ---------------------------------------------------------------------------------------------------------
-def test_batch_sequence_matches_oracle(ctx, po):
+def test_batch_sequence_matches_oracle(ctx, po, parity):
     nscans = 9
     dev = synth_device(ctx, nscans)
     host = dev.cpu().numpy()
@@ -273,11 +302,13 @@ def test_batch_sequence_matches_oracle(ctx, po):
         o = po.run(host[k], host[k + 1], dumps="small")
         o2, o64, nbad = oracle_with_gpu_signs(po, host[k], host[k + 1], g, o)
         unstable += nbad
-        d = check_final(res[k], o2, o64)
+        d = check_final(res[k], o2, o64, "synthetic pair %d" % k)
         worst = tuple(max(a, b) for a, b in zip(worst, d))
         assert res[k]["n_used"] == int(o2.used2[-1].sum())
     print("batch of %d synthetic pairs: worst |dX| %.2e m %.2e rad |dQ| %.2e; sign-unstable voxels injected: %d"
           % (nscans - 1, *worst, unstable))
+    parity.add("final", "configs[2] sample: %d synthetic 64-ch pairs" % (nscans - 1), dX_m=worst[0], dX_rad=worst[1],
+               dQ_rel=worst[2], sign_unstable_voxels_injected=unstable)
 
 
 def test_batch_equals_single_and_is_deterministic(ctx):
@@ -316,6 +347,15 @@ def test_persistent_loop_matches_split_loop(ctx):
     big = synth_device(ctx, 65, first=300)
     c = register_sequence(ctx, big, params(flags=api.FLAG_PERSISTENT_LOOP))
     assert c[:11].tobytes() == a.tobytes()
+    # the cluster form (default for single / chained pairs; forced here for a batch: one cluster per pair, round robin)
+    # against the two other forms
+    e = register_sequence(ctx, dev, params(flags=api.FLAG_CLUSTER_LOOP))
+    assert np.abs(e["X"] - b["X"]).max() < 2e-7 and np.abs(e["Q"] - b["Q"]).max() <= 1e-6 * np.abs(b["Q"]).max()
+    np.testing.assert_array_equal(e["n_used"], b["n_used"])
+    one_c = ctx.register(host[3], host[4])                      # default single pair = cluster form
+    assert one_c.tobytes() == e[3].tobytes()
+    e65 = register_sequence(ctx, big, params(flags=api.FLAG_CLUSTER_LOOP))   # more pairs than resident clusters
+    assert e65[:11].tobytes() == e.tobytes()
     # one and two compute lanes: same bits
     ctx.set_chunk(16)
     ctx.set_lanes(1)
@@ -338,7 +378,7 @@ def test_point_order_invariance(ctx):
     assert r0.tobytes() == r1.tobytes()
 
 
-def test_128_channel_config(ctx, po):
+def test_128_channel_config(ctx, po, parity):
     """BASELINE.json configs[3]: 128 x 2048 points, 150 x 48 voxels, 10 iterations."""
     dev = synth_device(ctx, 2, rings=128, azim=2048, first=3)
     host = dev.cpu().numpy()
@@ -350,7 +390,9 @@ def test_128_channel_config(ctx, po):
     np.testing.assert_array_equal(g["bounds"], o.bounds)
     o2, o64, nbad = oracle_with_gpu_signs(po, host[0], host[1], g, o, **kw)
     print("128-ch: gaussians %d, used %d, sign-unstable %d" % (r["n_gauss1"], r["n_used"], nbad))
-    check_final(r, o2, o64)
+    dm, dr, dq = check_final(r, o2, o64, "configs[3] 128-ch")
+    parity.add("final", "configs[3]: 128-ch pair, 150x48, 10 it", dX_m=dm, dX_rad=dr, dQ_rel=dq,
+               sign_unstable_voxels_injected=nbad, gaussians=int(r["n_gauss1"]), voxels_used=int(r["n_used"]))
 
 
 def test_submap_config_properties(ctx):
@@ -396,7 +438,7 @@ def test_submap_full_size_vs_golden(ctx, po, parity):
     o = po.run(mp, cur, dumps="small")
     np.testing.assert_array_equal(o.X, gold["X"])             # the oracle has not drifted from its stored outputs
     o2, o64, nbad = oracle_with_gpu_signs(po, mp, cur, g, o)
-    dm, dr, dq = check_final(r, o2, o64)
+    dm, dr, dq = check_final(r, o2, o64, "configs[4] submap 2M")
     # shuffled map rows: not a bit changes (integer statistics, value-based clustering)
     rng = np.random.default_rng(5)
     r2 = ctx.register(np.ascontiguousarray(mp[:, rng.permutation(mp.shape[1])]), cur)
@@ -569,7 +611,7 @@ def test_big_cells_bucket_clustering(ctx, po):
         np.testing.assert_array_equal(g["bounds"], o.bounds)
         np.testing.assert_array_equal(g["has1"], o.has1)
         o2, o64, nbad = oracle_with_gpu_signs(po, big, host[2], g, o, **kw)
-        check_final(r, o2, o64)
+        check_final(r, o2, o64, "big cells %s" % kw)
 
 
 @pytest.mark.parametrize("name", ["frame", "sample_pc"])
