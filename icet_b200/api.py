@@ -118,7 +118,8 @@ EXPORTS = ["icet_b200_version", "icet_b200_last_error", "icet_b200_create", "ice
            "icet_b200_ingest", "icet_b200_register_clouds", "icet_b200_node_push_cloud",
            "icet_b200_transform_cloud_device", "icet_b200_transform_cloud",
            "icet_b200_multi_create", "icet_b200_multi_destroy", "icet_b200_multi_devices", "icet_b200_multi_context",
-           "icet_b200_register_batch_multi", "icet_b200_register_sequence_multi_device", "icet_b200_multi_gathered"]
+           "icet_b200_register_batch_multi", "icet_b200_register_sequence_multi_device", "icet_b200_multi_gathered",
+           "icet_b200_multi_gathered_host"]
 NKERNELS = 11
 
 _LIB = None
@@ -194,6 +195,7 @@ def load_library() -> C.CDLL:
     L.icet_b200_register_batch_multi.argtypes = [vp, C.POINTER(Params), C.c_int32, vp, vp, vp, vp, vp, vp]
     L.icet_b200_register_sequence_multi_device.argtypes = [vp, C.POINTER(Params), C.c_int32, vp, C.c_int32]
     L.icet_b200_multi_gathered.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(C.c_int32)]
+    L.icet_b200_multi_gathered_host.argtypes = [vp, C.c_int32, vp]
     _LIB = L
     return L
 
@@ -469,6 +471,13 @@ class MultiContext:
         ptr, rows = C.c_void_p(), C.c_int32()
         self._check(self._L.icet_b200_multi_gathered(self._h, d, C.byref(ptr), C.byref(rows)))
         return ptr.value, rows.value
+
+    def gathered_host(self, d: int) -> np.ndarray:
+        """[ndev, rows_per_shard, 48] float32: the all-gathered rows (X 6 | pred_stds 6 | Q 36) as device slot d holds them"""
+        _, rows = self.gathered(d)
+        out = np.zeros((len(self.devices), rows, 48), np.float32)
+        self._check(self._L.icet_b200_multi_gathered_host(self._h, d, out.ctypes.data))
+        return out
 
 
 _DEFAULT_CTX: Context | None = None

@@ -14,8 +14,8 @@ int fail(int code, const std::string& msg) {
       return fail(ICET_B200_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
   } while (0)
 
-constexpr int FPB = 21;                 // fixed-point: |d * scale| <= 2^FPB
-constexpr int FP_LIM = (1 << FPB);
+constexpr int FPB = 21;                 // fixed-point basis: CellRec::scale maps the voxel's box diameter D to 2^(FPB-1)
+constexpr int FP_LIM = (1 << FPB);      // (the per-chunk multipliers Chunk::fs1 / fs2 refine it, see fp_bits in runtime.inl)
 constexpr unsigned FULL = 0xffffffffu;
 constexpr uint32_t F_STAT1 = 1u;        // scan-1 statistics wanted for this cell
 constexpr uint32_t F_ACTIVE2 = 2u;      // voxel takes part in the scan-2 loop
@@ -76,6 +76,11 @@ struct Chunk {  // everything a kernel needs, passed by value
   int npairs, ncell, nT, nP, n, runlen, flags;
   float thresh, buff;
   int n1max, n2max;
+  // fixed-point refinement per scan: offsets are quantised to round(d * CellRec::scale * fs), clamped to +-fl.  As fine
+  // as 64-bit sums of products allow for the chunk's largest cloud (131 072 points: 2^22 levels per box diameter, i.e.
+  // ~2 um at 50 m -- below the fp32 ulp of the coordinates themselves)
+  float fs1, fs2;
+  int fl1, fl2;
   // scan 1
   int32_t* cellid1;  // [P][n1max]
   float* r1;         // [P][n1max]
@@ -150,3 +155,12 @@ __device__ __forceinline__ unsigned atom_add(unsigned* p, unsigned v) {
   return r;
 }
 
+
+// Programmatic dependent launch (sm_90+): the kernels of the single-pair (latency) path are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so that the launch of kernel k+1 overlaps the tail of kernel k.
+// Every kernel of that path starts with pdl_prologue(): it lets ITS dependent launch right away and then waits until
+// the grid it depends on has completed and flushed (griddepcontrol.wait is a no-op for a normally launched kernel).
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}

@@ -26,6 +26,7 @@ __host__ __device__ inline int cluster_smem_bytes(int nT, int nP) {
 }
 
 __global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck) {
+  pdl_prologue();
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) unsigned char smem_raw[];

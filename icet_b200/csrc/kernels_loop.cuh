@@ -89,7 +89,7 @@ __device__ __forceinline__ void vox_algebra(const Chunk& ck, int pair, int cell,
 #pragma unroll
   for (int k = 0; k < NQ; k++) qp[k] = 0ull;
   double mean[3], cov[6];
-  stats_from_acc(q, rc, mean, cov);
+  stats_from_acc(q, rc, ck.fs2, mean, cov);
   vox_algebra_core(ck, pair, cell, iter, Jm, (long long)q[0], mean, cov, acc);
 }
 
@@ -177,6 +177,7 @@ __device__ __forceinline__ void vox_algebra_core(const Chunk& ck, int pair, int 
 // voxel, in the set the pair currently uses; nothing is cleared except, right after a rebuild, the other set.
 struct VoxMode {
   int set, rebuild;
+  float fs2;
   float trb[12], tr[12];
 };
 __device__ __forceinline__ void load_vox_mode(const Chunk& ck, int pair, VoxMode& vm) {
@@ -184,6 +185,7 @@ __device__ __forceinline__ void load_vox_mode(const Chunk& ck, int pair, VoxMode
   const int2 h = __ldcg(reinterpret_cast<const int2*>(pm));
   vm.set = h.x;
   vm.rebuild = h.y;
+  vm.fs2 = ck.fs2;
   const float4* tb = reinterpret_cast<const float4*>(pm->TRb);
   const float4* tp = reinterpret_cast<const float4*>(ck.TR + (size_t)pair * 12);
 #pragma unroll
@@ -227,7 +229,7 @@ __device__ __forceinline__ bool vox_gate2(const Chunk& ck, int pair, int cell, i
 __device__ __forceinline__ void stats2_from_moments(const unsigned long long* q, const CellRec* recs, int cell,
                                                     const VoxMode& vm, double mean[3], double cov[6]) {
   float ax, ay, az, sc;
-  vox_anchor2(recs, cell, vm.trb, ax, ay, az, sc);
+  vox_anchor2(recs, cell, vm.trb, vm.fs2, ax, ay, az, sc);
   const double nin = (double)(long long)q[1];
   const double inv = 1.0 / (double)sc;  // exact: the scale is a power of two
   const double in_ = 1.0 / nin;

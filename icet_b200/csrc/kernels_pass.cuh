@@ -62,12 +62,12 @@ __device__ __forceinline__ void point_stage1(const Chunk& ck, const float4* tth,
 // Stage 2 of an inside point: sph->cart round trip (statistics use round-tripped points, src/icet.cpp:159 / :303)
 // and conversion to the voxel's fixed-point frame.
 __device__ __forceinline__ void point_stage2(float r, float th, float ph, float refx, float refy, float refz, float sc,
-                                             int& fx, int& fy, int& fz) {
+                                             int lim, int& fx, int& fy, int& fz) {
   float cx, cy, cz;
   icet::s2c(r, th, ph, cx, cy, cz);
-  fx = max(-FP_LIM, min(FP_LIM, __float2int_rn((cx - refx) * sc)));
-  fy = max(-FP_LIM, min(FP_LIM, __float2int_rn((cy - refy) * sc)));
-  fz = max(-FP_LIM, min(FP_LIM, __float2int_rn((cz - refz) * sc)));
+  fx = max(-lim, min(lim, __float2int_rn((cx - refx) * sc)));
+  fy = max(-lim, min(lim, __float2int_rn((cy - refy) * sc)));
+  fz = max(-lim, min(lim, __float2int_rn((cz - refz) * sc)));
 }
 
 // The dropped returns of scan 2: points2_OG == (0,0,0) for all of them, so they all land on t * R
@@ -85,7 +85,7 @@ __device__ inline void pass_dropped_returns(const Chunk& ck, const float4* tth, 
   if (in) {
     const CellRec rc = recs[c];
     int ix, iy, iz;
-    point_stage2(r, th, ph, rc.refx, rc.refy, rc.refz, rc.scale, ix, iy, iz);
+    point_stage2(r, th, ph, rc.refx, rc.refy, rc.refz, rc.scale * ck.fs2, ck.fl2, ix, iy, iz);
     const long long fx = ix, fy = iy, fz = iz;
     red_add(q + 1, (unsigned long long)nz);
     red_add(q + 2, (unsigned long long)(nz * fx));
@@ -277,10 +277,11 @@ __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* th
       pxx = pxy = pxz = pyy = pyz = pzz = 0;
       const float4* rp = reinterpret_cast<const float4*>(recs + cur);
       const float4 ra = __ldg(rp), rb = __ldg(rp + 1);
-      sc = ra.w; refx = rb.x; refy = rb.y; refz = rb.z;
+      sc = ra.w * (SCAN2 ? ck.fs2 : ck.fs1); refx = rb.x; refy = rb.y; refz = rb.z;
     }
     int fx, fy, fz;
-    point_stage2(__int_as_float(v.y), __int_as_float(v.z), __int_as_float(v.w), refx, refy, refz, sc, fx, fy, fz);
+    point_stage2(__int_as_float(v.y), __int_as_float(v.z), __int_as_float(v.w), refx, refy, refz, sc,
+                 SCAN2 ? ck.fl2 : ck.fl1, fx, fy, fz);
     nin++;
     sx += fx; sy += fy; sz += fz;
     pxx += (long long)fx * fx; pxy += (long long)fx * fy; pxz += (long long)fx * fz;
@@ -292,6 +293,7 @@ __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* th
 
 template <bool SCAN2, int K = PASS_K, int MINB = PASS_MINB, int PF = 2, int G = 1>
 __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass(const Chunk ck) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int4* ent = reinterpret_cast<int4*>(smem_raw);
   float* tab = reinterpret_cast<float*>(smem_raw + PASS_WARPS * pass_wslots(K) * 16);
@@ -326,10 +328,10 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass(const Chunk ck) {
 }
 
 // exact-sum -> mean / covariance (double) of a voxel
-__device__ __forceinline__ void stats_from_acc(const unsigned long long* q, const CellRec& rc, double mean[3],
+__device__ __forceinline__ void stats_from_acc(const unsigned long long* q, const CellRec& rc, float fs, double mean[3],
                                                double cov[6]) {
   const double nin = (double)(long long)q[1];
-  const double inv = 1.0 / (double)rc.scale;  // exact: the scale is a power of two
+  const double inv = 1.0 / ((double)rc.scale * (double)fs);  // exact: both are powers of two
   const double in_ = 1.0 / nin;
   const double sx = (double)(long long)q[2], sy = (double)(long long)q[3], sz = (double)(long long)q[4];
   const double mx = sx * in_, my = sy * in_, mz = sz * in_;
@@ -350,6 +352,7 @@ __device__ __forceinline__ void stats_from_acc(const unsigned long long* q, cons
 // (fitCells1 src/icet.cpp:158-232, testSigmaPoints :654-696); constants for the iteration loop.
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_fit1(const Chunk ck) {
+  pdl_prologue();
   const int pair = blockIdx.y;
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= ck.ncell) return;
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(128) k_fit1(const Chunk ck) {
     if (3 * nin >= ck.n && nin >= 2) {
       has = true;
       double mean[3], cov[6];
-      stats_from_acc(q, rc, mean, cov);
+      stats_from_acc(q, rc, ck.fs1, mean, cov);
       Vox1 v;
       for (int k = 0; k < 3; k++) v.mu[k] = mean[k];
       const double d1 = (double)(rc.cnt1 - 1);  // `indices1.size() - 1` (:315)

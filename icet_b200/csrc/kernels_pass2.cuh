@@ -29,13 +29,21 @@ constexpr uint32_t CLS_IN = 0x40000000u;      // the point passes filterPointsIn
 constexpr uint32_t CLS_ACTIVE = 0x80000000u;  // its cell takes part in the loop (F_ACTIVE2)
 constexpr uint32_t CLS_CELL = 0x000fffffu;
 constexpr uint32_t CLS_NONE = 0x000fffffu;    // "no class yet"
-constexpr float INC_MAX_SA = 1.0e-3f;         // delta iterations while sum |dR|_F  <= this
-constexpr float INC_MAX_SB = 0.05f;           //                  and   sum |dt|    <= this (metres) since the last rebuild
-constexpr float INC_SCALE2 = 0.25f;           // fixed-point scale of scan-2 moments relative to CellRec::scale: the
-                                              // members of a voxel may sit up to 8 box diameters from the anchor
+// Delta iterations while the motion since the last rebuild stays below these bounds.  A delta iteration costs ~15
+// instructions per point plus a full evaluation (~300, gathered) for the points whose margin is used up; a rebuild
+// ~260 per point.  On the synthetic 64-channel sequence a motion of 1-2 cm re-evaluates ~25 % of the points, ~10 cm
+// about 70 %: the break-even is near 15 cm at typical ranges (r * SA + SB), so the bounds sit just below it.
+// (Measured on the bench pairs: 3.5 -> 2.8 rebuilds per pair against the first setting 1e-3 / 5 cm.)
+constexpr float INC_MAX_SA = 4.0e-3f;         // sum |dR|_F   (x 30 m = 12 cm)
+constexpr float INC_MAX_SB = 0.12f;           // sum |dt|     (metres)
+// (The members of a voxel sit within one box diameter D of its anchor when they are evaluated and the anchor drifts by
+// at most r * INC_MAX_SA + INC_MAX_SB < D (D >= 0.2 r + 0.2 m) before the next rebuild re-anchors it: the +-2 D range of
+// the fixed-point frame (Chunk::fl2) is never left.)
 
 struct Pass2Mode {  // block-uniform copy of the pair's PairMode + accumulator set
   bool rebuild;
+  float fs2;
+  int fl2;
   float SA, SB, C;
   float trb[12];
   unsigned long long* accp;
@@ -178,30 +186,30 @@ __device__ __forceinline__ void point_eval2_fast(const Chunk& ck, const float4* 
 
 // anchor of a voxel's scan-2 fixed-point frame: the centre of its box, taken back through the transform of the last
 // rebuild (p = q R^T - t), and the scale
-__device__ __forceinline__ void vox_anchor2(const CellRec* recs, int cell, const float* trb, float& ax, float& ay, float& az,
-                                            float& sc) {
+__device__ __forceinline__ void vox_anchor2(const CellRec* recs, int cell, const float* trb, float fs2, float& ax, float& ay,
+                                            float& az, float& sc) {
   const float4* rp = reinterpret_cast<const float4*>(recs + cell);
   const float4 ra = __ldg(rp), rb = __ldg(rp + 1);
   const float* R = trb + 3;
-  sc = ra.w * INC_SCALE2;
+  sc = ra.w * fs2;
   ax = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(rb.x, R[0]), __fmul_rn(rb.y, R[1])), __fmul_rn(rb.z, R[2])), -trb[0]);
   ay = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(rb.x, R[3]), __fmul_rn(rb.y, R[4])), __fmul_rn(rb.z, R[5])), -trb[1]);
   az = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(rb.x, R[6]), __fmul_rn(rb.y, R[7])), __fmul_rn(rb.z, R[8])), -trb[2]);
 }
-__device__ __forceinline__ void fix2(float px, float py, float pz, float ax, float ay, float az, float sc, int& fx, int& fy,
-                                     int& fz) {
-  fx = max(-FP_LIM, min(FP_LIM, __float2int_rn(__fmul_rn(__fadd_rn(px, -ax), sc))));
-  fy = max(-FP_LIM, min(FP_LIM, __float2int_rn(__fmul_rn(__fadd_rn(py, -ay), sc))));
-  fz = max(-FP_LIM, min(FP_LIM, __float2int_rn(__fmul_rn(__fadd_rn(pz, -az), sc))));
+__device__ __forceinline__ void fix2(float px, float py, float pz, float ax, float ay, float az, float sc, int lim, int& fx,
+                                     int& fy, int& fz) {
+  fx = max(-lim, min(lim, __float2int_rn(__fmul_rn(__fadd_rn(px, -ax), sc))));
+  fy = max(-lim, min(lim, __float2int_rn(__fmul_rn(__fadd_rn(py, -ay), sc))));
+  fz = max(-lim, min(lim, __float2int_rn(__fmul_rn(__fadd_rn(pz, -az), sc))));
 }
 
 // adds (w = +n) or removes (w = -n) n copies of an inside point to / from the moments of its voxel
-__device__ __forceinline__ void moments_add(unsigned long long* accp, const CellRec* recs, int cell, const float* trb,
+__device__ __forceinline__ void moments_add(unsigned long long* accp, const CellRec* recs, int cell, const Pass2Mode& md,
                                             float px, float py, float pz, long long w) {
   float ax, ay, az, sc;
-  vox_anchor2(recs, cell, trb, ax, ay, az, sc);
+  vox_anchor2(recs, cell, md.trb, md.fs2, ax, ay, az, sc);
   int ix, iy, iz;
-  fix2(px, py, pz, ax, ay, az, sc, ix, iy, iz);
+  fix2(px, py, pz, ax, ay, az, sc, md.fl2, ix, iy, iz);
   const long long fx = ix, fy = iy, fz = iz;
   unsigned long long* q = accp + (size_t)cell * NQ;
   red_add(q + 1, (unsigned long long)w);
@@ -217,7 +225,7 @@ __device__ __forceinline__ void moments_add(unsigned long long* accp, const Cell
 }
 
 // moves `w` copies of a point from class `oc` to class `nc` (either may be CLS_NONE / inactive)
-__device__ __forceinline__ void class_move(unsigned long long* accp, const CellRec* recs, const float* trb, uint32_t oc,
+__device__ __forceinline__ void class_move(unsigned long long* accp, const CellRec* recs, const Pass2Mode& md, uint32_t oc,
                                            uint32_t nc, float px, float py, float pz, long long w) {
   if (oc == nc) return;
   const int ocell = (int)(oc & CLS_CELL), ncell_ = (int)(nc & CLS_CELL);
@@ -226,8 +234,8 @@ __device__ __forceinline__ void class_move(unsigned long long* accp, const CellR
     if (oact) red_add(accp + (size_t)ocell * NQ, (unsigned long long)(-w));
     if (nact) red_add(accp + (size_t)ncell_ * NQ, (unsigned long long)w);
   }
-  if (oc & CLS_IN) moments_add(accp, recs, ocell, trb, px, py, pz, -w);
-  if (nc & CLS_IN) moments_add(accp, recs, ncell_, trb, px, py, pz, w);
+  if (oc & CLS_IN) moments_add(accp, recs, ocell, md, px, py, pz, -w);
+  if (nc & CLS_IN) moments_add(accp, recs, ncell_, md, px, py, pz, w);
 }
 
 // The dropped returns of scan 2 (points2_OG == (0,0,0) for all nz of them): one point with weight nz,
@@ -239,7 +247,7 @@ __device__ inline void pass2_dropped_returns(const Chunk& ck, const float4* tth,
   float2 mg;
   point_eval2(ck, tth, tph, recs, tr, 0.f, 0.f, 0.f, 0.f, 0.f, cls, mg);
   const uint32_t old = md.rebuild ? CLS_NONE : (uint32_t)__ldcg(&ck.pm[pair].zcls);
-  class_move(md.accp, recs, md.trb, old, cls, 0.f, 0.f, 0.f, nz);
+  class_move(md.accp, recs, md, old, cls, 0.f, 0.f, 0.f, nz);
   ck.pm[pair].zcls = (int)cls;
 }
 
@@ -313,10 +321,10 @@ __device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, con
         cur = v.x;
         nin = sx = sy = sz = 0;
         pxx = pxy = pxz = pyy = pyz = pzz = 0;
-        vox_anchor2(recs, cur, md.trb, ax, ay, az, sc);
+        vox_anchor2(recs, cur, md.trb, md.fs2, ax, ay, az, sc);
       }
       int fx, fy, fz;
-      fix2(__int_as_float(v.y), __int_as_float(v.z), __int_as_float(v.w), ax, ay, az, sc, fx, fy, fz);
+      fix2(__int_as_float(v.y), __int_as_float(v.z), __int_as_float(v.w), ax, ay, az, sc, md.fl2, fx, fy, fz);
       nin++;
       sx += fx; sy += fy; sz += fz;
       pxx += (long long)fx * fx; pxy += (long long)fx * fy; pxz += (long long)fx * fz;
@@ -373,7 +381,7 @@ __device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, con
       if (cls != old) {
         if (was_stable) atomicAdd(violations, 1);
         cls2[i] = cls;
-        class_move(accp, recs, md.trb, old, cls, x, y, z, 1);
+        class_move(accp, recs, md, old, cls, x, y, z, 1);
       }
     }
   }
@@ -384,6 +392,8 @@ __device__ __forceinline__ void load_pass2_mode(const Chunk& ck, int pair, Pass2
   const PairMode* pm = ck.pm + pair;
   const int4 h = __ldcg(reinterpret_cast<const int4*>(pm));             // set, rebuild, SA, C
   md.rebuild = h.y != 0;
+  md.fs2 = ck.fs2;
+  md.fl2 = ck.fl2;
   md.SA = __int_as_float(h.z);
   md.C = __int_as_float(h.w);
   md.SB = __ldcg(&pm->SB);

@@ -44,6 +44,7 @@ constexpr int32_t CELL_INBOX = 0x40000000;  // cellid1 flag: the point passes th
 __device__ __forceinline__ int bin_box(float a, const float4* rec, const icet::BinTable& bt, bool& inbox);
 
 __global__ void __launch_bounds__(256) k_scan1_bin(const Chunk ck) {
+  pdl_prologue();
   const int pair = blockIdx.y;
   const PairDesc d = ck.desc[pair];
   if ((int)(blockIdx.x * blockDim.x) >= d.n1) return;
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(256) k_scan1_bin(const Chunk ck) {
 // cnt1 >= n (src/icet.cpp:115), default cell records (the else-branch :243-251: inner = outer = 0).
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_cell_scan(const Chunk ck) {
+  pdl_prologue();
   const int pair = blockIdx.x;
   __shared__ int s_ws[8], s_ww[8];
   const int per = (ck.ncell + 255) / 256;
@@ -185,6 +187,7 @@ __global__ void __launch_bounds__(256) k_cell_scan(const Chunk ck) {
 
 // K2b: group the non-zero ranges by cell
 __global__ void __launch_bounds__(256) k_scatter(const Chunk ck) {
+  pdl_prologue();
   const int pair = blockIdx.y;
   const PairDesc d = ck.desc[pair];
   if ((int)(blockIdx.x * blockDim.x) >= d.n1) return;
@@ -366,6 +369,7 @@ struct PaddedRow {  // view of a shared-memory row written by warp_sort_cell
 // K2c: ONE WARP per cell with cnt1 >= n (a cell of a 64-ring scan holds ~260 ranges): register bitonic sort, then
 // ICET::findCluster on the sorted row.  Cells with more than WSORT_MAX ranges take the CTA path at the end of the kernel.
 __global__ void __launch_bounds__(CLUSTER_WARPS * 32) k_cluster(const Chunk ck) {
+  pdl_prologue();
   const int pair = blockIdx.y;
   constexpr int ROW = WSORT_MAX + WSORT_MAX / 32;
   constexpr int SM_FLOATS = CLUSTER_WARPS * ROW > SORT_SMEM ? CLUSTER_WARPS * ROW : SORT_SMEM;

@@ -29,6 +29,14 @@ struct icet_b200_multi {
       return fail(ICET_B200_E_CUDA, std::string(#call) + ": " + (m->GetErrorString ? m->GetErrorString(r_) : "NCCL error")); \
   } while (0)
 
+int icet_b200_multi_gathered_host_impl(icet_b200_multi* m, int32_t d, float* out) {
+  if (!m || d < 0 || d >= m->ndev || !out) return fail(ICET_B200_E_INVALID, "bad argument");
+  if (m->shard_rows == 0) return 0;
+  CK(cudaSetDevice(m->dev[d]));
+  CK(cudaMemcpy(out, m->recvbuf[d].p, (size_t)m->ndev * m->shard_rows * 48 * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 template <class F>
 static int multi_fan_out(icet_b200_multi* m, F&& per_device) {
   std::vector<int> rc(m->ndev, 0);
@@ -166,6 +174,10 @@ int icet_b200_multi_gathered(icet_b200_multi* m, int32_t d, const float** rows, 
   *rows = (const float*)m->recvbuf[d].p;
   *rows_per_shard = m->shard_rows;
   return 0;
+}
+
+int icet_b200_multi_gathered_host(icet_b200_multi* m, int32_t d, float* out) {
+  return icet_b200_multi_gathered_host_impl(m, d, out);
 }
 
 int icet_b200_register_batch_multi(icet_b200_multi* m, const icet_b200_params* p, int32_t npairs, const float* const* scan1,

@@ -107,6 +107,14 @@ struct Carve {
 };
 
 // Layout of the chunk workspace.  The first region (cnt1, cntz, cursor, acc) must be zero at chunk start.
+// Fixed-point bits of the per-voxel accumulators for a cloud of up to nmax points: offsets up to 2^bits, products up to
+// 2^(2 bits), 64-bit sums over at most nmax points: 2 bits + ceil(log2 nmax) <= 62.
+inline int fp_bits(int nmax) {
+  int lg = 1;
+  while ((1ll << lg) < (long long)std::max(nmax, 2)) lg++;
+  return std::max(12, std::min(23, (62 - lg) / 2));
+}
+
 inline bool huge_path(int n1max, bool shipped) { return !shipped && n1max > 8 * HUGE_MIN; }
 
 size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runlen, Chunk& ck, size_t* zero_bytes,
@@ -297,6 +305,8 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   ck.npairs = P; ck.ncell = ncell; ck.nT = nT; ck.nP = nP; ck.n = p->n; ck.runlen = p->runlen;
   ck.flags = p->flags; ck.thresh = p->thresh; ck.buff = p->buff;
   ck.n1max = n1max; ck.n2max = n2max;
+  ck.fl1 = 1 << fp_bits(n1max); ck.fs1 = ldexpf(1.0f, fp_bits(n1max) - FPB);
+  ck.fl2 = 1 << fp_bits(n2max); ck.fs2 = ldexpf(1.0f, fp_bits(n2max) - FPB);
   fill_tables(ctx, nT, nP, &ck.azE, &ck.elE, &ck.bth, &ck.bph, &ck.binrec);
   ck.x0 = d_x0;
   ck.res = d_res;
@@ -304,6 +314,7 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   ck.dump_on = dump ? 1 : 0;
   if (dump) ck.dump = ctx->dump_ptrs;
   cudaStream_t st = lane == 0 ? ctx->stream : ctx->lanes[lane];
+  ctx->loop_dbg[lane] = nullptr;  // the lane's workspace is re-carved: a watchdog record of an earlier chunk is gone
   CK(cudaMemsetAsync(ctx->ws[lane].p, 0, zero_bytes, st));
   // (k_prep2 strides over its pair: one block per 256 points for small chunks, at least 32 blocks per pair always)
   const dim3 g1((n1max + 255) / 256, P), g2(std::max(1, std::min((n2max + 255) / 256, std::max(32, 8192 / P))), P);
@@ -349,6 +360,21 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
     if (e1_) cudaEventRecord(e1_, st);                                    \
     ctx->launches++;                                                      \
   } while (0)
+  // Latency shape: kernel -> kernel edges of the set-up sequence are programmatic dependent launches (pdl_prologue)
+  const bool pdl = small_batch && !shipped && !ctx->profile_on;
+  auto launch_ex = [&](auto kernel, dim3 grid, dim3 block, size_t smem, bool dependent, auto... args) -> cudaError_t {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl && dependent) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+  };
   // Latency shape (one pair): prepScan2 does not depend on the scan-1 kernels, so it runs beside them on lane 1.
   const bool prep_aside = P == 1 && n2max > 0 && lane == 0 && !ctx->profile_on && ctx->lanes[1] != nullptr;
   if (prep_aside) {
@@ -358,8 +384,8 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
     ctx->launches++;
     CK(cudaEventRecord(ctx->ev_aux[1], ctx->lanes[1]));
   }
-  if (n1max > 0) LAUNCH(0, k_scan1_bin<<<g1, 256, 0, st>>>(ck));
-  LAUNCH(1, k_cell_scan<<<P, 256, 0, st>>>(ck));
+  if (n1max > 0) LAUNCH(0, CK(launch_ex(k_scan1_bin, g1, dim3(256), 0, false, ck)));  // (follows a memset: plain launch)
+  LAUNCH(1, CK(launch_ex(k_cell_scan, dim3(P), dim3(256), 0, n1max > 0, ck)));
   if (n1max > 0) {
     if (shipped) {
       // The row order the reference ends up with (src/icet.cpp:72-83), reproduced on the host from the ranges the
@@ -406,7 +432,7 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
       LAUNCH(2, k_scatter_shipped<<<g1, 256, 0, st>>>(ck));
       LAUNCH(3, k_cluster_shipped<<<dim3(std::max(1, std::min(ncell, 1024)), P), 128, 0, st>>>(ck));
     } else {
-    LAUNCH(2, k_scatter<<<g1, 256, 0, st>>>(ck));
+    LAUNCH(2, CK(launch_ex(k_scatter, g1, dim3(256), 0, true, ck)));
     if (ck.hbkt) {  // accumulated maps: cells with tens of thousands of ranges are clustered by many CTAs each
       LAUNCH(3, k_huge_init<<<dim3(HUGE_SPLIT, HUGE_SLOTS), 256, 0, st>>>(ck));
       LAUNCH(3, k_huge_hist<<<dim3(HUGE_SPLIT, HUGE_SLOTS), 256, 0, st>>>(ck));
@@ -415,16 +441,17 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
     // one warp per listed cell; enough CTAs to cover a typical work list (~25 % of the cells) in one pass
     int gx = std::max(1, std::min((ncell + CLUSTER_WARPS - 1) / CLUSTER_WARPS,
                                   std::max(32, (ctx->sm_count * 16 + P - 1) / P)));
-    LAUNCH(3, k_cluster<<<dim3(gx, P), CLUSTER_WARPS * 32, 0, st>>>(ck));
+    LAUNCH(3, CK(launch_ex(k_cluster, dim3(gx, P), dim3(CLUSTER_WARPS * 32), 0, !ck.hbkt, ck)));
     }
     if (small_batch) {  // latency shape: 128 points per warp
       const int tile_s = pass_tile_points(PASS_K_SMALL);
-      LAUNCH(4, k_pass<false, PASS_K_SMALL, 3, 1, PASS_K_SMALL><<<dim3((n1max + tile_s - 1) / tile_s, P), PASS_THREADS, psm2, st>>>(ck));
+      LAUNCH(4, CK(launch_ex(k_pass<false, PASS_K_SMALL, 3, 1, PASS_K_SMALL>, dim3((n1max + tile_s - 1) / tile_s, P),
+                             dim3(PASS_THREADS), psm2, true, ck)));
     } else {
       LAUNCH(4, k_pass<false><<<gp1, PASS_THREADS, psm, st>>>(ck));
     }
   }
-  LAUNCH(5, k_fit1<<<dim3((ncell + 127) / 128, P), 128, 0, st>>>(ck));
+  LAUNCH(5, CK(launch_ex(k_fit1, dim3((ncell + 127) / 128, P), dim3(128), 0, n1max > 0, ck)));
   if (prep_aside) CK(cudaStreamWaitEvent(st, ctx->ev_aux[1], 0));
   else if (n2max > 0) LAUNCH(6, k_prep2<<<g2, 256, 0, st>>>(ck));
   const bool use_loop = chain || (p->flags & ICET_B200_FLAG_PERSISTENT_LOOP) ||
@@ -469,11 +496,13 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
     cfg.blockDim = dim3(CL_THREADS);
     cfg.dynamicSmemBytes = cluster_smem_bytes(nT, nP);
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = (pdl && !prep_aside) ? 2 : 1;  // (after an event wait the edge is an ordinary one)
     LAUNCH(10, CK(cudaLaunchKernelEx(&cfg, k_loop_cluster, ck)));
   } else if (!use_loop) {
     for (int it = 0; it < p->runlen; it++) {

@@ -357,6 +357,8 @@ int icet_b200_register_sequence_multi_device(icet_b200_multi* multi, const icet_
 /* The all-gathered results on device slot d: DEVICE pointer to [ndev][rows_per_shard][48] floats (shard s holds the pairs
  * of device s in order; shards shorter than rows_per_shard are zero padded). */
 int icet_b200_multi_gathered(icet_b200_multi* multi, int32_t d, const float** rows, int32_t* rows_per_shard);
+/* The same rows copied to HOST memory (`out`: ndev * rows_per_shard * 48 floats), blocking. */
+int icet_b200_multi_gathered_host(icet_b200_multi* multi, int32_t d, float* out);
 
 /* -- synthetic 64-channel scans (bench / test utility) --------------------------- */
 /* Writes nscans consecutive scans (index first_scan ...) of rings x azim points each to DEVICE memory

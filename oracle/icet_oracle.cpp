@@ -451,6 +451,8 @@ struct Icet {
   // ICET::fitScan2, src/icet.cpp:372-436 and ICET::checkCondition :443-492
   void fit_scan2(int it) {
     const int n2 = (int)ogx.size();
+    if (out->X_in)  // test harness: start this iteration from the given iterate (see icet_oracle.h)
+      for (int k = 0; k < 6; k++) X[k] = out->X_in[(size_t)it * 6 + k];
     float R[9];
     rotR(X[3], X[4], X[5], R);
     std::vector<float> px(n2), py(n2), pz(n2);

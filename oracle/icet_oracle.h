@@ -107,6 +107,11 @@ typedef struct {
    * oracle uses evec1_in[cell*9..] (row-major V) instead of its own eigenvectors; eigenvalues stay.  */
   const float* evec1_in;
   const uint8_t* evec1_in_mask;
+  /* INPUT (optional, test harness only): iterate alignment.  When given, iteration `it` STARTS from X_in[it*6 .. +6]
+   * instead of the oracle's own X (its update is still computed and reported in dx / Xit).  Lets a test compare
+   * per-iteration classes and statistics of another implementation at that implementation's own iterates: after a large
+   * first step two correct implementations differ by ~1e-5 m in X, which moves many more boundary points than libm. */
+  const float* X_in;
 } oracle_out;
 
 /* Clouds are column-major N x 3 (x-plane | y-plane | z-plane) with leading

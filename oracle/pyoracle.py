@@ -65,7 +65,7 @@ STATS2_REFERENCE, STATS2_MOMENTS = 0, 1
 class _Out(C.Structure):
     _fields_ = ([("X", C.c_float * 6), ("pred_stds", C.c_float * 6), ("Q", C.c_float * 36),
                  ("status", C.c_int32)] + [(n, t) for n, t, _, _ in _DUMPS] +
-                [("evec1_in", _FP), ("evec1_in_mask", _BP)])
+                [("evec1_in", _FP), ("evec1_in_mask", _BP), ("X_in", _FP)])
 
 
 def _build(native: bool) -> str:
@@ -142,7 +142,7 @@ class OracleResult:
 
 def run(scan1, scan2, runlen=7, X0=None, bins_phi=24, bins_theta=75, n=25, thresh=0.1, buff=0.1,
         order_mode=ORDER_SORTED, eigen_flavor=EIGEN_337, precise=False, dumps="small",
-        native=False, evec_override=None, stats2_mode=STATS2_REFERENCE) -> OracleResult:
+        native=False, evec_override=None, stats2_mode=STATS2_REFERENCE, X_iterates=None) -> OracleResult:
     """Mirror of the reference constructor  ICET(scan1, scan2, runlen, X0, num_bins_phi,
     num_bins_theta, n, thresh, buff)  (include/icet.h:38-40).  dumps: None | "small" | "all"."""
     s1, s2 = as_planes(scan1), as_planes(scan2)
@@ -164,6 +164,10 @@ def run(scan1, scan2, runlen=7, X0=None, bins_phi=24, bins_theta=75, n=25, thres
         assert ev_in.size == 9 * dims["ncell"] and ev_mask.size == dims["ncell"]
         o.evec1_in = ev_in.ctypes.data_as(_FP)
         o.evec1_in_mask = ev_mask.ctypes.data_as(_BP)
+    if X_iterates is not None:  # [runlen, 6]: the X every iteration starts from (iterate alignment, see icet_oracle.h)
+        x_in = np.ascontiguousarray(X_iterates, np.float32)
+        assert x_in.shape == (runlen, 6)
+        o.X_in = x_in.ctypes.data_as(_FP)
     rc = lib(native).icet_oracle_run(C.byref(p), _fp(s1), n1, n1, _fp(s2), n2, n2, _fp(x0),
                                      C.byref(o))
     if rc != 0:
