@@ -19,13 +19,56 @@
 
 constexpr int CL_THREADS = 512;
 constexpr int CL_WARPS = CL_THREADS / 32;
-constexpr int CL_K = PASS_K_SMALL;  // rows per warp tile
+constexpr int CL_K = PASS_K_SMALL;  // rows per warp tile (128 points: ~4 tiles per warp of a 16-CTA cluster at 64 channels)
 
-__host__ __device__ inline int cluster_smem_bytes(int nT, int nP) {
-  return CL_WARPS * pass_wslots(CL_K) * 16 + pass_tab_floats(nT, nP) * 4 + (CL_WARPS + 1) * NRED * 8 + 32 * 4;
+__host__ __device__ inline int cluster_smem_bytes(int nT, int nP, int /*cs*/) {
+  return CL_WARPS * pass_wslots(CL_K) * 16 + pass_tab_floats(nT, nP) * 4 + (CL_WARPS + 1) * NRED * 8 + 64 * 4;
 }
 
-__global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck) {
+// phase 2 of an iteration (inlined: a non-inlined callee would read the Chunk through local memory instead of the
+// constant bank, which costs more than the spills it saves -- measured)
+__device__ __forceinline__ void cluster_vox_phase(const Chunk& ck, int pair, int iter, int rank, int cs, const float* s_J,
+                                               double* wpart, double* cpart) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; k++) acc[k] = 0.0;
+  // cell c -> CTA c % cs, thread c / cs: the occupied rows of the grid spread over all CTAs
+  for (int c = rank + cs * (int)threadIdx.x; c < ck.ncell; c += cs * CL_THREADS) vox_contrib(ck, pair, c, iter, s_J, acc);
+  const double tot = warp_sum_transposed(acc, lane);
+  if (lane < NRED) wpart[warp * NRED + lane] = tot;
+  __syncthreads();
+  if (threadIdx.x < NRED) {
+    double s = 0.0;
+    for (int w = 0; w < CL_WARPS; w++) s += wpart[w * NRED + threadIdx.x];
+    cpart[threadIdx.x] = s;
+  }
+}
+
+// phase 3 (warp 0 of CTA 0): the partial sums of all CTAs through distributed shared memory, then the 6x6 solve
+__device__ __noinline__ void cluster_solve_phase(const Chunk& ck, int pair, int iter, int cs, double* cpart, double* w_tot,
+                                                 const ModeNow* cur) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int lane = threadIdx.x & 31;
+  // every remote load is requested before the first addition (a rolled loop would pay the ~200-cycle DSMEM latency 16
+  // times in a row); the additions are in rank order
+  double pv[16];
+#pragma unroll
+  for (int r = 0; r < 16; r++) pv[r] = (lane < NRED && r < cs) ? cluster.map_shared_rank(cpart, r)[lane] : 0.0;
+  double tot = 0.0;
+#pragma unroll
+  for (int r = 0; r < 16; r++) tot += pv[r];
+  if (lane < NRED) w_tot[lane] = tot;  // (phase 2 is over: its scratch is reused)
+  __syncwarp();
+  bool done = false;
+  if (!(ck.flags & ICET_B200_FLAG_FULL_EIG)) done = solve_pair_warp(ck, pair, iter, w_tot, cur);
+  if (!done && lane == 0) solve_pair(ck, pair, iter, w_tot, cur);
+}
+
+// first_tiles_done: the tiles of iteration 0 of every pair have been processed by a GPU-wide k_pass2 launch already
+// (single pairs: the first rebuild then runs on 148 SMs instead of the cluster's 16)
+__global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck, int first_tiles_done) {
   pdl_prologue();
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
@@ -35,13 +78,13 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck) 
   double* wpart = reinterpret_cast<double*>(tab + pass_tab_floats(ck.nT, ck.nP));  // [CL_WARPS][NRED]
   double* cpart = wpart + CL_WARPS * NRED;                                         // [NRED]  this CTA's partial sums
   float* s_J = reinterpret_cast<float*>(cpart + NRED);                             // [27]
+  const unsigned cs = cluster.num_blocks(), rank = cluster.block_rank();
   {
     const int ntab = pass_tab_floats(ck.nT, ck.nP);
     for (int k = threadIdx.x; k < ntab; k += CL_THREADS) tab[k] = __ldg(ck.binrec + k);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned cs = cluster.num_blocks(), rank = cluster.block_rank();
   const int ncl = gridDim.x / cs, cl = blockIdx.x / cs;  // clusters of the launch, this cluster
   int4* went = ent + warp * pass_wslots(CL_K);
   const bool chain = (ck.flags & ICET_B200_FLAG_CHAIN_X0) != 0;
@@ -67,62 +110,43 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck) 
         tr[8] = c.x; tr[9] = c.y; tr[10] = c.z; tr[11] = c.w;
       }
       if (threadIdx.x < 27) s_J[threadIdx.x] = __ldcg(ck.J + (size_t)pair * 27 + threadIdx.x);
-      if (inc) {
-        Pass2Mode md;
-        load_pass2_mode(ck, pair, md);
-        for (int tile = gwarp; tile < tiles; tile += nwarp)
-          pass2_warp_tile<CL_K>(ck, went, tab, recs, tr, md, ck.pog + (size_t)pair * 3 * ck.n2max, (size_t)ck.n2max, n,
-                                tile * 32 * CL_K, ck.marg + (size_t)pair * ck.n2max, ck.cls2 + (size_t)pair * ck.n2max,
-                                (ck.flags & ICET_B200_FLAG_VERIFY_INCREMENTAL) ? &ck.res[pair].reserved[0] : nullptr);
-        if (gwarp == nwarp - 1 && lane == 0)  // (the last warp has the fewest tiles)
-          pass2_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 2,
-                                recs, tr, md, pair, __ldg(ck.nz2 + pair));
-      } else {
-        unsigned long long* accp = ck.acc + (size_t)pair * ck.ncell * NQ;
-        for (int tile = gwarp; tile < tiles; tile += nwarp)
-          pass_warp_tile<true, CL_K, 2, CL_K>(ck, went, tab, recs, tr, ck.pog + (size_t)pair * 3 * ck.n2max,
-                                              (size_t)ck.n2max, n, tile * 32 * CL_K, accp);
-        if (gwarp == nwarp - 1 && lane == 0)
-          pass_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 2,
-                               recs, tr, accp, __ldg(ck.nz2 + pair));
+      Pass2Mode md;
+      if (inc) load_pass2_mode(ck, pair, md);
+      const bool skip_tiles = first_tiles_done && iter == 0 && !(chain && pair > 0);
+      if (!skip_tiles) {
+        if (inc) {
+          for (int tile = gwarp; tile < tiles; tile += nwarp)
+            pass2_warp_tile<CL_K>(ck, went, tab, recs, tr, md, ck.pog + (size_t)pair * 3 * ck.n2max, (size_t)ck.n2max,
+                                        n, tile * 32 * CL_K, ck.marg + (size_t)pair * ck.n2max,
+                                        ck.cls2 + (size_t)pair * ck.n2max,
+                                        (ck.flags & ICET_B200_FLAG_VERIFY_INCREMENTAL) ? &ck.res[pair].reserved[0] : nullptr);
+          if (gwarp == nwarp - 1 && lane == 0)  // (the last warp has the fewest tiles)
+            pass2_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 2,
+                                  recs, tr, md, pair, __ldg(ck.nz2 + pair));
+        } else {
+          unsigned long long* accp = ck.acc + (size_t)pair * ck.ncell * NQ;
+          for (int tile = gwarp; tile < tiles; tile += nwarp)
+            pass_warp_tile<true, CL_K, 2, 4>(ck, went, tab, recs, tr, ck.pog + (size_t)pair * 3 * ck.n2max,
+                                             (size_t)ck.n2max, n, tile * 32 * CL_K, accp);
+          if (gwarp == nwarp - 1 && lane == 0)
+            pass_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 2,
+                                 recs, tr, accp, __ldg(ck.nz2 + pair));
+        }
       }
       CTL(1);
-      __threadfence();
+      // (barrier.cluster has release / acquire semantics at cluster scope: the moments -- RED to L2 -- and the records
+      // written above are visible to every thread of the cluster after it; no GPU-wide fence is needed)
       cluster.sync();
       CTL(2);
       // ------------------------------------------------------------------ phase 2: one thread per voxel
-      {
-        double acc[NRED];
-#pragma unroll
-        for (int k = 0; k < NRED; k++) acc[k] = 0.0;
-        // cell c -> CTA c % cs, thread c / cs: the occupied rows of the grid spread over all CTAs
-        for (int c = (int)rank + (int)cs * threadIdx.x; c < ck.ncell; c += (int)cs * CL_THREADS)
-          vox_contrib(ck, pair, c, iter, s_J, acc);
-        const double tot = warp_sum_transposed(acc, lane);
-        if (lane < NRED) wpart[warp * NRED + lane] = tot;
-        __syncthreads();
-        if (threadIdx.x < NRED) {
-          double s = 0.0;
-          for (int w = 0; w < CL_WARPS; w++) s += wpart[w * NRED + threadIdx.x];
-          cpart[threadIdx.x] = s;
-        }
-      }
+      cluster_vox_phase(ck, pair, iter, (int)rank, (int)cs, s_J, wpart, cpart);
       CTL(3);
-      __threadfence();
       cluster.sync();
       CTL(4);
       // ------------------------------------------------------------------ phase 3: DSMEM reduction + solve
       if (rank == 0 && warp == 0) {
-        double tot = 0.0;
-        if (lane < NRED)
-          for (unsigned r = 0; r < cs; r++) tot += cluster.map_shared_rank(cpart, r)[lane];
-        double* w_tot = wpart;  // (phase 2 is over: reuse)
-        if (lane < NRED) w_tot[lane] = tot;
-        __syncwarp();
-        bool done = false;
-        if (!(ck.flags & ICET_B200_FLAG_FULL_EIG)) done = solve_pair_warp(ck, pair, iter, w_tot);
-        if (!done && lane == 0) solve_pair(ck, pair, iter, w_tot);
-        __threadfence();
+        ModeNow now = {md.SA, md.SB, md.set};
+        cluster_solve_phase(ck, pair, iter, (int)cs, cpart, wpart, inc ? &now : nullptr);
       }
       CTL(5);
       cluster.sync();

@@ -71,7 +71,8 @@ __device__ __forceinline__ bool vox_gate(const Chunk& ck, int pair, int cell, in
 }
 
 __device__ __forceinline__ void vox_algebra_core(const Chunk& ck, int pair, int cell, int iter, const float* Jm,
-                                                 long long nbin, const double mean[3], const double cov[6], double acc[NRED]);
+                                                 long long nbin, const double mean[3], const double cov[6], double acc[NRED],
+                                                 const Vox1* vp = nullptr);
 
 // The algebra of one contributing voxel; takes (and clears) its accumulators.
 __device__ __forceinline__ void vox_algebra(const Chunk& ck, int pair, int cell, int iter, const float* Jm /* 27 */,
@@ -96,9 +97,9 @@ __device__ __forceinline__ void vox_algebra(const Chunk& ck, int pair, int cell,
 // from the scan-2 mean / covariance of a voxel to its contributions H^T W H_j, H^T W dz_j (src/icet.cpp:308-338)
 __device__ __forceinline__ void vox_algebra_core(const Chunk& ck, int pair, int cell, int iter, const float* Jm,
                                                  long long nbin, const double mean[3], const double cov[6],
-                                                 double acc[NRED]) {
+                                                 double acc[NRED], const Vox1* vp) {
   const size_t ci = (size_t)pair * ck.ncell + cell;
-  const Vox1 v = ck.vox[ci];
+  const Vox1 v = vp ? *vp : ck.vox[ci];  // (vp: the cluster loop keeps the records of its voxels in shared memory)
   if (ck.dump_on) {
     float* m2 = ck.dump.mu2 + ((size_t)iter * ck.ncell + cell) * 3;
     float* s2 = ck.dump.sigma2 + ((size_t)iter * ck.ncell + cell) * 9;
@@ -226,10 +227,17 @@ __device__ __forceinline__ bool vox_gate2(const Chunk& ck, int pair, int cell, i
 
 // mean / covariance of the voxel's scan-2 members at the current transform, from the moments of the untransformed
 // points:  mu2 = (mean_OG + t) R,  Sigma2 = R^T Cov_OG R   (what src/icet.cpp:375-378 + :303-306 compute point by point)
+__device__ __forceinline__ void stats2_from_moments_rec(const unsigned long long* q, float4 ra, float4 rb, const VoxMode& vm,
+                                                        double mean[3], double cov[6]);
 __device__ __forceinline__ void stats2_from_moments(const unsigned long long* q, const CellRec* recs, int cell,
                                                     const VoxMode& vm, double mean[3], double cov[6]) {
+  const float4* rp = reinterpret_cast<const float4*>(recs + cell);
+  stats2_from_moments_rec(q, __ldg(rp), __ldg(rp + 1), vm, mean, cov);
+}
+__device__ __forceinline__ void stats2_from_moments_rec(const unsigned long long* q, float4 ra, float4 rb, const VoxMode& vm,
+                                                        double mean[3], double cov[6]) {
   float ax, ay, az, sc;
-  vox_anchor2(recs, cell, vm.trb, vm.fs2, ax, ay, az, sc);
+  vox_anchor2_rec(ra, rb, vm.trb, vm.fs2, ax, ay, az, sc);
   const double nin = (double)(long long)q[1];
   const double inv = 1.0 / (double)sc;  // exact: the scale is a power of two
   const double in_ = 1.0 / nin;
@@ -313,12 +321,17 @@ __device__ __forceinline__ void chain_seed_next(const Chunk& ck, int pair, const
 
 // Incremental loop: after the solve of an iteration, decide how the next one runs (see kernels_pass2.cuh).  tro / trn:
 // the transform this iteration used / the next one will use.
-__device__ __forceinline__ void mode_after_solve(const Chunk& ck, int pair, const float* tro, const float* trn) {
+// cur (optional): {SA, SB, set} of the iteration that has just run, when the caller already holds them in registers (the
+// cluster loop) -- saves three dependent L2 round trips on the critical path.
+struct ModeNow { float SA, SB; int set; };
+__device__ __forceinline__ void mode_after_solve(const Chunk& ck, int pair, const float* tro, const float* trn,
+                                                 const ModeNow* cur = nullptr) {
   PairMode* pm = ck.pm + pair;
   float a2 = 0.f, b2 = 0.f;
   for (int k = 0; k < 3; k++) b2 += (trn[k] - tro[k]) * (trn[k] - tro[k]);
   for (int k = 3; k < 12; k++) a2 += (trn[k] - tro[k]) * (trn[k] - tro[k]);
-  const float SA = __ldcg(&pm->SA) + 1.001f * sqrtf(a2), SB = __ldcg(&pm->SB) + 1.001f * sqrtf(b2);
+  const float SA = (cur ? cur->SA : __ldcg(&pm->SA)) + 1.001f * sqrtf(a2);
+  const float SB = (cur ? cur->SB : __ldcg(&pm->SB)) + 1.001f * sqrtf(b2);
   const bool delta = !(ck.flags & ICET_B200_FLAG_FULL_REBUILD) && SA <= INC_MAX_SA && SB <= INC_MAX_SB;  // false for NaN
   if (delta) {
     pm->rebuild = 0;
@@ -326,7 +339,7 @@ __device__ __forceinline__ void mode_after_solve(const Chunk& ck, int pair, cons
     pm->SB = SB;
     pm->C = (SB + SA * SB) * 1.0001f;
   } else {
-    pm->set = __ldcg(&pm->set) ^ 1;
+    pm->set = (cur ? cur->set : __ldcg(&pm->set)) ^ 1;
     pm->rebuild = 1;
     pm->SA = 0.f;
     pm->SB = 0.f;
@@ -335,7 +348,7 @@ __device__ __forceinline__ void mode_after_solve(const Chunk& ck, int pair, cons
   }
 }
 
-__device__ __noinline__ void solve_pair(const Chunk& ck, int pair, int iter, const double* tot) {
+__device__ __noinline__ void solve_pair(const Chunk& ck, int pair, int iter, const double* tot, const ModeNow* cur = nullptr) {
   float* X = ck.X + pair * 6;
   double A[36], b[6];
   {
@@ -432,7 +445,7 @@ __device__ __noinline__ void solve_pair(const Chunk& ck, int pair, int iter, con
     TR[0] = Xn[0]; TR[1] = Xn[1]; TR[2] = Xn[2];
     icet::rotR(Xn[3], Xn[4], Xn[5], TR + 3);
     icet::getH_J(Xn[3], Xn[4], Xn[5], ck.J + (size_t)pair * 27);
-    if (loop_incremental(ck) && iter < ck.runlen - 1) mode_after_solve(ck, pair, tro, TR);
+    if (loop_incremental(ck) && iter < ck.runlen - 1) mode_after_solve(ck, pair, tro, TR, cur);
     if (iter == ck.runlen - 1) chain_seed_next(ck, pair, Xn);
   }
   if (ck.dump_on) {
@@ -453,7 +466,8 @@ __device__ __noinline__ void solve_pair(const Chunk& ck, int pair, int iter, con
 // per lane, no pivoting: A = H^T W H is symmetric positive definite whenever this path is valid).  Returns (warp
 // uniform) false when a pivot is not positive or the bound trace(A) trace(A^-1) cannot prove cond <= 1e6; the caller
 // then runs solve_pair (eigen-decomposition + the reference's truncation loop) on one thread.
-__device__ __forceinline__ bool solve_pair_warp(const Chunk& ck, int pair, int iter, const double* tot) {
+__device__ __forceinline__ bool solve_pair_warp(const Chunk& ck, int pair, int iter, const double* tot,
+                                                const ModeNow* cur = nullptr) {
   const int lane = threadIdx.x & 31;
   // requested now, used after the elimination: the current X and (last iteration) the transform it started from
   const float x_old = lane < 6 ? __ldcg(ck.X + pair * 6 + lane) : 0.f;
@@ -540,7 +554,7 @@ __device__ __forceinline__ bool solve_pair_warp(const Chunk& ck, int pair, int i
     float tro[12], trn[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) { tro[k] = __shfl_sync(FULL, tr_old, k); trn[k] = __shfl_sync(FULL, trv, k); }
-    if (lane == 0) mode_after_solve(ck, pair, tro, trn);
+    if (lane == 0) mode_after_solve(ck, pair, tro, trn, cur);
   }
   if (lane < 27) {
     ck.J[(size_t)pair * 27 + lane] = jv;

@@ -29,19 +29,21 @@ constexpr uint32_t CLS_IN = 0x40000000u;      // the point passes filterPointsIn
 constexpr uint32_t CLS_ACTIVE = 0x80000000u;  // its cell takes part in the loop (F_ACTIVE2)
 constexpr uint32_t CLS_CELL = 0x000fffffu;
 constexpr uint32_t CLS_NONE = 0x000fffffu;    // "no class yet"
-// Delta iterations while the motion since the last rebuild stays below these bounds.  A delta iteration costs ~15
-// instructions per point plus a full evaluation (~300, gathered) for the points whose margin is used up; a rebuild
-// ~260 per point.  On the synthetic 64-channel sequence a motion of 1-2 cm re-evaluates ~25 % of the points, ~10 cm
-// about 70 %: the break-even is near 15 cm at typical ranges (r * SA + SB), so the bounds sit just below it.
-// (Measured on the bench pairs: 3.5 -> 2.8 rebuilds per pair against the first setting 1e-3 / 5 cm.)
-constexpr float INC_MAX_SA = 4.0e-3f;         // sum |dR|_F   (x 30 m = 12 cm)
-constexpr float INC_MAX_SB = 0.12f;           // sum |dt|     (metres)
+// Delta iterations while the motion since the last rebuild stays below these bounds.  A delta iteration costs ~20
+// instructions and 8 bytes per point plus a full evaluation for the points whose margin is used up -- but those are
+// GATHERED (three 32-byte sectors for 12 useful bytes, scattered margin / class stores), so a delta iteration with more
+// than ~30 % of the points to re-evaluate takes as long as a rebuild although it executes a third fewer instructions.
+// Measured on the bench pairs (256-pair launches, 7 iterations): bounds 1e-3 / 5 cm: 3.5 rebuilds per pair, 162
+// instructions per point and iteration, 1.86 ms per chunk; 4e-3 / 12 cm: 2.8 rebuilds, 152 instructions, 1.92 ms.
+constexpr float INC_MAX_SA = 1.0e-3f;         // sum |dR|_F   (x 30 m = 3 cm)
+constexpr float INC_MAX_SB = 0.05f;           // sum |dt|     (metres)
 // (The members of a voxel sit within one box diameter D of its anchor when they are evaluated and the anchor drifts by
 // at most r * INC_MAX_SA + INC_MAX_SB < D (D >= 0.2 r + 0.2 m) before the next rebuild re-anchors it: the +-2 D range of
 // the fixed-point frame (Chunk::fl2) is never left.)
 
 struct Pass2Mode {  // block-uniform copy of the pair's PairMode + accumulator set
   bool rebuild;
+  int set;
   float fs2;
   int fl2;
   float SA, SB, C;
@@ -186,10 +188,15 @@ __device__ __forceinline__ void point_eval2_fast(const Chunk& ck, const float4* 
 
 // anchor of a voxel's scan-2 fixed-point frame: the centre of its box, taken back through the transform of the last
 // rebuild (p = q R^T - t), and the scale
+__device__ __forceinline__ void vox_anchor2_rec(float4 ra /* inner outer flags scale */, float4 rb /* ref xyz, cnt1 */,
+                                                const float* trb, float fs2, float& ax, float& ay, float& az, float& sc);
 __device__ __forceinline__ void vox_anchor2(const CellRec* recs, int cell, const float* trb, float fs2, float& ax, float& ay,
                                             float& az, float& sc) {
   const float4* rp = reinterpret_cast<const float4*>(recs + cell);
-  const float4 ra = __ldg(rp), rb = __ldg(rp + 1);
+  vox_anchor2_rec(__ldg(rp), __ldg(rp + 1), trb, fs2, ax, ay, az, sc);
+}
+__device__ __forceinline__ void vox_anchor2_rec(float4 ra, float4 rb, const float* trb, float fs2, float& ax, float& ay,
+                                                float& az, float& sc) {
   const float* R = trb + 3;
   sc = ra.w * fs2;
   ax = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(rb.x, R[0]), __fmul_rn(rb.y, R[1])), __fmul_rn(rb.z, R[2])), -trb[0]);
@@ -252,7 +259,7 @@ __device__ inline void pass2_dropped_returns(const Chunk& ck, const float4* tth,
 }
 
 // One warp tile of 32*K consecutive stored points of scan 2.  `went`: the warp's pass_wslots(K) 16-byte slots.
-template <int K>
+template <int K, int RD = ((K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1))>
 __device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, const float* tab, const CellRec* recs,
                                                 const float* tr, const Pass2Mode& md, const float* pog, size_t ld, int n,
                                                 int w0, float2* marg, uint32_t* cls2, int* violations) {
@@ -338,7 +345,8 @@ __device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, con
   // groups of 4)
   int* list = reinterpret_cast<int*>(went);  // indices of the points to re-evaluate (<= 32*K)
   int nre = 0;
-  constexpr int R = (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1);
+  constexpr int R = RD;  // rows whose margin records are requested together (latency shape: all of them)
+  static_assert(K % RD == 0, "rows per load group must divide the tile");
 #pragma unroll 1
   for (int j0 = 0; j0 < K; j0 += R) {
     float2 mg[R];
@@ -392,6 +400,7 @@ __device__ __forceinline__ void load_pass2_mode(const Chunk& ck, int pair, Pass2
   const PairMode* pm = ck.pm + pair;
   const int4 h = __ldcg(reinterpret_cast<const int4*>(pm));             // set, rebuild, SA, C
   md.rebuild = h.y != 0;
+  md.set = h.x;
   md.fs2 = ck.fs2;
   md.fl2 = ck.fl2;
   md.SA = __int_as_float(h.z);
@@ -406,6 +415,7 @@ __device__ __forceinline__ void load_pass2_mode(const Chunk& ck, int pair, Pass2
 
 template <int K = PASS_K, int MINB = PASS_MINB>
 __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass2(const Chunk ck) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int4* ent = reinterpret_cast<int4*>(smem_raw);
   float* tab = reinterpret_cast<float*>(smem_raw + PASS_WARPS * pass_wslots(K) * 16);

@@ -57,7 +57,7 @@ struct icet_b200_ctx {
   int pass_smem_set = 0;  // dynamic shared memory the pass kernels are currently allowed
   int* loop_dbg[ICET_NLANE] = {};  // watchdog record of the last k_loop launch per lane
   unsigned long long loop_timeout_ns = 20000000000ull;  // ICET_B200_LOOP_TIMEOUT_MS
-  int cluster_cs = 0, cluster_max = 0, cluster_smem_set = 0;  // k_loop_cluster: cluster size, clusters resident at once
+  int cluster_cs = 0, cluster_max = 0, cluster_nT = -1, cluster_nP = -1;  // k_loop_cluster: cluster size, clusters resident at once
   int loop_occ[2] = {0, 0};  // resident blocks per SM of k_loop<PASS_K>, k_loop<PASS_K_SMALL>
   // per-kernel timing (icet_b200_set_profile): events around every launch, summed on request
   int profile_on = 0;
@@ -330,6 +330,7 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
     CK(cudaFuncSetAttribute(k_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
     CK(cudaFuncSetAttribute(k_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
     CK(cudaFuncSetAttribute(k_pass2<>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
+    CK(cudaFuncSetAttribute(k_pass2<PASS_K_SMALL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
     CK(cudaFuncSetAttribute(k_loop<PASS_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
     CK(cudaFuncSetAttribute(k_loop<PASS_K_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->loop_occ[0], k_loop<PASS_K>, PASS_THREADS, psm));
@@ -461,13 +462,15 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   bool use_cluster = use_loop && p->runlen > 0 && !(p->flags & ICET_B200_FLAG_PERSISTENT_LOOP);
   if (p->flags & ICET_B200_FLAG_CLUSTER_LOOP) use_cluster = p->runlen > 0;
   if (use_cluster) {
-    const int csm = cluster_smem_bytes(nT, nP);
-    if (csm > ctx->cluster_smem_set || ctx->cluster_cs == 0) {
-      CK(cudaFuncSetAttribute(k_loop_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, csm));
+    if (ctx->cluster_cs == 0 || ctx->cluster_nT != nT || ctx->cluster_nP != nP) {
       CK(cudaFuncSetAttribute(k_loop_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      ctx->cluster_smem_set = csm;
       ctx->cluster_cs = 0;
       for (int cs : {16, 8, 4, 2, 1}) {
+        const int csm = cluster_smem_bytes(nT, nP, cs);
+        if (cudaFuncSetAttribute(k_loop_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, csm) != cudaSuccess) {
+          cudaGetLastError();
+          continue;
+        }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(cs);
         cfg.blockDim = dim3(CL_THREADS);
@@ -481,6 +484,8 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
         if (cudaOccupancyMaxActiveClusters(&ncl, k_loop_cluster, &cfg) == cudaSuccess && ncl >= 1) {
           ctx->cluster_cs = cs;
           ctx->cluster_max = ncl;
+          ctx->cluster_nT = nT;
+          ctx->cluster_nP = nP;
           break;
         }
         cudaGetLastError();
@@ -491,10 +496,17 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   if (use_cluster) {
     const int cs = ctx->cluster_cs;
     const int ncl = chain ? 1 : std::max(1, std::min(P, ctx->cluster_max));
+    // single pairs: the tiles of iteration 0 (always a rebuild) run GPU-wide first, the cluster starts at its voxel phase
+    const int first_tiles = (!chain && P == 1 && n2max > 0 && !(p->flags & ICET_B200_FLAG_EXACT_PASS)) ? 1 : 0;
+    if (first_tiles) {
+      const int tile_s = pass_tile_points(PASS_K_SMALL);
+      LAUNCH(7, CK(launch_ex(k_pass2<PASS_K_SMALL, 3>, dim3((n2max + tile_s - 1) / tile_s, P), dim3(PASS_THREADS), psm2,
+                             !prep_aside, ck)));
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ncl * cs);
     cfg.blockDim = dim3(CL_THREADS);
-    cfg.dynamicSmemBytes = cluster_smem_bytes(nT, nP);
+    cfg.dynamicSmemBytes = cluster_smem_bytes(nT, nP, cs);
     cfg.stream = st;
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -502,8 +514,8 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = (pdl && !prep_aside) ? 2 : 1;  // (after an event wait the edge is an ordinary one)
-    LAUNCH(10, CK(cudaLaunchKernelEx(&cfg, k_loop_cluster, ck)));
+    cfg.numAttrs = (pdl && (first_tiles || !prep_aside)) ? 2 : 1;  // (after an event wait the edge is an ordinary one)
+    LAUNCH(10, CK(cudaLaunchKernelEx(&cfg, k_loop_cluster, ck, first_tiles)));
   } else if (!use_loop) {
     for (int it = 0; it < p->runlen; it++) {
       if (n2max > 0) {
