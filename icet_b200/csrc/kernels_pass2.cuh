@@ -259,7 +259,9 @@ __device__ inline void pass2_dropped_returns(const Chunk& ck, const float4* tth,
 }
 
 // One warp tile of 32*K consecutive stored points of scan 2.  `went`: the warp's pass_wslots(K) 16-byte slots.
-template <int K, int RD = ((K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1))>
+// RD: rows whose margin records a lane requests together in a delta iteration.  All K of them: a delta iteration is
+// latency-bound (ncu r02g: issue slots 49 % busy, DRAM 28 %), what it needs is bytes in flight, not fewer instructions.
+template <int K, int RD = K>
 __device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, const float* tab, const CellRec* recs,
                                                 const float* tr, const Pass2Mode& md, const float* pog, size_t ld, int n,
                                                 int w0, float2* marg, uint32_t* cls2, int* violations) {

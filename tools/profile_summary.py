@@ -66,34 +66,40 @@ def raw_table(rep):
 
 
 def traffic_of(rep, tag, pairs_per_launch=256):
-    """{bench kernel name: dram bytes per launch} from the raw page (first launch of each kernel)."""
+    """{bench kernel name: dram bytes per launch} from the raw page.  The scan-2 pass of the incremental loop (k_pass2) is
+    captured for the 7 iterations of one chunk (rebuilds and deltas differ a lot): their AVERAGE, like bench.py's
+    avg_launch_ms; other kernels: first launch."""
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     if len(rows) < 3:
         return {}
     h, u = rows[0], rows[1]
-    res = {}
+    acc = {}
     for r in rows[2:]:
         name = r[h.index("Kernel Name")]
         key = None
-        if "k_pass<(bool)1" in name or "k_pass<true" in name or "k_pass<1," in name:
+        if "k_pass2<" in name or "k_pass<(bool)1" in name or "k_pass<true" in name or "k_pass<1," in name:
             key = "k_pass<scan2>"
         elif "k_pass<(bool)0" in name or "k_pass<false" in name or "k_pass<0," in name:
             key = "k_pass<scan1>"
         elif "k_loop" in name:
             key = "k_loop"
-        if not key or key in res:
+        if not key or (key in acc and key != "k_pass<scan2>"):
             continue
+
         def val(k):
             i = h.index(k)
             v = float(r[i].replace(",", ""))
             unit = u[i].lower()
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1)
         try:
-            res[key] = {"visit": tag, "pairs_per_launch": pairs_per_launch,
-                        "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum")}
+            acc.setdefault(key, []).append((val("dram__bytes_read.sum"), val("dram__bytes_write.sum")))
         except ValueError:
             pass
+    res = {}
+    for key, v in acc.items():
+        res[key] = {"visit": tag, "pairs_per_launch": pairs_per_launch, "launches_averaged": len(v),
+                    "dram_bytes_read": sum(a for a, _ in v) / len(v), "dram_bytes_write": sum(b for _, b in v) / len(v)}
     return res
 
 
@@ -119,7 +125,7 @@ def main():
     if os.path.exists(p):
         md += ["## ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: "
                "compare shares)", "", launches_table(p), ""]
-    reps = sorted(f for f in os.listdir(d) if f.endswith(".ncu-rep"))
+    reps = sorted((f for f in os.listdir(d) if f.endswith(".ncu-rep")), key=lambda f: (-len(f), f))  # prof.ncu-rep (7 iterations) last
     for rep in reps:
         md += ["## ncu --set full: %s" % rep, "", raw_table(os.path.join(d, rep)), ""]
         if len(sys.argv) > 2:
