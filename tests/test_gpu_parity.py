@@ -810,3 +810,57 @@ def test_multi_gpu_cpp_example(ctx, tmp_path):
     r0 = ctx.register(sc[0], sc[1])
     x = [float(v) for v in lines[0].split("X =")[1].split("pred_stds")[0].split()]
     np.testing.assert_allclose(x, r0["X"], atol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the CUDA path against the REFERENCE BUILD directly (tests/golden/ref_*.npz: the reference's own sources)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["frame_presorted", "sample_pc_presorted", "synth100_presorted", "synth100_presorted_fine",
+                                  "corridor_presorted", "frame_shipped", "frame_shipped_x0demo", "sample_pc_shipped",
+                                  "synth100_shipped", "all_zero"])
+def test_against_reference_build(ctx, po, parity, name):
+    """The committed outputs of the reference's OWN `class ICET` (oracle/_ref, tools/pin_against_ref.py) on the same inputs:
+    *_presorted -- scan 1 pre-sorted by range, where the reference's broken permutation loop is a no-op and it computes
+    what the product computes by default; *_shipped -- the reference as shipped, against FLAG_SHIPPED_ORDER.  Cell
+    counts, cluster bounds and the set of Gaussians bit for bit; X within north_star's tolerance (sign-unstable voxels:
+    the reference's eigenvectors are injected through the oracle, which reproduces the reference, to tell a sign flip
+    from an error)."""
+    import os
+    from conftest import GOLDEN
+    from icet_b200 import api
+    from test_ref_pin import _inputs
+    g = np.load(os.path.join(GOLDEN, "ref_%s.npz" % name))
+    s1, s2 = _inputs(name, g)
+    rl, nphi, nth = (int(v) for v in g["params"])
+    shipped = int(g["order_mode"]) == po.ORDER_REF_SHIPPED
+    p = params(runlen=rl, bins_phi=nphi, bins_theta=nth, flags=api.FLAG_SHIPPED_ORDER if shipped else 0)
+    r, d = ctx.register(s1, s2, X0=g["x0"], params=p, dump=True)
+    np.testing.assert_array_equal(d["cnt1"], g["cnt1"])
+    np.testing.assert_array_equal(d["bounds"], g["clusterBounds"])
+    np.testing.assert_array_equal(d["has1"], g["has1"])
+    assert r["n_gauss1"] == int(g["n_ellipsoids"])
+    has = g["has1"] > 0
+    if has.any():
+        mu_e = np.abs(d["mu1"][has] - g["mu1"][has]).max(1) / np.abs(g["mu1"][has]).max(1)
+        assert mu_e.max() < TOL_STAT
+        # U = V^T (src/icet.cpp:184): voxels whose eigenvectors agree with the reference's (up to rounding)
+        same_basis = np.abs(d["evec1"][has].transpose(0, 2, 1) - g["U"][has]).reshape(-1, 9).max(1) < 1e-3
+        np.testing.assert_array_equal(d["lmask"][has][same_basis],
+                                      np.diagonal(g["L"][has][same_basis], axis1=1, axis2=2).astype(np.uint8))
+        nflip = int((~same_basis).sum())
+        assert nflip <= max(2, int(0.01 * has.sum()))
+    else:
+        nflip = 0
+    dm, dr = float(np.abs(r["X"][:3] - g["X"][:3]).max()), float(np.abs(r["X"][3:] - g["X"][3:]).max())
+    if nflip == 0:
+        assert dm < TOL_M and dr < TOL_RAD, (dm, dr)
+    else:  # the reference with the GPU's eigenvectors in those voxels (via the oracle, bit-identical to the reference otherwise)
+        bad = np.zeros(len(has), bool)
+        bad[np.where(has)[0][~same_basis]] = True
+        o = po.run(s1, s2, X0=g["x0"], dumps=None, order_mode=int(g["order_mode"]), runlen=rl, bins_phi=nphi, bins_theta=nth,
+                   evec_override=(d["evec1"], bad.astype(np.uint8)))
+        dm, dr = float(np.abs(r["X"][:3] - o.X[:3]).max()), float(np.abs(r["X"][3:] - o.X[3:]).max())
+        assert dm < TOL_M and dr < TOL_RAD, (dm, dr)
+    parity.add("gpu_vs_reference_build", name, gaussians=int(has.sum()), dX_m=dm, dX_rad=dr, sign_unstable_voxels=nflip,
+               bounds_cnt1_has1_bit_identical=True)
+    print("%s: GPU vs the reference build: |dX| %.1e m %.1e rad, %d Gaussians, %d sign-unstable" % (name, dm, dr, has.sum(), nflip))
