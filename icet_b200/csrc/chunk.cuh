@@ -27,6 +27,11 @@ constexpr int HUGE_MIN = 32768;         // cells with more non-zero ranges (accu
 constexpr int HUGE_SLOTS = 64;          //   ... at most this many per chunk (the rest take the one-CTA path)
 constexpr int HUGE_NB = 32768;          //   ... through a global table of this many half-threshold buckets per cell
 constexpr int HUGE_SPLIT = 128;         //   ... filled by this many CTAs per cell
+// class word of a stored point of scan 2 (incremental loop, kernels_pass2.cuh): 24 bits, packed into its margin record
+constexpr uint32_t CLS_CELL = 0x003fffffu;    // cell index (validate(): bins_phi * bins_theta <= 2^20)
+constexpr uint32_t CLS_IN = 0x00400000u;      // the point passes filterPointsInsideCluster of its cell
+constexpr uint32_t CLS_ACTIVE = 0x00800000u;  // its cell takes part in the loop (F_ACTIVE2)
+constexpr uint32_t CLS_NONE = 0x003fffffu;    // "no class yet"
 
 struct PairDesc {
   const float* s1;
@@ -114,12 +119,15 @@ struct Chunk {  // everything a kernel needs, passed by value
   float* J;          // [P][27] get_H derivative matrices Jx | Jy | Jz of the current iteration
   double* part;      // [P][nblk][NRED] per-block partial sums of the voxel contributions
   // scan 2
-  float* pog;        // [P][3][n2max]  points2_OG without the dropped returns (compacted, any order)
+  float* pog;        // [P][3][n2max]  points2_OG without the dropped returns (compacted, any order); n2max is a multiple
+                     //               of 4 so that every plane (and every 32-point row of it) starts on a 16-byte boundary:
+                     //               the pass kernels stage their tiles with bulk async copies (cp.async.bulk)
   int32_t* n2c;      // [P] points stored in pog
   int32_t* nz2;      // [P] dropped returns of scan 2 (points2_OG == 0)
-  float2* marg;      // [P][n2max]  incremental loop: {u, r_e} of every stored point: its class cannot have changed while
-                     //               r_e * SA + C < u   (kernels_pass2.cuh)
-  uint32_t* cls2;    // [P][n2max]  incremental loop: cell | CLS_IN | CLS_ACTIVE of the point's last evaluation
+  uint2* mrec;       // [P][n2max]  incremental loop: one 64-bit margin record per stored point (rec2_pack, kernels_pass2.cuh):
+                     //               {u (24 significant bits, rounded down), r_e (bf16, rounded up), class word (24 bits)};
+                     //               the class of the point's last evaluation cannot have changed while r_e * SA + C < u
+  float inc_max_sa, inc_max_sb;  // a pair rebuilds when its motion odometers exceed these (INC_MAX_SA / INC_MAX_SB)
   PairMode* pm;      // [P]
   float* X;          // [P][6]
   const float* x0;   // [P][6] or null
@@ -163,4 +171,41 @@ __device__ __forceinline__ unsigned atom_add(unsigned* p, unsigned v) {
 __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// ---- bulk asynchronous copies global -> shared (TMA engine, sm_90+ / sm_100a; SASS UBLKCP) completing on an mbarrier.
+// The scan-2 pass stages the coordinates of a warp tile with three of them (one per plane) issued by one lane: no
+// per-lane address arithmetic, no registers held across the load latency.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy before the first copy
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// dst / src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// (try_wait suspends the thread in hardware for a bounded time per call; a copy that never completes -- a bug -- traps
+// instead of hanging the device)
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  for (unsigned spin = 0; !mbar_try_wait(bar, parity); spin++)
+    if (spin > (1u << 22)) __trap();
 }

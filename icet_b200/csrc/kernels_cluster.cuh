@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck, 
   double* wpart = reinterpret_cast<double*>(tab + pass_tab_floats(ck.nT, ck.nP));  // [CL_WARPS][NRED]
   double* cpart = wpart + CL_WARPS * NRED;                                         // [NRED]  this CTA's partial sums
   float* s_J = reinterpret_cast<float*>(cpart + NRED);                             // [27]
+  __shared__ unsigned long long s_mbar[CL_WARPS];  // one mbarrier per warp: completion of its staged scan-2 tiles
   const unsigned cs = cluster.num_blocks(), rank = cluster.block_rank();
   {
     const int ntab = pass_tab_floats(ck.nT, ck.nP);
@@ -87,6 +88,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck, 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ncl = gridDim.x / cs, cl = blockIdx.x / cs;  // clusters of the launch, this cluster
   int4* went = ent + warp * pass_wslots(CL_K);
+  if (lane == 0) mbar_init(&s_mbar[warp], 1);
+  __syncwarp();
+  unsigned mphase = 0u;
   const bool chain = (ck.flags & ICET_B200_FLAG_CHAIN_X0) != 0;
   const bool inc = loop_incremental(ck);
   const int gwarp = (int)rank * CL_WARPS + warp, nwarp = (int)cs * CL_WARPS;
@@ -116,9 +120,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck, 
       if (!skip_tiles) {
         if (inc) {
           for (int tile = gwarp; tile < tiles; tile += nwarp)
-            pass2_warp_tile<CL_K>(ck, went, tab, recs, tr, md, ck.pog + (size_t)pair * 3 * ck.n2max, (size_t)ck.n2max,
-                                        n, tile * 32 * CL_K, ck.marg + (size_t)pair * ck.n2max,
-                                        ck.cls2 + (size_t)pair * ck.n2max,
+            pass2_warp_tile<CL_K>(ck, went, &s_mbar[warp], mphase, false, tab, recs, tr, md,
+                                        ck.pog + (size_t)pair * 3 * ck.n2max, (size_t)ck.n2max, n, tile * 32 * CL_K,
+                                        ck.mrec + (size_t)pair * ck.n2max,
                                         (ck.flags & ICET_B200_FLAG_VERIFY_INCREMENTAL) ? &ck.res[pair].reserved[0] : nullptr);
           if (gwarp == nwarp - 1 && lane == 0)  // (the last warp has the fewest tiles)
             pass2_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 2,

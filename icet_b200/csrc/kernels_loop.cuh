@@ -332,7 +332,7 @@ __device__ __forceinline__ void mode_after_solve(const Chunk& ck, int pair, cons
   for (int k = 3; k < 12; k++) a2 += (trn[k] - tro[k]) * (trn[k] - tro[k]);
   const float SA = (cur ? cur->SA : __ldcg(&pm->SA)) + 1.001f * sqrtf(a2);
   const float SB = (cur ? cur->SB : __ldcg(&pm->SB)) + 1.001f * sqrtf(b2);
-  const bool delta = !(ck.flags & ICET_B200_FLAG_FULL_REBUILD) && SA <= INC_MAX_SA && SB <= INC_MAX_SB;  // false for NaN
+  const bool delta = !(ck.flags & ICET_B200_FLAG_FULL_REBUILD) && SA <= ck.inc_max_sa && SB <= ck.inc_max_sb;  // false for NaN
   if (delta) {
     pm->rebuild = 0;
     pm->SA = SA;
@@ -750,12 +750,16 @@ template <int K>
 __global__ void __launch_bounds__(PASS_THREADS, 3) k_loop(const Chunk ck, int tiles, int vt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* tab = reinterpret_cast<float*>(smem_raw + PASS_WARPS * pass_wslots(K) * 16);
+  __shared__ unsigned long long s_mbar[PASS_WARPS];  // one mbarrier per warp: completion of its staged scan-2 tiles
   {
     const int ntab = pass_tab_floats(ck.nT, ck.nP);
     for (int k = threadIdx.x; k < ntab; k += PASS_THREADS) tab[k] = __ldg(ck.binrec + k);
   }
   __syncthreads();  // the only block-wide barrier: from here on warps are independent workers
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) mbar_init(&s_mbar[warp], 1);
+  __syncwarp();
+  unsigned mphase = 0u;
   int4* went = reinterpret_cast<int4*>(smem_raw) + warp * pass_wslots(K);
   static_assert(pass_wslots(K) * 16 >= 512, "warp scratch too small");
   double* w_tot = reinterpret_cast<double*>(went);                          // [28]   (vox tasks only)
@@ -822,8 +826,8 @@ __global__ void __launch_bounds__(PASS_THREADS, 3) k_loop(const Chunk ck, int ti
         if (loop_incremental(ck)) {
           Pass2Mode md;
           load_pass2_mode(ck, pair, md);
-          pass2_warp_tile<K>(ck, went, tab, recs, tr, md, ck.pog + (size_t)pair * 3 * ck.n2max, (size_t)ck.n2max, n, w0,
-                             ck.marg + (size_t)pair * ck.n2max, ck.cls2 + (size_t)pair * ck.n2max,
+          pass2_warp_tile<K>(ck, went, &s_mbar[warp], mphase, false, tab, recs, tr, md, ck.pog + (size_t)pair * 3 * ck.n2max,
+                             (size_t)ck.n2max, n, w0, ck.mrec + (size_t)pair * ck.n2max,
                              (ck.flags & ICET_B200_FLAG_VERIFY_INCREMENTAL) ? &ck.res[pair].reserved[0] : nullptr);
           if (tile == 0 && lane == 0)
             pass2_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 2,

@@ -25,10 +25,6 @@
 // point, averaged over the voxel) and are closer to the exact statistics of the transformed points.
 #pragma once
 
-constexpr uint32_t CLS_IN = 0x40000000u;      // the point passes filterPointsInsideCluster of its cell
-constexpr uint32_t CLS_ACTIVE = 0x80000000u;  // its cell takes part in the loop (F_ACTIVE2)
-constexpr uint32_t CLS_CELL = 0x000fffffu;
-constexpr uint32_t CLS_NONE = 0x000fffffu;    // "no class yet"
 // Delta iterations while the motion since the last rebuild stays below these bounds.  A delta iteration costs ~20
 // instructions and 8 bytes per point plus a full evaluation for the points whose margin is used up -- but those are
 // GATHERED (three 32-byte sectors for 12 useful bytes, scattered margin / class stores), so a delta iteration with more
@@ -47,9 +43,25 @@ struct Pass2Mode {  // block-uniform copy of the pair's PairMode + accumulator s
   float fs2;
   int fl2;
   float SA, SB, C;
-  float trb[12];
+  const float* trbp;  // PairMode::TRb (global): transform of the last rebuild, loaded only where a class changes --
+                      // in a rebuild iteration it IS the current transform
   unsigned long long* accp;
 };
+
+// ---- margin record of a stored point: 64 bits {u | class low byte, r_e | class high 16 bits}.
+//   r_e is rounded UP to bf16 (<= 0.8 % more motion charged to the point: < 1 mm at 30 m for the SA bounds used) and u,
+//   which is computed with that rounded r_e, is rounded DOWN to 24 significant bits (< 2^-16 relative) and clamped at
+//   0: both make the stability test r_e * SA + C < u more conservative, never less.  u = 0 (also for NaN): the point is
+//   evaluated in every iteration.
+__device__ __forceinline__ float rec2_round_re(float r) {
+  return __uint_as_float((__float_as_uint(r * 1.000001f) + 0xffffu) & 0xffff0000u);
+}
+__device__ __forceinline__ uint2 rec2_pack(float u, float re /* rec2_round_re */, uint32_t cls) {
+  return make_uint2((__float_as_uint(fmaxf(u, 0.f)) & 0xffffff00u) | (cls & 0xffu), __float_as_uint(re) | (cls >> 8));
+}
+__device__ __forceinline__ float rec2_u(uint2 v) { return __uint_as_float(v.x & 0xffffff00u); }
+__device__ __forceinline__ float rec2_re(uint2 v) { return __uint_as_float(v.y & 0xffff0000u); }
+__device__ __forceinline__ uint32_t rec2_cls(uint2 v) { return (v.x & 0xffu) | ((v.y & 0xffffu) << 8); }
 
 // bin + box look-up (see bin_box) that also returns the distance of the angle to the nearest threshold that decided it
 __device__ __forceinline__ int bin_box_m(float a, const float4* rec, const icet::BinTable& bt, bool& inbox, float& dist) {
@@ -97,10 +109,11 @@ __device__ __forceinline__ void point_eval2(const Chunk& ck, const float4* tth, 
   float m = fminf((dth - 2e-6f) * rho - 3e-6f * r, (dph - 4e-6f * k) * r);
   m = fminf(m, 0.25f * rho);
   if (active) m = fminf(m, fminf(fabsf(r - ra.x), fabsf(ra.y - r)) - 4e-6f * r);
-  float u = fmaf(0.9f, m, -1e-6f) + fmaf(r, SA, SB);
+  const float re = rec2_round_re(r);
+  float u = fmaf(0.9f, m, -1e-6f) + fmaf(re, SA, SB);
   // non-finite coordinates (NaN rows take the 1000.0 sentinels, :116): evaluated every time
   if (!(__fadd_rn(sxy, __fmul_rn(z, z)) < 3e38f) || !(sxy > 1e-30f) || !(u == u)) u = 0.f;
-  mg = make_float2(u, r);
+  mg = make_float2(u, re);
 }
 
 // ---- Filtered evaluation.  The incremental loop needs the CLASS of a point and a conservative margin, not the values
@@ -183,7 +196,8 @@ __device__ __forceinline__ void point_eval2_fast(const Chunk& ck, const float4* 
   float m = fminf((dth - 2e-6f) * rho - 3e-6f * r, (dph - 4e-6f * k) * r);
   m = fminf(m, 0.25f * rho);
   if (active) m = fminf(m, dr - (TAU_R + 4e-6f) * r);
-  mg = make_float2(fmaf(0.9f, m, -1e-6f) + fmaf(r * 1.000001f, SA, SB), r * 1.000001f);
+  const float re = rec2_round_re(r);
+  mg = make_float2(fmaf(0.9f, m, -1e-6f) + fmaf(re, SA, SB), re);
 }
 
 // anchor of a voxel's scan-2 fixed-point frame: the centre of its box, taken back through the transform of the last
@@ -210,11 +224,19 @@ __device__ __forceinline__ void fix2(float px, float py, float pz, float ax, flo
   fz = max(-lim, min(lim, __float2int_rn(__fmul_rn(__fadd_rn(pz, -az), sc))));
 }
 
-// adds (w = +n) or removes (w = -n) n copies of an inside point to / from the moments of its voxel
+// adds (w = +n) or removes (w = -n) n copies of an inside point to / from the moments of its voxel (rare: only where the
+// class of a point changed in a delta iteration; the anchor transform comes straight from global memory)
 __device__ __forceinline__ void moments_add(unsigned long long* accp, const CellRec* recs, int cell, const Pass2Mode& md,
                                             float px, float py, float pz, long long w) {
+  float trb[12];
+  {
+    const float4* tb = reinterpret_cast<const float4*>(md.trbp);
+    const float4 a = __ldcg(tb), b = __ldcg(tb + 1), c = __ldcg(tb + 2);
+    trb[0] = a.x; trb[1] = a.y; trb[2] = a.z; trb[3] = a.w; trb[4] = b.x; trb[5] = b.y; trb[6] = b.z; trb[7] = b.w;
+    trb[8] = c.x; trb[9] = c.y; trb[10] = c.z; trb[11] = c.w;
+  }
   float ax, ay, az, sc;
-  vox_anchor2(recs, cell, md.trb, md.fs2, ax, ay, az, sc);
+  vox_anchor2(recs, cell, trb, md.fs2, ax, ay, az, sc);
   int ix, iy, iz;
   fix2(px, py, pz, ax, ay, az, sc, md.fl2, ix, iy, iz);
   const long long fx = ix, fy = iy, fz = iz;
@@ -258,37 +280,81 @@ __device__ inline void pass2_dropped_returns(const Chunk& ck, const float4* tth,
   ck.pm[pair].zcls = (int)cls;
 }
 
-// One warp tile of 32*K consecutive stored points of scan 2.  `went`: the warp's pass_wslots(K) 16-byte slots.
+// publishes what one lane collected over a run of consecutive ACTIVE points of one cell: the bin count, and the sums of
+// the inside points among them
+__device__ __forceinline__ void flush_run2(unsigned long long* accp, int cell, int nb, int nin, int sx, int sy, int sz,
+                                           long long pxx, long long pxy, long long pxz, long long pyy, long long pyz,
+                                           long long pzz) {
+  if (cell < 0) return;
+  unsigned long long* q = accp + (size_t)cell * NQ;
+  red_add(q, (unsigned long long)nb);
+  if (nin == 0) return;
+  red_add(q + 1, (unsigned long long)nin);
+  red_add(q + 2, (unsigned long long)(long long)sx);
+  red_add(q + 3, (unsigned long long)(long long)sy);
+  red_add(q + 4, (unsigned long long)(long long)sz);
+  red_add(q + 5, (unsigned long long)pxx);
+  red_add(q + 6, (unsigned long long)pxy);
+  red_add(q + 7, (unsigned long long)pxz);
+  red_add(q + 8, (unsigned long long)pyy);
+  red_add(q + 9, (unsigned long long)pyz);
+  red_add(q + 10, (unsigned long long)pzz);
+}
+
+// ---- staging of a warp tile.  The warp's scratch (pass_wslots(K) 16-byte slots = 16 bytes per point) holds the three
+// coordinate planes of the tile (12 bytes per point, filled by the TMA engine: three bulk copies issued by one lane,
+// completion on the warp's mbarrier) and a 4-byte list entry per point.
+// src: first point of the tile in the x plane of pog (16-byte aligned: Chunk::pog), ld: plane stride, cnt: points.
+template <int K>
+__device__ __forceinline__ void pass2_request_tile(int4* went, const float* src, size_t ld, int cnt, unsigned long long* mbar) {
+  float* tx = reinterpret_cast<float*>(went);
+  const unsigned bytes = (unsigned)((cnt + 3) & ~3) * 4u;  // (the planes are padded to a multiple of 4 points)
+  mbar_expect_tx(mbar, 3u * bytes);
+  bulk_g2s(tx, src, bytes, mbar);
+  bulk_g2s(tx + 32 * K, src + ld, bytes, mbar);
+  bulk_g2s(tx + 64 * K, src + 2 * ld, bytes, mbar);
+}
+
+// One warp tile of 32*K consecutive stored points of scan 2.
+//   went / mbar / mphase: the warp's scratch, its mbarrier and the parity of the barrier's next completion (the caller
+//   keeps it across calls); requested: the caller has already issued pass2_request_tile for this tile (k_pass2 does so
+//   before it stages the tables).
 // RD: rows whose margin records a lane requests together in a delta iteration.  All K of them: a delta iteration is
 // latency-bound (ncu r02g: issue slots 49 % busy, DRAM 28 %), what it needs is bytes in flight, not fewer instructions.
 template <int K, int RD = K>
-__device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, const float* tab, const CellRec* recs,
-                                                const float* tr, const Pass2Mode& md, const float* pog, size_t ld, int n,
-                                                int w0, float2* marg, uint32_t* cls2, int* violations) {
+__device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, unsigned long long* mbar, unsigned& mphase,
+                                                bool requested, const float* tab, const CellRec* recs, const float* tr,
+                                                const Pass2Mode& md, const float* pog, size_t ld, int n, int w0, uint2* mrec,
+                                                int* violations) {
+  static_assert(K <= 16, "list entries keep the point's index within the tile in 9 bits");
   const int lane = threadIdx.x & 31;
   if (w0 >= n) return;
+  const int cnt = min(n - w0, 32 * K);
   const float4* tth = reinterpret_cast<const float4*>(tab);
   const float4* tph = tth + ck.nT + 2;
   const unsigned lt = (1u << lane) - 1u;
   unsigned long long* accp = md.accp;
+  const float* tx = reinterpret_cast<const float*>(went);
+  const float* ty = tx + 32 * K;
+  const float* tz = tx + 64 * K;
+  int* list = reinterpret_cast<int*>(went) + 96 * K;
+  uint2* rp = mrec + w0;
   if (md.rebuild) {
-    // ---- phase A: every point.  Coordinates of row j + 2 are requested before row j is worked on.
-    int nin_tile = 0;
-    float bx[2], by[2], bz[2];
-#pragma unroll
-    for (int p = 0; p < 2; p++) {
-      const int i = w0 + p * 32 + lane;
-      bx[p] = by[p] = bz[p] = 0.f;
-      if (p < K && i < n) { bx[p] = __ldg(pog + i); by[p] = __ldg(pog + ld + i); bz[p] = __ldg(pog + 2 * ld + i); }
+    if (!requested) {
+      __syncwarp();  // (every lane is done with the scratch of the previous tile)
+      if (lane == 0) pass2_request_tile<K>(went, pog + w0, ld, cnt, mbar);
     }
+    mbar_wait(mbar, mphase);
+    mphase ^= 1u;
+    // ---- phase A: every point, lane per point, coordinates from the staged tile.  ACTIVE points (their cell takes
+    // part in the loop) are listed as {index in tile, in-box flag, cell}.
+    int nact = 0;
 #pragma unroll(K % 4 == 0 ? 4 : 2)
     for (int j = 0; j < K; j++) {
-      const int i = w0 + j * 32 + lane;
-      const float x = bx[j & 1], y = by[j & 1], z = bz[j & 1];
-      const int ip = i + 64;
-      if (j + 2 < K && ip < n) { bx[j & 1] = __ldg(pog + ip); by[j & 1] = __ldg(pog + ld + ip); bz[j & 1] = __ldg(pog + 2 * ld + ip); }
-      uint32_t cls = CLS_NONE;
-      if (i < n) {
+      const int li = j * 32 + lane;
+      uint32_t cls = 0u;
+      if (li < cnt) {
+        const float x = tx[li], y = ty[li], z = tz[li];
         float2 mg;
         point_eval2_fast(ck, tth, tph, recs, tr, 0.f, 0.f, x, y, z, cls, mg);
         if (violations) {  // self-check: the filtered evaluation must give the class of the exact pipeline
@@ -297,87 +363,95 @@ __device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, con
           point_eval2(ck, tth, tph, recs, tr, 0.f, 0.f, x, y, z, cx, mx);
           if (cx != cls) atomicAdd(violations + 1, 1);
         }
-        marg[i] = mg;
-        cls2[i] = cls;
+        rp[li] = rec2_pack(mg.x, mg.y, cls);
       }
-      // bin counts: one RED per run of equal (participating) cell in this row
-      const int key = (cls & CLS_ACTIVE) ? (int)(cls & CLS_CELL) : -1;
-      const int prev = __shfl_up_sync(FULL, key, 1);
-      const bool head = (lane == 0) || (key != prev);
-      const unsigned hm = __ballot_sync(FULL, head);
-      if (head && key >= 0) {
-        const unsigned nh = (lane == 31) ? 0u : (hm >> (lane + 1));
-        const int len = nh ? __ffs(nh) : 32 - lane;
-        red_add(accp + (size_t)key * NQ, (unsigned long long)len);
-      }
-      const bool in = (cls & CLS_IN) != 0;
-      const unsigned im = __ballot_sync(FULL, in);
-      if (in) went[nin_tile + __popc(im & lt)] = make_int4((int)(cls & CLS_CELL), __float_as_int(x), __float_as_int(y), __float_as_int(z));
-      nin_tile += __popc(im);
+      const bool act = (cls & CLS_ACTIVE) != 0;
+      const unsigned am = __ballot_sync(FULL, act);
+      if (act) list[nact + __popc(am & lt)] = (li << 23) | (int)(cls & (CLS_CELL | CLS_IN));
+      nact += __popc(am);
     }
     __syncwarp();
-    // ---- phase B: lane takes entries [lane*q, lane*q + q); q odd => conflict-free 16-byte shared loads
-    const int q = ((nin_tile + 31) >> 5) | 1;
-    const int e0 = lane * q, e1 = min(nin_tile, e0 + q);
-    int cur = -1, nin = 0, sx = 0, sy = 0, sz = 0;
+    // ---- phase B: lane takes entries [lane*q, lane*q + q); q odd => conflict-free shared loads of the entries.  A run
+    // of equal cell stays in the lane's registers: one flush (bin count + moments) per run.  In a rebuild iteration the
+    // anchor transform of the voxel frames IS the current transform.
+    const int q = ((nact + 31) >> 5) | 1;
+    const int e0 = lane * q, e1 = min(nact, e0 + q);
+    int cur = -1, nb = 0, nin = 0, sx = 0, sy = 0, sz = 0;
     long long pxx = 0, pxy = 0, pxz = 0, pyy = 0, pyz = 0, pzz = 0;
     float ax = 0.f, ay = 0.f, az = 0.f, sc = 0.f;
 #pragma unroll 2
     for (int e = e0; e < e1; e++) {
-      const int4 v = went[e];
-      if (v.x != cur) {
-        flush_in_run(accp, cur, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
-        cur = v.x;
-        nin = sx = sy = sz = 0;
+      const unsigned v = (unsigned)list[e];
+      const int c = (int)(v & CLS_CELL);
+      if (c != cur) {
+        flush_run2(accp, cur, nb, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
+        cur = c;
+        nb = nin = sx = sy = sz = 0;
         pxx = pxy = pxz = pyy = pyz = pzz = 0;
-        vox_anchor2(recs, cur, md.trb, md.fs2, ax, ay, az, sc);
+        vox_anchor2(recs, cur, tr, md.fs2, ax, ay, az, sc);
       }
-      int fx, fy, fz;
-      fix2(__int_as_float(v.y), __int_as_float(v.z), __int_as_float(v.w), ax, ay, az, sc, md.fl2, fx, fy, fz);
-      nin++;
-      sx += fx; sy += fy; sz += fz;
-      pxx += (long long)fx * fx; pxy += (long long)fx * fy; pxz += (long long)fx * fz;
-      pyy += (long long)fy * fy; pyz += (long long)fy * fz; pzz += (long long)fz * fz;
+      nb++;
+      if (v & CLS_IN) {
+        const int li = (int)(v >> 23);
+        int fx, fy, fz;
+        fix2(tx[li], ty[li], tz[li], ax, ay, az, sc, md.fl2, fx, fy, fz);
+        nin++;
+        sx += fx; sy += fy; sz += fz;
+        pxx += (long long)fx * fx; pxy += (long long)fx * fy; pxz += (long long)fx * fz;
+        pyy += (long long)fy * fy; pyz += (long long)fy * fz; pzz += (long long)fz * fz;
+      }
     }
-    flush_in_run(accp, cur, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
+    flush_run2(accp, cur, nb, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
     __syncwarp();
     return;
   }
-  // ---- DELTA, phase T: which points have used up their margin?  (8 bytes per point, all rows requested up front in
-  // groups of 4)
-  int* list = reinterpret_cast<int*>(went);  // indices of the points to re-evaluate (<= 32*K)
+  // ---- DELTA, phase T: which points have used up their margin?  (8 bytes per point, all rows requested up front)
   int nre = 0;
   constexpr int R = RD;  // rows whose margin records are requested together (latency shape: all of them)
   static_assert(K % RD == 0, "rows per load group must divide the tile");
 #pragma unroll 1
   for (int j0 = 0; j0 < K; j0 += R) {
-    float2 mg[R];
+    uint2 rv[R];
 #pragma unroll
     for (int g = 0; g < R; g++) {
-      const int i = w0 + (j0 + g) * 32 + lane;
-      mg[g] = make_float2(3e38f, 0.f);
-      if (i < n) mg[g] = __ldcg(marg + i);  // (L2: written by another SM in the previous iteration)
+      const int li = (j0 + g) * 32 + lane;
+      rv[g] = make_uint2(0x7f000000u, 0u);  // (huge u, r_e = 0: stable)
+      if (li < cnt) rv[g] = __ldcg(rp + li);  // (L2: written by another SM in the previous iteration)
     }
 #pragma unroll
     for (int g = 0; g < R; g++) {
-      const int i = w0 + (j0 + g) * 32 + lane;
-      const bool stable = fmaf(mg[g].y, md.SA, md.C) < mg[g].x;
+      const int li = (j0 + g) * 32 + lane;
+      const bool stable = fmaf(rec2_re(rv[g]), md.SA, md.C) < rec2_u(rv[g]);
       // ICET_B200_FLAG_VERIFY_INCREMENTAL: evaluate the stable points as well and count those whose class changed
-      const bool redo = i < n && (!stable || violations != nullptr);
+      const bool redo = li < cnt && (!stable || violations != nullptr);
       const unsigned rm = __ballot_sync(FULL, redo);
-      if (redo) list[nre + __popc(rm & lt)] = stable ? (i | (int)0x80000000) : i;
+      if (redo) list[nre + __popc(rm & lt)] = stable ? (li | (int)0x80000000) : li;
       nre += __popc(rm);
     }
   }
+  if (nre == 0) return;
+  // ---- phase E: full evaluation of the listed points, lane per point.  With more than one point in eight listed the
+  // whole tile is staged (12 bytes per point, coalesced) instead of gathering three 32-byte sectors per listed point.
+  const bool staged = nre * 8 > cnt;  // warp-uniform
   __syncwarp();
-  // ---- phase E: full evaluation of the listed points, lane per point
+  if (staged) {
+    if (lane == 0) pass2_request_tile<K>(went, pog + w0, ld, cnt, mbar);
+    mbar_wait(mbar, mphase);
+    mphase ^= 1u;
+  }
   for (int e0 = 0; e0 < nre; e0 += 32) {
     const int e = e0 + lane;
     if (e < nre) {
       const bool was_stable = list[e] < 0;
-      const int i = list[e] & 0x7fffffff;
-      const float x = __ldg(pog + i), y = __ldg(pog + ld + i), z = __ldg(pog + 2 * ld + i);
-      const uint32_t old = __ldcg(cls2 + i);
+      const int li = list[e] & 0x7fffffff;
+      float x, y, z;
+      if (staged) {
+        x = tx[li]; y = ty[li]; z = tz[li];
+      } else {
+        const float* pp = pog + w0 + li;
+        x = __ldg(pp); y = __ldg(pp + ld); z = __ldg(pp + 2 * ld);
+      }
+      const uint32_t old = rec2_cls(__ldcg(rp + li));
       uint32_t cls;
       float2 mg;
       point_eval2_fast(ck, tth, tph, recs, tr, md.SA, md.SB, x, y, z, cls, mg);
@@ -387,10 +461,9 @@ __device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, con
         point_eval2(ck, tth, tph, recs, tr, md.SA, md.SB, x, y, z, cx, mx);
         if (cx != cls) atomicAdd(violations + 1, 1);
       }
-      marg[i] = mg;
+      rp[li] = rec2_pack(mg.x, mg.y, cls);
       if (cls != old) {
         if (was_stable) atomicAdd(violations, 1);
-        cls2[i] = cls;
         class_move(accp, recs, md, old, cls, x, y, z, 1);
       }
     }
@@ -408,10 +481,7 @@ __device__ __forceinline__ void load_pass2_mode(const Chunk& ck, int pair, Pass2
   md.SA = __int_as_float(h.z);
   md.C = __int_as_float(h.w);
   md.SB = __ldcg(&pm->SB);
-  const float4* tb = reinterpret_cast<const float4*>(pm->TRb);
-  const float4 a = __ldcg(tb), b = __ldcg(tb + 1), c = __ldcg(tb + 2);
-  md.trb[0] = a.x; md.trb[1] = a.y; md.trb[2] = a.z; md.trb[3] = a.w; md.trb[4] = b.x; md.trb[5] = b.y; md.trb[6] = b.z;
-  md.trb[7] = b.w; md.trb[8] = c.x; md.trb[9] = c.y; md.trb[10] = c.z; md.trb[11] = c.w;
+  md.trbp = pm->TRb;
   md.accp = ck.acc + ((size_t)h.x * ck.npairs + pair) * ck.ncell * NQ;
 }
 
@@ -419,14 +489,24 @@ template <int K = PASS_K, int MINB = PASS_MINB>
 __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass2(const Chunk ck) {
   pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned long long s_mbar[PASS_WARPS];
   int4* ent = reinterpret_cast<int4*>(smem_raw);
   float* tab = reinterpret_cast<float*>(smem_raw + PASS_WARPS * pass_wslots(K) * 16);
   const int pair = blockIdx.y;
   const int n = ck.n2c[pair];
   const int tile0 = blockIdx.x * pass_tile_points(K);
   if (tile0 >= n && blockIdx.x != 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int4* went = ent + warp * pass_wslots(K);
+  const int w0 = tile0 + warp * 32 * K;
+  const float* pog = ck.pog + (size_t)pair * 3 * ck.n2max;
   Pass2Mode md;
   load_pass2_mode(ck, pair, md);
+  if (lane == 0) mbar_init(&s_mbar[warp], 1);
+  __syncwarp();
+  // a rebuild iteration reads every coordinate of the tile: request it before anything else
+  const bool requested = md.rebuild && w0 < n;
+  if (requested && lane == 0) pass2_request_tile<K>(went, pog + w0, (size_t)ck.n2max, min(n - w0, 32 * K), &s_mbar[warp]);
   // delta iterations only read the look-up tables for the few points they re-evaluate: straight from global memory
   const float* tabp = ck.binrec;
   if (md.rebuild) {
@@ -443,9 +523,9 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass2(const Chunk ck) {
     tr[8] = c.x; tr[9] = c.y; tr[10] = c.z; tr[11] = c.w;
   }
   const CellRec* recs = ck.rec + (size_t)pair * ck.ncell;
-  pass2_warp_tile<K>(ck, ent + (threadIdx.x >> 5) * pass_wslots(K), tabp, recs, tr, md, ck.pog + (size_t)pair * 3 * ck.n2max,
-                     (size_t)ck.n2max, n, tile0 + (threadIdx.x >> 5) * 32 * K, ck.marg + (size_t)pair * ck.n2max,
-                     ck.cls2 + (size_t)pair * ck.n2max,
+  unsigned mphase = 0u;
+  pass2_warp_tile<K>(ck, went, &s_mbar[warp], mphase, requested, tabp, recs, tr, md, pog, (size_t)ck.n2max, n, w0,
+                     ck.mrec + (size_t)pair * ck.n2max,
                      (ck.flags & ICET_B200_FLAG_VERIFY_INCREMENTAL) ? &ck.res[pair].reserved[0] : nullptr);
   if (blockIdx.x == 0 && threadIdx.x == 0)
     pass2_dropped_returns(ck, reinterpret_cast<const float4*>(tabp), reinterpret_cast<const float4*>(tabp) + ck.nT + 2, recs,

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) k_cell_scan(const Chunk ck) {
     for (int k = 0; k < 12; k++) ck.TRprev[(size_t)pair * 12 + k] = TR[k];
     // incremental scan-2 loop: the first iteration builds the moments from zero in set 0, anchored at this transform
     PairMode* pm = ck.pm + pair;
-    pm->set = 0; pm->rebuild = 1; pm->SA = 0.f; pm->C = 0.f; pm->SB = 0.f; pm->zcls = (int)0x000fffff;
+    pm->set = 0; pm->rebuild = 1; pm->SA = 0.f; pm->C = 0.f; pm->SB = 0.f; pm->zcls = (int)CLS_NONE;
     for (int k = 0; k < 12; k++) pm->TRb[k] = TR[k];
   }
   __syncthreads();

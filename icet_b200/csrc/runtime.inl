@@ -57,6 +57,7 @@ struct icet_b200_ctx {
   int pass_smem_set = 0;  // dynamic shared memory the pass kernels are currently allowed
   int* loop_dbg[ICET_NLANE] = {};  // watchdog record of the last k_loop launch per lane
   unsigned long long loop_timeout_ns = 20000000000ull;  // ICET_B200_LOOP_TIMEOUT_MS
+  float inc_max_sa = INC_MAX_SA, inc_max_sb = INC_MAX_SB;  // rebuild bounds of the incremental loop (ICET_B200_INC_SA / _SB: A/B runs)
   int cluster_cs = 0, cluster_max = 0, cluster_nT = -1, cluster_nP = -1;  // k_loop_cluster: cluster size, clusters resident at once
   int loop_occ[2] = {0, 0};  // resident blocks per SM of k_loop<PASS_K>, k_loop<PASS_K_SMALL>
   // per-kernel timing (icet_b200_set_profile): events around every launch, summed on request
@@ -153,8 +154,7 @@ size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runle
   ck.kbuf = shipped ? c.take<unsigned long long>((size_t)P * n1max) : nullptr;
   ck.pos1 = shipped ? c.take<int32_t>((size_t)P * n1max) : nullptr;
   ck.pog = c.take<float>((size_t)P * 3 * n2max);
-  ck.marg = c.take<float2>((size_t)P * n2max);
-  ck.cls2 = c.take<uint32_t>((size_t)P * n2max);
+  ck.mrec = c.take<uint2>((size_t)P * n2max);
   ck.X = c.take<float>((size_t)P * 6);
   ck.TR = c.take<float>((size_t)P * 12);
   ck.TRprev = c.take<float>((size_t)P * 12);
@@ -290,6 +290,7 @@ int prof_events(icet_b200_ctx* ctx, int id, cudaEvent_t* e0, cudaEvent_t* e1) {
 // Enqueue the whole registration of one chunk (descriptors already on the device).
 int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDesc* d_desc, int n1max, int n2max,
               const float* d_x0, icet_b200_result* d_res, bool dump, int lane = 0) {
+  n2max = (n2max + 3) & ~3;  // plane stride of pog: every plane / tile row on a 16-byte boundary (bulk async copies)
   const int nT = p->bins_theta, nP = p->bins_phi, ncell = nT * nP;
   int rc = ensure_edges(ctx, nT, nP);
   if (rc) return rc;
@@ -311,6 +312,8 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
   ck.x0 = d_x0;
   ck.res = d_res;
   ck.loop_timeout_ns = ctx->loop_timeout_ns;
+  ck.inc_max_sa = ctx->inc_max_sa;
+  ck.inc_max_sb = ctx->inc_max_sb;
   ck.dump_on = dump ? 1 : 0;
   if (dump) ck.dump = ctx->dump_ptrs;
   cudaStream_t st = lane == 0 ? ctx->stream : ctx->lanes[lane];
