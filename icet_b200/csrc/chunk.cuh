@@ -127,6 +127,8 @@ struct Chunk {  // everything a kernel needs, passed by value
   uint2* mrec;       // [P][n2max]  incremental loop: one 64-bit margin record per stored point (rec2_pack, kernels_pass2.cuh):
                      //               {u (24 significant bits, rounded down), r_e (bf16, rounded up), class word (24 bits)};
                      //               the class of the point's last evaluation cannot have changed while r_e * SA + C < u
+  float4* anch;      // [P][ncell]  {anchor xyz, scale} of the scan-2 fixed-point frame of every active voxel at the transform
+                     //               of the pair's last rebuild (written by k_fit1 / k_solve6, read by k_pass2)
   float inc_max_sa, inc_max_sb;  // a pair rebuilds when its motion odometers exceed these (INC_MAX_SA / INC_MAX_SB)
   PairMode* pm;      // [P]
   float* X;          // [P][6]
@@ -208,4 +210,27 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   for (unsigned spin = 0; !mbar_try_wait(bar, parity); spin++)
     if (spin > (1u << 22)) __trap();
+}
+
+// Shared-memory accesses through explicit 32-bit shared addresses.  The pass kernels run at 64 registers per thread;
+// left to itself the compiler REMATERIALISES the address of a warp's scratch (S2R tid, shifts, the CTA's shared window
+// base: six instructions, two of them with S2R latency) at every use instead of keeping it in a register.  An address
+// that comes out of an opaque asm cannot be recomputed.
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }

@@ -88,6 +88,7 @@ int icet_b200_create(int device, icet_b200_ctx** out) {
     CK(cudaStreamCreateWithFlags(&c->lanes[l], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_join[l], cudaEventDisableTiming));
   }
+  for (int l = 0; l < ICET_NLANE; l++) CK(cudaEventCreateWithFlags(&c->ev_lane[l], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   for (int k = 0; k < 2; k++) CK(cudaEventCreateWithFlags(&c->ev_aux[k], cudaEventDisableTiming));
   for (int i = 0; i < ICET_NSLOT; i++) {
@@ -120,6 +121,10 @@ int icet_b200_destroy(icet_b200_ctx* c) {
   for (int l = 1; l < ICET_NLANE; l++) {
     if (c->lanes[l]) cudaStreamDestroy(c->lanes[l]);
     if (c->ev_join[l]) cudaEventDestroy(c->ev_join[l]);
+  }
+  for (int l = 0; l < ICET_NLANE; l++) {
+    c->lane_desc[l].release();
+    if (c->ev_lane[l]) cudaEventDestroy(c->ev_lane[l]);
   }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (int k = 0; k < 2; k++)
@@ -162,7 +167,7 @@ int icet_b200_synchronize(icet_b200_ctx* c) {
 
 int icet_b200_set_lanes(icet_b200_ctx* c, int32_t n) {
   if (!c) return fail(ICET_B200_E_INVALID, "ctx is NULL");
-  if (n < 0 || n > ICET_NLANE) return fail(ICET_B200_E_INVALID, "lanes must be 0 (default) .. 4");
+  if (n < 0 || n > ICET_NLANE) return fail(ICET_B200_E_INVALID, "lanes must be 0 (default) .. 8");
   c->nlanes = n == 0 ? c->nlanes_default : n;
   return 0;
 }
@@ -221,7 +226,7 @@ static int batch_device_impl(icet_b200_ctx* c, const icet_b200_params* p, int32_
   // h_desc lives in host memory; descriptors are uploaded per chunk through the pinned bounce buffer.
   // d_desc_all (callers layer): the descriptors are already on the device -- built there, with data-dependent
   // sizes no larger than nmax_dev -- and h_desc is not read.
-  int rc = ensure_pinned(c, (size_t)std::min(npairs, c->chunk_pairs) * sizeof(PairDesc) * ICET_NSLOT + 4096);
+  int rc = ensure_pinned(c, (size_t)std::min(npairs, c->chunk_pairs) * sizeof(PairDesc) * ICET_NLANE + 4096);
   if (rc) return rc;
   // consecutive chunks alternate between the two compute lanes (own stream + workspace each); lane 1 starts after
   // everything already queued on the caller's stream and the caller's stream resumes after lane 1
@@ -238,7 +243,6 @@ static int batch_device_impl(icet_b200_ctx* c, const icet_b200_params* p, int32_
     CK(cudaEventRecord(c->ev_fork, c->stream));
     for (int l = 1; l < nl; l++) CK(cudaStreamWaitEvent(c->lanes[l], c->ev_fork, 0));
   }
-  static_assert(ICET_NLANE <= ICET_NSLOT, "one descriptor slot per lane");
   int chunk_no = 0;
   for (int base = 0; base < npairs; base += chunk_pairs, chunk_no++) {
     const int P = std::min(chunk_pairs, npairs - base);
@@ -252,15 +256,17 @@ static int batch_device_impl(icet_b200_ctx* c, const icet_b200_params* p, int32_
         n1max = std::max(n1max, h_desc[base + i].n1);
         n2max = std::max(n2max, h_desc[base + i].n2);
       }
-      rc = c->descbuf[slot].ensure((size_t)P * sizeof(PairDesc));
+      // (the device buffer may grow: everything the lane has queued must be done with the old one first)
+      if ((size_t)P * sizeof(PairDesc) > c->lane_desc[slot].cap) CK(cudaStreamSynchronize(st));
+      rc = c->lane_desc[slot].ensure((size_t)P * sizeof(PairDesc));
       if (rc) return rc;
-      // the pinned half `slot` may still be in flight from two chunks ago
-      CK(cudaEventSynchronize(c->ev_done[slot]));
+      // the pinned part of this lane may still be in flight from its previous chunk
+      CK(cudaEventSynchronize(c->ev_lane[slot]));
       PairDesc* hp = (PairDesc*)c->pinned + (size_t)slot * std::min(npairs, c->chunk_pairs);
       memcpy(hp, h_desc + base, (size_t)P * sizeof(PairDesc));
-      CK(cudaMemcpyAsync(c->descbuf[slot].p, hp, (size_t)P * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
-      CK(cudaEventRecord(c->ev_done[slot], st));
-      d_desc = (const PairDesc*)c->descbuf[slot].p;
+      CK(cudaMemcpyAsync(c->lane_desc[slot].p, hp, (size_t)P * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+      CK(cudaEventRecord(c->ev_lane[slot], st));
+      d_desc = (const PairDesc*)c->lane_desc[slot].p;
     }
     const float* x0c = d_x0 ? d_x0 + (chain ? 0 : (size_t)base * 6) : nullptr;
     if (chain && base > 0) x0c = d_out[base - 1].X;  // stream order: the previous chunk has finished by then

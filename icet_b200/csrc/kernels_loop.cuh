@@ -877,10 +877,13 @@ __global__ void __launch_bounds__(VOX_THREADS) k_vox2(const Chunk ck, int iter) 
   if (wid == 0 && lane < NRED) out[lane] = tot + s_red[lane];
 }
 
-__global__ void __launch_bounds__(32) k_solve6(const Chunk ck, int iter, int nblk) {
+constexpr int SOLVE_THREADS = 128;
+__global__ void __launch_bounds__(SOLVE_THREADS) k_solve6(const Chunk ck, int iter, int nblk) {
   const int pair = blockIdx.x;
   const int lane = threadIdx.x;
   __shared__ double s_tot[NRED];
+  __shared__ float s_trb[12];
+  __shared__ int s_rebuild;
   if (lane < NRED) {
     double mine = 0.0;
     const double* pp = ck.part + (size_t)pair * nblk * NRED + lane;
@@ -890,7 +893,21 @@ __global__ void __launch_bounds__(32) k_solve6(const Chunk ck, int iter, int nbl
   __syncwarp();
   // (one thread: this kernel is bound by instruction fetch of once-executed code, the warp-parallel solve of
   // k_loop is not faster here)
-  if (lane == 0) solve_pair(ck, pair, iter, s_tot);
+  if (lane == 0) {
+    solve_pair(ck, pair, iter, s_tot);
+    s_rebuild = 0;
+    if (loop_incremental(ck) && iter < ck.runlen - 1) {
+      s_rebuild = ck.pm[pair].rebuild;  // (written by this thread a moment ago)
+      for (int k = 0; k < 12; k++) s_trb[k] = ck.pm[pair].TRb[k];
+    }
+  }
+  __syncthreads();
+  // the next iteration rebuilds: the anchors of the voxel frames at ITS transform, for k_pass2 (all threads)
+  if (s_rebuild) {
+    float trb[12];
+    for (int k = 0; k < 12; k++) trb[k] = s_trb[k];
+    anchors_update(ck, pair, trb, threadIdx.x, SOLVE_THREADS);
+  }
 }
 
 // public member `points2` of the reference: scan 2 as transformed by the last iteration

@@ -351,6 +351,8 @@ __device__ __forceinline__ void stats_from_acc(const unsigned long long* q, cons
 // K4: per voxel of scan 1: mean / covariance, 3x3 eigen-decomposition, sigma points, L mask
 // (fitCells1 src/icet.cpp:158-232, testSigmaPoints :654-696); constants for the iteration loop.
 // ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void vox_anchor2_rec(float4 ra, float4 rb, const float* trb, float fs2, float& ax, float& ay, float& az,
+                                                float& sc);  // kernels_pass2.cuh
 __global__ void __launch_bounds__(128) k_fit1(const Chunk ck) {
   pdl_prologue();
   const int pair = blockIdx.y;
@@ -422,6 +424,13 @@ __global__ void __launch_bounds__(128) k_fit1(const Chunk ck) {
   uint32_t fl = rc.flags & ~F_ACTIVE2;
   if (has && rc.cnt1 > ck.n && rc.outer > 1.0f) fl |= F_ACTIVE2;
   if (fl != rc.flags) ck.rec[ci].flags = fl;
+  if (fl & F_ACTIVE2) {  // anchor of the voxel's scan-2 frame at the transform of the first rebuild (k_cell_scan: TRb = R(X0))
+    float trb[12], ax, ay, az, sc;
+    for (int k = 0; k < 12; k++) trb[k] = ck.pm[pair].TRb[k];
+    vox_anchor2_rec(make_float4(rc.inner, rc.outer, __uint_as_float(fl), rc.scale),
+                    make_float4(rc.refx, rc.refy, rc.refz, __int_as_float(rc.cnt1)), trb, ck.fs2, ax, ay, az, sc);
+    ck.anch[ci] = make_float4(ax, ay, az, sc);
+  }
   if (rc.flags & F_STAT1)
     for (int k = 0; k < NQ; k++) q[k] = 0ull;  // hand the accumulators to the scan-2 loop
   if (has) atomicAdd(&ck.res[pair].n_gauss1, 1);

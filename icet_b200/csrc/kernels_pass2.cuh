@@ -217,6 +217,20 @@ __device__ __forceinline__ void vox_anchor2_rec(float4 ra, float4 rb, const floa
   ay = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(rb.x, R[3]), __fmul_rn(rb.y, R[4])), __fmul_rn(rb.z, R[5])), -trb[1]);
   az = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(rb.x, R[6]), __fmul_rn(rb.y, R[7])), __fmul_rn(rb.z, R[8])), -trb[2]);
 }
+// Anchor table of a pair (Chunk::anch) at the transform `trb` of the rebuild that comes next: the threads of a block,
+// `nth` of them, cell by cell.  Same function and inputs as the per-voxel algebra uses (stats2_from_moments): bit-identical.
+__device__ __forceinline__ void anchors_update(const Chunk& ck, int pair, const float* trb, int tid, int nth) {
+  const CellRec* recs = ck.rec + (size_t)pair * ck.ncell;
+  float4* an = ck.anch + (size_t)pair * ck.ncell;
+  for (int c = tid; c < ck.ncell; c += nth) {
+    const float4* rp = reinterpret_cast<const float4*>(recs + c);
+    const float4 ra = __ldcg(rp);
+    if (!(__float_as_uint(ra.z) & F_ACTIVE2)) continue;
+    float ax, ay, az, sc;
+    vox_anchor2_rec(ra, __ldcg(rp + 1), trb, ck.fs2, ax, ay, az, sc);
+    an[c] = make_float4(ax, ay, az, sc);
+  }
+}
 __device__ __forceinline__ void fix2(float px, float py, float pz, float ax, float ay, float az, float sc, int lim, int& fx,
                                      int& fy, int& fz) {
   fx = max(-lim, min(lim, __float2int_rn(__fmul_rn(__fadd_rn(px, -ax), sc))));
@@ -321,11 +335,12 @@ __device__ __forceinline__ void pass2_request_tile(int4* went, const float* src,
 //   before it stages the tables).
 // RD: rows whose margin records a lane requests together in a delta iteration.  All K of them: a delta iteration is
 // latency-bound (ncu r02g: issue slots 49 % busy, DRAM 28 %), what it needs is bytes in flight, not fewer instructions.
-template <int K, int RD = K>
+// anch: table of the voxels' anchors at the transform of this rebuild (k_pass2), or null: computed per run (loop kernels)
+template <int K, int RD = K, bool ANCH = false>
 __device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, unsigned long long* mbar, unsigned& mphase,
                                                 bool requested, const float* tab, const CellRec* recs, const float* tr,
                                                 const Pass2Mode& md, const float* pog, size_t ld, int n, int w0, uint2* mrec,
-                                                int* violations) {
+                                                int* violations, const float4* anch = nullptr) {
   static_assert(K <= 16, "list entries keep the point's index within the tile in 9 bits");
   const int lane = threadIdx.x & 31;
   if (w0 >= n) return;
@@ -334,10 +349,11 @@ __device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, uns
   const float4* tph = tth + ck.nT + 2;
   const unsigned lt = (1u << lane) - 1u;
   unsigned long long* accp = md.accp;
-  const float* tx = reinterpret_cast<const float*>(went);
-  const float* ty = tx + 32 * K;
-  const float* tz = tx + 64 * K;
-  int* list = reinterpret_cast<int*>(went) + 96 * K;
+  // shared addresses (bytes) of the warp's scratch: planes x | y | z of the tile (32*K floats each), then the list
+  const uint32_t sb = opaque_u32(smem_u32(went));
+  const uint32_t sbl = sb + 4u * lane;
+  constexpr uint32_t PL = 128u * K;   // bytes per plane
+  constexpr uint32_t LO = 3u * PL;    // offset of the list
   uint2* rp = mrec + w0;
   if (md.rebuild) {
     if (!requested) {
@@ -354,7 +370,7 @@ __device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, uns
       const int li = j * 32 + lane;
       uint32_t cls = 0u;
       if (li < cnt) {
-        const float x = tx[li], y = ty[li], z = tz[li];
+        const float x = lds_f32(sbl + 128u * j), y = lds_f32(sbl + 128u * j + PL), z = lds_f32(sbl + 128u * j + 2u * PL);
         float2 mg;
         point_eval2_fast(ck, tth, tph, recs, tr, 0.f, 0.f, x, y, z, cls, mg);
         if (violations) {  // self-check: the filtered evaluation must give the class of the exact pipeline
@@ -367,7 +383,7 @@ __device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, uns
       }
       const bool act = (cls & CLS_ACTIVE) != 0;
       const unsigned am = __ballot_sync(FULL, act);
-      if (act) list[nact + __popc(am & lt)] = (li << 23) | (int)(cls & (CLS_CELL | CLS_IN));
+      if (act) sts_u32(sb + LO + 4u * (nact + __popc(am & lt)), ((uint32_t)li << 23) | (cls & (CLS_CELL | CLS_IN)));
       nact += __popc(am);
     }
     __syncwarp();
@@ -381,20 +397,25 @@ __device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, uns
     float ax = 0.f, ay = 0.f, az = 0.f, sc = 0.f;
 #pragma unroll 2
     for (int e = e0; e < e1; e++) {
-      const unsigned v = (unsigned)list[e];
+      const unsigned v = lds_u32(sb + LO + 4u * e);
       const int c = (int)(v & CLS_CELL);
       if (c != cur) {
         flush_run2(accp, cur, nb, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
         cur = c;
         nb = nin = sx = sy = sz = 0;
         pxx = pxy = pxz = pyy = pyz = pzz = 0;
-        vox_anchor2(recs, cur, tr, md.fs2, ax, ay, az, sc);
+        if (ANCH) {
+          const float4 an = __ldg(anch + cur);
+          ax = an.x; ay = an.y; az = an.z; sc = an.w;
+        } else {
+          vox_anchor2(recs, cur, tr, md.fs2, ax, ay, az, sc);
+        }
       }
       nb++;
       if (v & CLS_IN) {
-        const int li = (int)(v >> 23);
+        const uint32_t pa = sb + 4u * (v >> 23);
         int fx, fy, fz;
-        fix2(tx[li], ty[li], tz[li], ax, ay, az, sc, md.fl2, fx, fy, fz);
+        fix2(lds_f32(pa), lds_f32(pa + PL), lds_f32(pa + 2u * PL), ax, ay, az, sc, md.fl2, fx, fy, fz);
         nin++;
         sx += fx; sy += fy; sz += fz;
         pxx += (long long)fx * fx; pxy += (long long)fx * fy; pxz += (long long)fx * fz;
@@ -425,7 +446,7 @@ __device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, uns
       // ICET_B200_FLAG_VERIFY_INCREMENTAL: evaluate the stable points as well and count those whose class changed
       const bool redo = li < cnt && (!stable || violations != nullptr);
       const unsigned rm = __ballot_sync(FULL, redo);
-      if (redo) list[nre + __popc(rm & lt)] = stable ? (li | (int)0x80000000) : li;
+      if (redo) sts_u32(sb + LO + 4u * (nre + __popc(rm & lt)), stable ? ((uint32_t)li | 0x80000000u) : (uint32_t)li);
       nre += __popc(rm);
     }
   }
@@ -442,11 +463,12 @@ __device__ __forceinline__ void pass2_warp_tile(const Chunk& ck, int4* went, uns
   for (int e0 = 0; e0 < nre; e0 += 32) {
     const int e = e0 + lane;
     if (e < nre) {
-      const bool was_stable = list[e] < 0;
-      const int li = list[e] & 0x7fffffff;
+      const uint32_t le = lds_u32(sb + LO + 4u * e);
+      const bool was_stable = (le & 0x80000000u) != 0;
+      const int li = (int)(le & 0x7fffffffu);
       float x, y, z;
       if (staged) {
-        x = tx[li]; y = ty[li]; z = tz[li];
+        x = lds_f32(sb + 4u * li); y = lds_f32(sb + 4u * li + PL); z = lds_f32(sb + 4u * li + 2u * PL);
       } else {
         const float* pp = pog + w0 + li;
         x = __ldg(pp); y = __ldg(pp + ld); z = __ldg(pp + 2 * ld);
@@ -524,9 +546,10 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass2(const Chunk ck) {
   }
   const CellRec* recs = ck.rec + (size_t)pair * ck.ncell;
   unsigned mphase = 0u;
-  pass2_warp_tile<K>(ck, went, &s_mbar[warp], mphase, requested, tabp, recs, tr, md, pog, (size_t)ck.n2max, n, w0,
+  pass2_warp_tile<K, K, true>(ck, went, &s_mbar[warp], mphase, requested, tabp, recs, tr, md, pog, (size_t)ck.n2max, n, w0,
                      ck.mrec + (size_t)pair * ck.n2max,
-                     (ck.flags & ICET_B200_FLAG_VERIFY_INCREMENTAL) ? &ck.res[pair].reserved[0] : nullptr);
+                     (ck.flags & ICET_B200_FLAG_VERIFY_INCREMENTAL) ? &ck.res[pair].reserved[0] : nullptr,
+                     ck.anch + (size_t)pair * ck.ncell);
   if (blockIdx.x == 0 && threadIdx.x == 0)
     pass2_dropped_returns(ck, reinterpret_cast<const float4*>(tabp), reinterpret_cast<const float4*>(tabp) + ck.nT + 2, recs,
                           tr, md, pair, ck.nz2[pair]);

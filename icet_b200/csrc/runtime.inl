@@ -34,7 +34,7 @@ struct DevBuf {
 
 constexpr int ICET_LOOP_MAX_PAIRS = 1;  // chunks up to this size run the Gauss-Newton loop as one persistent kernel
 constexpr int ICET_NSLOT = 4;  // staging slots of the host-buffer pipeline
-constexpr int ICET_NLANE = 4;  // compute lanes: consecutive chunks rotate over up to four streams (each with its own
+constexpr int ICET_NLANE = 8;  // compute lanes: consecutive chunks rotate over up to eight streams (each with its own
                                // workspace) so that the latency-bound ends of one chunk's kernels overlap the other's
 
 struct icet_b200_ctx {
@@ -74,6 +74,8 @@ struct icet_b200_ctx {
   int edges_nT = -1, edges_nP = -1;
   DevBuf stage[ICET_NSLOT];  // host-input staging of scans (double buffered)
   DevBuf descbuf[ICET_NSLOT];
+  DevBuf lane_desc[ICET_NLANE];        // device-resident batches: pair descriptors of the chunk a lane is working on
+  cudaEvent_t ev_lane[ICET_NLANE] = {};  //   ... and "its upload has been consumed"
   DevBuf x0buf[ICET_NSLOT];
   DevBuf resbuf;    // device results for host-facing calls
   DevBuf dumpbuf;
@@ -155,6 +157,7 @@ size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runle
   ck.pos1 = shipped ? c.take<int32_t>((size_t)P * n1max) : nullptr;
   ck.pog = c.take<float>((size_t)P * 3 * n2max);
   ck.mrec = c.take<uint2>((size_t)P * n2max);
+  ck.anch = c.take<float4>((size_t)P * ncell);
   ck.X = c.take<float>((size_t)P * 6);
   ck.TR = c.take<float>((size_t)P * 12);
   ck.TRprev = c.take<float>((size_t)P * 12);
@@ -526,7 +529,7 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
         else LAUNCH(7, k_pass2<><<<gp2, PASS_THREADS, psm, st>>>(ck));
       }
       LAUNCH(8, k_vox2<<<dim3(nblk, P), VOX_THREADS, 0, st>>>(ck, it));
-      LAUNCH(9, k_solve6<<<P, 32, 0, st>>>(ck, it, nblk));
+      LAUNCH(9, k_solve6<<<P, SOLVE_THREADS, 0, st>>>(ck, it, nblk));
     }
   } else if (p->runlen > 0) {
     // persistent: as many blocks as can be resident (more would only queue behind them)
