@@ -507,9 +507,9 @@ __device__ __forceinline__ void load_pass2_mode(const Chunk& ck, int pair, Pass2
   md.accp = ck.acc + ((size_t)h.x * ck.npairs + pair) * ck.ncell * NQ;
 }
 
-// TPW: warp tiles per warp (consecutive CTA tiles of PASS_WARPS warp tiles each): the per-CTA set-up (mode, transform,
-// tables, barrier) is paid once per TPW * pass_tile_points(K) points
-template <int K = PASS_K, int MINB = PASS_MINB, int TPW = 1>
+// (Measured and dropped, r02: several warp tiles per warp without double buffering (-4 %); requesting the margin records
+// before the pair's mode is known (no gain, more registers).)
+template <int K = PASS_K, int MINB = PASS_MINB>
 __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass2(const Chunk ck) {
   pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -518,18 +518,18 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass2(const Chunk ck) {
   float* tab = reinterpret_cast<float*>(smem_raw + PASS_WARPS * pass_wslots(K) * 16);
   const int pair = blockIdx.y;
   const int n = ck.n2c[pair];
-  const int tile0 = blockIdx.x * (TPW * pass_tile_points(K));
+  const int tile0 = blockIdx.x * pass_tile_points(K);
   if (tile0 >= n && blockIdx.x != 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int4* went = ent + warp * pass_wslots(K);
-  int w0 = tile0 + warp * 32 * K;
+  const int w0 = tile0 + warp * 32 * K;
   const float* pog = ck.pog + (size_t)pair * 3 * ck.n2max;
   Pass2Mode md;
   load_pass2_mode(ck, pair, md);
   if (lane == 0) mbar_init(&s_mbar[warp], 1);
   __syncwarp();
   // a rebuild iteration reads every coordinate of the tile: request it before anything else
-  bool requested = md.rebuild && w0 < n;
+  const bool requested = md.rebuild && w0 < n;
   if (requested && lane == 0) pass2_request_tile<K>(went, pog + w0, (size_t)ck.n2max, min(n - w0, 32 * K), &s_mbar[warp]);
   // delta iterations only read the look-up tables for the few points they re-evaluate: straight from global memory
   const float* tabp = ck.binrec;
@@ -548,12 +548,10 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass2(const Chunk ck) {
   }
   const CellRec* recs = ck.rec + (size_t)pair * ck.ncell;
   unsigned mphase = 0u;
-#pragma unroll 1
-  for (int t = 0; t < TPW; t++, w0 += pass_tile_points(K), requested = false)
-    pass2_warp_tile<K, K, true>(ck, went, &s_mbar[warp], mphase, requested, tabp, recs, tr, md, pog, (size_t)ck.n2max, n, w0,
-                                ck.mrec + (size_t)pair * ck.n2max,
-                                (ck.flags & ICET_B200_FLAG_VERIFY_INCREMENTAL) ? &ck.res[pair].reserved[0] : nullptr,
-                                ck.anch + (size_t)pair * ck.ncell);
+  pass2_warp_tile<K, K, true>(ck, went, &s_mbar[warp], mphase, requested, tabp, recs, tr, md, pog, (size_t)ck.n2max, n, w0,
+                              ck.mrec + (size_t)pair * ck.n2max,
+                              (ck.flags & ICET_B200_FLAG_VERIFY_INCREMENTAL) ? &ck.res[pair].reserved[0] : nullptr,
+                              ck.anch + (size_t)pair * ck.ncell);
   if (blockIdx.x == 0 && threadIdx.x == 0)
     pass2_dropped_returns(ck, reinterpret_cast<const float4*>(tabp), reinterpret_cast<const float4*>(tabp) + ck.nT + 2, recs,
                           tr, md, pair, ck.nz2[pair]);
