@@ -84,13 +84,13 @@ __global__ void __launch_bounds__(256) k_scan1_bin(const Chunk ck) {
     ck.th1[o] = th;
     ck.ph1[o] = ph;
   }
-  // warp-aggregated histogram
+  // warp-aggregated histogram.  Every lane takes part in the match and in the vote (rows beyond the cloud form their
+  // own group with cell -1): collectives under a divergent mask cost a WARPSYNC round per group.
   const int lane = threadIdx.x & 31;
-  const unsigned act = __ballot_sync(FULL, cell >= 0);
-  if (cell >= 0) {
-    const unsigned m = __match_any_sync(act, cell);
-    const unsigned mz = __ballot_sync(m, zero);
-    if (lane == __ffs(m) - 1) {
+  {
+    const unsigned m = __match_any_sync(FULL, cell);
+    const unsigned mz = __ballot_sync(FULL, zero) & m;
+    if (cell >= 0 && lane == __ffs(m) - 1) {
       atomicAdd(&ck.cnt1[(size_t)pair * ck.ncell + cell], __popc(m));
       if (mz) atomicAdd(&ck.cntz[(size_t)pair * ck.ncell + cell], __popc(mz));
     }
@@ -199,15 +199,16 @@ __global__ void __launch_bounds__(256) k_scatter(const Chunk ck) {
     if (r != 0.0f) cell = ck.cellid1[(size_t)pair * ck.n1max + i] & ~CELL_INBOX;
   }
   const int lane = threadIdx.x & 31;
-  const unsigned act = __ballot_sync(FULL, cell >= 0);
+  // (every lane takes part in the match and the shuffle; zero ranges / rows beyond the cloud: group of cell -1)
+  const unsigned m = __match_any_sync(FULL, cell);
+  const int leader = __ffs(m) - 1;
+  int base = 0, off = 0;
+  if (cell >= 0) off = __ldg(&ck.off[(size_t)pair * ck.ncell + cell]);  // (requested beside the atomic)
+  if (cell >= 0 && lane == leader) base = atomicAdd(&ck.cursor[(size_t)pair * ck.ncell + cell], __popc(m));
+  base = __shfl_sync(FULL, base, leader);
   if (cell >= 0) {
-    const unsigned m = __match_any_sync(act, cell);
-    const int leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&ck.cursor[(size_t)pair * ck.ncell + cell], __popc(m));
-    base = __shfl_sync(m, base, leader);
     const int rank = __popc(m & ((1u << lane) - 1));
-    ck.rbuf[(size_t)pair * ck.n1max + ck.off[(size_t)pair * ck.ncell + cell] + base + rank] = r;
+    ck.rbuf[(size_t)pair * ck.n1max + off + base + rank] = r;
   }
 }
 
