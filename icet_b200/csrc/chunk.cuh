@@ -92,6 +92,10 @@ struct Chunk {  // everything a kernel needs, passed by value
   float* th1;        // [P][n1max]  theta, phi of scan 1 (K1 -> K3: the second pass over scan 1 does not redo the
   float* ph1;        // [P][n1max]  spherical conversion)
   float* rbuf;       // [P][n1max]  non-zero ranges grouped by cell
+  int32_t* cellg;    // [P][n1max]  ... and, in the same grouped order, cell | CELL_INBOX, theta, phi of those points: the
+  float* thg;        // [P][n1max]  second pass over scan 1 (K3) walks the points cell by cell (long runs of equal cell,
+  float* phg;        // [P][n1max]  also for an unordered cloud such as an accumulated map).  Null in shipped-order mode.
+  int32_t* n1g;      // [P]         number of grouped (non-zero) points
   unsigned long long* kbuf;  // [n1max]  ICET_B200_FLAG_SHIPPED_ORDER: (row position << 32 | range bits) grouped by cell
   int32_t* pos1;     // [n1max]  ... position of every row of scan 1 in the reference's shipped row order
   int32_t* cnt1;     // [P][ncell]

@@ -267,10 +267,12 @@ __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* th
   int cur = -1, nin = 0, sx = 0, sy = 0, sz = 0;
   long long pxx = 0, pxy = 0, pxz = 0, pyy = 0, pyz = 0, pzz = 0;
   float refx = 0.f, refy = 0.f, refz = 0.f, sc = 0.f;
+  bool flushed = false;  // this lane has published a run already (its slice spans more than one cell)
 #pragma unroll 2
   for (int e = e0; e < e1; e++) {
     const int4 v = went[e];
     if (v.x != cur) {
+      if (cur >= 0) flushed = true;
       flush_in_run(accp, cur, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
       cur = v.x;
       nin = sx = sy = sz = 0;
@@ -287,6 +289,29 @@ __device__ __forceinline__ void pass_warp_tile(const Chunk& ck, int4* went /* th
     pxx += (long long)fx * fx; pxy += (long long)fx * fy; pxz += (long long)fx * fz;
     pyy += (long long)fy * fy; pyz += (long long)fy * fz; pzz += (long long)fz * fz;
   }
+  if (!SCAN2) {
+    // Scan 1 walks its points cell by cell: usually every lane of the tile has collected sums of ONE and the same cell.
+    // Then the warp adds them up (shuffles) and publishes them once -- 11 REDs per tile instead of 11 per lane, which is
+    // what keeps the few hot voxels of an accumulated map (10^5 points each) from serialising in the L2 atomic units.
+    const int c0 = __shfl_sync(FULL, cur, 0);
+    if (__all_sync(FULL, !flushed && (cur == c0 || cur < 0))) {
+      long long v[9] = {(long long)sx, (long long)sy, (long long)sz, pxx, pxy, pxz, pyy, pyz, pzz};
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        nin += __shfl_xor_sync(FULL, nin, o);
+#pragma unroll
+        for (int k = 0; k < 9; k++) v[k] += __shfl_xor_sync(FULL, v[k], o);
+      }
+      if (lane == 0 && c0 >= 0 && nin > 0) {
+        unsigned long long* q = accp + (size_t)c0 * NQ;
+        red_add(q + 1, (unsigned long long)nin);
+#pragma unroll
+        for (int k = 0; k < 9; k++) red_add(q + 2 + k, (unsigned long long)v[k]);
+      }
+      __syncwarp();
+      return;
+    }
+  }
   flush_in_run(accp, cur, nin, sx, sy, sz, pxx, pxy, pxz, pyy, pyz, pzz);
   __syncwarp();
 }
@@ -299,7 +324,9 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass(const Chunk ck) {
   float* tab = reinterpret_cast<float*>(smem_raw + PASS_WARPS * pass_wslots(K) * 16);
   const int pair = blockIdx.y;
   const PairDesc d = ck.desc[pair];
-  const int n = SCAN2 ? ck.n2c[pair] : d.n1;
+  // scan 1: the points grouped by cell (k_scatter) unless the chunk runs in shipped-order mode
+  const bool grouped = !SCAN2 && ck.cellg != nullptr;
+  const int n = SCAN2 ? ck.n2c[pair] : (grouped ? ck.n1g[pair] : d.n1);
   const int tile0 = blockIdx.x * pass_tile_points(K);
   if (tile0 >= n && !(SCAN2 && blockIdx.x == 0)) return;
   {
@@ -314,14 +341,15 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass(const Chunk ck) {
     tr[8] = c.x; tr[9] = c.y; tr[10] = c.z; tr[11] = c.w;
   }
   const size_t o1 = (size_t)pair * ck.n1max;
-  const float* px_ = SCAN2 ? ck.pog + (size_t)pair * 3 * ck.n2max : ck.r1 + o1;
+  const float* px_ = SCAN2 ? ck.pog + (size_t)pair * 3 * ck.n2max : (grouped ? ck.rbuf : ck.r1) + o1;
   const size_t ld = SCAN2 ? (size_t)ck.n2max : (size_t)d.ld1;
   const CellRec* recs = ck.rec + (size_t)pair * ck.ncell;
   unsigned long long* accp = ck.acc + (size_t)pair * ck.ncell * NQ;
   __syncthreads();
   pass_warp_tile<SCAN2, K, PF, G>(ck, ent + (threadIdx.x >> 5) * pass_wslots(K), tab, recs, tr, px_, ld, n,
-                           tile0 + (threadIdx.x >> 5) * 32 * K, accp, nullptr, SCAN2 ? nullptr : ck.cellid1 + o1,
-                           SCAN2 ? nullptr : ck.th1 + o1, SCAN2 ? nullptr : ck.ph1 + o1);
+                           tile0 + (threadIdx.x >> 5) * 32 * K, accp, nullptr,
+                           SCAN2 ? nullptr : (grouped ? ck.cellg : ck.cellid1) + o1,
+                           SCAN2 ? nullptr : (grouped ? ck.thg : ck.th1) + o1, SCAN2 ? nullptr : (grouped ? ck.phg : ck.ph1) + o1);
   if (SCAN2 && blockIdx.x == 0 && threadIdx.x == 0)
     pass_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 2, recs, tr,
                          accp, ck.nz2[pair]);

@@ -165,7 +165,10 @@ __global__ void __launch_bounds__(256) k_cell_scan(const Chunk ck) {
   __syncthreads();
   int a = is - s, b = iw - w;
   for (int q = 0; q < warp; q++) { a += s_ws[q]; b += s_ww[q]; }
-  if (threadIdx.x == 255) ck.nwork[pair] = b + w;
+  if (threadIdx.x == 255) {
+    ck.nwork[pair] = b + w;
+    ck.n1g[pair] = a + s;  // every non-zero range of the pair
+  }
   for (int c = c0; c < c1; c++) {
     ck.off[(size_t)pair * ck.ncell + c] = a;
     a += cnt1[c] - cntz[c];
@@ -192,11 +195,14 @@ __global__ void __launch_bounds__(256) k_scatter(const Chunk ck) {
   const PairDesc d = ck.desc[pair];
   if ((int)(blockIdx.x * blockDim.x) >= d.n1) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int cell = -1;
-  float r = 0.f;
+  int cell = -1, cid = 0;
+  float r = 0.f, th = 0.f, ph = 0.f;
   if (i < d.n1) {
-    r = ck.r1[(size_t)pair * ck.n1max + i];
-    if (r != 0.0f) cell = ck.cellid1[(size_t)pair * ck.n1max + i] & ~CELL_INBOX;
+    const size_t o = (size_t)pair * ck.n1max + i;
+    r = ck.r1[o];
+    cid = ck.cellid1[o];
+    if (ck.cellg) { th = ck.th1[o]; ph = ck.ph1[o]; }
+    if (r != 0.0f) cell = cid & ~CELL_INBOX;
   }
   const int lane = threadIdx.x & 31;
   // (every lane takes part in the match and the shuffle; zero ranges / rows beyond the cloud: group of cell -1)
@@ -208,7 +214,9 @@ __global__ void __launch_bounds__(256) k_scatter(const Chunk ck) {
   base = __shfl_sync(FULL, base, leader);
   if (cell >= 0) {
     const int rank = __popc(m & ((1u << lane) - 1));
-    ck.rbuf[(size_t)pair * ck.n1max + off + base + rank] = r;
+    const size_t g = (size_t)pair * ck.n1max + off + base + rank;
+    ck.rbuf[g] = r;
+    if (ck.cellg) { ck.cellg[g] = cid; ck.thg[g] = th; ck.phg[g] = ph; }
   }
 }
 

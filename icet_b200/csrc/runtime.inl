@@ -153,6 +153,10 @@ size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runle
   ck.th1 = c.take<float>((size_t)P * n1max);
   ck.ph1 = c.take<float>((size_t)P * n1max);
   ck.rbuf = c.take<float>((size_t)P * n1max);
+  ck.cellg = shipped ? nullptr : c.take<int32_t>((size_t)P * n1max);
+  ck.thg = shipped ? nullptr : c.take<float>((size_t)P * n1max);
+  ck.phg = shipped ? nullptr : c.take<float>((size_t)P * n1max);
+  ck.n1g = c.take<int32_t>((size_t)P);
   ck.kbuf = shipped ? c.take<unsigned long long>((size_t)P * n1max) : nullptr;
   ck.pos1 = shipped ? c.take<int32_t>((size_t)P * n1max) : nullptr;
   ck.pog = c.take<float>((size_t)P * 3 * n2max);
