@@ -600,49 +600,168 @@ __global__ void __launch_bounds__(256) k_huge_hist(const Chunk ck) {
   if (__any_sync(FULL, overflow) && lane == 0) atomicOr(&ck.hflag[slot], 1);
 }
 
-__global__ void __launch_bounds__(32) k_huge_walk(const Chunk ck) {
+// The walk over the bucket table of one huge cell, by one CTA.  The sequential walk (see the CTA path of k_cluster) is
+//     for every non-empty bucket j in ascending order:  a BREAK in front of j  <=>  something precedes j and
+//     !(|max of the previous non-empty bucket - min of j| <= thresh);  the run that ends at the first break whose run
+//     holds >= n elements is the cluster (src/icet.cpp:572-582); else the last run, with the zero check (:592-603)
+// i.e. a segmented scan: thread t owns HW_PER consecutive buckets; three block scans carry (elements so far, max of the
+// last non-empty bucket so far, position / min of the last break so far) across the threads.  One serial warp over
+// 32 768 buckets with dependent loads took 1.39 ms for a 2 M-point map; this form takes microseconds.
+constexpr int HW_THREADS = 1024;
+constexpr int HW_PER = HUGE_NB / HW_THREADS;  // 32 buckets per thread
+static_assert(HUGE_NB % HW_THREADS == 0 && HW_PER % 4 == 0, "bucket table / walk shape");
+
+struct HwCarry {     // "last one wins" summaries of a range of buckets
+  int cnt;           // elements in the range
+  int has;           // the range has a non-empty bucket
+  int lastmax;       // ... max (bits) of its last non-empty bucket
+  int hasbrk;        // the range has a break
+  int brkidx;        // ... elements in front of its last break (within the range: relative, made absolute by the caller)
+  int brkmin;        // ... min (bits) of the bucket behind that break
+};
+
+// inclusive block scan of a value with an associative operator; returns the EXCLUSIVE prefix of the calling thread
+template <class T, class Op>
+__device__ __forceinline__ T block_scan_excl(T v, T ident, Op op, T* s_w /* [32] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    T u;
+    unsigned char* pu = reinterpret_cast<unsigned char*>(&u);
+    const unsigned char* pi = reinterpret_cast<const unsigned char*>(&inc);
+    static_assert(sizeof(T) % 4 == 0, "word-sized scan values");
+    for (int k = 0; k < (int)sizeof(T) / 4; k++)
+      reinterpret_cast<int*>(pu)[k] = __shfl_up_sync(FULL, reinterpret_cast<const int*>(pi)[k], o);
+    if (lane >= o) inc = op(u, inc);
+  }
+  __syncthreads();  // (s_w may still be read from a previous scan)
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  T pre = ident;
+  for (int w = 0; w < warp; w++) pre = op(pre, s_w[w]);
+  // exclusive within the warp
+  T exw;
+  {
+    unsigned char* pu = reinterpret_cast<unsigned char*>(&exw);
+    const unsigned char* pi = reinterpret_cast<const unsigned char*>(&inc);
+    for (int k = 0; k < (int)sizeof(T) / 4; k++)
+      reinterpret_cast<int*>(pu)[k] = __shfl_up_sync(FULL, reinterpret_cast<const int*>(pi)[k], 1);
+  }
+  return lane == 0 ? pre : op(pre, exw);
+}
+
+__global__ void __launch_bounds__(HW_THREADS) k_huge_walk(const Chunk ck) {
   const int slot = blockIdx.x;
   if (slot >= min(*ck.nhuge, HUGE_SLOTS) || ck.hflag[slot] != 0) return;
   const int pair = ck.hpair[slot], cell = ck.hcell[slot];
   const size_t ci = (size_t)pair * ck.ncell + cell;
   const int cnt = ck.cnt1[ci], nz = ck.cntz[ci], m = cnt - nz;
   const int32_t* t = ck.hbkt + (size_t)slot * 3 * HUGE_NB;
-  const int lane = threadIdx.x;
-  // the walk of the CTA path of k_cluster (see there), over one window that covers every range
-  int idx = nz, start = 0;
-  float start_val = 0.f, prev_val = 0.f, inner = 0.f, outer = 0.f;
-  bool found = false;
-  for (int base = 0; base < HUGE_NB && !found && idx < nz + m; base += 32) {
-    const int c = t[base + lane];
-    unsigned mask = __ballot_sync(FULL, c > 0);
-    while (mask && !found) {
-      const int kb = base + __ffs(mask) - 1;
-      mask &= mask - 1;
-      const int bc = t[kb];
-      const float mn = __int_as_float(t[HUGE_NB + kb]), mxv = __int_as_float(t[2 * HUGE_NB + kb]);
-      if (idx > 0) {
-        if (!(fabsf(prev_val - mn) <= ck.thresh)) {  // a break in front of this bucket (reference :572)
-          if (idx - start >= ck.n) {
-            inner = start_val - ck.buff;             // :577-582, no zero check
-            outer = prev_val + ck.buff;
-            found = true;
-            break;
-          }
-          start = idx;
-          start_val = mn;
+  const int b0 = threadIdx.x * HW_PER;
+  __shared__ int2 s_a[32];
+  __shared__ int4 s_b[32];
+  __shared__ int s_best;
+  __shared__ float s_res[2];
+  if (threadIdx.x == 0) s_best = 0x7fffffff;
+  // the thread's buckets: counts, mins, maxs (vector loads; the table is L2-resident, k_huge_hist has just filled it)
+  int c[HW_PER], mn[HW_PER], mx[HW_PER];
+#pragma unroll
+  for (int k = 0; k < HW_PER; k += 4) {
+    const int4 a = *reinterpret_cast<const int4*>(t + b0 + k);
+    const int4 b = *reinterpret_cast<const int4*>(t + HUGE_NB + b0 + k);
+    const int4 d = *reinterpret_cast<const int4*>(t + 2 * HUGE_NB + b0 + k);
+    c[k] = a.x; c[k + 1] = a.y; c[k + 2] = a.z; c[k + 3] = a.w;
+    mn[k] = b.x; mn[k + 1] = b.y; mn[k + 2] = b.z; mn[k + 3] = b.w;
+    mx[k] = d.x; mx[k + 1] = d.y; mx[k + 2] = d.z; mx[k + 3] = d.w;
+  }
+  // scan 1: elements in front of the thread's buckets, max of the last non-empty bucket in front of them
+  int2 mine = make_int2(0, -1);  // {count, last max bits or -1}
+#pragma unroll
+  for (int k = 0; k < HW_PER; k++)
+    if (c[k] > 0) { mine.x += c[k]; mine.y = mx[k]; }
+  const int2 pre = block_scan_excl(mine, make_int2(0, -1),
+                                   [](int2 a, int2 b) { return make_int2(a.x + b.x, b.y >= 0 ? b.y : a.y); }, s_a);
+  // local pass: breaks.  idx = elements in front of bucket k (the nz zeros first); prev = max of the previous non-empty
+  // bucket, 0.0 for the zeros / the start
+  int idx = nz + pre.x;
+  float prev = pre.y >= 0 ? __int_as_float(pre.y) : 0.0f;
+  bool any_before = nz > 0 || pre.y >= 0;  // (idx > 0 in the sequential walk)
+  // the thread's breaks: {first: position, idx}, {last: idx, min}; run lengths between its own breaks are checked here
+  int first_brk_idx = -1, last_brk_idx = -1, last_brk_min = 0;
+  int found_k = -1;          // first bucket of this thread whose break ends a run of >= n that STARTED in this thread
+  float found_in = 0.f, found_out = 0.f;
+  int first_brk_k = -1;
+  float first_brk_prev = 0.f;  // max in front of the thread's first break (the run that ends there began earlier)
+#pragma unroll
+  for (int k = 0; k < HW_PER; k++) {
+    if (c[k] > 0) {
+      const float mnv = __int_as_float(mn[k]);
+      if (any_before && !(fabsf(prev - mnv) <= ck.thresh)) {
+        if (first_brk_idx < 0) {
+          first_brk_idx = idx; first_brk_k = k; first_brk_prev = prev;
+        } else if (found_k < 0 && idx - last_brk_idx >= ck.n) {
+          found_k = k; found_in = __int_as_float(last_brk_min) - ck.buff; found_out = prev + ck.buff;
         }
-      } else {
-        start_val = mn;
+        last_brk_idx = idx; last_brk_min = mn[k];
       }
-      idx += bc;
-      prev_val = mxv;
+      idx += c[k];
+      prev = __int_as_float(mx[k]);
+      any_before = true;
     }
   }
-  if (!found && nz + m - start >= ck.n && start_val != 0.0f) {  // end of the data (:592-603)
-    inner = start_val - ck.buff;
-    outer = prev_val + ck.buff;
+  // scan 2: the last break in front of the thread: {has, idx, min bits}
+  const int4 lb = block_scan_excl(make_int4(last_brk_idx >= 0 ? 1 : 0, last_brk_idx, last_brk_min, 0), make_int4(0, 0, 0, 0),
+                                  [](int4 a, int4 b) { return b.x ? b : a; }, s_b);
+  // the run that ends at the thread's FIRST break started at the last break in front of the thread, or at element 0
+  // (then its first value is 0.0 if there are zeros, else the min of the very first non-empty bucket: thread-uniform
+  // quantity found below)
+  int cand = 0x7fffffff;  // global bucket index of the thread's first qualifying break
+  bool cand_first = false;
+  if (first_brk_idx >= 0 && first_brk_idx - (lb.x ? lb.y : 0) >= ck.n) { cand = b0 + first_brk_k; cand_first = true; }
+  else if (found_k >= 0) cand = b0 + found_k;
+  __syncthreads();
+  if (cand != 0x7fffffff) atomicMin(&s_best, cand);
+  // min of the very first non-empty bucket of the table (start value of the first run when there are no zeros)
+  __shared__ int s_firstmin_k, s_firstmin;
+  if (threadIdx.x == 0) s_firstmin_k = 0x7fffffff;
+  __syncthreads();
+  int fk = -1, fmn = 0;
+#pragma unroll
+  for (int k = HW_PER - 1; k >= 0; k--)
+    if (c[k] > 0) { fk = k; fmn = mn[k]; }
+  if (fk >= 0) atomicMin(&s_firstmin_k, b0 + fk);
+  __syncthreads();
+  if (fk >= 0 && s_firstmin_k == b0 + fk) s_firstmin = fmn;
+  __syncthreads();
+  const float first_val = (nz > 0 || s_firstmin_k == 0x7fffffff) ? 0.0f : __int_as_float(s_firstmin);
+  if (cand != 0x7fffffff && cand == s_best) {  // exactly one thread
+    if (cand_first) {
+      s_res[0] = (lb.x ? __int_as_float(lb.z) : first_val) - ck.buff;
+      s_res[1] = first_brk_prev + ck.buff;
+    } else {
+      s_res[0] = found_in;
+      s_res[1] = found_out;
+    }
   }
-  if (lane == 0) write_cluster_rec(ck, pair, cell, cnt, inner, outer);
+  __syncthreads();
+  float inner = 0.f, outer = 0.f;
+  if (s_best != 0x7fffffff) {
+    inner = s_res[0];
+    outer = s_res[1];
+  } else if (threadIdx.x == HW_THREADS - 1) {
+    // end of the data (:592-603): the run behind the last break of the whole table (inclusive of this thread's)
+    const int st = last_brk_idx >= 0 ? last_brk_idx : (lb.x ? lb.y : 0);
+    const float sv = last_brk_idx >= 0 ? __int_as_float(last_brk_min) : (lb.x ? __int_as_float(lb.z) : first_val);
+    if (nz + m - st >= ck.n && sv != 0.0f) {
+      inner = sv - ck.buff;
+      outer = prev + ck.buff;  // max of the last non-empty bucket of the table
+    }
+    s_res[0] = inner;
+    s_res[1] = outer;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) write_cluster_rec(ck, pair, cell, cnt, s_res[0], s_res[1]);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -447,7 +447,7 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
     if (ck.hbkt) {  // accumulated maps: cells with tens of thousands of ranges are clustered by many CTAs each
       LAUNCH(3, k_huge_init<<<dim3(HUGE_SPLIT, HUGE_SLOTS), 256, 0, st>>>(ck));
       LAUNCH(3, k_huge_hist<<<dim3(HUGE_SPLIT, HUGE_SLOTS), 256, 0, st>>>(ck));
-      LAUNCH(3, k_huge_walk<<<HUGE_SLOTS, 32, 0, st>>>(ck));
+      LAUNCH(3, k_huge_walk<<<HUGE_SLOTS, HW_THREADS, 0, st>>>(ck));
     }
     // one warp per listed cell; enough CTAs to cover a typical work list (~25 % of the cells) in one pass
     int gx = std::max(1, std::min((ncell + CLUSTER_WARPS - 1) / CLUSTER_WARPS,
