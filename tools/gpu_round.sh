@@ -18,8 +18,11 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
   echo "== ncu launch list"
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 1 --warmup 3 --pairs-per-gpu 256 --lanes 1 --no-cpu-baseline --no-latency --no-e2e --no-callers --no-configs > $OUT/ncu_bench.log 2>&1
-  echo "== ncu full capture of k_pass<scan2>, k_pass<scan1>"
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pass -s 3 -c 2 -f -o $OUT/prof_kpass \
-    python bench.py --steps 1 --warmup 3 --pairs-per-gpu 256 --lanes 1 --no-cpu-baseline --no-latency --no-e2e --no-callers --no-configs > $OUT/ncu_full.log 2>&1
-  cp icet_b200/lib/libicet_b200.so $OUT/libicet_b200.so; ls -la $OUT
+  echo "== ncu full capture: the 7 scan-2 pass launches of one 256-pair chunk; the first launch of each scan-1 kernel"
+  NARGS="--steps 1 --warmup 1 --pairs-per-gpu 256 --lanes 1 --no-cpu-baseline --no-latency --no-e2e --no-callers --no-configs"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pass2 -s 7 -c 7 -f -o $OUT/prof \
+    python bench.py $NARGS > $OUT/ncu_full.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:k_scan1_bin|k_scatter|k_cluster|k_pass<' -s 0 -c 4 -f -o $OUT/prof_setup \
+    python bench.py $NARGS > $OUT/ncu_setup.log 2>&1
+  ls -la $OUT
 fi

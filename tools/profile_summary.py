@@ -3,7 +3,7 @@
 profiles/<tag>.md: bench lines, the ncu launch list aggregated per kernel, the key metrics of the
 `ncu --set full` capture of the dominant kernel and its hottest source lines.
 
-    python tools/profile_summary.py <tag> [kernel-regex-for-lines]
+    python tools/profile_summary.py <tag>
 """
 import collections
 import csv
@@ -128,10 +128,11 @@ def main():
     reps = sorted((f for f in os.listdir(d) if f.endswith(".ncu-rep")), key=lambda f: (-len(f), f))  # prof.ncu-rep (7 iterations) last
     for rep in reps:
         md += ["## ncu --set full: %s" % rep, "", raw_table(os.path.join(d, rep)), ""]
-        if len(sys.argv) > 2:
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), os.path.join(d, rep),
-                                sys.argv[2], "30"], capture_output=True, text=True)
-            md += ["Hottest source lines (executed instructions / stall samples):", "```", r.stdout.strip(), "```", ""]
+        for launch in ((0, 6) if rep == "prof.ncu-rep" else (0,)):  # the scan-2 pass: a rebuild and the last delta launch
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_srclines.py"), os.path.join(d, rep), "32",
+                                str(launch)], capture_output=True, text=True)
+            md += ["Hottest source lines of launch %d (ncu's own source correlation: executed warp instructions / stall "
+                   "samples / average active threads):" % launch, "```", "\n".join(l[:170] for l in r.stdout.strip().splitlines()), "```", ""]
     # raw launch list next to the summary; DRAM traffic of the dominant kernel for bench.py's roofline.traffic
     p = os.path.join(d, "launches.csv")
     if os.path.exists(p):

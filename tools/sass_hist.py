@@ -9,7 +9,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "icet_b200", "lib", "libicet_b200.so")
-WANT = [("k_pass2", r"k_pass2ILi12ELi4"), ("k_pass<scan2> (EXACT_PASS)", r"k_passILb1ELi12ELi4ELi2ELi1"),
+WANT = [("k_pass2", r"k_pass2ILi12ELi4"), ("k_huge_walk", r"k_huge_walk"), ("k_pass<scan2> (EXACT_PASS)", r"k_passILb1ELi12ELi4ELi2ELi1"),
         ("k_loop_cluster", r"k_loop_cluster"), ("k_loop<4>", r"k_loopILi4"), ("k_scan1_bin", r"k_scan1_bin"),
         ("k_vox2", r"k_vox2"), ("k_huge_hist", r"k_huge_hist")]
 GROUPS = [("fp32 arithmetic", r"^(FADD|FMUL|FFMA|FMNMX|FSEL|FSET|FSETP|FCHK|FRND)"), ("fp64", r"^(DADD|DMUL|DFMA|DSETP|DMNMX)"),
@@ -18,7 +18,7 @@ GROUPS = [("fp32 arithmetic", r"^(FADD|FMUL|FFMA|FMNMX|FSEL|FSET|FSETP|FCHK|FRND
           ("moves", r"^(MOV|S2R|CS2R|S2UR|R2UR|UMOV)"), ("global / local loads", r"^(LDG|LD\b|LDL|LDC|ULDC)"),
           ("global / local stores", r"^(STG|ST\b|STL)"), ("shared memory", r"^(LDS|STS|LDSM|ATOMS)"),
           ("atomics / reductions to L2", r"^(RED|ATOMG|ATOM\b)"), ("warp collectives", r"^(SHFL|VOTE|MATCH|REDUX)"),
-          ("barriers / fences / cluster", r"^(BAR|MEMBAR|ERRBAR|CCTL|UCGABAR|WARPSYNC|NANOSLEEP|ACQBULK|DEPBAR)"),
+          ("barriers / fences / cluster / mbarrier", r"^(BAR|MEMBAR|ERRBAR|CCTL|UCGABAR|WARPSYNC|NANOSLEEP|ACQBULK|DEPBAR|SYNCS|FENCE)"),
           ("control flow", r"^(BRA|BSSY|BSYNC|EXIT|CALL|RET|BRX|JMP|BREAK|YIELD|NOP|BPT)"),
           ("tensor core / TMA (UTC*MMA, UTMA*, HMMA)", r"^(UTC|UTMA|UBLKCP|HMMA|LDTM|STTM)")]
 
@@ -37,8 +37,9 @@ def main():
             funcs[cur].append(m.group(2))
     print("# SASS instruction histograms (static; `cuobjdump -sass icet_b200/lib/libicet_b200.so`, tools/sass_hist.py)\n")
     print("Static counts of the compiled code (all paths, unrolled copies included), NOT executed instructions -- those are in "
-          "the ncu summaries (`smsp__inst_executed.sum`).  No `UTC*MMA` / `UTMA*`: the path has no dense contraction and no "
-          "tile-shaped bulk copies (SURVEY.md 8d); `UCGABAR_*` = thread-block-cluster barriers of `k_loop_cluster`.\n")
+          "the ncu summaries (`smsp__inst_executed.sum`).  No `UTC*MMA`: the path has no dense contraction (SURVEY.md 8d).  "
+          "`UBLKCP.S.G` = the bulk asynchronous copies (TMA engine, `cp.async.bulk`) that stage the scan-2 tiles, `SYNCS.*` = "
+          "their mbarrier arrive / try_wait; `UCGABAR_*` = thread-block-cluster barriers of `k_loop_cluster`.\n")
     for title, pat in WANT:
         name = next((f for f in funcs if re.search(pat, f)), None)
         if not name:
@@ -62,7 +63,7 @@ def main():
             top = ", ".join("%s %d" % kv for kv in sorted(left.items(), key=lambda kv: -kv[1])[:6])
             print("| other | %d | %.1f %% | %s |" % (n, 100.0 * n / len(ops), top))
         full = collections.Counter(ops)
-        extra = {k: v for k, v in full.items() if k.startswith(("MUFU", "UCGABAR", "RED", "ATOMG", "MATCH"))}
+        extra = {k: v for k, v in full.items() if k.startswith(("MUFU", "UCGABAR", "RED", "ATOMG", "MATCH", "UBLKCP", "SYNCS"))}
         if extra:
             print("\nDetail: " + ", ".join("`%s` %d" % kv for kv in sorted(extra.items())))
         print()
