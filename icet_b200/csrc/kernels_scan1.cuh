@@ -40,6 +40,13 @@ __device__ __forceinline__ void prep2_compact(const Chunk& ck, int pair, float x
   }
 }
 
+// Cells with up to this many non-zero ranges are clustered by one warp (k_cluster): WSORT_MAX with the bucket form; when
+// the threshold is too small / too large for buckets, only what the small register sort holds -- bigger cells then take
+// the CTA path (its own bucket windows or a block sort).  Chunk-uniform: k_cell_scan counts the others into nbig.
+constexpr int WB_SORT_MAX = 128;  // cells up to this many ranges use the register sort (cheaper than buckets there)
+__device__ __forceinline__ bool warp_buckets_ok(float thresh) { return thresh > 1e-3f && thresh < 1e30f; }
+__device__ __forceinline__ int warp_cell_max(float thresh) { return warp_buckets_ok(thresh) ? WSORT_MAX : WB_SORT_MAX; }
+
 constexpr int32_t CELL_INBOX = 0x40000000;  // cellid1 flag: the point passes the fp32 az / el box test of its own bin
 __device__ __forceinline__ int bin_box(float a, const float4* rec, const icet::BinTable& bt, bool& inbox);
 
@@ -116,7 +123,7 @@ __global__ void __launch_bounds__(256) k_cell_scan(const Chunk ck) {
     const int m = cnt1[c] - cntz[c];
     s += m;
     w += (cnt1[c] >= ck.n) ? 1 : 0;
-    big += (cnt1[c] >= ck.n && m > WSORT_MAX) ? 1 : 0;
+    big += (cnt1[c] >= ck.n && m > warp_cell_max(ck.thresh)) ? 1 : 0;
   }
   {
     const int anybig = __syncthreads_count(big > 0);  // (number of threads that own a big cell: only zero / non-zero matters)
@@ -385,9 +392,63 @@ struct PaddedRow {  // view of a shared-memory row written by warp_sort_cell
 // first such break wins.  Bit-identical bounds to the sorted form (tests); ~550 warp instructions for a 260-range cell
 // against ~2500 for the 512-element bitonic network it replaces.
 constexpr int WB = 512;           // buckets per window (25.6 m at the default threshold of 0.1 m)
-constexpr int WB_SORT_MAX = 128;  // cells up to this many ranges keep the register sort (cheaper there)
 
-// Returns false (warp-uniform) without a result when a range is not finite / absurdly large: the caller sorts instead.
+// Exact but slow form for a cell whose ranges the buckets cannot index (a range that is inf or beyond 10^7 m: garbage
+// input): the distinct ranges in ascending order by repeated selection (one pass over the cell per distinct value),
+// fed to the sequential walk.  NaN never reaches a cell list (cartesianToSpherical replaces it, src/utils.cpp:116).
+__device__ inline void find_cluster_select_warp(const float* __restrict__ g, int m, int nz, int n, float thresh, float buff,
+                                                float& inner, float& outer) {
+  const int lane = threadIdx.x & 31;
+  int idx = nz, start = 0;
+  float start_val = 0.f, prev_val = 0.f;
+  int curb = -1;  // bit pattern of the last value taken (ranges are > 0)
+  inner = 0.f;
+  outer = 0.f;
+  while (idx < nz + m) {
+    int nb = 0x7fffffff;
+    for (int i = lane; i < m; i += 32) {
+      const int b = __float_as_int(__ldg(g + i));
+      if (b > curb) nb = min(nb, b);
+    }
+    nb = __reduce_min_sync(FULL, nb);
+    if (nb == 0x7fffffff) break;  // (only NaN payloads left)
+    int mult = 0;
+    for (int i = lane; i < m; i += 32) mult += (__float_as_int(__ldg(g + i)) == nb) ? 1 : 0;
+    mult = __reduce_add_sync(FULL, mult);
+    const float v = __int_as_float(nb);
+    if (idx > 0) {
+      if (!(fabsf(prev_val - v) <= thresh)) {  // reference :572
+        if (idx - start >= n) {                // :577-582
+          inner = start_val - buff;
+          outer = prev_val + buff;
+          return;
+        }
+        start = idx;
+        start_val = v;
+      }
+    } else {
+      start_val = v;
+    }
+    // (equal values: |v - v| <= thresh unless v is inf, where the reference breaks between every two of them)
+    if (mult > 1 && !(fabsf(v - v) <= thresh)) {
+      for (int k = 1; k < mult; k++) {
+        if (idx + k - start >= n) { inner = start_val - buff; outer = v + buff; return; }
+        start = idx + k;
+        start_val = v;
+      }
+    }
+    idx += mult;
+    prev_val = v;
+    curb = nb;
+  }
+  if (nz + m - start >= n && start_val != 0.0f) {  // :592-603
+    inner = start_val - buff;
+    outer = prev_val + buff;
+  }
+}
+
+// Returns false (warp-uniform) without a result when a range is not finite / absurdly large: the caller takes the
+// selection form instead.
 __device__ inline bool find_cluster_buckets_warp(const float* __restrict__ g, int m, int nz, int n, float thresh, float buff,
                                                  int* sb /* [3 * WB] */, float& inner, float& outer) {
   const int lane = threadIdx.x & 31;
@@ -419,7 +480,17 @@ __device__ inline bool find_cluster_buckets_warp(const float* __restrict__ g, in
   inner = 0.f;
   outer = 0.f;
   while (seen < m && !found) {
-    for (int k = lane; k < WB; k += 32) { b_cnt[k] = 0; b_min[k] = 0x7f800000; b_max[k] = 0; }
+    {
+      int4* c4 = reinterpret_cast<int4*>(b_cnt);
+      int4* n4 = reinterpret_cast<int4*>(b_min);
+      int4* x4 = reinterpret_cast<int4*>(b_max);
+#pragma unroll
+      for (int k = 0; k < WB / 128; k++) {
+        c4[k * 32 + lane] = make_int4(0, 0, 0, 0);
+        n4[k * 32 + lane] = make_int4(0x7f800000, 0x7f800000, 0x7f800000, 0x7f800000);
+        x4[k * 32 + lane] = make_int4(0, 0, 0, 0);
+      }
+    }
     __syncwarp();
     int nxt = 0x7f800000;  // smallest range behind this window: the next window starts at its bucket
     for (int i = lane; i < m; i += 32) {
@@ -437,9 +508,13 @@ __device__ inline bool find_cluster_buckets_warp(const float* __restrict__ g, in
     __syncwarp();
     // compaction of the non-empty buckets, in place (an entry never moves behind the bucket it came from)
     int L = 0;
+#pragma unroll 4
     for (int k0 = 0; k0 < WB; k0 += 32) {
-      const int c = b_cnt[k0 + lane], mn = b_min[k0 + lane], mx = b_max[k0 + lane];
+      const int c = b_cnt[k0 + lane];
       const unsigned ne = __ballot_sync(FULL, c > 0);
+      if (ne == 0u) continue;  // (most 32-bucket groups of a window are empty)
+      int mn = 0, mx = 0;
+      if (c > 0) { mn = b_min[k0 + lane]; mx = b_max[k0 + lane]; }
       __syncwarp();
       if (c > 0) {
         const int p = L + __popc(ne & lt);
@@ -509,29 +584,31 @@ __global__ void __launch_bounds__(CLUSTER_WARPS * 32) k_cluster(const Chunk ck) 
   const int pair = blockIdx.y;
   constexpr int ROW = WSORT_MAX + WSORT_MAX / 32;
   constexpr int SM_FLOATS = CLUSTER_WARPS * ROW > SORT_SMEM ? CLUSTER_WARPS * ROW : SORT_SMEM;
-  __shared__ float s_all[SM_FLOATS];
-  __shared__ int s_bkt[CLUSTER_WARPS * 3 * WB];
+  // (the bucket tables of the warp path and the tables / sort buffer of the CTA path share the block's shared memory:
+  // the CTA path starts after a block-wide barrier)
+  constexpr int SM_WORDS = SM_FLOATS > CLUSTER_WARPS * 3 * WB ? SM_FLOATS : CLUSTER_WARPS * 3 * WB;
+  __shared__ __align__(16) float s_all[SM_WORDS];
+  int* s_bkt = reinterpret_cast<int*>(s_all);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* srow = s_all + warp * ROW;
-  // the bucket form needs a sane threshold (bucket indices of ranges up to ~10^5 m must fit an int); else: sort
-  const bool buckets_ok = ck.thresh > 1e-3f && ck.thresh < 1e30f;
+  constexpr int ROW4 = WB_SORT_MAX + WB_SORT_MAX / 32;  // row of the small register sort
+  float* srow = s_all + warp * 3 * WB;                  // (inside the warp's own bucket region)
+  const bool buckets_ok = warp_buckets_ok(ck.thresh);
+  const int wmax = warp_cell_max(ck.thresh);
   const int nw = ck.nwork[pair];
   for (int w = blockIdx.x * CLUSTER_WARPS + warp; w < nw; w += gridDim.x * CLUSTER_WARPS) {
     const int cell = ck.work[(size_t)pair * ck.ncell + w];
     const int cnt = ck.cnt1[(size_t)pair * ck.ncell + cell];
     const int nz = ck.cntz[(size_t)pair * ck.ncell + cell];
     const int m = cnt - nz;
-    if (m > WSORT_MAX) continue;
+    if (m > wmax) continue;
     const float* g = ck.rbuf + (size_t)pair * ck.n1max + ck.off[(size_t)pair * ck.ncell + cell];
     float inner, outer;
-    if (m > WB_SORT_MAX && buckets_ok &&
-        find_cluster_buckets_warp(g, m, nz, ck.n, ck.thresh, ck.buff, s_bkt + warp * 3 * WB, inner, outer)) {
-    } else {
-      if (m <= 128) warp_sort_cell<4>(g, m, srow);
-      else if (m <= 256) warp_sort_cell<8>(g, m, srow);
-      else if (m <= 512) warp_sort_cell<16>(g, m, srow);
-      else warp_sort_cell<32>(g, m, srow);
+    if (m <= WB_SORT_MAX) {
+      static_assert(ROW4 <= 3 * WB, "sort row inside the bucket region");
+      warp_sort_cell<4>(g, m, srow);
       find_cluster_warp(PaddedRow{srow}, m, nz, ck.n, ck.thresh, ck.buff, inner, outer);
+    } else if (!(buckets_ok && find_cluster_buckets_warp(g, m, nz, ck.n, ck.thresh, ck.buff, s_bkt + warp * 3 * WB, inner, outer))) {
+      find_cluster_select_warp(g, m, nz, ck.n, ck.thresh, ck.buff, inner, outer);
     }
     if (lane == 0) write_cluster_rec(ck, pair, cell, cnt, inner, outer);
     __syncwarp();
@@ -554,7 +631,7 @@ __global__ void __launch_bounds__(CLUSTER_WARPS * 32) k_cluster(const Chunk ck) 
     const int cnt = ck.cnt1[(size_t)pair * ck.ncell + cell];
     const int nz = ck.cntz[(size_t)pair * ck.ncell + cell];
     const int m = cnt - nz;
-    if (m <= WSORT_MAX) continue;  // block-uniform
+    if (m <= wmax) continue;  // block-uniform
     if (ck.hbkt) {  // clustered by k_huge_* already (unless a range fell outside its table)
       const int hs = ck.hslot[(size_t)pair * ck.ncell + cell];
       if (hs > 0 && ck.hflag[hs - 1] == 0) continue;  // block-uniform

@@ -611,6 +611,33 @@ def test_big_cells_bucket_clustering(ctx, po):
         check_final(r, o2, o64, "big cells %s" % kw)
 
 
+def test_cluster_forms_of_ordinary_cells(ctx, po):
+    """findCluster of an ordinary cell (a few hundred ranges) by one warp: the bucket form (windows of half-threshold
+    buckets, data-parallel walk), for thresholds that make one / several windows per cell; a threshold too small for
+    buckets (cells beyond the small register sort then take the CTA path); and a scan with a few absurd ranges (the
+    buckets cannot index them: exact selection form).  Cluster bounds bit-identical to the oracle's sorted walk
+    (src/icet.cpp:557-607) in every case."""
+    dev = synth_device(ctx, 2, first=140)
+    host = dev.cpu().numpy()
+    for kw in (dict(), dict(thresh=0.02, buff=0.05), dict(thresh=1.5, buff=0.3, n=40), dict(thresh=5e-4, buff=0.1, n=10)):
+        p = params(**kw)
+        r, g = ctx.register(host[0], host[1], params=p, dump=True)
+        o = po.run(host[0], host[1], dumps="small", **kw)
+        assert g["cnt1"].max() > 128                      # beyond the small register sort
+        np.testing.assert_array_equal(g["cnt1"], o.cnt1)
+        np.testing.assert_array_equal(g["bounds"], o.bounds)
+        np.testing.assert_array_equal(g["has1"], o.has1)
+    # a handful of returns at 3e8 m (finite, beyond what an int bucket index holds at thresh 0.1) in well-filled cells
+    s1 = host[0].copy()
+    idx = np.nonzero(np.abs(s1[0]) + np.abs(s1[1]) > 5.0)[0][::9001][:12]
+    s1[:, idx] *= np.float32(3e8) / np.linalg.norm(s1[:, idx], axis=0).astype(np.float32)
+    r, g = ctx.register(s1, host[1], dump=True)
+    o = po.run(s1, host[1], dumps="small")
+    np.testing.assert_array_equal(g["cnt1"], o.cnt1)
+    np.testing.assert_array_equal(g["bounds"], o.bounds)
+    np.testing.assert_array_equal(g["has1"], o.has1)
+
+
 @pytest.mark.parametrize("name", ["frame", "sample_pc"])
 def test_shipped_order_mode_matches_reference_as_shipped(ctx, po, name):
     """ICET_B200_FLAG_SHIPPED_ORDER: clustering in the row order the reference's permutation loop really leaves
