@@ -483,9 +483,11 @@ __global__ void __launch_bounds__(256) k_prep2(const Chunk ck) {
     bool keep = false, zero = false;
     if (i < d.n2) {
       x = __ldg(d.s2 + i); y = __ldg(d.s2 + d.ld2 + i); z = __ldg(d.s2 + 2 * (size_t)d.ld2 + i);
-      float r, th, ph;
-      icet::c2s(x, y, z, r, th, ph);
-      icet::s2c(r, th, ph, x, y, z);
+      if ((__float_as_uint(x) | __float_as_uint(y) | __float_as_uint(z)) != 0u) {  // (+0,+0,+0) round-trips to itself, see k_scan1_bin
+        float r, th, ph;
+        icet::c2s(x, y, z, r, th, ph);
+        icet::s2c(r, th, ph, x, y, z);
+      }
       // Dropped returns: (0,0,0) stays (+0,+0,+0).  They are all the same point in every iteration, so they are
       // counted here and evaluated once per iteration by k_pass<true> instead of being stored.
       zero = (__float_as_uint(x) | __float_as_uint(y) | __float_as_uint(z)) == 0u;

@@ -71,9 +71,18 @@ __global__ void __launch_bounds__(256) k_scan1_bin(const Chunk ck) {
   if (i < d.n1) {
     float x = __ldg(d.s1 + i), y = __ldg(d.s1 + d.ld1 + i), z = __ldg(d.s1 + 2 * (size_t)d.ld1 + i);
     float r, th, ph;
-    icet::c2s(x, y, z, r, th, ph);
+    // Dropped returns are stored as (+0,+0,+0): a tenth of a scan, spread over every warp, and each of them takes the
+    // slow paths of the IEEE square root / division and the library atan2f / acosf.  Their result is known:
+    // cartesianToSpherical gives r = sqrt(0) = 0, theta = atan2f(+0,+0) = +0, phi = acosf(0/0) = NaN -> 1000.0
+    // (src/utils.cpp:98-116), and sphericalToCartesian of that is (+0,+0,+0) again (sin 1000 > 0, cos 1000 > 0).
+    const bool origin = (__float_as_uint(x) | __float_as_uint(y) | __float_as_uint(z)) == 0u;
+    if (origin) {
+      r = 0.0f; th = 0.0f; ph = 1000.0f;
+    } else {
+      icet::c2s(x, y, z, r, th, ph);
+    }
     if (prev_shares) {
-      icet::s2c(r, th, ph, px, py, pz);
+      if (!origin) icet::s2c(r, th, ph, px, py, pz);
       pzero = (__float_as_uint(px) | __float_as_uint(py) | __float_as_uint(pz)) == 0u;
       pkeep = !pzero;
     }
