@@ -114,6 +114,8 @@ struct Chunk {  // everything a kernel needs, passed by value
   CellRec* rec;      // [P][ncell]
   unsigned long long* acc;  // [2][P][ncell][NQ]  (set 1 is used by the incremental scan-2 loop only)
   Vox1* vox;         // [P][ncell]
+  int32_t* vlist;    // [P][ncell]  split loop: the pair's active voxels (F_ACTIVE2) in ascending cell order (k_vox_list)
+  int32_t* nvox;     // [P]         ... and their number
   const float* azE;  // [nT+1] float azimuth bin edges  (src/icet.cpp:136-137)
   const float* elE;  // [nP+1] float elevation bin edges (src/icet.cpp:138-139)
   icet::BinTable bth, bph;  // exact bin lookup tables (src/icet.cpp:545-546)

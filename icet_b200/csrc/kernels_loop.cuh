@@ -854,15 +854,50 @@ __global__ void __launch_bounds__(PASS_THREADS, 3) k_loop(const Chunk ck, int ti
   }
 }
 
-// Legacy split form of the loop (ICET_B200_FLAG_UNFUSED_LOOP): k_pass<true>, then these two, per iteration.
+// Split form of the loop (chunks of more than one pair): k_pass2 / k_pass<true>, then these two, per iteration.
+constexpr int VOX_GRID = 8;  // blocks per pair of k_vox2 (each strides over the pair's active voxels)
+
+// the pair's active voxels in ascending cell order (once per chunk, after k_fit1 has set F_ACTIVE2)
+__global__ void __launch_bounds__(256) k_vox_list(const Chunk ck) {
+  const int pair = blockIdx.x;
+  __shared__ int s_w[8];
+  const int per = (ck.ncell + 255) / 256;
+  const int c0 = threadIdx.x * per, c1 = min(ck.ncell, c0 + per);
+  const CellRec* recs = ck.rec + (size_t)pair * ck.ncell;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int mine = 0;
+  for (int c = c0; c < c1; c++) mine += (recs[c].flags & F_ACTIVE2) ? 1 : 0;
+  int inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(FULL, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  int base = inc - mine;
+  for (int w = 0; w < warp; w++) base += s_w[w];
+  int32_t* out = ck.vlist + (size_t)pair * ck.ncell;
+  for (int c = c0; c < c1; c++)
+    if (recs[c].flags & F_ACTIVE2) out[base++] = c;
+  if (threadIdx.x == 255) ck.nvox[pair] = base;
+}
+
 __global__ void __launch_bounds__(VOX_THREADS) k_vox2(const Chunk ck, int iter) {
   const int pair = blockIdx.y;
-  const int cell = blockIdx.x * VOX_THREADS + threadIdx.x;
   __shared__ double s_red[NRED];
   double acc[NRED];
 #pragma unroll
   for (int k = 0; k < NRED; k++) acc[k] = 0.0;
-  if (cell < ck.ncell) vox_contrib(ck, pair, cell, iter, ck.J + (size_t)pair * 27, acc);
+  if (ck.dump_on) {  // every cell (grid: one block per VOX_THREADS cells)
+    const int cell = blockIdx.x * VOX_THREADS + threadIdx.x;
+    if (cell < ck.ncell) vox_contrib(ck, pair, cell, iter, ck.J + (size_t)pair * 27, acc);
+  } else {
+    const int nv = ck.nvox[pair];
+    const int32_t* vl = ck.vlist + (size_t)pair * ck.ncell;
+    for (int k = blockIdx.x * VOX_THREADS + threadIdx.x; k < nv; k += gridDim.x * VOX_THREADS)
+      vox_contrib(ck, pair, __ldg(vl + k), iter, ck.J + (size_t)pair * 27, acc);
+  }
   // fixed-order reduction: xor butterfly inside each warp, then warp 1 + warp 0
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const bool any = __syncthreads_or(acc[27] != 0.0);

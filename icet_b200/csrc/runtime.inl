@@ -148,6 +148,8 @@ size_t carve_chunk(void* base, int P, int ncell, int n1max, int n2max, int runle
   ck.pm = c.take<PairMode>((size_t)P);
   ck.rec = c.take<CellRec>((size_t)P * ncell);
   ck.vox = c.take<Vox1>((size_t)P * ncell);
+  ck.vlist = c.take<int32_t>((size_t)P * ncell);
+  ck.nvox = c.take<int32_t>((size_t)P);
   ck.cellid1 = c.take<int32_t>((size_t)P * n1max);
   ck.r1 = c.take<float>((size_t)P * n1max);
   ck.th1 = c.take<float>((size_t)P * n1max);
@@ -527,13 +529,18 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
     cfg.numAttrs = (pdl && (first_tiles || !prep_aside)) ? 2 : 1;  // (after an event wait the edge is an ordinary one)
     LAUNCH(10, CK(cudaLaunchKernelEx(&cfg, k_loop_cluster, ck, first_tiles)));
   } else if (!use_loop) {
+    // the per-voxel algebra walks the pair's ACTIVE voxels (a sixth of the cells): VOX_GRID blocks per pair instead of
+    // one per 64 cells (a 256-pair launch had 7 424 blocks in six waves, most of them without a voxel).  With per-voxel
+    // dumps every cell is visited (the dump records the inactive ones as well).
+    const int vgrid = dump ? nblk : std::min(nblk, VOX_GRID);
+    if (p->runlen > 0) LAUNCH(5, k_vox_list<<<P, 256, 0, st>>>(ck));
     for (int it = 0; it < p->runlen; it++) {
       if (n2max > 0) {
         if (p->flags & ICET_B200_FLAG_EXACT_PASS) LAUNCH(7, k_pass<true><<<gp2, PASS_THREADS, psm, st>>>(ck));
         else LAUNCH(7, k_pass2<><<<gp2, PASS_THREADS, psm, st>>>(ck));
       }
-      LAUNCH(8, k_vox2<<<dim3(nblk, P), VOX_THREADS, 0, st>>>(ck, it));
-      LAUNCH(9, k_solve6<<<P, SOLVE_THREADS, 0, st>>>(ck, it, nblk));
+      LAUNCH(8, k_vox2<<<dim3(vgrid, P), VOX_THREADS, 0, st>>>(ck, it));
+      LAUNCH(9, k_solve6<<<P, SOLVE_THREADS, 0, st>>>(ck, it, vgrid));
     }
   } else if (p->runlen > 0) {
     // persistent: as many blocks as can be resident (more would only queue behind them)
