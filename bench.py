@@ -36,6 +36,7 @@ SEED = 20240
 METRIC = "registrations/s (64-ch, 75x24 vox, 7 it)"
 README_PAIRS_PER_S = 1000.0 / 35.0  # reference README.md:59: 35 ms / pair on a Ryzen 5800X (other hardware)
 B_ALG_PER_PAIR = 12 * (NPTS + NPTS) + 192
+DEFAULT_CHUNK = 512  # pairs per launch of the device-resident batch (the library's default, icet_b200_set_chunk)
 
 
 def peaks():
@@ -377,8 +378,7 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     if args.host_chunk:
         ctx.set_host_chunk(args.host_chunk)
-    if args.chunk:
-        ctx.set_chunk(args.chunk)
+    ctx.set_chunk(args.chunk or DEFAULT_CHUNK)
     if args.lanes:
         ctx.set_lanes(args.lanes)
     params = api.make_params(RUNLEN, BINS_PHI, BINS_THETA, NMIN, THRESH, BUFF,
@@ -446,7 +446,7 @@ def main():
     peak, peak_src = peaks()
     # algorithmic bytes of one k_pass<scan2> launch: every scan-2 coordinate of the chunk read once
     # (12 B / point) -- DESIGN.md "Kernels"; other kernels: see DESIGN.md
-    chunk_pairs = min(P, 256)
+    chunk_pairs = min(P, args.chunk or DEFAULT_CHUNK)
     alg_bytes = {"k_pass<scan2>": 12.0 * NPTS * chunk_pairs, "k_pass<scan1>": 12.0 * NPTS * chunk_pairs,
                  "k_prep2": 24.0 * NPTS * chunk_pairs, "k_scan1_bin": 20.0 * NPTS * chunk_pairs}.get(dom)
     roofline = {"bound": "hbm", "kernel": dom, "unit": "GB/s", "peak": peak, "peak_source": peak_src,

@@ -146,7 +146,7 @@ int icet_b200_set_stream(icet_b200_ctx* c, void* stream) {
 int icet_b200_set_chunk(icet_b200_ctx* c, int32_t m) {
   if (!c) return fail(ICET_B200_E_INVALID, "ctx is NULL");
   if (m < 0) return fail(ICET_B200_E_INVALID, "chunk must be >= 0");
-  c->chunk_pairs = m == 0 ? 256 : std::min(m, 65535);
+  c->chunk_pairs = m == 0 ? ICET_DEFAULT_CHUNK : std::min(m, 65535);
   return 0;
 }
 

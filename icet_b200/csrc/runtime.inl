@@ -33,6 +33,7 @@ struct DevBuf {
 }  // namespace
 
 constexpr int ICET_LOOP_MAX_PAIRS = 1;  // chunks up to this size run the Gauss-Newton loop as one persistent kernel
+constexpr int ICET_DEFAULT_CHUNK = 512;  // pairs per chunk of a device-resident batch (measured r02: 512 -> +1.3 % over 256)
 constexpr int ICET_NSLOT = 4;  // staging slots of the host-buffer pipeline
 constexpr int ICET_NLANE = 8;  // compute lanes: consecutive chunks rotate over up to eight streams (each with its own
                                // workspace) so that the latency-bound ends of one chunk's kernels overlap the other's
@@ -49,7 +50,7 @@ struct icet_b200_ctx {
   int nlanes = 4;
   cudaEvent_t ev_copy[ICET_NSLOT] = {};
   cudaEvent_t ev_done[ICET_NSLOT] = {};
-  int chunk_pairs = 256;
+  int chunk_pairs = ICET_DEFAULT_CHUNK;
   int host_chunk = 64;  // pairs per chunk of the host-buffer pipeline (upload of chunk k+1 || registration of chunk k)
   int64_t launches = 0;
   int dump_on = 0;

@@ -124,8 +124,8 @@ int icet_b200_destroy(icet_b200_ctx* ctx);
 /* All work of a context is issued on one stream (default: a private non-blocking stream).
  * `stream` is a cudaStream_t; pass the caller's stream to order against its own work. */
 int icet_b200_set_stream(icet_b200_ctx* ctx, void* stream);
-/* Upper bound on the number of pairs processed per internal chunk (workspace ~3.7 MB/pair at
- * 131 072-point scans). 0 restores the default (256). */
+/* Upper bound on the number of pairs processed per internal chunk (workspace ~7.3 MB/pair at
+ * 131 072-point scans, per compute lane in use). 0 restores the default (512). */
 int icet_b200_set_chunk(icet_b200_ctx* ctx, int32_t max_pairs_per_chunk);
 /* Chunk size of the HOST-buffer batch entry point (icet_b200_register_batch): the upload of one chunk overlaps the
  * registration of the previous one, so smaller chunks hide more of the PCIe transfer. 0 restores the default (64). */
@@ -160,7 +160,7 @@ int icet_b200_register_sequence_device(icet_b200_ctx* ctx, const icet_b200_param
                                        const float* scans, int32_t n, icet_b200_result* out);
 
 int icet_b200_synchronize(icet_b200_ctx* ctx);
-/* Number of compute lanes (streams with their own workspace) consecutive chunks rotate over: 1 .. 4
+/* Number of compute lanes (streams with their own workspace) consecutive chunks rotate over: 1 .. 8
  * (0 = default 4). */
 int icet_b200_set_lanes(icet_b200_ctx* ctx, int32_t lanes);
 
