@@ -46,8 +46,8 @@ struct icet_b200_ctx {
   cudaStream_t lanes[ICET_NLANE] = {};  // compute lanes 1.. (lane 0 is `stream`)
   cudaEvent_t ev_fork = nullptr, ev_join[ICET_NLANE] = {};
   cudaEvent_t ev_aux[2] = {};  // single-pair chunks: prepScan2 runs beside the scan-1 kernels on lane 1
-  int nlanes_default = 4;
-  int nlanes = 4;
+  int nlanes_default = 8;
+  int nlanes = 8;
   cudaEvent_t ev_copy[ICET_NSLOT] = {};
   cudaEvent_t ev_done[ICET_NSLOT] = {};
   int chunk_pairs = ICET_DEFAULT_CHUNK;

@@ -161,7 +161,7 @@ int icet_b200_register_sequence_device(icet_b200_ctx* ctx, const icet_b200_param
 
 int icet_b200_synchronize(icet_b200_ctx* ctx);
 /* Number of compute lanes (streams with their own workspace) consecutive chunks rotate over: 1 .. 8
- * (0 = default 4). */
+ * (0 = default 8; a batch uses at most one lane per 512-pair chunk, batches below 4096 pairs at most four). */
 int icet_b200_set_lanes(icet_b200_ctx* ctx, int32_t lanes);
 
 /* -- per-voxel state of the most recent single-pair call (icet_b200_register) ------------------
