@@ -211,11 +211,20 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
       : "memory");
   return ok != 0;
 }
-// (try_wait suspends the thread in hardware for a bounded time per call; a copy that never completes -- a bug -- traps
-// instead of hanging the device)
+// (try_wait suspends the thread in hardware for a bounded time per call.  A copy that never completes -- a bug, not a
+// slow device: the limit is 20 s of %globaltimer, far beyond compute-sanitizer / time-sliced GPUs -- traps instead of
+// hanging the device.)
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  for (unsigned spin = 0; !mbar_try_wait(bar, parity); spin++)
-    if (spin > (1u << 22)) __trap();
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0 = 0;
+  for (unsigned spin = 1; !mbar_try_wait(bar, parity); spin++) {
+    if ((spin & 1023u) == 0u) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 20000000000ull) __trap();
+    }
+  }
 }
 
 // Shared-memory accesses through explicit 32-bit shared addresses.  The pass kernels run at 64 registers per thread;

@@ -6,8 +6,10 @@
 // and take mean / covariance per voxel.  From the second or third iteration on the transform moves the points by
 // millimetres and almost none of them changes its voxel or its side of a cluster box.  This pass therefore keeps, per
 // voxel, EXACT integer moments (count, sum, sum of products) of the UNTRANSFORMED members (points2_OG, prepScan2) and,
-// per point, the class (cell | in-box) of its last evaluation together with a margin: a bound on how far the point can
-// move before ANY comparison that decided its class can change.  An iteration then
+// per point, ONE 64-bit margin record: the class (cell | in-box) of its last evaluation together with a margin, a bound
+// on how far the point can move before ANY comparison that decided its class can change.  A warp works on a tile of
+// 32*K consecutive stored points whose coordinates the TMA engine stages in shared memory (three bulk asynchronous
+// copies issued by one lane, completion on the warp's mbarrier).  An iteration then
 //   * REBUILD (first iteration, or when the transform has moved by more than INC_MAX_SA / INC_MAX_SB since the last
 //     rebuild): evaluates every point like the per-point pass (transform, spherical, bin + box look-up, range test),
 //     records class and margin, and accumulates the moments of the inside points from zero;
@@ -26,11 +28,10 @@
 #pragma once
 
 // Delta iterations while the motion since the last rebuild stays below these bounds.  A delta iteration costs ~20
-// instructions and 8 bytes per point plus a full evaluation for the points whose margin is used up -- but those are
-// GATHERED (three 32-byte sectors for 12 useful bytes, scattered margin / class stores), so a delta iteration with more
-// than ~30 % of the points to re-evaluate takes as long as a rebuild although it executes a third fewer instructions.
-// Measured on the bench pairs (256-pair launches, 7 iterations): bounds 1e-3 / 5 cm: 3.5 rebuilds per pair, 162
-// instructions per point and iteration, 1.86 ms per chunk; 4e-3 / 12 cm: 2.8 rebuilds, 152 instructions, 1.92 ms.
+// instructions and 8 bytes per point plus a full evaluation for the points whose margin is used up (from a staged tile
+// when more than one point in eight is listed, gathered otherwise).  Measured on the bench pairs (256-pair launches, 7
+// iterations, r02j): bounds 1e-3 / 5 cm: 24.3 ms per 4096 pairs; 2e-3 / 8 cm: 24.4; 4e-3 / 12 cm: 25.4 -- the heavy
+// delta iterations that wider bounds create cost what the rebuilds they replace did (ICET_B200_INC_SA / _SB: A/B runs).
 constexpr float INC_MAX_SA = 1.0e-3f;         // sum |dR|_F   (x 30 m = 3 cm)
 constexpr float INC_MAX_SB = 0.05f;           // sum |dt|     (metres)
 // (The members of a voxel sit within one box diameter D of its anchor when they are evaluated and the anchor drifts by
