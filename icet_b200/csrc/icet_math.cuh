@@ -505,41 +505,52 @@ __device__ __noinline__ int cod_pinv(const double* A, int rows, int cols, double
 // embedded in zeros -- the pseudo-inverse of L*A*L^T when the kept block is comfortably
 // full rank.  Returns false (W untouched) when the block is not safely invertible; the caller
 // then falls back to cod_pinv.
-__device__ inline bool masked_inv3(const double M[9], int mask, double W[9]) {
+// (Every index is a compile-time constant -- the kept rows / columns are selected by a switch on the mask -- so that M
+// and W stay in registers: with run-time indices they live in local memory and every access of the per-voxel algebra to
+// them is a load / store on the critical path of an iteration.)
+template <int I0, int I1>
+__device__ __forceinline__ bool masked_inv3_2(const double M[9], double W[9]) {
+  const double a = M[I0 * 3 + I0], b = M[I0 * 3 + I1], d = M[I1 * 3 + I1];
+  const double det = a * d - b * b;
+  if (!(a > 0.0) || !(d > 0.0) || !(det > 0.0)) return false;
+  const double ia = d / det, ib = -b / det, id = a / det;
+  const double tr = a + d;
+  const double tri = ia + id;
+  if (!(tr * tri < 5e5)) return false;  // cond < 5e5: far from the COD rank threshold (pivot ratio 3.6e-7)
+  W[I0 * 3 + I0] = ia;
+  W[I0 * 3 + I1] = ib;
+  W[I1 * 3 + I0] = ib;
+  W[I1 * 3 + I1] = id;
+  return true;
+}
+template <int I0>
+__device__ __forceinline__ bool masked_inv3_1(const double M[9], double W[9]) {
+  const double a = M[I0 * 3 + I0];
+  if (!(a > 0.0)) return false;
+  W[I0 * 3 + I0] = 1.0 / a;
+  return true;
+}
+__device__ __forceinline__ bool masked_inv3(const double M[9], int mask, double W[9]) {
+#pragma unroll
   for (int i = 0; i < 9; i++) W[i] = 0.0;
-  int idx[3], k = 0;
-  for (int i = 0; i < 3; i++)
-    if (mask & (1 << i)) idx[k++] = i;
-  if (k == 0) return true;
-  double tr = 0.0, tri = 0.0;
-  if (k == 1) {
-    double a = M[idx[0] * 3 + idx[0]];
-    if (!(a > 0.0)) return false;
-    W[idx[0] * 3 + idx[0]] = 1.0 / a;
-    return true;
+  switch (mask & 7) {
+    case 0: return true;
+    case 1: return masked_inv3_1<0>(M, W);
+    case 2: return masked_inv3_1<1>(M, W);
+    case 4: return masked_inv3_1<2>(M, W);
+    case 3: return masked_inv3_2<0, 1>(M, W);
+    case 5: return masked_inv3_2<0, 2>(M, W);
+    case 6: return masked_inv3_2<1, 2>(M, W);
+    default: break;
   }
-  if (k == 2) {
-    double a = M[idx[0] * 3 + idx[0]], b = M[idx[0] * 3 + idx[1]], d = M[idx[1] * 3 + idx[1]];
-    double det = a * d - b * b;
-    if (!(a > 0.0) || !(d > 0.0) || !(det > 0.0)) return false;
-    double ia = d / det, ib = -b / det, id = a / det;
-    tr = a + d;
-    tri = ia + id;
-    if (!(tr * tri < 5e5)) return false;  // cond < 5e5: far from the COD rank threshold (pivot ratio 3.6e-7)
-    W[idx[0] * 3 + idx[0]] = ia;
-    W[idx[0] * 3 + idx[1]] = ib;
-    W[idx[1] * 3 + idx[0]] = ib;
-    W[idx[1] * 3 + idx[1]] = id;
-    return true;
-  }
-  double a = M[0], b = M[1], c = M[2], d = M[4], e = M[5], f = M[8];
-  double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
-  double det = a * c00 + b * c01 + c * c02;
+  const double a = M[0], b = M[1], c = M[2], d = M[4], e = M[5], f = M[8];
+  const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+  const double det = a * c00 + b * c01 + c * c02;
   if (!(a > 0.0) || !(d > 0.0) || !(f > 0.0) || !(det > 0.0)) return false;
-  double c11 = a * f - c * c, c12 = b * c - a * e, c22 = a * d - b * b;
-  double id = 1.0 / det;
-  tr = a + d + f;
-  tri = (c00 + c11 + c22) * id;
+  const double c11 = a * f - c * c, c12 = b * c - a * e, c22 = a * d - b * b;
+  const double id = 1.0 / det;
+  const double tr = a + d + f;
+  const double tri = (c00 + c11 + c22) * id;
   if (!(tr * tri < 1e5)) return false;
   W[0] = c00 * id; W[1] = c01 * id; W[2] = c02 * id;
   W[3] = c01 * id; W[4] = c11 * id; W[5] = c12 * id;

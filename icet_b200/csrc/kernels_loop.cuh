@@ -132,7 +132,14 @@ __device__ __forceinline__ void vox_algebra_core(const Chunk& ck, int pair, int 
       M[3 * a + b] = T[3 * a] * v.LV[3 * b] + T[3 * a + 1] * v.LV[3 * b + 1] + T[3 * a + 2] * v.LV[3 * b + 2];
   // W = pinv(M)  (:320-321)
   double W[9];
-  if (!icet::masked_inv3(M, v.lmask, W)) icet::cod_pinv(M, 3, 3, W);
+  if (!icet::masked_inv3(M, v.lmask, W)) {  // (rare; the copies keep M / W of the common path out of local memory)
+    double Mc[9], Wc[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Mc[k] = M[k];
+    icet::cod_pinv(Mc, 3, 3, Wc);
+#pragma unroll
+    for (int k = 0; k < 9; k++) W[k] = Wc[k];
+  }
   // H_z = L U^T [ -I | Jx mu | Jy mu | Jz mu ]  (:324-329)
   double H[18];
 #pragma unroll
