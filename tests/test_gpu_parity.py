@@ -638,6 +638,58 @@ def test_cluster_forms_of_ordinary_cells(ctx, po):
     np.testing.assert_array_equal(g["has1"], o.has1)
 
 
+def test_cluster_forms_adversarial_cells(ctx, po):
+    """Constructed cells for findCluster (src/icet.cpp:557-607): runs whose gaps are (up to the rounding of the range) equal
+    to the threshold, just above and just below it; duplicates; runs of exactly n - 1, n and n + 1 points; the first
+    qualifying run far behind the cell's smallest range (several bucket windows); a qualifying run only at the end of the
+    data; cells of every size class (register sort <= 128, warp buckets <= 1024, CTA buckets beyond).  Cluster bounds and
+    Gaussian sets bit-identical to the oracle's sorted walk."""
+    rng = np.random.default_rng(7)
+    nT, nP, n, thresh = 75, 24, 25, 0.1
+    pts = []
+
+    def cell_dir(bt, bp, k):
+        th = (bt + 0.5 + 0.6 * (rng.random(k) - 0.5)) * 2 * np.pi / nT
+        ph = (bp + 0.5 + 0.6 * (rng.random(k) - 0.5)) * np.pi / nP
+        return np.stack([np.sin(ph) * np.cos(th), np.sin(ph) * np.sin(th), np.cos(ph)])
+
+    def add(bt, bp, ranges):
+        r = np.asarray(ranges, np.float64)
+        rng.shuffle(r)
+        pts.append((cell_dir(bt, bp, len(r)) * r).astype(np.float32))
+
+    steps = [thresh, thresh * (1 + 2e-6), thresh * (1 - 2e-6), 0.5 * thresh, 0.03, 0.0]
+    cells = [(bt, bp) for bp in range(8, 16) for bt in range(0, nT, 2)]
+    ci = 0
+    for size in (60, 128, 129, 300, 700, 1024, 1025, 3000):
+        for step in steps:
+            for lead in (0, n - 1, n, n + 1):
+                bt, bp = cells[ci]; ci += 1
+                r0 = 3.0 + 20.0 * rng.random()
+                run = r0 + step * np.arange(size - lead)            # the big run (gaps == step)
+                head = r0 - 5.0 + 0.01 * np.arange(lead) if lead else np.zeros(0)   # a short run in front of it
+                add(bt, bp, np.concatenate([head, run]))
+    # qualifying run far behind the smallest range: isolated points every 3 m over 90 m, then a dense run
+    for size in (200, 900):
+        bt, bp = cells[ci]; ci += 1
+        add(bt, bp, np.concatenate([2.0 + 3.0 * np.arange(30), 95.0 + 0.02 * np.arange(size)]))
+    # no run of n anywhere except the one that reaches the end of the data
+    bt, bp = cells[ci]; ci += 1
+    add(bt, bp, np.concatenate([2.0 + 0.5 * np.arange(100), 60.0 + 0.05 * np.arange(n + 3)]))
+    # nothing qualifies at all
+    bt, bp = cells[ci]; ci += 1
+    add(bt, bp, 2.0 + 0.5 * np.arange(200))
+    s1 = np.ascontiguousarray(np.concatenate(pts, axis=1))
+    s2 = synth_device(ctx, 1, first=7).cpu().numpy()[0]
+    r, g = ctx.register(s1, s2, dump=True)
+    o = po.run(s1, s2, dumps="small")
+    np.testing.assert_array_equal(g["cnt1"], o.cnt1)
+    assert (o.cnt1 > 1024).sum() >= 20 and ((o.cnt1 > 128) & (o.cnt1 <= 1024)).sum() >= 60
+    np.testing.assert_array_equal(g["bounds"], o.bounds)
+    np.testing.assert_array_equal(g["has1"], o.has1)
+    assert (o.bounds[:, 5] > 0).sum() >= 120          # most constructed cells do hold a cluster
+
+
 @pytest.mark.parametrize("name", ["frame", "sample_pc"])
 def test_shipped_order_mode_matches_reference_as_shipped(ctx, po, name):
     """ICET_B200_FLAG_SHIPPED_ORDER: clustering in the row order the reference's permutation loop really leaves
