@@ -35,8 +35,11 @@ __device__ __forceinline__ void cluster_vox_phase(const Chunk& ck, int pair, int
   for (int k = 0; k < NRED; k++) acc[k] = 0.0;
   // cell c -> CTA c % cs, thread c / cs: the occupied rows of the grid spread over all CTAs
   for (int c = rank + cs * (int)threadIdx.x; c < ck.ncell; c += cs * CL_THREADS) vox_contrib(ck, pair, c, iter, s_J, acc);
+  // debug timeline (per-voxel dumps only): when the LAST thread of CTA 0 is through its voxel / the warp reduction
+  if (ck.dump_on && rank == 0) atomicMax(&ck.dump.tl[(size_t)iter * 16 + 8], gtime());
   const double tot = warp_sum_transposed(acc, lane);
   if (lane < NRED) wpart[warp * NRED + lane] = tot;
+  if (ck.dump_on && rank == 0) atomicMax(&ck.dump.tl[(size_t)iter * 16 + 9], gtime());
   __syncthreads();
   if (threadIdx.x < NRED) {
     double s = 0.0;

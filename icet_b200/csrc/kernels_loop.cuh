@@ -10,6 +10,13 @@
 // iteration.
 // ----------------------------------------------------------------------------------------------
 constexpr int VOX_THREADS = 64;
+// a0 b0 + a1 b1 + a2 b2 with fused multiply-adds.  The translation unit is compiled with -fmad=false for the point-wise
+// fp32 geometry (which must round like the reference's scalar code); the per-voxel double algebra has no such
+// constraint, and it is a serial chain on the critical path of every iteration: explicit fma halves its arithmetic
+// instructions and shortens the dependency chains.
+__device__ __forceinline__ double dot3(double a0, double b0, double a1, double b1, double a2, double b2) {
+  return fma(a2, b2, fma(a1, b1, a0 * b0));
+}
 constexpr int NRED = 28;  // 21 (upper triangle of H^T W H) + 6 (H^T W dz) + 1 (voxels used)
 
 // Sum over the 32 lanes of each of the NRED (28) per-lane values; lane k < NRED returns the total of value k.
@@ -124,12 +131,12 @@ __device__ __forceinline__ void vox_algebra_core(const Chunk& ck, int pair, int 
   for (int a = 0; a < 3; a++)
 #pragma unroll
     for (int b = 0; b < 3; b++)
-      T[3 * a + b] = v.LV[3 * a] * Rn[b] + v.LV[3 * a + 1] * Rn[3 + b] + v.LV[3 * a + 2] * Rn[6 + b];
+      T[3 * a + b] = dot3(v.LV[3 * a], Rn[b], v.LV[3 * a + 1], Rn[3 + b], v.LV[3 * a + 2], Rn[6 + b]);
 #pragma unroll
   for (int a = 0; a < 3; a++)
 #pragma unroll
     for (int b = 0; b < 3; b++)
-      M[3 * a + b] = T[3 * a] * v.LV[3 * b] + T[3 * a + 1] * v.LV[3 * b + 1] + T[3 * a + 2] * v.LV[3 * b + 2];
+      M[3 * a + b] = dot3(T[3 * a], v.LV[3 * b], T[3 * a + 1], v.LV[3 * b + 1], T[3 * a + 2], v.LV[3 * b + 2]);
   // W = pinv(M)  (:320-321)
   double W[9];
   if (!icet::masked_inv3(M, v.lmask, W)) {  // (rare; the copies keep M / W of the common path out of local memory)
@@ -149,35 +156,35 @@ __device__ __forceinline__ void vox_algebra_core(const Chunk& ck, int pair, int 
     H[6 * a + 2] = (a == 2) ? -1.0 : 0.0;
 #pragma unroll
     for (int j = 0; j < 3; j++)
-      H[6 * a + 3 + j] = (double)Jm[9 * j + 3 * a] * mean[0] + (double)Jm[9 * j + 3 * a + 1] * mean[1] +
-                         (double)Jm[9 * j + 3 * a + 2] * mean[2];
+      H[6 * a + 3 + j] = dot3((double)Jm[9 * j + 3 * a], mean[0], (double)Jm[9 * j + 3 * a + 1], mean[1],
+                              (double)Jm[9 * j + 3 * a + 2], mean[2]);
   }
   double Hz[18];
 #pragma unroll
   for (int a = 0; a < 3; a++)
 #pragma unroll
     for (int c = 0; c < 6; c++)
-      Hz[6 * a + c] = v.LV[3 * a] * H[c] + v.LV[3 * a + 1] * H[6 + c] + v.LV[3 * a + 2] * H[12 + c];
+      Hz[6 * a + c] = dot3(v.LV[3 * a], H[c], v.LV[3 * a + 1], H[6 + c], v.LV[3 * a + 2], H[12 + c]);
   // dz = L U^T (mean2 - mu1)   (:335-337)
   const double dm[3] = {mean[0] - v.mu[0], mean[1] - v.mu[1], mean[2] - v.mu[2]};
   double dz[3];
 #pragma unroll
-  for (int a = 0; a < 3; a++) dz[a] = v.LV[3 * a] * dm[0] + v.LV[3 * a + 1] * dm[1] + v.LV[3 * a + 2] * dm[2];
+  for (int a = 0; a < 3; a++) dz[a] = dot3(v.LV[3 * a], dm[0], v.LV[3 * a + 1], dm[1], v.LV[3 * a + 2], dm[2]);
   double WH[18], Wdz[3];
 #pragma unroll
   for (int a = 0; a < 3; a++) {
 #pragma unroll
     for (int c = 0; c < 6; c++)
-      WH[6 * a + c] = W[3 * a] * Hz[c] + W[3 * a + 1] * Hz[6 + c] + W[3 * a + 2] * Hz[12 + c];
-    Wdz[a] = W[3 * a] * dz[0] + W[3 * a + 1] * dz[1] + W[3 * a + 2] * dz[2];
+      WH[6 * a + c] = dot3(W[3 * a], Hz[c], W[3 * a + 1], Hz[6 + c], W[3 * a + 2], Hz[12 + c]);
+    Wdz[a] = dot3(W[3 * a], dz[0], W[3 * a + 1], dz[1], W[3 * a + 2], dz[2]);
   }
   int t = 0;
 #pragma unroll
   for (int a = 0; a < 6; a++)
 #pragma unroll
-    for (int b = a; b < 6; b++) acc[t++] += Hz[a] * WH[b] + Hz[6 + a] * WH[6 + b] + Hz[12 + a] * WH[12 + b];
+    for (int b = a; b < 6; b++) acc[t++] += dot3(Hz[a], WH[b], Hz[6 + a], WH[6 + b], Hz[12 + a], WH[12 + b]);
 #pragma unroll
-  for (int a = 0; a < 6; a++) acc[21 + a] += Hz[a] * Wdz[0] + Hz[6 + a] * Wdz[1] + Hz[12 + a] * Wdz[2];
+  for (int a = 0; a < 6; a++) acc[21 + a] += dot3(Hz[a], Wdz[0], Hz[6 + a], Wdz[1], Hz[12 + a], Wdz[2]);
   acc[27] += 1.0;
 }
 
@@ -264,17 +271,17 @@ __device__ __forceinline__ void stats2_from_moments_rec(const unsigned long long
 #pragma unroll
   for (int k = 0; k < 9; k++) R[k] = (double)vm.tr[3 + k];
 #pragma unroll
-  for (int i = 0; i < 3; i++) mean[i] = po[0] * R[i] + po[1] * R[3 + i] + po[2] * R[6 + i];
+  for (int i = 0; i < 3; i++) mean[i] = dot3(po[0], R[i], po[1], R[3 + i], po[2], R[6 + i]);
   double T[9];  // T = Cov_OG R
 #pragma unroll
   for (int a = 0; a < 3; a++)
 #pragma unroll
-    for (int j = 0; j < 3; j++) T[3 * a + j] = co[3 * a] * R[j] + co[3 * a + 1] * R[3 + j] + co[3 * a + 2] * R[6 + j];
+    for (int j = 0; j < 3; j++) T[3 * a + j] = dot3(co[3 * a], R[j], co[3 * a + 1], R[3 + j], co[3 * a + 2], R[6 + j]);
   int t = 0;
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
-    for (int j = i; j < 3; j++) cov[t++] = R[i] * T[j] + R[3 + i] * T[3 + j] + R[6 + i] * T[6 + j];
+    for (int j = i; j < 3; j++) cov[t++] = dot3(R[i], T[j], R[3 + i], T[3 + j], R[6 + i], T[6 + j]);
 }
 
 __device__ __forceinline__ void vox_algebra2(const Chunk& ck, int pair, int cell, int iter, const float* Jm, const VoxMode& vm,
