@@ -71,7 +71,28 @@ __device__ __noinline__ void cluster_solve_phase(const Chunk& ck, int pair, int 
 
 // first_tiles_done: the tiles of iteration 0 of every pair have been processed by a GPU-wide k_pass2 launch already
 // (single pairs: the first rebuild then runs on 148 SMs instead of the cluster's 16)
-__global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck, int first_tiles_done) {
+// nhelp > 0 (single pair / chained pairs): the launch has 1 + nhelp clusters.  Cluster 0 is the pair's cluster as
+// described above; the others are HELPERS that take their share of the scan-2 tiles in REBUILD iterations (every point
+// evaluated: 21 us on the 16 SMs of one cluster, the longest phase of such an iteration) and do nothing else.  Two words
+// in global memory order them: `go` = (sequence number of the iteration << 1 | shared rebuild), published by the master
+// when the iteration starts; `done` = helper warps through with their tiles, awaited by the master before its first
+// cluster barrier.  A helper that finds `go` beyond the iteration it waits for knows that iteration was not shared.
+__device__ __forceinline__ int cluster_spin_ge(const int* p, int need) {  // value >= need, by lane 0; traps after 20 s
+  int v = ld_acquire(p);
+  unsigned long long t0 = 0;
+  for (unsigned spin = 1; v < need; spin++) {
+    __nanosleep(64);
+    v = ld_acquire(p);
+    if ((spin & 1023u) == 0u) {
+      const unsigned long long t = gtime();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 20000000000ull) __trap();
+    }
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck, int first_tiles_done, int nhelp) {
   pdl_prologue();
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
@@ -97,8 +118,46 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck, 
   const bool chain = (ck.flags & ICET_B200_FLAG_CHAIN_X0) != 0;
   const bool inc = loop_incremental(ck);
   const int gwarp = (int)rank * CL_WARPS + warp, nwarp = (int)cs * CL_WARPS;
-  // chained pairs: one cluster walks them in order (the launch has one cluster); independent pairs: round robin
-  for (int pair = chain ? 0 : cl; pair < ck.npairs; pair += chain ? 1 : ncl) {
+  int* go = ck.iter_done;                                  // (words of the persistent kernel, unused in this form)
+  int* done = reinterpret_cast<int*>(ck.tiles_done);
+  const int gw_all = cl * nwarp + gwarp, nw_all = (1 + nhelp) * nwarp;  // this warp among those of all clusters
+  if (nhelp > 0 && cl > 0) {
+    // ------------------------------------------------------------------ helper cluster
+    for (int pair = 0; pair < ck.npairs; pair++) {
+      const int n = __ldg(ck.n2c + pair);
+      const int tiles = max(1, (n + 32 * CL_K - 1) / (32 * CL_K));
+      const CellRec* recs = ck.rec + (size_t)pair * ck.ncell;
+      for (int iter = 0; iter < ck.runlen; iter++) {
+        const int seq = pair * ck.runlen + iter + 1;
+        int g = 0;
+        if (lane == 0) g = cluster_spin_ge(go, seq << 1);
+        g = __shfl_sync(FULL, g, 0);
+        if ((g >> 1) != seq || !(g & 1)) continue;  // not shared (or the master is past it already: it was not)
+        float tr[12];
+        {
+          const float4* tp = reinterpret_cast<const float4*>(ck.TR + (size_t)pair * 12);
+          const float4 a = __ldcg(tp), b = __ldcg(tp + 1), c = __ldcg(tp + 2);
+          tr[0] = a.x; tr[1] = a.y; tr[2] = a.z; tr[3] = a.w; tr[4] = b.x; tr[5] = b.y; tr[6] = b.z; tr[7] = b.w;
+          tr[8] = c.x; tr[9] = c.y; tr[10] = c.z; tr[11] = c.w;
+        }
+        Pass2Mode md;
+        load_pass2_mode(ck, pair, md);
+        for (int tile = gw_all; tile < tiles; tile += nw_all)
+          pass2_warp_tile<CL_K>(ck, went, &s_mbar[warp], mphase, false, tab, recs, tr, md,
+                                ck.pog + (size_t)pair * 3 * ck.n2max, (size_t)ck.n2max, n, tile * 32 * CL_K,
+                                ck.mrec + (size_t)pair * ck.n2max,
+                                (ck.flags & ICET_B200_FLAG_VERIFY_INCREMENTAL) ? &ck.res[pair].reserved[0] : nullptr);
+        __threadfence();  // every lane: its records and moment updates before the warp is counted
+        __syncwarp();
+        if (lane == 0) red_add(reinterpret_cast<unsigned*>(done), 1u);
+      }
+    }
+    return;
+  }
+  int nshared = 0;  // rebuild iterations shared with the helpers so far
+  // chained pairs: one cluster walks them in order; independent pairs: round robin over the clusters of the launch
+  const int pstride = (chain || nhelp > 0) ? 1 : ncl;
+  for (int pair = (chain || nhelp > 0) ? 0 : cl; pair < ck.npairs; pair += pstride) {
     const int n = __ldg(ck.n2c + pair);
     const int tiles = max(1, (n + 32 * CL_K - 1) / (32 * CL_K));
     const CellRec* recs = ck.rec + (size_t)pair * ck.ncell;
@@ -120,9 +179,15 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck, 
       Pass2Mode md;
       if (inc) load_pass2_mode(ck, pair, md);
       const bool skip_tiles = first_tiles_done && iter == 0 && !(chain && pair > 0);
+      // a rebuild iteration is shared with the helper clusters (the mode is what the last solve published: uniform)
+      const bool share = nhelp > 0 && inc && md.rebuild && !skip_tiles;
+      if (nhelp > 0 && rank == 0 && threadIdx.x == 0) {
+        __threadfence();  // (X / TR / mode of this iteration, observed through the cluster barrier, before the flag)
+        st_release(go, ((pair * ck.runlen + iter + 1) << 1) | (share ? 1 : 0));
+      }
       if (!skip_tiles) {
         if (inc) {
-          for (int tile = gwarp; tile < tiles; tile += nwarp)
+          for (int tile = share ? gw_all : gwarp; tile < tiles; tile += share ? nw_all : nwarp)
             pass2_warp_tile<CL_K>(ck, went, &s_mbar[warp], mphase, false, tab, recs, tr, md,
                                         ck.pog + (size_t)pair * 3 * ck.n2max, (size_t)ck.n2max, n, tile * 32 * CL_K,
                                         ck.mrec + (size_t)pair * ck.n2max,
@@ -139,6 +204,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck, 
             pass_dropped_returns(ck, reinterpret_cast<const float4*>(tab), reinterpret_cast<const float4*>(tab) + ck.nT + 2,
                                  recs, tr, accp, __ldg(ck.nz2 + pair));
         }
+      }
+      if (share) {  // (uniform) the helpers' tiles before the voxel phase
+        nshared++;
+        if (rank == 0 && threadIdx.x == 0) cluster_spin_ge(done, nshared * nhelp * nwarp);
       }
       CTL(1);
       // (barrier.cluster has release / acquire semantics at cluster scope: the moments -- RED to L2 -- and the records

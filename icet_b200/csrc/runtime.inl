@@ -59,6 +59,7 @@ struct icet_b200_ctx {
   int* loop_dbg[ICET_NLANE] = {};  // watchdog record of the last k_loop launch per lane
   unsigned long long loop_timeout_ns = 20000000000ull;  // ICET_B200_LOOP_TIMEOUT_MS
   float inc_max_sa = INC_MAX_SA, inc_max_sb = INC_MAX_SB;  // rebuild bounds of the incremental loop (ICET_B200_INC_SA / _SB: A/B runs)
+  int cluster_helpers = 3;  // helper clusters of a single / chained pair (ICET_B200_CLUSTER_HELPERS: A/B runs, 0 = none)
   int cluster_cs = 0, cluster_max = 0, cluster_nT = -1, cluster_nP = -1;  // k_loop_cluster: cluster size, clusters resident at once
   int loop_occ[2] = {0, 0};  // resident blocks per SM of k_loop<PASS_K>, k_loop<PASS_K_SMALL>
   // per-kernel timing (icet_b200_set_profile): events around every launch, summed on request
@@ -516,8 +517,11 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
       LAUNCH(7, CK(launch_ex(k_pass2<PASS_K_SMALL, 3>, dim3((n2max + tile_s - 1) / tile_s, P), dim3(PASS_THREADS), psm2,
                              !prep_aside, ck)));
     }
+    // single pair / chained pairs: helper clusters share the tiles of the rebuild iterations (kernels_cluster.cuh)
+    const int nhelp = ((chain || P == 1) && !(p->flags & ICET_B200_FLAG_EXACT_PASS) && n2max > 0)
+                          ? std::max(0, std::min(ctx->cluster_helpers, ctx->cluster_max - 1)) : 0;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ncl * cs);
+    cfg.gridDim = dim3((nhelp > 0 ? 1 + nhelp : ncl) * cs);
     cfg.blockDim = dim3(CL_THREADS);
     cfg.dynamicSmemBytes = cluster_smem_bytes(nT, nP, cs);
     cfg.stream = st;
@@ -528,7 +532,7 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = (pdl && (first_tiles || !prep_aside)) ? 2 : 1;  // (after an event wait the edge is an ordinary one)
-    LAUNCH(10, CK(cudaLaunchKernelEx(&cfg, k_loop_cluster, ck, first_tiles)));
+    LAUNCH(10, CK(cudaLaunchKernelEx(&cfg, k_loop_cluster, ck, first_tiles, nhelp)));
   } else if (!use_loop) {
     // the per-voxel algebra walks the pair's ACTIVE voxels (a sixth of the cells): VOX_GRID blocks per pair instead of
     // one per 64 cells (a 256-pair launch had 7 424 blocks in six waves, most of them without a voxel).  With per-voxel
