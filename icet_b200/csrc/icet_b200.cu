@@ -79,6 +79,7 @@ int icet_b200_create(int device, icet_b200_ctx** out) {
     const long long ms = atoll(e);
     if (ms > 0) c->loop_timeout_ns = (unsigned long long)ms * 1000000ull;
   }
+  if (const char* e = getenv("ICET_B200_FIRST_TILES")) c->first_tiles_wide = atoi(e) != 0;
   if (const char* e = getenv("ICET_B200_CLUSTER_HELPERS")) { const int v = atoi(e); if (v >= 0 && v <= 8) c->cluster_helpers = v; }
   if (const char* e = getenv("ICET_B200_INC_SA")) { const double v = atof(e); if (v > 0 && v <= 4e-3) c->inc_max_sa = (float)v; }
   if (const char* e = getenv("ICET_B200_INC_SB")) { const double v = atof(e); if (v > 0 && v <= 0.15) c->inc_max_sb = (float)v; }

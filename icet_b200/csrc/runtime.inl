@@ -59,6 +59,7 @@ struct icet_b200_ctx {
   int* loop_dbg[ICET_NLANE] = {};  // watchdog record of the last k_loop launch per lane
   unsigned long long loop_timeout_ns = 20000000000ull;  // ICET_B200_LOOP_TIMEOUT_MS
   float inc_max_sa = INC_MAX_SA, inc_max_sb = INC_MAX_SB;  // rebuild bounds of the incremental loop (ICET_B200_INC_SA / _SB: A/B runs)
+  int first_tiles_wide = 1;  // single pair: the tiles of iteration 0 by a GPU-wide k_pass2 launch (ICET_B200_FIRST_TILES)
   int cluster_helpers = 3;  // helper clusters of a single / chained pair (ICET_B200_CLUSTER_HELPERS: A/B runs, 0 = none)
   int cluster_cs = 0, cluster_max = 0, cluster_nT = -1, cluster_nP = -1;  // k_loop_cluster: cluster size, clusters resident at once
   int loop_occ[2] = {0, 0};  // resident blocks per SM of k_loop<PASS_K>, k_loop<PASS_K_SMALL>
@@ -511,7 +512,7 @@ int run_chunk(icet_b200_ctx* ctx, const icet_b200_params* p, int P, const PairDe
     const int cs = ctx->cluster_cs;
     const int ncl = chain ? 1 : std::max(1, std::min(P, ctx->cluster_max));
     // single pairs: the tiles of iteration 0 (always a rebuild) run GPU-wide first, the cluster starts at its voxel phase
-    const int first_tiles = (!chain && P == 1 && n2max > 0 && !(p->flags & ICET_B200_FLAG_EXACT_PASS)) ? 1 : 0;
+    const int first_tiles = (!chain && P == 1 && n2max > 0 && !(p->flags & ICET_B200_FLAG_EXACT_PASS) && ctx->first_tiles_wide) ? 1 : 0;
     if (first_tiles) {
       const int tile_s = pass_tile_points(PASS_K_SMALL);
       LAUNCH(7, CK(launch_ex(k_pass2<PASS_K_SMALL, 3>, dim3((n2max + tile_s - 1) / tile_s, P), dim3(PASS_THREADS), psm2,
