@@ -589,6 +589,39 @@ def test_chained_batch_equals_seeded_single_calls(ctx):
     assert d["X"].tobytes() == out["X"].tobytes()
 
 
+def test_helper_clusters_stress(ctx):
+    """The helper clusters of the latency shape (kernels_cluster.cuh: three more clusters share the tiles of rebuild
+    iterations, ordered by the `go` / `done` words): many single and chained calls back to back -- real pairs whose
+    iterations mix rebuilds and deltas, far seeds that rebuild in every iteration, degenerate clouds without a single
+    active voxel, zero / one / many iterations.  Every call must return (a protocol failure traps after 20 s instead of
+    hanging) and give the bits of the first call; the one-thread-per-point diagnostic mode (no helpers) must agree."""
+    from icet_b200 import api
+    from tools import synth_host
+    scans = synth_host.scans(5, first_scan=200, seed=20240, rings=64, azim=2048)
+    z = np.zeros((3, 4096), np.float32)
+    far = np.array([1.5, 0.4, 0.0, 0.0, 0.0, 0.05], np.float32)
+    cases = [(scans[0], scans[1], None, 7), (scans[1], scans[2], far, 7), (z, z, far, 7), (scans[2], scans[3], None, 1),
+             (scans[2], scans[3], None, 20), (np.ones((3, 10), np.float32), scans[1], None, 3)]
+    first = [ctx.register(a, b, X0=x, params=params(runlen=rl)).copy() for a, b, x, rl in cases]
+    for rep in range(60):
+        for (a, b, x, rl), f in zip(cases, first):
+            r = ctx.register(a, b, X0=x, params=params(runlen=rl))
+            assert r["status"] == f["status"]
+            assert r["X"].tobytes() == f["X"].tobytes() and r["Q"].tobytes() == f["Q"].tobytes()
+    # chained calls of different lengths in between single ones
+    pc = api.make_params(flags=api.FLAG_CHAIN_X0)
+    ref = None
+    for rep in range(20):
+        out = ctx.register_batch([scans[k] for k in range(4)], [scans[k + 1] for k in range(4)], far, pc)
+        ref = out.copy() if ref is None else ref
+        assert out["X"].tobytes() == ref["X"].tobytes()
+        r = ctx.register(scans[0], scans[1])
+        assert r["X"].tobytes() == first[0]["X"].tobytes()
+    # the per-point form of the loop runs without helpers: same classes, statistics within rounding -> same transform
+    e = ctx.register(scans[0], scans[1], params=params(flags=api.FLAG_EXACT_PASS))
+    assert np.abs(e["X"] - first[0]["X"]).max() < 2e-6
+
+
 def test_big_cells_bucket_clustering(ctx, po):
     """Cells with thousands of ranges (an accumulated map as scan 1, coarse grids) take the bucket form of findCluster
     (no sort: count / min / max per half-threshold bucket, walked in ascending order).  Cluster bounds must be
