@@ -74,9 +74,13 @@ __device__ __noinline__ void cluster_solve_phase(const Chunk& ck, int pair, int 
 // nhelp > 0 (single pair / chained pairs): the launch has 1 + nhelp clusters.  Cluster 0 is the pair's cluster as
 // described above; the others are HELPERS that take their share of the scan-2 tiles in REBUILD iterations (every point
 // evaluated: 21 us on the 16 SMs of one cluster, the longest phase of such an iteration) and do nothing else.  Two words
-// in global memory order them: `go` = (sequence number of the iteration << 1 | shared rebuild), published by the master
-// when the iteration starts; `done` = helper warps through with their tiles, awaited by the master before its first
-// cluster barrier.  A helper that finds `go` beyond the iteration it waits for knows that iteration was not shared.
+// in global memory order them: `go` = (sequence number of the iteration << 1 | shared rebuild), published by the solve
+// warp of the master as soon as it has written the transform and the mode of that iteration (the helpers start on the
+// tiles while the master is still in the barrier that ends the previous one); `done` = helper warps through with their
+// tiles, awaited by the master before its first cluster barrier.  A helper that finds `go` beyond the iteration it
+// waits for knows that iteration was not shared.  An iteration is shared only if every helper cluster has reported
+// itself RESIDENT (`alive`) when the solve warp decides: the master never waits for a cluster that is not running, so
+// the scheme cannot deadlock however the clusters of concurrent launches are placed.
 __device__ __forceinline__ int cluster_spin_ge(const int* p, int need) {  // value >= need, by lane 0; traps after 20 s
   int v = ld_acquire(p);
   unsigned long long t0 = 0;
@@ -120,9 +124,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck, 
   const int gwarp = (int)rank * CL_WARPS + warp, nwarp = (int)cs * CL_WARPS;
   int* go = ck.iter_done;                                  // (words of the persistent kernel, unused in this form)
   int* done = reinterpret_cast<int*>(ck.tiles_done);
+  int* alive = reinterpret_cast<int*>(ck.vox_done);
   const int gw_all = cl * nwarp + gwarp, nw_all = (1 + nhelp) * nwarp;  // this warp among those of all clusters
   if (nhelp > 0 && cl > 0) {
     // ------------------------------------------------------------------ helper cluster
+    if (rank == 0 && threadIdx.x == 0) red_add(reinterpret_cast<unsigned*>(alive), 1u);  // (a cluster is co-scheduled)
     for (int pair = 0; pair < ck.npairs; pair++) {
       const int n = __ldg(ck.n2c + pair);
       const int tiles = max(1, (n + 32 * CL_K - 1) / (32 * CL_K));
@@ -180,10 +186,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck, 
       if (inc) load_pass2_mode(ck, pair, md);
       const bool skip_tiles = first_tiles_done && iter == 0 && !(chain && pair > 0);
       // a rebuild iteration is shared with the helper clusters (the mode is what the last solve published: uniform)
-      const bool share = nhelp > 0 && inc && md.rebuild && !skip_tiles;
-      if (nhelp > 0 && rank == 0 && threadIdx.x == 0) {
-        __threadfence();  // (X / TR / mode of this iteration, observed through the cluster barrier, before the flag)
-        st_release(go, ((pair * ck.runlen + iter + 1) << 1) | (share ? 1 : 0));
+      const bool first_iter = pair == 0 && iter == 0;  // (no solve of this launch in front of it: never shared)
+      const bool share = nhelp > 0 && inc && md.rebuild && !skip_tiles && !first_iter && __ldcg(&ck.pm[pair].pad[0]) != 0;
+      if (nhelp > 0 && first_iter && rank == 0 && threadIdx.x == 0) {
+        __threadfence();
+        st_release(go, 1 << 1);
       }
       if (!skip_tiles) {
         if (inc) {
@@ -221,8 +228,24 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck, 
       CTL(4);
       // ------------------------------------------------------------------ phase 3: DSMEM reduction + solve
       if (rank == 0 && warp == 0) {
+        int nalive = 0;
+        if (nhelp > 0 && lane == 0) nalive = ld_relaxed(alive);  // (requested now, needed after the solve)
         ModeNow now = {md.SA, md.SB, md.set};
         cluster_solve_phase(ck, pair, iter, (int)cs, cpart, wpart, inc ? &now : nullptr);
+        // the NEXT iteration (of this pair, or the first one of the next chained pair) is announced right here
+        if (nhelp > 0) {
+          int npair = pair, niter = iter + 1;
+          if (niter == ck.runlen) { npair = pair + 1; niter = 0; }
+          if (npair < ck.npairs) {
+            __syncwarp();  // (the lanes' stores of X / TR / J / mode before lane 0 publishes)
+            if (lane == 0) {
+              const int sh = (inc && __ldcg(&ck.pm[npair].rebuild) != 0 && nalive == nhelp) ? 1 : 0;
+              ck.pm[npair].pad[0] = sh;
+              __threadfence();
+              st_release(go, ((npair * ck.runlen + niter + 1) << 1) | sh);
+            }
+          }
+        }
       }
       CTL(5);
       cluster.sync();
