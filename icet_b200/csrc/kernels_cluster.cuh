@@ -17,7 +17,7 @@
 #pragma once
 // (icet_b200.cu includes <cooperative_groups.h> at global scope)
 
-constexpr int CL_THREADS = 512;
+constexpr int CL_THREADS = 256;
 constexpr int CL_WARPS = CL_THREADS / 32;
 constexpr int CL_K = PASS_K_SMALL;  // rows per warp tile (128 points: ~4 tiles per warp of a 16-CTA cluster at 64 channels)
 

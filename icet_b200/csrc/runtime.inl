@@ -60,7 +60,7 @@ struct icet_b200_ctx {
   unsigned long long loop_timeout_ns = 20000000000ull;  // ICET_B200_LOOP_TIMEOUT_MS
   float inc_max_sa = INC_MAX_SA, inc_max_sb = INC_MAX_SB;  // rebuild bounds of the incremental loop (ICET_B200_INC_SA / _SB: A/B runs)
   int first_tiles_wide = 1;  // single pair: the tiles of iteration 0 by a GPU-wide k_pass2 launch (ICET_B200_FIRST_TILES)
-  int cluster_helpers = 3;  // helper clusters of a single / chained pair (ICET_B200_CLUSTER_HELPERS: A/B runs, 0 = none)
+  int cluster_helpers = 7;  // helper clusters of a single / chained pair (ICET_B200_CLUSTER_HELPERS: A/B runs, 0 = none)
   int cluster_cs = 0, cluster_max = 0, cluster_nT = -1, cluster_nP = -1;  // k_loop_cluster: cluster size, clusters resident at once
   int loop_occ[2] = {0, 0};  // resident blocks per SM of k_loop<PASS_K>, k_loop<PASS_K_SMALL>
   // per-kernel timing (icet_b200_set_profile): events around every launch, summed on request
