@@ -81,19 +81,20 @@ __device__ __noinline__ void cluster_solve_phase(const Chunk& ck, int pair, int 
 // waits for knows that iteration was not shared.  An iteration is shared only if every helper cluster has reported
 // itself RESIDENT (`alive`) when the solve warp decides: the master never waits for a cluster that is not running, so
 // the scheme cannot deadlock however the clusters of concurrent launches are placed.
-__device__ __forceinline__ int cluster_spin_ge(const int* p, int need) {  // value >= need, by lane 0; traps after 20 s
-  int v = ld_acquire(p);
+__device__ __forceinline__ int cluster_spin_ge(const int* p, int need) {  // value >= need, by one lane; traps after 20 s
+  // (relaxed polling: an acquire load invalidates the SM's L1 every time; one acquire load once the value is there)
+  int v = ld_relaxed(p);
   unsigned long long t0 = 0;
   for (unsigned spin = 1; v < need; spin++) {
-    __nanosleep(64);
-    v = ld_acquire(p);
+    __nanosleep(32);
+    v = ld_relaxed(p);
     if ((spin & 1023u) == 0u) {
       const unsigned long long t = gtime();
       if (t0 == 0) t0 = t;
       else if (t - t0 > 20000000000ull) __trap();
     }
   }
-  return v;
+  return ld_acquire(p);
 }
 
 __global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck, int first_tiles_done, int nhelp) {
@@ -188,10 +189,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck, 
       // a rebuild iteration is shared with the helper clusters (the mode is what the last solve published: uniform)
       const bool first_iter = pair == 0 && iter == 0;  // (no solve of this launch in front of it: never shared)
       const bool share = nhelp > 0 && inc && md.rebuild && !skip_tiles && !first_iter && __ldcg(&ck.pm[pair].pad[0]) != 0;
-      if (nhelp > 0 && first_iter && rank == 0 && threadIdx.x == 0) {
-        __threadfence();
-        st_release(go, 1 << 1);
-      }
+      if (nhelp > 0 && first_iter && rank == 0 && threadIdx.x == 0) st_release(go, 1 << 1);
       if (!skip_tiles) {
         if (inc) {
           for (int tile = share ? gw_all : gwarp; tile < tiles; tile += share ? nw_all : nwarp)
@@ -241,7 +239,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck, 
             if (lane == 0) {
               const int sh = (inc && __ldcg(&ck.pm[npair].rebuild) != 0 && nalive == nhelp) ? 1 : 0;
               ck.pm[npair].pad[0] = sh;
-              __threadfence();
               st_release(go, ((npair * ck.runlen + niter + 1) << 1) | sh);
             }
           }
