@@ -72,8 +72,9 @@ __device__ __noinline__ void cluster_solve_phase(const Chunk& ck, int pair, int 
 // first_tiles_done: the tiles of iteration 0 of every pair have been processed by a GPU-wide k_pass2 launch already
 // (single pairs: the first rebuild then runs on 148 SMs instead of the cluster's 16)
 // nhelp > 0 (single pair / chained pairs): the launch has 1 + nhelp clusters.  Cluster 0 is the pair's cluster as
-// described above; the others are HELPERS that take their share of the scan-2 tiles in REBUILD iterations (every point
-// evaluated: 21 us on the 16 SMs of one cluster, the longest phase of such an iteration) and do nothing else.  Two words
+// described above; the others are HELPERS that take their share of the scan-2 tiles of every iteration (a rebuild
+// evaluates every point: 21 us on the 16 SMs of one cluster; the delta iterations right after it re-evaluate a good
+// part of them) and do nothing else.  Two words
 // in global memory order them: `go` = (sequence number of the iteration << 1 | shared rebuild), published by the solve
 // warp of the master as soon as it has written the transform and the mode of that iteration (the helpers start on the
 // tiles while the master is still in the barrier that ends the previous one); `done` = helper warps through with their
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck, 
       const bool skip_tiles = first_tiles_done && iter == 0 && !(chain && pair > 0);
       // a rebuild iteration is shared with the helper clusters (the mode is what the last solve published: uniform)
       const bool first_iter = pair == 0 && iter == 0;  // (no solve of this launch in front of it: never shared)
-      const bool share = nhelp > 0 && inc && md.rebuild && !skip_tiles && !first_iter && __ldcg(&ck.pm[pair].pad[0]) != 0;
+      const bool share = nhelp > 0 && inc && !skip_tiles && !first_iter && __ldcg(&ck.pm[pair].pad[0]) != 0;
       if (nhelp > 0 && first_iter && rank == 0 && threadIdx.x == 0) st_release(go, 1 << 1);
       if (!skip_tiles) {
         if (inc) {
@@ -237,7 +238,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck, 
           if (npair < ck.npairs) {
             __syncwarp();  // (the lanes' stores of X / TR / J / mode before lane 0 publishes)
             if (lane == 0) {
-              const int sh = (inc && __ldcg(&ck.pm[npair].rebuild) != 0 && nalive == nhelp) ? 1 : 0;
+              // every iteration is shared when the helpers are there (measured: sharing only rebuilds 0.2015 ms /
+              // 6.3 k chained pairs/s; rebuilds + deltas after a step of millimetres 0.196 / 6.5 k; everything 0.188 / 7.0 k)
+              const int sh = (inc && nalive == nhelp) ? 1 : 0;
               ck.pm[npair].pad[0] = sh;
               st_release(go, ((npair * ck.runlen + niter + 1) << 1) | sh);
             }
