@@ -64,6 +64,7 @@ __device__ __noinline__ void cluster_solve_phase(const Chunk& ck, int pair, int 
   for (int r = 0; r < 16; r++) tot += pv[r];
   if (lane < NRED) w_tot[lane] = tot;  // (phase 2 is over: its scratch is reused)
   __syncwarp();
+  if (ck.dump_on && lane == 0) ck.dump.tl[(size_t)iter * 16 + 11] = gtime();  // (debug timeline: partial sums gathered)
   bool done = false;
   if (!(ck.flags & ICET_B200_FLAG_FULL_EIG)) done = solve_pair_warp(ck, pair, iter, w_tot, cur);
   if (!done && lane == 0) solve_pair(ck, pair, iter, w_tot, cur);
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_loop_cluster(const Chunk ck, 
         if (nhelp > 0 && lane == 0) nalive = ld_relaxed(alive);  // (requested now, needed after the solve)
         ModeNow now = {md.SA, md.SB, md.set};
         cluster_solve_phase(ck, pair, iter, (int)cs, cpart, wpart, inc ? &now : nullptr);
+        if (ck.dump_on && lane == 0) ck.dump.tl[(size_t)iter * 16 + 12] = gtime();  // (debug timeline: solved)
         // the NEXT iteration (of this pair, or the first one of the next chained pair) is announced right here
         if (nhelp > 0) {
           int npair = pair, niter = iter + 1;

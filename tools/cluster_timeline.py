@@ -31,6 +31,9 @@ for it in range(p.runlen):
     d = np.diff(tl[it, :7]) / 1e3
     print("%9d   " % it + "  ".join("%7.2f" % v for v in d) + "   %7.2f" % ((tl[it, 6] - tl[it, 0]) / 1e3))
 print("loop total %.1f us" % ((tl[p.runlen - 1, 6] - tl[0, 0]) / 1e3))
+print("solve phase: partial sums gathered (DSMEM) / solved and stored / next iteration announced, us after the phase began")
+for it in range(p.runlen):
+    print("%9d   %7.2f %7.2f %7.2f" % (it, (tl[it, 11] - tl[it, 4]) / 1e3, (tl[it, 12] - tl[it, 4]) / 1e3, (tl[it, 5] - tl[it, 4]) / 1e3))
 print("voxel phase of CTA 0: last voxel done / last warp reduced, us after the phase began")
 for it in range(p.runlen):
     print("%9d   %7.2f %7.2f   (phase %.2f)" % (it, (tl[it, 8] - tl[it, 2]) / 1e3, (tl[it, 9] - tl[it, 2]) / 1e3, (tl[it, 3] - tl[it, 2]) / 1e3))
