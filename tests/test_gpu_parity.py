@@ -622,6 +622,41 @@ def test_helper_clusters_stress(ctx):
     assert np.abs(e["X"] - first[0]["X"]).max() < 2e-6
 
 
+def test_concurrent_contexts_single_pairs(ctx):
+    """Several host threads, one context each, registering single pairs on the SAME device at the same time (the
+    reference: "run multiple ICETs at once", include/icet.h:43).  Every launch asks for 1 + 7 clusters while the device
+    holds about eight: a launch whose helper clusters are not resident must carry on alone (the `alive` rule of the
+    cluster loop), never wait for them.  Results equal the serial ones bit for bit."""
+    import threading
+    import icet_b200
+    from tools import synth_host
+    scans = synth_host.scans(4, first_scan=300, seed=20240, rings=64, azim=2048)
+    ref = [ctx.register(scans[k], scans[k + 1]).copy() for k in range(3)]
+    errors = []
+
+    def worker(tid):
+        try:
+            c = icet_b200.Context(0)
+            try:
+                for rep in range(40):
+                    k = (rep + tid) % 3
+                    r = c.register(scans[k], scans[k + 1])
+                    if r["X"].tobytes() != ref[k]["X"].tobytes() or r["Q"].tobytes() != ref[k]["Q"].tobytes():
+                        errors.append((tid, rep, k))
+            finally:
+                c.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append((tid, repr(e)))
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=240)
+    assert not any(t.is_alive() for t in th), "a registration did not return"
+    assert not errors, errors[:5]
+
+
 def test_big_cells_bucket_clustering(ctx, po):
     """Cells with thousands of ranges (an accumulated map as scan 1, coarse grids) take the bucket form of findCluster
     (no sort: count / min / max per half-threshold bucket, walked in ascending order).  Cluster bounds must be
